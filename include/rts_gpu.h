@@ -1,0 +1,232 @@
+/*
+ * rts_gpu.h — C ABI of the B200-native agent-update hot path of RTSEngine.
+ *
+ * One call to rts_step() advances every agent by one 1/60 s frame and replaces, for the
+ * Physics and Seek systems, what ECSystem::update does on the CPU
+ * (reference: src/ECS.cpp:65-113):
+ *
+ *   bin agents into the neighbour-search grid        src/Utils/NeighbourSearcherContext.cpp:18-64
+ *   physics neighbour pass  (|dr|^2 < r_max2)        src/Utils/NeighbourSearcherStrategy.cpp:10-68
+ *   boids forces, clamp, inertia decay               src/Systems/PhysicsSystem.cpp:16-117
+ *   wall constraint, applied twice                   src/Systems/PhysicsSystem.cpp:130-162, src/Edges.cpp:245-296
+ *   seek toward the funnel waypoint, turn, advance   src/Systems/SeekSystem.cpp:76-111,181-233,277-304,344-385
+ *   merge velocities, integrate                      src/Systems/*System.cpp communicate(), src/ECS.cpp:92-113
+ *   point-in-triangle walk on the CDT                src/PathFinding/Triangulation.cpp:1497-1567
+ *
+ * The structs are plain data; every pointer is a HOST pointer unless its name ends in _dev.
+ * A handle is single-caller (the reference drives its systems from one thread, src/main.cpp:80).
+ * All functions return RTS_OK or a negative RtsStatus; rts_last_error() gives the text.
+ * There is no CPU fallback: every entry point that computes needs a CUDA device.
+ */
+#ifndef RTS_GPU_H
+#define RTS_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum RtsStatus {
+    RTS_OK = 0,
+    RTS_E_CUDA = -1,     /* a CUDA runtime call failed                                   */
+    RTS_E_NCCL = -2,     /* an NCCL call failed                                          */
+    RTS_E_ARG = -3,      /* bad argument (null pointer, size mismatch, out of range)     */
+    RTS_E_CAPACITY = -4, /* a fixed-capacity buffer overflowed (halo / migration)        */
+    RTS_E_STATE = -5     /* call order violated (step before map/agents are uploaded)    */
+} RtsStatus;
+
+/* MoveState, src/core.h:311-315 */
+enum { RTS_MOVING = 0, RTS_STANDING = 1, RTS_HOLDING = 2 };
+
+/* per-agent flag bits reported by rts_download (RtsAgentView.flags) */
+enum {
+    RTS_FLAG_REPLAN = 1u,     /* updateTarget() shifted the window and asked for a re-plan (SeekSystem.cpp:294-303) */
+    RTS_FLAG_WALK_FAILED = 2u /* triangle walk hit its hop limit or an inconsistent table                           */
+};
+
+/* Simulation parameters. rts_default_params() fills the reference's values. */
+typedef struct RtsParams {
+    /* MapGrid (wall lookup grid): cells of map_cell_size units, src/Geometry.h:3-7 */
+    int32_t map_nx, map_ny;
+    float map_cell_size; /* 5 */
+    /* physics neighbour-search grid: ns_n = int(W / ns_cell_size) + 1, cell = 20*RHARD = 60
+       (NeighbourSearcherContext.cpp:70-71, PhysicsSystem.cpp:5-9) */
+    int32_t ns_nx, ns_ny;
+    float ns_cell_size;
+    float r_max2; /* 30: "10*RHARD" is passed where a squared radius is expected (Context.cpp:13) */
+    /* triangle cache grid (SearchGrid of the Triangulation), src/main.cpp:50 */
+    int32_t tri_nx, tri_ny;
+    float tri_cell_size; /* 40 */
+    /* PhysicsSystem::force_multipliers, defaults from src/UI.cpp:124-131 */
+    float mul_push, mul_repulse, mul_scatter, mul_align, mul_seek, mul_decay, mul_velocity;
+    float dt;           /* 1/60, src/ECS.h:18 */
+    float rhard;        /* 3,  src/core.h:95 */
+    float rscatter;     /* 50, src/core.h:94 */
+    float sys_max_speed;/* PhysicsSystem::max_speed = 25 (PhysicsSystem.h:37); inert clamp at PhysicsSystem.cpp:27-30 */
+    /* SeekSystemSettings, src/Settings.cpp:53-56 (used by the arrival rule) */
+    float finish_angle, finish_radius, finish_n_steps, finish_cone_len;
+    /* behaviour switches */
+    uint32_t enable_arrival; /* 0: finalizeSeek is skipped (single-step parity mode); 1: two-phase arrival rule */
+    uint32_t walk_all;       /* 1: keep tri_idx for every agent; 0: MOVING agents only (as SeekSystem.cpp:206) */
+    /* multi-GPU slab owned by this handle: physics-grid rows [slab_row_lo, slab_row_hi); 0,ns_ny = whole map */
+    int32_t slab_row_lo, slab_row_hi;
+    uint32_t reserved[6];
+} RtsParams;
+
+/* CDT triangle, counter-clockwise; neighbours[k] is across edge (verts[k], verts[k+1]).
+   Mirrors `Triangle` of src/PathFinding/Triangulation.h:35-48 (44 B there, 48 B here). */
+typedef struct RtsTriangle {
+    int32_t vx[3], vy[3];
+    uint32_t neighbours[3]; /* 0xFFFFFFFF = none */
+    uint8_t is_constrained[3];
+    uint8_t type;
+    uint32_t pad_[2];
+} RtsTriangle;
+
+/* wall segment, `Edgef` of src/core.h:217-232; outward normal is (t.y, -t.x) */
+typedef struct RtsEdge {
+    float from_x, from_y, t_x, t_y, l;
+} RtsEdge;
+
+/* The four orientation-indexed 1-D edge finders of `Edges` (src/Edges.h:15-46, EdgesFinder1D.h:11-48)
+   flattened to CSR: line_offsets[o] has n_lines[o]+1 entries into edges[o]; every line keeps the
+   order of edge_array2_[line] (sorted by the map builder, MapGrid.cpp:1277-1303). */
+typedef struct RtsWallTable {
+    const RtsEdge* edges[4];
+    const uint32_t* line_offsets[4];
+    uint32_t n_lines[4]; /* ny+1, nx+ny+1, nx+1, nx+ny+1  (Edges.cpp:6-19) */
+} RtsWallTable;
+
+/* Funnel paths. Path p owns waypoints [offsets[p], offsets[p+1]); waypoint k carries the portal
+   the agent crosses to reach it (PathFinder2::PathAndPortals, PathFinder2.h:62-66). An agent at
+   waypoint index w steers to r_next (initially waypoint w) with portal_next = portal w,
+   r_next_next = waypoint min(w+1, last), portal_next_next likewise: exactly the two-entry window
+   of PathFinderComponent (src/Systems/Components.h:96-119).  A drop-in host that keeps the
+   reference planner uploads one 2-waypoint path per agent. */
+typedef struct RtsPathTable {
+    uint32_t n_paths;
+    const uint32_t* offsets;  /* n_paths + 1 */
+    const float* waypoints;   /* 2 floats per waypoint */
+    const RtsEdge* portals;   /* one per waypoint */
+    const float* path_end;    /* 2 floats per path: the commanded destination (PathFinderComponent::path_end) */
+} RtsPathTable;
+
+/* per-unit-type constants (UnitTypes.txt + component defaults, Components.h:84-119) */
+typedef struct RtsUnitType {
+    float lambda;         /* 0.169 inertia decay        */
+    float max_speed;      /* 25   PhysicsComponent      */
+    float seek_max_speed; /* 50   PathFinderComponent   */
+    float turn_rate;      /* 5 degrees / frame          */
+    float desired_angle;  /* 0                          */
+    float pad_[3];
+} RtsUnitType;
+
+/* Agent state, structure of arrays in the caller's component order (index = component index of the
+   reference's dense component vectors; it defines the summation order of the force pass).
+   In rts_set_agents every pointer except r may be NULL (defaults in brackets). In rts_download a
+   NULL pointer means "not wanted". */
+typedef struct RtsAgentView {
+    float* r;            /* 2n  position                                               */
+    float* vel;          /* 2n  download only: merged velocity of the last step before ECS.cpp:112 zeroes it */
+    float* inertia;      /* 2n  PhysicsComponent::inertia_vel                     [0]  */
+    float* angle;        /* n   degrees                                           [0]  */
+    float* angle_vel;    /* n                                                     [0]  */
+    float* radius;       /* n                                                     [3]  */
+    float* mass;         /* n                                                     [1]  */
+    uint8_t* state;      /* n   MoveState                                  [STANDING]  */
+    uint8_t* player;     /* n                                                     [0]  */
+    uint8_t* unit_type;  /* n   index into the unit-type table                    [0]  */
+    int32_t* path_id;    /* n   index into the path table, -1 = none             [-1]  */
+    int32_t* waypoint;   /* n   waypoint index within the path                    [0]  */
+    float* r_next;       /* 2n  current steering target; NaN = take it from the path table [NaN] */
+    uint32_t* gid;       /* n   global id: orders neighbours inside a cell (= component index) [index] */
+    uint32_t* tri_idx;   /* n   download only: containing CDT triangle                 */
+    uint32_t* ns_cell;   /* n   download only: physics neighbour-grid cell (Grid::coordToCell) */
+    uint32_t* map_cell;  /* n   download only: MapGrid cell (Grid::coordToCell, 5-unit grid)   */
+    uint32_t* flags;     /* n   download only: RTS_FLAG_*                               */
+} RtsAgentView;
+
+typedef struct RtsTimings {
+    double last_step_ms; /* CUDA-event time of the last rts_step call / n_steps */
+    double kernel_ms[8]; /* bin, scan, reorder, step, (reserved)              */
+    uint64_t kernel_launches;
+    uint64_t steps;
+} RtsTimings;
+
+typedef struct RtsContext* RtsHandle;
+
+/* reference defaults for a map of map_nx × map_ny cells (5 units each) */
+void rts_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny);
+
+/* replaces: construction of PhysicsSystem / SeekSystem (PhysicsSystem.cpp:5-9, SeekSystem.cpp:5-10) */
+int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out);
+int32_t rts_destroy(RtsHandle h);
+const char* rts_last_error(RtsHandle h);
+/* replaces: the UI writing PhysicsSystem::force_multipliers / SeekSystem::settings_ (UI.cpp:121-165) */
+int32_t rts_set_params(RtsHandle h, const RtsParams* params);
+
+/* replaces: the tables PhysicsSystem::p_map_ (Edges*) and SeekSystem::p_cdt_ (Triangulation*) point at;
+   call again after Game::updateTriangulation (Game.cpp:38-48). cell2tri has tri_nx*tri_ny entries. */
+int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
+                       const RtsWallTable* walls);
+int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_types);
+/* replaces: PathFinder2::setPathOfAgent writing windows into PathFinderComponents (PathFinder2.cpp:326-380) */
+int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths);
+
+/* replaces: System2::addComponent for every agent (ECS.h:165-174) — sets the whole population */
+int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents);
+/* replaces: System2::addComponent — appends m agents at indices n..n+m-1 */
+int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents);
+/* replaces: System2::remove (swap-with-last, ECS.h:197-214); indices are component indices */
+int32_t rts_remove_agents(RtsHandle h, const uint32_t* indices, uint32_t m);
+/* replaces: ECSystem::setMoveState + SeekSystem::issuePaths2 (Game.cpp:211-231): assign path/state to m agents */
+int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int32_t path_id, uint8_t state);
+uint32_t rts_agent_count(RtsHandle h);
+
+/* replaces: PhysicsSystem::update + SeekSystem::update + communicate + avoidWall + integration
+   (ECS.cpp:65-113), n_steps frames, asynchronous on the handle's stream */
+int32_t rts_step(RtsHandle h, uint32_t n_steps);
+/* replaces: System2::communicate → SharedData (ECS.h:136-145); synchronises */
+int32_t rts_download(RtsHandle h, const RtsAgentView* out);
+int32_t rts_sync(RtsHandle h);
+int32_t rts_get_timings(RtsHandle h, RtsTimings* out);
+/* device time (ms, CUDA events on the handle's stream) of the last `count` kernels of kind `which`
+   0 = fused step kernel, 1 = bin/count, 2 = scan, 3 = reorder; used by bench.py for the roofline line */
+int32_t rts_kernel_time_ms(RtsHandle h, int32_t which, double* avg_ms, uint64_t* launches);
+int32_t rts_reset_timings(RtsHandle h);
+
+/* stand-alone data-parallel queries (each replaces a per-point loop over the reference function) */
+/* Grid::coordToCell (Grid.cpp:18-24) for n points on an nx×ny grid of cell size cs */
+int32_t rts_coord_to_cell(RtsHandle h, const float* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out);
+/* Triangulation::findTriangle(Vector2f,false) (Triangulation.cpp:1588-1590) against the uploaded CDT */
+int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* out);
+/* Edges::calcContactEdgesO (Edges.cpp:245-296): per point the number of contact walls, and up to `cap`
+   of them in visit order (5 floats each) */
+int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uint32_t n, uint32_t cap,
+                          uint32_t* counts, float* edges_out);
+
+/* ---- multi-GPU slab decomposition (one handle = one y-slab of physics-grid rows) ----------------
+   Per step: rts_halo_pack → exchange → rts_halo_unpack → rts_step → rts_migrate_pack → exchange →
+   rts_migrate_unpack.  Buffers are DEVICE pointers owned by the handle so the host can hand them to
+   NCCL (ncclSend/ncclRecv or torch.distributed) without staging.  dir: 0 = towards lower rows, 1 = higher. */
+typedef struct RtsExchangeBuf {
+    void* data_dev;      /* records                                  */
+    uint32_t* count_dev; /* number of valid records (device scalar)  */
+    uint32_t capacity;   /* records                                   */
+    uint32_t record_bytes;
+} RtsExchangeBuf;
+int32_t rts_exchange_buffers(RtsHandle h, int32_t kind /*0 halo,1 migrate*/, int32_t dir, int32_t send_or_recv,
+                             RtsExchangeBuf* out);
+int32_t rts_halo_pack(RtsHandle h);
+int32_t rts_halo_unpack(RtsHandle h);
+int32_t rts_migrate_pack(RtsHandle h);
+int32_t rts_migrate_unpack(RtsHandle h);
+/* raw CUDA stream of the handle (cudaStream_t as void*) so the host can order NCCL work after the pack kernels */
+void* rts_stream(RtsHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTS_GPU_H */
