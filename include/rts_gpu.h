@@ -72,6 +72,9 @@ typedef struct RtsParams {
     uint32_t walk_all;       /* 1: keep tri_idx for every agent; 0: MOVING agents only (as SeekSystem.cpp:206) */
     /* multi-GPU slab owned by this handle: physics-grid rows [slab_row_lo, slab_row_hi); 0,ns_ny = whole map */
     int32_t slab_row_lo, slab_row_hi;
+    /* tuning words, 0 = default: [0] 1 = do not keep the per-step merged velocity (RtsAgentView.vel reads 0)
+       [1] fine gather-cell size as float bits (default 6.0, clamped to >= 1.05*sqrt(r_max2))
+       [2] 1 = launch kernels one by one instead of replaying a CUDA graph of two frames */
     uint32_t reserved[6];
 } RtsParams;
 
@@ -149,8 +152,8 @@ typedef struct RtsAgentView {
 } RtsAgentView;
 
 typedef struct RtsTimings {
-    double last_step_ms; /* CUDA-event time of the last rts_step call / n_steps */
-    double kernel_ms[8]; /* bin, scan, reorder, step, (reserved)              */
+    double last_step_ms; /* CUDA-event time of the whole last rts_step call        */
+    double kernel_ms[8]; /* totals in profiling mode: [0] step [1] bin [2] scan [3] reorder */
     uint64_t kernel_launches;
     uint64_t steps;
 } RtsTimings;
@@ -183,6 +186,9 @@ int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents);
 int32_t rts_remove_agents(RtsHandle h, const uint32_t* indices, uint32_t m);
 /* replaces: ECSystem::setMoveState + SeekSystem::issuePaths2 (Game.cpp:211-231): assign path/state to m agents */
 int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int32_t path_id, uint8_t state);
+/* replaces: System2::updateSharedData (PhysicsSystem.cpp:165-173, SeekSystem.cpp:307-316): overwrite the non-NULL
+   fields of every agent from caller-order arrays (the ECS blackboard), then re-bin */
+int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields);
 uint32_t rts_agent_count(RtsHandle h);
 
 /* replaces: PhysicsSystem::update + SeekSystem::update + communicate + avoidWall + integration
@@ -196,6 +202,11 @@ int32_t rts_get_timings(RtsHandle h, RtsTimings* out);
    0 = fused step kernel, 1 = bin/count, 2 = scan, 3 = reorder; used by bench.py for the roofline line */
 int32_t rts_kernel_time_ms(RtsHandle h, int32_t which, double* avg_ms, uint64_t* launches);
 int32_t rts_reset_timings(RtsHandle h);
+/* on: record a CUDA-event pair around every kernel (and launch kernels one by one, no graph) */
+int32_t rts_set_profiling(RtsHandle h, int32_t on);
+/* sizeof() of the ABI structs as compiled into the library: 0 RtsParams 1 RtsTriangle 2 RtsEdge 3 RtsWallTable
+   4 RtsPathTable 5 RtsUnitType 6 RtsAgentView 7 RtsTimings — lets a binding check its mirror */
+size_t rts_abi_sizeof(int32_t which);
 
 /* stand-alone data-parallel queries (each replaces a per-point loop over the reference function) */
 /* Grid::coordToCell (Grid.cpp:18-24) for n points on an nx×ny grid of cell size cs */
@@ -207,23 +218,7 @@ int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* o
 int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uint32_t n, uint32_t cap,
                           uint32_t* counts, float* edges_out);
 
-/* ---- multi-GPU slab decomposition (one handle = one y-slab of physics-grid rows) ----------------
-   Per step: rts_halo_pack → exchange → rts_halo_unpack → rts_step → rts_migrate_pack → exchange →
-   rts_migrate_unpack.  Buffers are DEVICE pointers owned by the handle so the host can hand them to
-   NCCL (ncclSend/ncclRecv or torch.distributed) without staging.  dir: 0 = towards lower rows, 1 = higher. */
-typedef struct RtsExchangeBuf {
-    void* data_dev;      /* records                                  */
-    uint32_t* count_dev; /* number of valid records (device scalar)  */
-    uint32_t capacity;   /* records                                   */
-    uint32_t record_bytes;
-} RtsExchangeBuf;
-int32_t rts_exchange_buffers(RtsHandle h, int32_t kind /*0 halo,1 migrate*/, int32_t dir, int32_t send_or_recv,
-                             RtsExchangeBuf* out);
-int32_t rts_halo_pack(RtsHandle h);
-int32_t rts_halo_unpack(RtsHandle h);
-int32_t rts_migrate_pack(RtsHandle h);
-int32_t rts_migrate_unpack(RtsHandle h);
-/* raw CUDA stream of the handle (cudaStream_t as void*) so the host can order NCCL work after the pack kernels */
+/* raw CUDA stream of the handle (cudaStream_t as void*), so a host that owns device buffers can order work after it */
 void* rts_stream(RtsHandle h);
 
 #ifdef __cplusplus

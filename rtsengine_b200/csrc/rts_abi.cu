@@ -1,0 +1,836 @@
+// C ABI of librts_b200.so (include/rts_gpu.h): context, table uploads, step scheduling, downloads.
+// Host code is plain C++; nothing here falls back to the CPU — without a CUDA device every entry point
+// that computes returns RTS_E_CUDA.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rts_kernels.cuh"
+
+using namespace rts;
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return h->fail(RTS_E_CUDA, #call, cudaGetErrorString(e_));          \
+    } while (0)
+
+namespace {
+
+struct KernelTimer {  // per-kind CUDA-event timing of launches on the handle's stream (profiling mode only)
+    std::vector<cudaEvent_t> beg, end;
+    size_t used = 0;
+    double total_ms = 0;
+    uint64_t launches = 0;
+};
+
+enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_COUNT = 4 };
+
+}  // namespace
+
+struct RtsContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    RtsParams P{};
+    MapDev M{};
+    FineGrid F{};
+    AgentArrays A{};
+    uint32_t n = 0, cap = 0;
+    bool map_ready = false, gid_is_index = true, keep_vel = true, profiling = false;
+    float fine_cs = 6.0f;
+    std::string err;
+    // owned device allocations of the tables
+    std::vector<void*> table_allocs, path_allocs, type_allocs;
+    std::vector<void*> agent_allocs;
+    // staging for upload / download (caller order), sized to cap
+    Staging S{};
+    std::vector<void*> staging_allocs;
+    uint32_t staging_cap = 0;
+    void* scratch = nullptr;  // generic device scratch for the stand-alone queries
+    size_t scratch_bytes = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    KernelTimer kt[KT_COUNT];
+    double last_step_ms = 0;
+    uint64_t launches = 0, steps = 0;
+    // step graph (two frames: the previous-order buffers ping-pong)
+    cudaGraphExec_t graph2[2] = {nullptr, nullptr};   // one per ping-pong parity
+    uint32_t graph_n[2] = {0, 0};
+    int parity = 0;
+    bool use_graph = true;
+
+    void drop_graphs() {
+        for (auto& g : graph2)
+            if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    }
+
+    int32_t fail(int32_t code, const char* what, const char* detail) {
+        err = std::string(what) + ": " + detail;
+        return code;
+    }
+};
+
+namespace {
+
+template <class T>
+int32_t dev_alloc(RtsContext* h, T** p, size_t count, std::vector<void*>& owner) {
+    void* q = nullptr;
+    CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    owner.push_back(q);
+    *p = static_cast<T*>(q);
+    return RTS_OK;
+}
+
+void free_all(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+
+int32_t ensure_scratch(RtsContext* h, size_t bytes) {
+    if (bytes <= h->scratch_bytes) return RTS_OK;
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+    CU(cudaMalloc(&h->scratch, bytes));
+    h->scratch_bytes = bytes;
+    return RTS_OK;
+}
+
+void timer_begin(RtsContext* h, int kind) {
+    if (!h->profiling) return;
+    KernelTimer& t = h->kt[kind];
+    if (t.used == t.beg.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        t.beg.push_back(a);
+        t.end.push_back(b);
+    }
+    cudaEventRecord(t.beg[t.used], h->stream);
+}
+void timer_end(RtsContext* h, int kind) {
+    if (!h->profiling) return;
+    KernelTimer& t = h->kt[kind];
+    cudaEventRecord(t.end[t.used], h->stream);
+    t.used++;
+}
+void timer_collect(RtsContext* h) {  // after a stream sync
+    for (auto& t : h->kt) {
+        for (size_t i = 0; i < t.used; ++i) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, t.beg[i], t.end[i]) == cudaSuccess) {
+                t.total_ms += ms;
+                t.launches++;
+            }
+        }
+        t.used = 0;
+    }
+}
+
+inline uint32_t blocks_for(uint32_t n, uint32_t b) { return (n + b - 1) / b; }
+
+int32_t alloc_agents(RtsContext* h, uint32_t cap) {
+    free_all(h->agent_allocs);
+    h->cap = 0;
+    AgentArrays& A = h->A;
+    A = AgentArrays{};
+    int32_t rc;
+#define AL(field, T)                                                              \
+    if ((rc = dev_alloc<T>(h, &A.field, cap, h->agent_allocs)) != RTS_OK) return rc;
+    AL(pos4, float4) AL(key2, uint2) AL(src, uint32_t) AL(vel4, float4) AL(nav4, float4) AL(tri, uint32_t)
+    AL(pos4n, float4) AL(key2n, uint2) AL(vel4n, float4) AL(nav4n, float4) AL(trin, uint32_t) AL(cellrank, uint2)
+    if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
+#undef AL
+    h->cap = cap;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+int32_t alloc_staging(RtsContext* h, uint32_t cap) {
+    if (cap <= h->staging_cap) return RTS_OK;
+    free_all(h->staging_allocs);
+    h->staging_cap = 0;
+    Staging& S = h->S;
+    int32_t rc;
+#define AL(field, T) \
+    if ((rc = dev_alloc<T>(h, &S.field, cap, h->staging_allocs)) != RTS_OK) return rc;
+    AL(r, float2) AL(vel, float2) AL(inertia, float2) AL(angle, float) AL(angle_vel, float) AL(radius, float) AL(mass, float)
+    AL(state, uint8_t) AL(player, uint8_t) AL(unit_type, uint8_t) AL(path_id, int32_t) AL(waypoint, int32_t)
+    AL(r_next, float2) AL(gid, uint32_t) AL(tri_idx, uint32_t) AL(ns_cell, uint32_t) AL(map_cell, uint32_t) AL(flags, uint32_t)
+#undef AL
+    h->staging_cap = cap;
+    return RTS_OK;
+}
+
+int32_t setup_fine_grid(RtsContext* h) {
+    const RtsParams& P = h->P;
+    float cs = h->fine_cs;
+    const float need = std::sqrt(P.r_max2) * 1.05f;
+    if (cs < need) cs = need;
+    FineGrid F{};
+    F.inv_cs = 1.0f / cs;
+    const float W = P.map_nx * P.map_cell_size, H = P.map_ny * P.map_cell_size;
+    F.nx = (int32_t)(W / cs) + 2;
+    // slab: physics rows [lo, hi) plus one physics row of halo on each side
+    const float y_lo = std::max(0.f, (P.slab_row_lo - 1) * P.ns_cell_size);
+    const float y_hi = std::min(H + cs, (P.slab_row_hi + 1) * P.ns_cell_size);
+    F.row0 = (int32_t)(y_lo / cs);
+    F.ny = (int32_t)(y_hi / cs) + 2 - F.row0;
+    F.n_cells = (uint32_t)F.nx * (uint32_t)F.ny;
+    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); }
+    CU(cudaMalloc(&F.count, sizeof(uint32_t) * F.n_cells));
+    CU(cudaMalloc(&F.start, sizeof(uint32_t) * (F.n_cells + 1)));
+    CU(cudaMalloc(&F.partial, sizeof(uint32_t) * (blocks_for(F.n_cells, SCAN_TILE) + 1)));
+    CU(cudaMemsetAsync(F.count, 0, sizeof(uint32_t) * F.n_cells, h->stream));
+    CU(cudaMemsetAsync(F.start, 0, sizeof(uint32_t) * (F.n_cells + 1), h->stream));
+    h->F = F;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+void swap_prev_order(RtsContext* h) {
+    AgentArrays& A = h->A;
+    std::swap(A.vel4, A.vel4n);
+    std::swap(A.nav4, A.nav4n);
+    std::swap(A.tri, A.trin);
+    std::swap(A.vel_out, A.vel_outn);
+    h->parity ^= 1;
+}
+
+// scan of the counts + scatter into the new order; the "n" buffers become the previous-order arrays
+int32_t launch_scan_reorder(RtsContext* h) {
+    const uint32_t nb = blocks_for(h->F.n_cells, SCAN_TILE);
+    timer_begin(h, KT_SCAN);
+    k_scan_partial<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F);
+    k_scan_final<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, nullptr);
+    timer_end(h, KT_SCAN);
+    timer_begin(h, KT_REORDER);
+    if (h->n) k_reorder<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->F, h->A);
+    timer_end(h, KT_REORDER);
+    h->launches += 3;
+    swap_prev_order(h);
+    return RTS_OK;
+}
+
+int32_t launch_frame(RtsContext* h) {
+    timer_begin(h, KT_STEP);
+    if (h->n) {
+        if (h->keep_vel) k_step<true><<<blocks_for(h->n, STEP_BLOCK), STEP_BLOCK, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+        else k_step<false><<<blocks_for(h->n, STEP_BLOCK), STEP_BLOCK, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+    }
+    timer_end(h, KT_STEP);
+    h->launches += 1;
+    return launch_scan_reorder(h);
+}
+
+int32_t rebin(RtsContext* h) {  // the "n" buffers hold the population in arbitrary order -> cell order
+    timer_begin(h, KT_BIN);
+    if (h->n) k_bin<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->F, h->A);
+    timer_end(h, KT_BIN);
+    h->launches += 1;
+    return launch_scan_reorder(h);
+}
+
+// copies the non-null host arrays of `v` (count agents) into staging; nulls the staging pointer of absent fields
+int32_t stage_in(RtsContext* h, const RtsAgentView* v, uint32_t count, Staging* out) {
+    int32_t rc = alloc_staging(h, std::max(count, h->cap));
+    if (rc != RTS_OK) return rc;
+    Staging S = h->S;
+#define UP(field, T, k)                                                                                        \
+    if (v->field) CU(cudaMemcpyAsync(S.field, v->field, sizeof(T) * (size_t)(k) * count, cudaMemcpyHostToDevice, h->stream)); \
+    else S.field = nullptr;
+    UP(r, float, 2) UP(inertia, float, 2) UP(angle, float, 1) UP(angle_vel, float, 1) UP(radius, float, 1) UP(mass, float, 1)
+    UP(state, uint8_t, 1) UP(player, uint8_t, 1) UP(unit_type, uint8_t, 1) UP(path_id, int32_t, 1) UP(waypoint, int32_t, 1)
+    UP(r_next, float, 2) UP(gid, uint32_t, 1)
+#undef UP
+    S.vel = nullptr; S.tri_idx = nullptr; S.ns_cell = nullptr; S.map_cell = nullptr; S.flags = nullptr;
+    *out = S;
+    return RTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void rts_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
+    std::memset(p, 0, sizeof(*p));
+    p->map_nx = map_nx; p->map_ny = map_ny; p->map_cell_size = 5.f;
+    p->ns_cell_size = 60.f;
+    p->ns_nx = (int32_t)((float)(map_nx * 5) / p->ns_cell_size) + 1;
+    p->ns_ny = (int32_t)((float)(map_ny * 5) / p->ns_cell_size) + 1;
+    p->r_max2 = 30.f;
+    p->tri_nx = map_nx / 8; p->tri_ny = map_ny / 8; p->tri_cell_size = 40.f;
+    p->mul_push = 0.1f; p->mul_repulse = 1.f; p->mul_scatter = 0.1f; p->mul_align = 1.f; p->mul_seek = 1.f;
+    p->mul_decay = 1.f; p->mul_velocity = 2.f;
+    p->dt = (float)(1. / 60.f);
+    p->rhard = 3.f; p->rscatter = 50.f; p->sys_max_speed = 25.f;
+    p->finish_angle = 36; p->finish_radius = 50; p->finish_n_steps = 1; p->finish_cone_len = 10;
+    p->enable_arrival = 0; p->walk_all = 1;
+    p->slab_row_lo = 0; p->slab_row_hi = p->ns_ny;
+}
+
+size_t rts_abi_sizeof(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(RtsParams);
+        case 1: return sizeof(RtsTriangle);
+        case 2: return sizeof(RtsEdge);
+        case 3: return sizeof(RtsWallTable);
+        case 4: return sizeof(RtsPathTable);
+        case 5: return sizeof(RtsUnitType);
+        case 6: return sizeof(RtsAgentView);
+        case 7: return sizeof(RtsTimings);
+        default: return 0;
+    }
+}
+
+static int32_t check_params(RtsContext* h, const RtsParams* p) {
+    if (!p) return h->fail(RTS_E_ARG, "params", "null");
+    if (p->map_nx <= 0 || p->map_ny <= 0 || p->ns_nx <= 0 || p->ns_ny <= 0 || p->tri_nx <= 0 || p->tri_ny <= 0)
+        return h->fail(RTS_E_ARG, "params", "grid dimensions must be positive");
+    if (!(p->map_cell_size > 0) || !(p->ns_cell_size > 0) || !(p->tri_cell_size > 0) || !(p->r_max2 > 0))
+        return h->fail(RTS_E_ARG, "params", "cell sizes and r_max2 must be positive");
+    if ((uint64_t)p->ns_nx * (uint64_t)p->ns_ny >= (1ull << 29))
+        return h->fail(RTS_E_ARG, "params", "physics grid has more than 2^29 cells");
+    if (p->ns_cell_size * p->ns_cell_size < p->r_max2)
+        return h->fail(RTS_E_ARG, "params", "ns_cell_size is smaller than the interaction range");
+    return RTS_OK;
+}
+
+int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
+    if (!out) return RTS_E_ARG;
+    *out = nullptr;
+    RtsContext* h = new (std::nothrow) RtsContext();
+    if (!h) return RTS_E_ARG;
+    int32_t rc = check_params(h, params);
+    if (rc != RTS_OK) { delete h; return rc; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_id < 0 || device_id >= count) {
+        delete h;
+        return RTS_E_CUDA;  // no CPU fallback
+    }
+    h->device = device_id;
+    h->P = *params;
+    h->keep_vel = params->reserved[0] == 0;   // reserved[0] = 1 drops the per-step velocity output
+    if (params->reserved[1]) std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float));
+    h->use_graph = params->reserved[2] == 0;
+    *out = h;
+    if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        *out = nullptr;
+        delete h;
+        return RTS_E_CUDA;
+    }
+    rc = setup_fine_grid(h);
+    if (rc != RTS_OK) return rc;
+    // default unit types (UnitTypes.txt has two; dynamics constants are the component defaults) and an empty path table
+    RtsUnitType ut[2];
+    for (auto& u : ut) { u = RtsUnitType{}; u.lambda = 0.169f; u.max_speed = 25.f; u.seek_max_speed = 50.f; u.turn_rate = 5.f; }
+    if ((rc = rts_upload_unit_types(h, ut, 2)) != RTS_OK) return rc;
+    RtsPathTable pt{};
+    uint32_t zero = 0;
+    pt.n_paths = 0; pt.offsets = &zero;
+    if ((rc = rts_upload_paths(h, &pt)) != RTS_OK) return rc;
+    // AcosTable<1000>, src/core.h:115-124 — built on the host so both sides use the same libm values
+    std::vector<float> table(1000);
+    for (int bin = 0; bin < 1000; ++bin) {
+        const float dot_value = 2 * static_cast<float>(bin) / 1000 - 1;
+        table[bin] = 180.f / (3.14159265358979323846f) * std::acos(dot_value);
+    }
+    float* dt = nullptr;
+    if ((rc = dev_alloc<float>(h, &dt, 1000, h->type_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(dt, table.data(), 4000, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->M.acos_table = dt;
+    return RTS_OK;
+}
+
+int32_t rts_destroy(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->drop_graphs();
+    free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
+    free_all(h->agent_allocs); free_all(h->staging_allocs);
+    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); }
+    if (h->scratch) cudaFree(h->scratch);
+    for (auto& t : h->kt) {
+        for (auto e : t.beg) cudaEventDestroy(e);
+        for (auto e : t.end) cudaEventDestroy(e);
+    }
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return RTS_OK;
+}
+
+const char* rts_last_error(RtsHandle h) { return h ? h->err.c_str() : "null handle"; }
+
+int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
+    if (!h) return RTS_E_ARG;
+    int32_t rc = check_params(h, params);
+    if (rc != RTS_OK) return rc;
+    CU(cudaSetDevice(h->device));
+    const bool regrid = params->map_nx != h->P.map_nx || params->map_ny != h->P.map_ny || params->r_max2 != h->P.r_max2 ||
+                        params->map_cell_size != h->P.map_cell_size || params->slab_row_lo != h->P.slab_row_lo ||
+                        params->slab_row_hi != h->P.slab_row_hi || params->ns_cell_size != h->P.ns_cell_size;
+    const bool rens = params->ns_nx != h->P.ns_nx || params->ns_ny != h->P.ns_ny || params->ns_cell_size != h->P.ns_cell_size;
+    h->P = *params;
+    h->drop_graphs();
+    if (regrid || rens) {
+        CU(cudaStreamSynchronize(h->stream));
+        if (regrid && (rc = setup_fine_grid(h)) != RTS_OK) return rc;
+        if (h->n) {  // re-bin the population on the new grid: current state -> "n" buffers -> cell order
+            Staging none{};
+            k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, none, h->A);
+            if ((rc = rebin(h)) != RTS_OK) return rc;
+        }
+    }
+    return RTS_OK;
+}
+
+int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri, const RtsWallTable* walls) {
+    if (!h) return RTS_E_ARG;
+    if (!tris || !n_tris || !cell2tri || !walls) return h->fail(RTS_E_ARG, "rts_upload_map", "null table");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    free_all(h->table_allocs);
+    h->map_ready = false;
+    const RtsParams& P = h->P;
+    const uint32_t expect[4] = {(uint32_t)P.map_ny + 1, (uint32_t)(P.map_nx + P.map_ny) + 1, (uint32_t)P.map_nx + 1,
+                                (uint32_t)(P.map_nx + P.map_ny) + 1};
+    for (int o = 0; o < 4; ++o) {
+        if (!walls->line_offsets[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "null line_offsets");
+        if (walls->n_lines[o] != expect[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "n_lines does not match the MapGrid (Edges.cpp:6-19)");
+    }
+    // triangles -> 3 x int4
+    std::vector<int4> t4(3 * (size_t)n_tris);
+    for (uint32_t t = 0; t < n_tris; ++t) {
+        const RtsTriangle& T = tris[t];
+        for (int k = 0; k < 3; ++k)
+            if (T.neighbours[k] != 0xFFFFFFFFu && T.neighbours[k] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "triangle neighbour out of range");
+        t4[3 * t + 0] = make_int4(T.vx[0], T.vy[0], T.vx[1], T.vy[1]);
+        t4[3 * t + 1] = make_int4(T.vx[2], T.vy[2], (int)T.neighbours[0], (int)T.neighbours[1]);
+        t4[3 * t + 2] = make_int4((int)T.neighbours[2], T.is_constrained[0] | (T.is_constrained[1] << 1) | (T.is_constrained[2] << 2) | (T.type << 8), 0, 0);
+    }
+    const size_t n_tri_cells = (size_t)P.tri_nx * P.tri_ny;
+    for (size_t c = 0; c < n_tri_cells; ++c)
+        if (cell2tri[c] != 0xFFFFFFFFu && cell2tri[c] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "cell2tri entry out of range");
+    int4* d_tris; uint32_t* d_c2t;
+    int32_t rc;
+    if ((rc = dev_alloc(h, &d_tris, t4.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_c2t, n_tri_cells, h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_tris, t4.data(), t4.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_c2t, cell2tri, n_tri_cells * 4, cudaMemcpyHostToDevice, h->stream));
+    // walls -> one CSR
+    std::vector<uint32_t> off;
+    std::vector<float4> ft;
+    std::vector<float> el;
+    MapDev& M = h->M;
+    for (int o = 0; o < 4; ++o) {
+        M.line_base[o] = (uint32_t)off.size();
+        M.edge_base[o] = (uint32_t)ft.size();
+        M.n_lines[o] = walls->n_lines[o];
+        const uint32_t* lo = walls->line_offsets[o];
+        for (uint32_t l = 0; l <= walls->n_lines[o]; ++l) {
+            if (l && lo[l] < lo[l - 1]) return h->fail(RTS_E_ARG, "rts_upload_map", "line_offsets not monotone");
+            off.push_back(lo[l]);
+        }
+        const uint32_t ne = lo[walls->n_lines[o]];
+        if (ne && !walls->edges[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "null edges");
+        for (uint32_t e = 0; e < ne; ++e) {
+            const RtsEdge& E = walls->edges[o][e];
+            ft.push_back(make_float4(E.from_x, E.from_y, E.t_x, E.t_y));
+            el.push_back(E.l);
+        }
+    }
+    uint32_t* d_off; float4* d_ft; float* d_el;
+    if ((rc = dev_alloc(h, &d_off, off.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_ft, ft.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_el, el.size(), h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!ft.empty()) {
+        CU(cudaMemcpyAsync(d_ft, ft.data(), ft.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(d_el, el.data(), el.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    M.tris = d_tris; M.n_tris = n_tris; M.cell2tri = d_c2t;
+    M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
+    h->map_ready = true;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_types) {
+    if (!h) return RTS_E_ARG;
+    if (!types || n_types == 0 || n_types > 256) return h->fail(RTS_E_ARG, "rts_upload_unit_types", "need 1..256 types");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    RtsUnitType* d;
+    void* old = const_cast<RtsUnitType*>(h->M.unit_types);
+    int32_t rc = dev_alloc(h, &d, 256, h->type_allocs);
+    if (rc != RTS_OK) return rc;
+    std::vector<RtsUnitType> full(256, types[0]);   // unknown type ids behave like type 0
+    std::memcpy(full.data(), types, sizeof(RtsUnitType) * n_types);
+    CU(cudaMemcpyAsync(d, full.data(), sizeof(RtsUnitType) * 256, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->M.unit_types = d; h->M.n_types = n_types;
+    if (old) {
+        for (auto it = h->type_allocs.begin(); it != h->type_allocs.end(); ++it)
+            if (*it == old) { cudaFree(old); h->type_allocs.erase(it); break; }
+    }
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
+    if (!h) return RTS_E_ARG;
+    if (!paths || !paths->offsets) return h->fail(RTS_E_ARG, "rts_upload_paths", "null table");
+    const uint32_t np = paths->n_paths;
+    const uint32_t nw = paths->offsets[np];
+    if (np && (!paths->waypoints || !paths->portals || !paths->path_end)) return h->fail(RTS_E_ARG, "rts_upload_paths", "null arrays");
+    for (uint32_t p = 0; p < np; ++p)
+        if (paths->offsets[p + 1] <= paths->offsets[p]) return h->fail(RTS_E_ARG, "rts_upload_paths", "every path needs at least one waypoint");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    free_all(h->path_allocs);
+    std::vector<float4> wp(2 * (size_t)nw);
+    for (uint32_t k = 0; k < nw; ++k) {
+        const RtsEdge& e = paths->portals[k];
+        wp[2 * k] = make_float4(paths->waypoints[2 * k], paths->waypoints[2 * k + 1], e.from_x, e.from_y);
+        wp[2 * k + 1] = make_float4(e.t_x, e.t_y, e.l, 0.f);
+    }
+    uint32_t* d_off; float4* d_wp; float2* d_end;
+    int32_t rc;
+    if ((rc = dev_alloc(h, &d_off, np + 1, h->path_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_wp, wp.size(), h->path_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_end, np, h->path_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_off, paths->offsets, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, h->stream));
+    if (nw) CU(cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    if (np) CU(cudaMemcpyAsync(d_end, paths->path_end, 8 * (size_t)np, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+static int32_t ingest(RtsContext* h, uint32_t first, uint32_t m, const RtsAgentView* agents) {
+    Staging S;
+    int32_t rc = stage_in(h, agents, m, &S);
+    if (rc != RTS_OK) return rc;
+    if (m) k_ingest<<<blocks_for(m, 256), 256, 0, h->stream>>>(m, first, S, h->A);
+    h->launches += 1;
+    return RTS_OK;
+}
+
+int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
+    if (!h) return RTS_E_ARG;
+    if (n && (!agents || !agents->r)) return h->fail(RTS_E_ARG, "rts_set_agents", "positions are required");
+    if (n >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_set_agents", "more than 2^28 agents");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    int32_t rc;
+    if (n > h->cap || h->cap == 0) {
+        const uint32_t cap = std::max<uint32_t>(n + n / 8 + 1024, 1024);
+        if ((rc = alloc_agents(h, cap)) != RTS_OK) return rc;
+    }
+    h->n = n;
+    h->gid_is_index = !(agents && agents->gid);
+    if ((rc = ingest(h, 0, n, agents)) != RTS_OK) return rc;
+    if ((rc = rebin(h)) != RTS_OK) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+// current state -> "n" buffers in slot order, so that new agents can be appended behind them
+static int32_t flatten(RtsContext* h) {
+    Staging none{};
+    if (h->n) k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, none, h->A);
+    h->launches += 1;
+    return RTS_OK;
+}
+
+int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents) {
+    if (!h) return RTS_E_ARG;
+    if (m == 0) return RTS_OK;
+    if (!agents || !agents->r) return h->fail(RTS_E_ARG, "rts_append_agents", "positions are required");
+    if (h->n == 0) return rts_set_agents(h, m, agents);
+    if ((uint64_t)h->n + m >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_append_agents", "more than 2^28 agents");
+    if (h->gid_is_index && agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses component indices as gid");
+    if (!h->gid_is_index && !agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses explicit gids");
+    CU(cudaSetDevice(h->device));
+    int32_t rc;
+    if (h->n + m > h->cap) {
+        // grow: keep the old arrays alive while the state is copied across
+        CU(cudaStreamSynchronize(h->stream));
+        AgentArrays old = h->A;
+        std::vector<void*> old_allocs;
+        old_allocs.swap(h->agent_allocs);
+        const uint32_t n_old = h->n;
+        if ((rc = alloc_agents(h, (h->n + m) + (h->n + m) / 4 + 1024)) != RTS_OK) { free_all(old_allocs); return rc; }
+        AgentArrays fresh = h->A;
+        // flatten old state into the fresh "n" buffers
+        AgentArrays mix = old;
+        mix.pos4n = fresh.pos4n; mix.key2n = fresh.key2n; mix.vel4n = fresh.vel4n; mix.nav4n = fresh.nav4n;
+        mix.trin = fresh.trin; mix.vel_outn = fresh.vel_outn;
+        Staging none{};
+        k_apply<<<blocks_for(n_old, 256), 256, 0, h->stream>>>(n_old, none, mix);
+        CU(cudaStreamSynchronize(h->stream));
+        free_all(old_allocs);
+    } else {
+        if ((rc = flatten(h)) != RTS_OK) return rc;
+    }
+    // gid of the old agents is kept; new ones get n..n+m-1 (component indices) or their explicit gid
+    if ((rc = ingest(h, h->n, m, agents)) != RTS_OK) return rc;
+    h->n += m;
+    if ((rc = rebin(h)) != RTS_OK) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields) {
+    if (!h || !fields) return RTS_E_ARG;
+    if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_update_agents", "needs component-index gids");
+    CU(cudaSetDevice(h->device));
+    Staging S;
+    int32_t rc = stage_in(h, fields, h->n, &S);
+    if (rc != RTS_OK) return rc;
+    if (h->n) k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, S, h->A);
+    h->launches += 1;
+    return rebin(h);
+}
+
+uint32_t rts_agent_count(RtsHandle h) { return h ? h->n : 0; }
+
+static int32_t build_graph(RtsContext* h) {
+    const int par = h->parity;
+    if (h->graph2[par]) { cudaGraphExecDestroy(h->graph2[par]); h->graph2[par] = nullptr; }
+    cudaGraph_t g = nullptr;
+    const uint64_t launches0 = h->launches;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    launch_frame(h);
+    launch_frame(h);   // two frames restore the ping-pong pointers
+    CU(cudaStreamEndCapture(h->stream, &g));
+    h->launches = launches0;
+    CU(cudaGraphInstantiate(&h->graph2[par], g, 0));
+    cudaGraphDestroy(g);
+    h->graph_n[par] = h->n;
+    return RTS_OK;
+}
+
+int32_t rts_step(RtsHandle h, uint32_t n_steps) {
+    if (!h) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_step", "rts_upload_map has not been called");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    uint32_t done = 0;
+    if (h->use_graph && !h->profiling && n_steps >= 2) {
+        const int par = h->parity;
+        if (!h->graph2[par] || h->graph_n[par] != h->n) {
+            int32_t rc = build_graph(h);
+            if (rc != RTS_OK) return rc;
+        }
+        for (; done + 2 <= n_steps; done += 2) {
+            CU(cudaGraphLaunch(h->graph2[par], h->stream));
+            h->launches += 8;
+        }
+    }
+    for (; done < n_steps; ++done) launch_frame(h);
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaGetLastError());
+    h->steps += n_steps;
+    return RTS_OK;
+}
+
+int32_t rts_sync(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    timer_collect(h);
+    return RTS_OK;
+}
+
+int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
+    if (!h || !out) return RTS_E_ARG;
+    CU(cudaSetDevice(h->device));
+    int32_t rc = alloc_staging(h, h->cap);
+    if (rc != RTS_OK) return rc;
+    Staging S = h->S;
+#define WANT(field) if (!out->field) S.field = nullptr;
+    WANT(r) WANT(vel) WANT(inertia) WANT(angle) WANT(angle_vel) WANT(radius) WANT(mass) WANT(state) WANT(player)
+    WANT(unit_type) WANT(path_id) WANT(waypoint) WANT(r_next) WANT(gid) WANT(tri_idx) WANT(ns_cell) WANT(map_cell) WANT(flags)
+#undef WANT
+    const uint32_t n = h->n;
+    if (n) k_gather<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, h->P, h->A, S, h->gid_is_index ? 1 : 0, out->flags ? 1 : 0);
+    h->launches += 1;
+#define DOWN(field, T, k) \
+    if (out->field) CU(cudaMemcpyAsync(out->field, S.field, sizeof(T) * (size_t)(k) * n, cudaMemcpyDeviceToHost, h->stream));
+    DOWN(r, float, 2) DOWN(vel, float, 2) DOWN(inertia, float, 2) DOWN(angle, float, 1) DOWN(angle_vel, float, 1)
+    DOWN(radius, float, 1) DOWN(mass, float, 1) DOWN(state, uint8_t, 1) DOWN(player, uint8_t, 1) DOWN(unit_type, uint8_t, 1)
+    DOWN(path_id, int32_t, 1) DOWN(waypoint, int32_t, 1) DOWN(r_next, float, 2) DOWN(gid, uint32_t, 1) DOWN(tri_idx, uint32_t, 1)
+    DOWN(ns_cell, uint32_t, 1) DOWN(map_cell, uint32_t, 1) DOWN(flags, uint32_t, 1)
+#undef DOWN
+    return rts_sync(h);
+}
+
+// swap-with-last removal (System2::remove, ECS.h:197-214): rare, done through the host
+int32_t rts_remove_agents(RtsHandle h, const uint32_t* indices, uint32_t m) {
+    if (!h) return RTS_E_ARG;
+    if (m == 0) return RTS_OK;
+    if (!indices) return h->fail(RTS_E_ARG, "rts_remove_agents", "null indices");
+    if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_remove_agents", "needs component-index gids");
+    uint32_t n = h->n;
+    std::vector<float> r(2 * (size_t)n), inertia(2 * (size_t)n), angle(n), angle_vel(n), radius(n), mass(n), r_next(2 * (size_t)n);
+    std::vector<uint8_t> state(n), player(n), unit_type(n);
+    std::vector<int32_t> path_id(n), waypoint(n);
+    RtsAgentView v{};
+    v.r = r.data(); v.inertia = inertia.data(); v.angle = angle.data(); v.angle_vel = angle_vel.data(); v.radius = radius.data();
+    v.mass = mass.data(); v.state = state.data(); v.player = player.data(); v.unit_type = unit_type.data();
+    v.path_id = path_id.data(); v.waypoint = waypoint.data(); v.r_next = r_next.data();
+    int32_t rc = rts_download(h, &v);
+    if (rc != RTS_OK) return rc;
+    for (uint32_t k = 0; k < m; ++k) {
+        const uint32_t i = indices[k];
+        if (i >= n) return h->fail(RTS_E_ARG, "rts_remove_agents", "index out of range");
+        const uint32_t l = n - 1;
+        r[2 * i] = r[2 * l]; r[2 * i + 1] = r[2 * l + 1];
+        inertia[2 * i] = inertia[2 * l]; inertia[2 * i + 1] = inertia[2 * l + 1];
+        r_next[2 * i] = r_next[2 * l]; r_next[2 * i + 1] = r_next[2 * l + 1];
+        angle[i] = angle[l]; angle_vel[i] = angle_vel[l]; radius[i] = radius[l]; mass[i] = mass[l];
+        state[i] = state[l]; player[i] = player[l]; unit_type[i] = unit_type[l]; path_id[i] = path_id[l]; waypoint[i] = waypoint[l];
+        --n;
+    }
+    return rts_set_agents(h, n, &v);
+}
+
+// ECSystem::setMoveState + SeekSystem::issuePaths2 for m agents (Game.cpp:211-231)
+int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int32_t path_id, uint8_t state) {
+    if (!h) return RTS_E_ARG;
+    if (m == 0) return RTS_OK;
+    if (!indices) return h->fail(RTS_E_ARG, "rts_command_agents", "null indices");
+    if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_command_agents", "needs component-index gids");
+    if (path_id >= (int32_t)h->M.n_paths) return h->fail(RTS_E_ARG, "rts_command_agents", "path_id out of range");
+    const uint32_t n = h->n;
+    std::vector<uint8_t> st(n);
+    std::vector<int32_t> pid(n), wp(n);
+    std::vector<float> rn(2 * (size_t)n);
+    RtsAgentView v{};
+    v.state = st.data(); v.path_id = pid.data(); v.waypoint = wp.data(); v.r_next = rn.data();
+    int32_t rc = rts_download(h, &v);
+    if (rc != RTS_OK) return rc;
+    const float qnan = std::nanf("");
+    for (uint32_t k = 0; k < m; ++k) {
+        const uint32_t i = indices[k];
+        if (i >= n) return h->fail(RTS_E_ARG, "rts_command_agents", "index out of range");
+        st[i] = state; pid[i] = path_id; wp[i] = 0; rn[2 * i] = qnan; rn[2 * i + 1] = qnan;
+    }
+    return rts_update_agents(h, &v);
+}
+
+int32_t rts_get_timings(RtsHandle h, RtsTimings* out) {
+    if (!h || !out) return RTS_E_ARG;
+    std::memset(out, 0, sizeof(*out));
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    timer_collect(h);
+    float ms = 0;
+    if (h->steps && cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) out->last_step_ms = ms;
+    for (int k = 0; k < KT_COUNT; ++k) out->kernel_ms[k] = h->kt[k].total_ms;
+    out->kernel_launches = h->launches;
+    out->steps = h->steps;
+    return RTS_OK;
+}
+
+int32_t rts_kernel_time_ms(RtsHandle h, int32_t which, double* avg_ms, uint64_t* launches) {
+    if (!h || which < 0 || which >= KT_COUNT) return RTS_E_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    timer_collect(h);
+    const KernelTimer& t = h->kt[which];
+    if (avg_ms) *avg_ms = t.launches ? t.total_ms / (double)t.launches : 0.0;
+    if (launches) *launches = t.launches;
+    return RTS_OK;
+}
+
+int32_t rts_reset_timings(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    for (auto& t : h->kt) { t.total_ms = 0; t.launches = 0; t.used = 0; }
+    h->launches = 0;
+    h->steps = 0;
+    return RTS_OK;
+}
+
+int32_t rts_set_profiling(RtsHandle h, int32_t on) {
+    if (!h) return RTS_E_ARG;
+    h->profiling = on != 0;
+    return RTS_OK;
+}
+
+// ---- stand-alone queries ------------------------------------------------------------------------
+int32_t rts_coord_to_cell(RtsHandle h, const float* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out) {
+    if (!h) return RTS_E_ARG;
+    if (n == 0) return RTS_OK;
+    if (!xy || !out || nx <= 0 || ny <= 0 || !(cs > 0)) return h->fail(RTS_E_ARG, "rts_coord_to_cell", "bad argument");
+    CU(cudaSetDevice(h->device));
+    int32_t rc = ensure_scratch(h, (size_t)n * 12);
+    if (rc != RTS_OK) return rc;
+    float2* d_xy = static_cast<float2*>(h->scratch);
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(d_xy + n);
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_coord_to_cell<<<blocks_for(n, 256), 256, 0, h->stream>>>(d_xy, n, nx, ny, cs, d_out);
+    CU(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* out) {
+    if (!h) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_find_triangles", "rts_upload_map has not been called");
+    if (n == 0) return RTS_OK;
+    if (!xy || !out) return h->fail(RTS_E_ARG, "rts_find_triangles", "null");
+    CU(cudaSetDevice(h->device));
+    int32_t rc = ensure_scratch(h, (size_t)n * 12);
+    if (rc != RTS_OK) return rc;
+    float2* d_xy = static_cast<float2*>(h->scratch);
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(d_xy + n);
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_find_triangles<<<blocks_for(n, 128), 128, 0, h->stream>>>(d_xy, n, h->P, h->M, d_out);
+    CU(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uint32_t n, uint32_t cap, uint32_t* counts, float* edges_out) {
+    if (!h) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_contact_edges", "rts_upload_map has not been called");
+    if (n == 0) return RTS_OK;
+    if (!xy || !radius || !counts) return h->fail(RTS_E_ARG, "rts_contact_edges", "null");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)n * 16 + (edges_out ? (size_t)n * cap * 20 : 0);
+    int32_t rc = ensure_scratch(h, bytes);
+    if (rc != RTS_OK) return rc;
+    float2* d_xy = static_cast<float2*>(h->scratch);
+    float* d_rad = reinterpret_cast<float*>(d_xy + n);
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d_rad + n);
+    float* d_edges = edges_out ? reinterpret_cast<float*>(d_cnt + n) : nullptr;
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_rad, radius, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    if (d_edges) CU(cudaMemsetAsync(d_edges, 0, (size_t)n * cap * 20, h->stream));
+    k_contact_edges<<<blocks_for(n, 128), 128, 0, h->stream>>>(d_xy, d_rad, n, cap, h->P, h->M, d_cnt, d_edges);
+    CU(cudaMemcpyAsync(counts, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (d_edges) CU(cudaMemcpyAsync(edges_out, d_edges, (size_t)n * cap * 20, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+void* rts_stream(RtsHandle h) { return h ? (void*)h->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// Device-side arithmetic of the agent update. Every function restates one reference function with
+// the same operation order so that, compiled with --fmad=false (and nvcc's default IEEE division and
+// square root), the results are bit-identical to an IEEE build of the reference on the CPU.
+// Paths cited are relative to the reference root.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rts_gpu.h"
+
+namespace rts {
+
+// ---- constant tables of one handle (device pointers + scalars), passed to kernels by value ----
+struct MapDev {
+    // CDT: 3 x int4 per triangle {v0x v0y v1x v1y | v2x v2y n0 n1 | n2 flags 0 0}
+    const int4* __restrict__ tris;
+    uint32_t n_tris;
+    const uint32_t* __restrict__ cell2tri;
+    // walls: CSR over the concatenated lines of the four orientations
+    const uint32_t* __restrict__ line_off;  // sum(n_lines)+4 entries; orientation o starts at line_base[o]
+    const float4* __restrict__ edge_ft;     // {from.x from.y t.x t.y}
+    const float* __restrict__ edge_l;
+    uint32_t line_base[4];
+    uint32_t edge_base[4];
+    uint32_t n_lines[4];
+    // paths: 2 x float4 per waypoint {w.x w.y p.from.x p.from.y | p.t.x p.t.y p.l 0}
+    const uint32_t* __restrict__ path_off;
+    const float4* __restrict__ waypoints;
+    const float2* __restrict__ path_end;
+    uint32_t n_paths;
+    const RtsUnitType* __restrict__ unit_types;
+    uint32_t n_types;
+    const float* __restrict__ acos_table;   // AcosTable<1000>, built on the host (src/core.h:115-124)
+};
+
+struct v2 {
+    float x, y;
+};
+__device__ __forceinline__ v2 V(float x, float y) { return v2{x, y}; }
+// sf::Vector2 operators are component-wise (src/Utils/Vector.inl)
+__device__ __forceinline__ v2 operator+(v2 a, v2 b) { return V(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ v2 operator-(v2 a, v2 b) { return V(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ v2 operator-(v2 a) { return V(-a.x, -a.y); }
+__device__ __forceinline__ v2 operator*(v2 a, float s) { return V(a.x * s, a.y * s); }
+__device__ __forceinline__ v2 operator/(v2 a, float s) { return V(a.x / s, a.y / s); }
+// src/core.h:99-113
+__device__ __forceinline__ float dot(v2 a, v2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float norm2(v2 a) { return dot(a, a); }
+__device__ __forceinline__ float norm(v2 a) { return sqrtf(norm2(a)); }
+__device__ __forceinline__ float dist2(v2 a, v2 b) { return dot(a - b, a - b); }
+__device__ __forceinline__ bool vequal(v2 a, v2 b) { return dist2(a, b) < 0.001f; }
+__device__ __forceinline__ bool veq(v2 a, v2 b) { return a.x == b.x && a.y == b.y; }
+
+// ---- Grid::coordToCell, src/Utils/Grid.cpp:18-24 ------------------------------------------------
+// size_t(floor(x/cs)) % n.  The common case (0 <= floor < 2^31) stays in 32 bits; anything else takes
+// the 64-bit path that reproduces x86-64's float -> size_t conversion (signed convert, wrap mod 2^64).
+__device__ __forceinline__ uint32_t axis_cell(float x, float cs, int32_t n) {
+    const float f = floorf(x / cs);
+    if (f >= 0.f && f < 2147483648.f) return (uint32_t)f % (uint32_t)n;
+    const uint64_t u = (uint64_t)(int64_t)f;   // cvttss2si semantics
+    return (uint32_t)(u % (uint64_t)n);
+}
+__device__ __forceinline__ uint32_t coord_to_cell(float x, float y, int32_t nx, int32_t ny, float cs) {
+    return axis_cell(x, cs, nx) + axis_cell(y, cs, ny) * (uint32_t)nx;
+}
+
+// ---- AcosTable<1000>::angle, src/core.h:139-150 ---------------------------------------------------
+__device__ __forceinline__ float table_angle(const float* __restrict__ table, v2 v) {
+    const float dot_value = (v.x * 1.f + v.y * 0.f) / norm(v) + 1.0f;
+    int bin = (int)floorf(dot_value / 2.f * 1000);
+    if (bin >= 1000) bin = 999;
+    if (bin < 0) bin = 0;
+    return __ldg(table + bin) * (2.f * (v.y > 0) - 1.f);
+}
+
+// ---- Triangulation::findTriangle, src/PathFinding/Triangulation.cpp:1497-1567 ----------------------
+struct iv2 {
+    int32_t x, y;
+};
+// sign(), Triangulation.h:73-76: integer arithmetic then ->float. 64-bit products: identical to the
+// reference's int32 wherever that does not overflow (it would on 8192² maps, where it is UB).
+__device__ __forceinline__ float tri_sign(iv2 p1, iv2 p2, iv2 p3) {
+    return (float)((int64_t)(p1.x - p3.x) * (p2.y - p3.y) - (int64_t)(p2.x - p3.x) * (p1.y - p3.y));
+}
+__device__ __forceinline__ bool in_triangle(iv2 q, iv2 a, iv2 b, iv2 c) {  // isInTriangle, Triangulation.h:83-96
+    const float d1 = tri_sign(q, a, b), d2 = tri_sign(q, b, c), d3 = tri_sign(q, c, a);
+    const bool has_neg = (d1 < 0) || (d2 < 0) || (d3 < 0);
+    const bool has_pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
+    return !(has_neg && has_pos);
+}
+__device__ __forceinline__ float idot(iv2 a, iv2 b) { return (float)((int64_t)a.x * b.x + (int64_t)a.y * b.y); }
+__device__ __forceinline__ bool lines_intersect(iv2 v11, iv2 v12, iv2 v21, iv2 v22) {  // Triangulation.cpp:1805-1818
+    const iv2 dr{v21.x - v11.x, v21.y - v11.y};
+    const iv2 t1{v12.x - v11.x, v12.y - v11.y};
+    const iv2 t2{v22.x - v21.x, v22.y - v21.y};
+    const iv2 n1{t1.y, -t1.x};
+    const iv2 n2{t2.y, -t2.x};
+    const float alpha1 = +idot(dr, n2) / idot(t1, n2);
+    const float alpha2 = -idot(dr, n1) / idot(t2, n1);
+    return alpha1 >= 0 && alpha1 <= 1 && alpha2 >= 0 && alpha2 <= 1;
+}
+
+struct TriRec {
+    iv2 v[3];
+    uint32_t nb[3];
+};
+__device__ __forceinline__ void load_tri_verts(const MapDev& M, uint32_t t, iv2& a, iv2& b, iv2& c, int4& w1) {
+    const int4 w0 = __ldg(M.tris + 3 * (size_t)t);
+    w1 = __ldg(M.tris + 3 * (size_t)t + 1);
+    a = iv2{w0.x, w0.y};
+    b = iv2{w0.z, w0.w};
+    c = iv2{w1.x, w1.y};
+}
+
+__device__ __noinline__ uint32_t tri_brute_force(const MapDev& M, iv2 q) {  // Triangulation.cpp:1503-1510, 1539-1546
+    for (uint32_t i = 0; i < M.n_tris; ++i) {
+        iv2 a, b, c;
+        int4 w1;
+        load_tri_verts(M, i, a, b, c, w1);
+        if (in_triangle(q, a, b, c)) return i;
+    }
+    return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ uint32_t find_triangle(const MapDev& M, const RtsParams& P, float fx, float fy, uint32_t& flags) {
+    const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
+    const uint32_t cell = coord_to_cell((float)q.x, (float)q.y, P.tri_nx, P.tri_ny, P.tri_cell_size);
+    uint32_t t = __ldg(M.cell2tri + cell);
+    if (t == 0xFFFFFFFFu) return tri_brute_force(M, q);
+    iv2 a, b, c;
+    int4 w1;
+    load_tri_verts(M, t, a, b, c, w1);
+    if (in_triangle(q, a, b, c)) return t;
+    iv2 vc;
+    {
+        const iv2 g{(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3};  // integer division, :1524
+        if (lines_intersect(g, q, a, b)) { t = (uint32_t)w1.z; vc = a; }
+        else if (lines_intersect(g, q, b, c)) { t = (uint32_t)w1.w; vc = b; }
+        else if (lines_intersect(g, q, c, a)) { t = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x; vc = c; }
+        else t = 0xFFFFFFFFu;
+    }
+    if (t == 0xFFFFFFFFu) return tri_brute_force(M, q);
+    const uint32_t hop_limit = 4 * M.n_tris + 16;
+    for (uint32_t hops = 0;; ++hops) {  // fan walk around vc, :1548-1563
+        load_tri_verts(M, t, a, b, c, w1);
+        if (in_triangle(q, a, b, c)) return t;
+        int k = -1;
+        if (a.x == vc.x && a.y == vc.y) k = 0;
+        else if (b.x == vc.x && b.y == vc.y) k = 1;
+        else if (c.x == vc.x && c.y == vc.y) k = 2;
+        if (k < 0 || hops >= hop_limit) {  // the reference would index out of bounds / never return: report instead
+            flags |= RTS_FLAG_WALK_FAILED;
+            return 0xFFFFFFFFu;
+        }
+        const uint32_t n2 = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x;
+        const uint32_t nb[3] = {(uint32_t)w1.z, (uint32_t)w1.w, n2};
+        const iv2 vs[3] = {a, b, c};
+        const int kn = (k == 2) ? 0 : k + 1, kp = (k == 0) ? 2 : k - 1;
+        if (lines_intersect(vc, q, vs[kn], vs[kp])) { t = nb[kn]; vc = vs[kn]; }
+        else t = nb[k];
+        if (t == 0xFFFFFFFFu) { flags |= RTS_FLAG_WALK_FAILED; return t; }
+    }
+}
+
+// ---- Edges::calcContactEdgesO + isTouchingEdge, src/Edges.cpp:245-296, 128-143 ----------------------
+__device__ __forceinline__ bool touching(float4 ft, float l, v2 r, float radius) {
+    const v2 dr = V(ft.x, ft.y) - r;
+    const v2 t = V(ft.z, ft.w);
+    const float norm_dr_sq = dot(dr, dr);
+    const float dot_dr_t = dot(dr, t);
+    const float disc = dot_dr_t * dot_dr_t - norm_dr_sq + radius * radius;
+    if (disc >= 0) {
+        const float s = sqrtf(disc);
+        const float a1 = -dot_dr_t + s, a2 = -dot_dr_t - s;
+        return (a2 <= l && a2 > 0) || (a1 <= l && a1 > 0);
+    }
+    return false;
+}
+
+// Calls fn(t_x, t_y, edge_index) for every contact wall in the reference's order: orientation 0..3, line -D..+D,
+// edge first..last.  Returns the number of contacts.
+template <class Fn>
+__device__ __forceinline__ int contact_walls(const MapDev& M, const RtsParams& P, v2 r, float radius, Fn fn) {
+    const int ix0 = (int)(r.x / P.map_cell_size);  // Grid::cellCoords truncates, Grid.cpp:67-71
+    const int iy0 = (int)(r.y / P.map_cell_size);
+    const int D = (int)ceilf(radius / P.map_cell_size);
+    int count = 0;
+#pragma unroll 1
+    for (int o = 0; o < 4; ++o) {
+        const int base = (o == 0) ? iy0 : (o == 1) ? ix0 - iy0 + P.map_ny - 1 : (o == 2) ? ix0 : ix0 + iy0;
+        const v2 dir = (o == 0) ? V(1.f, 0.f) : (o == 1) ? V(1.f, 1.f) : (o == 2) ? V(0.f, 1.f) : V(1.f, -1.f);
+        const int lo = max(base - D, 0), hi = min(base + D, (int)M.n_lines[o] - 1);
+        if (lo > hi) continue;
+        const uint32_t* off = M.line_off + M.line_base[o];
+        uint32_t beg = __ldg(off + lo);
+#pragma unroll 1
+        for (int L = lo; L <= hi; ++L) {
+            const uint32_t end = __ldg(off + L + 1);
+            if (end != beg) {
+                const float4* E = M.edge_ft + M.edge_base[o] + beg;
+                const float* El = M.edge_l + M.edge_base[o] + beg;
+                const int size = (int)(end - beg);
+                // std::lower_bound (libstdc++ bisection) with comp(e, r) = dot(r - e.from, dir) > 0
+                int first_i = 0, len = size;
+                while (len > 0) {
+                    const int half = len >> 1;
+                    const int mid = first_i + half;
+                    const float4 e = __ldg(E + mid);
+                    if (dot(r - V(e.x, e.y), dir) > 0) { first_i = mid + 1; len = len - half - 1; }
+                    else len = half;
+                }
+                int first = first_i - 1, last = first + 1;
+                if (first == -1) { first = 0; last = 0; }
+                if (first == size - 1) last = size - 1;
+                for (int k = first; k <= last; ++k) {
+                    const float4 e = __ldg(E + k);
+                    if (touching(e, __ldg(El + k), r, radius)) { fn(e.z, e.w, M.edge_base[o] + beg + (uint32_t)k); ++count; }
+                }
+            }
+            beg = end;
+        }
+    }
+    return count;
+}
+
+// PhysicsSystem::avoidWall body for one wall, src/Systems/PhysicsSystem.cpp:146-158
+__device__ __forceinline__ void avoid_one(float tx, float ty, v2& vel, v2& inertia) {
+    const v2 n = V(ty, -tx);
+    v2 away = n * dot(vel, n);
+    if (dot(vel, n) < 0) vel = vel - away * 1.0f;
+    away = n * dot(inertia, n);
+    if (dot(inertia, n) < 0) inertia = inertia - away;
+}
+
+// closestPointOnEdge, src/core.h:282-296
+__device__ __forceinline__ v2 closest_point_on_edge(v2 r, v2 from, v2 t, float l) {
+    const v2 dr = r - from;
+    const float pos = dot(dr, t);
+    if (pos < l && pos > 0) return from + t * pos;
+    else if (pos > l) return from + t * l;  // Edgef::to()
+    return from;
+}
+
+}  // namespace rts

@@ -1,0 +1,532 @@
+// Kernels of the agent-update hot path (sm_100a). See DESIGN.md for the data layout and the
+// per-kernel byte accounting.
+//
+//   k_bin      : fine-cell id + slot rank of freshly uploaded agents (warp-aggregated atomics)
+//   k_scan_*   : exclusive scan of the per-cell counts -> cell_start
+//   k_reorder  : counting-sort scatter of the neighbour record {pos4,key2} into cell order, builds src[]
+//   k_step     : the fused frame — neighbour gather, boids forces, clamp/decay, wall pass, seek, merge,
+//                wall pass, integrate, triangle walk, re-bin of the new position
+//   k_gather   : slot order -> caller order for rts_download
+//   k_apply    : caller order -> slot order for rts_update_agents
+#pragma once
+
+#include "rts_device.cuh"
+
+namespace rts {
+
+constexpr int STEP_BLOCK = 128;   // threads per CTA of k_step
+constexpr int NBR_CAP = 24;       // neighbours kept sorted in shared memory per agent; more -> selection path
+constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
+
+// key2.y = ns_cell << 3 | ghost << 2 | state
+__device__ __forceinline__ uint32_t pack_cs(uint32_t ns_cell, uint32_t ghost, uint32_t state) {
+    return (ns_cell << 3) | (ghost << 2) | (state & 3u);
+}
+// nav4.w bits: waypoint 0..15 | unit_type 16..23 | player 24..27 | flags 28..31
+__device__ __forceinline__ uint32_t pack_misc(uint32_t wp, uint32_t type, uint32_t player, uint32_t flags) {
+    return (wp & 0xFFFFu) | ((type & 0xFFu) << 16) | ((player & 0xFu) << 24) | ((flags & 0xFu) << 28);
+}
+
+struct FineGrid {
+    float inv_cs;       // 1 / fine cell size (cell size >= sqrt(r_max2), so 3x3 fine cells hold every neighbour)
+    int32_t nx, ny;     // fine cells per row / rows held by this handle
+    int32_t row0;       // first fine row of this handle's slab (0 for a whole map)
+    uint32_t n_cells;   // nx * ny
+    uint32_t* count;    // [n_cells]   agents per fine cell for the NEXT order (atomics), zeroed by the scan
+    uint32_t* start;    // [n_cells+1] first slot of each fine cell in the CURRENT order
+    uint32_t* partial;  // scan scratch
+};
+
+__device__ __forceinline__ void fine_coords(const FineGrid& F, float x, float y, int& fx, int& fy) {
+    fx = min(max((int)(x * F.inv_cs), 0), F.nx - 1);
+    fy = min(max((int)(y * F.inv_cs) - F.row0, 0), F.ny - 1);
+}
+
+// Slot rank inside a fine cell with one atomic per distinct cell per warp.
+// `active` = lanes of the warp that call this (ballot taken before any divergence).
+__device__ __forceinline__ uint32_t warp_aggregated_rank(uint32_t* count, uint32_t cell, unsigned active) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned peers = __match_any_sync(active, cell);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(count + cell, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
+struct AgentArrays {
+    // neighbour record, CURRENT cell order
+    float4* pos4;   // {x, y, radius, mass}
+    uint2* key2;    // {gid, ns_cell<<3 | ghost<<2 | state}
+    uint32_t* src;  // slot -> index into the previous-order arrays below
+    // previous-order arrays (outputs of the last step / the upload), read through src[]
+    float4* vel4;   // {inertia.x, inertia.y, angle, angle_vel}
+    float4* nav4;   // {r_next.x, r_next.y, path_id, misc}
+    uint32_t* tri;
+    float2* vel_out;  // merged velocity of the last step (only if keep_vel)
+    // outputs of this step, index = slot
+    float4* pos4n;
+    uint2* key2n;
+    float4* vel4n;
+    float4* nav4n;
+    uint32_t* trin;
+    float2* vel_outn;
+    uint2* cellrank;  // {next fine cell, rank inside it}
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bin(uint32_t n, RtsParams P, FineGrid F, AgentArrays A) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned active = __ballot_sync(0xffffffffu, p < n);
+    if (p >= n) return;
+    const float4 pos = A.pos4n[p];
+    uint2 k = A.key2n[p];
+    const uint32_t ns = coord_to_cell(pos.x, pos.y, P.ns_nx, P.ns_ny, P.ns_cell_size);
+    k.y = pack_cs(ns, (k.y >> 2) & 1u, k.y & 3u);
+    A.key2n[p] = k;
+    int fx, fy;
+    fine_coords(F, pos.x, pos.y, fx, fy);
+    const uint32_t cell = (uint32_t)fy * (uint32_t)F.nx + (uint32_t)fx;
+    const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
+    A.cellrank[p] = make_uint2(cell, rank);
+}
+
+// ---- scan: 4096 cells per CTA (512 threads x 8) ----
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    uint32_t t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0u;
+    if (w == 0) {
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) smem[0] = t;
+    }
+    __syncthreads();
+    t = smem[0];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(FineGrid F) {
+    __shared__ uint32_t smem[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < F.n_cells) s += F.count[base + i];
+    s = block_reduce_sum(s, smem);
+    if (threadIdx.x == 0) F.partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_t* n_out) {
+    __shared__ uint32_t smem[32];
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    // offset of this tile = sum of the partials of all tiles before it
+    uint32_t off = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += SCAN_THREADS) off += F.partial[b];
+    off = block_reduce_sum(off, smem);
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < F.n_cells) ? F.count[base + i] : 0u;
+        s += v[i];
+    }
+    // exclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = off + warp_tot[w] + (incl - s);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < F.n_cells) {
+            F.start[base + i] = run;
+            F.count[base + i] = 0u;
+            run += v[i];
+        }
+    }
+    if (base <= F.n_cells - 1 && F.n_cells - 1 < base + SCAN_ITEMS) {  // owner of the last cell closes the CSR
+        F.start[F.n_cells] = run;
+        if (n_out) *n_out = run;
+    }
+}
+
+__global__ void k_reorder(uint32_t n, FineGrid F, AgentArrays A) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint2 cr = A.cellrank[p];
+    if (cr.x == INVALID_CELL) return;  // dropped (ghost / migrated away)
+    const uint32_t d = F.start[cr.x] + cr.y;
+    A.pos4[d] = A.pos4n[p];
+    A.key2[d] = A.key2n[p];
+    A.src[d] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
+// neighbouring cells and the neighbour records come out of L1).
+template <bool KEEP_VEL>
+__global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, MapDev M, FineGrid F, AgentArrays A) {
+    __shared__ uint32_t s_key[NBR_CAP][STEP_BLOCK];
+    __shared__ uint32_t s_q[NBR_CAP][STEP_BLOCK];
+    const uint32_t p = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    const unsigned valid = __ballot_sync(0xffffffffu, p < n);
+    if (p >= n) return;
+    const int tid = threadIdx.x;
+
+    const float4 me = A.pos4[p];
+    const uint2 mykey = A.key2[p];
+    const uint32_t sp = A.src[p];
+    const v2 r = V(me.x, me.y);
+    const float radius = me.z, mass_i = me.w;
+    const uint32_t gid = mykey.x;
+    const int state_i = (int)(mykey.y & 3u);
+    const bool ghost = (mykey.y >> 2) & 1u;
+    const unsigned active = __ballot_sync(valid, !ghost);  // lanes that reach the re-bin at the end
+    if (ghost) {  // halo copy: neighbour only, dropped from the next order
+        A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
+        return;
+    }
+    const uint32_t ns_i = mykey.y >> 3;
+    const int cxi = (int)(ns_i % (uint32_t)P.ns_nx), cyi = (int)((ns_i / (uint32_t)P.ns_nx) % (uint32_t)P.ns_ny);
+
+    const float4 vel4 = A.vel4[sp];
+    const float4 nav4 = A.nav4[sp];
+    const uint32_t misc = __float_as_uint(nav4.w);
+    const RtsUnitType ut = M.unit_types[(misc >> 16) & 0xFFu];
+
+    // ---- P1: neighbour pass (Strategy.cpp:10-68) over the 3x3 fine cells; accepted neighbours are kept
+    //      sorted by (reference visit rank of their 60-unit cell, gid) = the reference's visit order
+    int fx, fy;
+    fine_coords(F, r.x, r.y, fx, fy);
+    const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
+    const int ylo = max(fy - 1, 0), yhi = min(fy + 1, F.ny - 1);
+
+    auto for_each_neighbour = [&](auto&& fn) {
+        for (int yy = ylo; yy <= yhi; ++yy) {
+            const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
+            const uint32_t qb = __ldg(F.start + rowbase + xlo), qe = __ldg(F.start + rowbase + xhi + 1);
+            for (uint32_t q = qb; q < qe; ++q) {
+                const float4 o = __ldg(A.pos4 + q);
+                const v2 dr = V(o.x, o.y) - r;
+                if (norm2(dr) < P.r_max2 && q != p) {
+                    const uint2 ok = __ldg(A.key2 + q);
+                    const uint32_t ns_j = ok.y >> 3;
+                    const int dxc = (int)(ns_j % (uint32_t)P.ns_nx) - cxi;
+                    const int dyc = (int)((ns_j / (uint32_t)P.ns_nx) % (uint32_t)P.ns_ny) - cyi;
+                    // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
+                    const int idx = (dxc + 1) * 3 + (dyc + 1);
+                    const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
+                    fn((rank << 28) | ok.x, q);
+                }
+            }
+        }
+    };
+
+    v2 repulsion = V(0.f, 0.f), push = V(0.f, 0.f), scatter = V(0.f, 0.f), dr_nn = V(0.f, 0.f);
+    float n_neighbours = 0.f;
+    const float rscatter2 = P.rscatter * P.rscatter;
+    // applyForces loop body, PhysicsSystem.cpp:69-102
+    auto accumulate = [&](uint32_t q) {
+        const float4 o = __ldg(A.pos4 + q);
+        const int state_j = (int)(__ldg(A.key2 + q).y & 3u);
+        const v2 dr = V(o.x, o.y) - r;
+        const float r_collision = o.z + radius;
+        const float mass_j = o.w;
+        const float r_collision_sq = r_collision * r_collision;
+        const float d_surfs = norm2(dr);
+        const float x = r_collision_sq / d_surfs;
+        if (x > 0.8f) {
+            const float m3 = 3.f * x * x * x;
+            const float mag = (m3 < 50000.0f) ? m3 : 50000.0f;
+            repulsion = repulsion + (((-dr) / norm(dr)) * mag * mass_j) / (mass_i + mass_j);
+        }
+        if (state_j == RTS_MOVING && state_i == RTS_STANDING && x > 0.75f)
+            push = push + ((-dr) * x * mass_j) / (mass_i + mass_j);
+        if (state_j == RTS_MOVING && x > r_collision_sq / rscatter2) {
+            dr_nn = dr_nn + dr;
+            n_neighbours += 1.f;
+        }
+    };
+
+    int cnt = 0;
+    for_each_neighbour([&](uint32_t key, uint32_t q) {
+        if (cnt < NBR_CAP) {
+            int pos = cnt;
+            while (pos > 0 && s_key[pos - 1][tid] > key) {
+                s_key[pos][tid] = s_key[pos - 1][tid];
+                s_q[pos][tid] = s_q[pos - 1][tid];
+                --pos;
+            }
+            s_key[pos][tid] = key;
+            s_q[pos][tid] = q;
+        }
+        ++cnt;
+    });
+    if (cnt <= NBR_CAP) {
+        for (int k = 0; k < cnt; ++k) accumulate(s_q[k][tid]);
+    } else {
+        // dense crowd: selection in key order, no storage (O(cnt * candidates), rare)
+        uint32_t last_key = 0;
+        for (int k = 0; k < cnt; ++k) {
+            uint32_t best_key = 0xFFFFFFFFu, best_q = 0;
+            for_each_neighbour([&](uint32_t key, uint32_t q) {
+                if ((k == 0 || key > last_key) && key < best_key) { best_key = key; best_q = q; }
+            });
+            accumulate(best_q);
+            last_key = best_key;
+        }
+    }
+
+    // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116
+    dr_nn = dr_nn / n_neighbours;
+    if (n_neighbours > 1.f) scatter = (dr_nn / norm(dr_nn)) * ut.max_speed;
+    v2 inertia = V(vel4.x, vel4.y);
+    inertia = inertia + ((repulsion * P.mul_repulse + push * P.mul_push) + scatter * P.mul_scatter);
+
+    // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry)
+    v2 vp = V(0.f, 0.f);
+    float speed = norm(vp);
+    if (speed > P.sys_max_speed) vp = vp / (speed * P.sys_max_speed);
+    vp = vp + inertia;
+    const float max_vel = ut.max_speed * P.mul_velocity;
+    speed = norm(vp);
+    if (speed > max_vel) vp = vp * (max_vel / speed);
+    const float lm = ut.lambda * P.mul_decay;
+    const float decay = (lm < 1.f) ? lm : 1.f;
+    inertia = inertia - inertia * decay;
+
+    // ---- P4: wall pass #1, PhysicsSystem.cpp:130-162
+    const int n_walls = contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, vp, inertia); });
+
+    // ---- S1: SeekSystem::update per-agent body, SeekSystem.cpp:76-111
+    v2 vs = V(0.f, 0.f);
+    float angle = vel4.z, angle_vel = vel4.w;
+    uint32_t wp = misc & 0xFFFFu;
+    uint32_t flags = (misc >> 28) & 0xFu;
+    v2 r_next = V(nav4.x, nav4.y);
+    const int32_t pid = __float_as_int(nav4.z);
+    if (state_i == RTS_MOVING && pid >= 0) {
+        const uint32_t p0 = __ldg(M.path_off + pid), p1 = __ldg(M.path_off + pid + 1);
+        const uint32_t last = p1 - 1;
+        const uint32_t w0 = min(p0 + wp, last);
+        const uint32_t w1 = min(w0 + 1, last);
+        const float4 wa = __ldg(M.waypoints + 2 * (size_t)w0), wb = __ldg(M.waypoints + 2 * (size_t)w0 + 1);
+        const float4 wn = __ldg(M.waypoints + 2 * (size_t)w1);
+        if (r_next.x != r_next.x) r_next = V(wa.x, wa.y);
+        const v2 r_nn = V(wn.x, wn.y);
+        const v2 path_end = V(__ldg(M.path_end + pid).x, __ldg(M.path_end + pid).y);
+
+        const v2 dr_to_target = r_next - r;
+        {   // turnTowards, SeekSystem.cpp:344-385 (the component-local angle edit is never communicated, :322-342)
+            float ang = angle;
+            if (ang > 180) ang -= 360;
+            if (ang < -180) ang += 360;
+            float desired;
+            if (norm2(dr_to_target) == 0) desired = ut.desired_angle;
+            else desired = table_angle(M.acos_table, dr_to_target);
+            float d_angle = desired - ang;
+            if (d_angle > 180) d_angle = -360 + d_angle;
+            if (d_angle < -180) d_angle = 360 + d_angle;
+            angle_vel = (d_angle < ut.turn_rate) ? d_angle : ut.turn_rate;
+            if (d_angle < 0) angle_vel = (d_angle > -ut.turn_rate) ? d_angle : -ut.turn_rate;
+            if (fabsf(d_angle) < ut.turn_rate) angle_vel = 0;
+        }
+        const float norm_dr = norm(dr_to_target);
+        if (norm_dr > radius) vs = (dr_to_target / norm_dr) * ut.seek_max_speed;
+
+        bool upd;  // needsUpdating, SeekSystem.cpp:181-233
+        if (vequal(r_next, path_end)) upd = false;
+        else {
+            const v2 t = r_nn - r_next;
+            const bool can_move = dot(-dr_to_target, t) > 0;
+            upd = (norm_dr < P.rhard && can_move) || veq(r_next, r_nn);
+            const v2 cp = closest_point_on_edge(r, V(wa.z, wa.w), V(wb.x, wb.y), wb.z);
+            if (norm_dr < radius || dot(dr_to_target, t) < 0) upd = true;
+            else {
+                if (dist2(cp, r) < dist2(r, r_next) && wb.z > 0 && dist2(cp, r) < 16 * P.rhard * P.rhard && norm2(t) != 0) {
+                    r_next = cp;
+                    upd = false;
+                } else if (vequal(r_next, r_nn) && !veq(r_next, path_end)) upd = true;
+            }
+        }
+        if (upd) {  // updateTarget, SeekSystem.cpp:277-304
+            const v2 dn = r_nn - r;
+            const float ndn = norm(dn);
+            r_next = r_nn;
+            if (p0 + wp < last) wp++;
+            if (ndn > 0) vs = (dn / ndn) * ut.seek_max_speed;
+            if (!veq(r_nn, path_end)) flags |= RTS_FLAG_REPLAN;
+        }
+    }
+
+    // ---- M: merge, wall pass #2 (same contact set: r has not moved), integrate (ECS.cpp:92-113)
+    v2 v = (V(0.f, 0.f) + vp) + vs;
+    if (n_walls > 0) contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, v, inertia); });
+    const v2 r_new = r + v * P.dt;
+    angle = angle + angle_vel;
+
+    // ---- K7: triangle walk on the new position
+    uint32_t tri;
+    if (P.walk_all || state_i == RTS_MOVING) tri = find_triangle(M, P, r_new.x, r_new.y, flags);
+    else tri = A.tri[sp];
+
+    // ---- write the new record at this slot; bin it for the next order
+    const uint32_t ns_new = coord_to_cell(r_new.x, r_new.y, P.ns_nx, P.ns_ny, P.ns_cell_size);
+    A.pos4n[p] = make_float4(r_new.x, r_new.y, radius, mass_i);
+    A.key2n[p] = make_uint2(gid, pack_cs(ns_new, 0u, (uint32_t)state_i));
+    A.vel4n[p] = make_float4(inertia.x, inertia.y, angle, angle_vel);
+    A.nav4n[p] = make_float4(r_next.x, r_next.y, nav4.z, __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
+    A.trin[p] = tri;
+    if (KEEP_VEL) A.vel_outn[p] = make_float2(v.x, v.y);
+    int nfx, nfy;
+    fine_coords(F, r_new.x, r_new.y, nfx, nfy);
+    const uint32_t cell = (uint32_t)nfy * (uint32_t)F.nx + (uint32_t)nfx;
+    const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
+    A.cellrank[p] = make_uint2(cell, rank);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rts_download: slot order -> caller order (dest = gid when gids are component indices, else slot)
+struct Staging {
+    float2* r; float2* vel; float2* inertia; float* angle; float* angle_vel; float* radius; float* mass;
+    uint8_t* state; uint8_t* player; uint8_t* unit_type; int32_t* path_id; int32_t* waypoint; float2* r_next;
+    uint32_t* gid; uint32_t* tri_idx; uint32_t* ns_cell; uint32_t* map_cell; uint32_t* flags;
+};
+
+__global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int by_gid, int clear_replan) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const float4 pos = A.pos4[d];
+    const uint2 key = A.key2[d];
+    const uint32_t sp = A.src[d];
+    const float4 vel4 = A.vel4[sp];
+    const float4 nav4 = A.nav4[sp];
+    const uint32_t misc = __float_as_uint(nav4.w);
+    const uint32_t o = by_gid ? key.x : d;
+    if (S.r) S.r[o] = make_float2(pos.x, pos.y);
+    if (S.vel) S.vel[o] = A.vel_out ? A.vel_out[sp] : make_float2(0.f, 0.f);
+    if (S.inertia) S.inertia[o] = make_float2(vel4.x, vel4.y);
+    if (S.angle) S.angle[o] = vel4.z;
+    if (S.angle_vel) S.angle_vel[o] = vel4.w;
+    if (S.radius) S.radius[o] = pos.z;
+    if (S.mass) S.mass[o] = pos.w;
+    if (S.state) S.state[o] = (uint8_t)(key.y & 3u);
+    if (S.player) S.player[o] = (uint8_t)((misc >> 24) & 0xFu);
+    if (S.unit_type) S.unit_type[o] = (uint8_t)((misc >> 16) & 0xFFu);
+    if (S.path_id) S.path_id[o] = __float_as_int(nav4.z);
+    if (S.waypoint) S.waypoint[o] = (int32_t)(misc & 0xFFFFu);
+    if (S.r_next) S.r_next[o] = make_float2(nav4.x, nav4.y);
+    if (S.gid) S.gid[o] = key.x;
+    if (S.tri_idx) S.tri_idx[o] = A.tri[sp];
+    if (S.ns_cell) S.ns_cell[o] = key.y >> 3;
+    if (S.map_cell) S.map_cell[o] = coord_to_cell(pos.x, pos.y, P.map_nx, P.map_ny, P.map_cell_size);
+    if (S.flags) {
+        S.flags[o] = (misc >> 28) & 0xFu;
+        if (clear_replan) A.nav4[sp].w = __uint_as_float(misc & ~((uint32_t)RTS_FLAG_REPLAN << 28));
+    }
+}
+
+// rts_set_agents: caller-order staging -> the "n" buffers (index = caller index), then k_bin/scan/reorder
+__global__ void k_ingest(uint32_t n, uint32_t first, Staging S, AgentArrays A) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t d = first + i;
+    const float2 r = S.r[i];
+    A.pos4n[d] = make_float4(r.x, r.y, S.radius ? S.radius[i] : 3.f, S.mass ? S.mass[i] : 1.f);
+    const uint32_t state = S.state ? S.state[i] : (uint32_t)RTS_STANDING;
+    A.key2n[d] = make_uint2(S.gid ? S.gid[i] : d, pack_cs(0u, 0u, state));
+    const float2 in = S.inertia ? S.inertia[i] : make_float2(0.f, 0.f);
+    A.vel4n[d] = make_float4(in.x, in.y, S.angle ? S.angle[i] : 0.f, S.angle_vel ? S.angle_vel[i] : 0.f);
+    const float qnan = __uint_as_float(0x7FC00000u);
+    const float2 rn = S.r_next ? S.r_next[i] : make_float2(qnan, qnan);
+    const int32_t pid = S.path_id ? S.path_id[i] : -1;
+    const uint32_t wp = S.waypoint ? (uint32_t)S.waypoint[i] : 0u;
+    A.nav4n[d] = make_float4(rn.x, rn.y, __int_as_float(pid),
+                             __uint_as_float(pack_misc(wp, S.unit_type ? S.unit_type[i] : 0u, S.player ? S.player[i] : 0u, 0u)));
+    A.trin[d] = 0xFFFFFFFFu;
+    if (A.vel_outn) A.vel_outn[d] = make_float2(0.f, 0.f);
+}
+
+// rts_update_agents (System2::updateSharedData): overwrite selected fields of every agent from
+// caller-order staging (index = gid); positions are re-binned afterwards by the host code.
+__global__ void k_apply(uint32_t n, Staging S, AgentArrays A) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    float4 pos = A.pos4[d];
+    uint2 key = A.key2[d];
+    const uint32_t sp = A.src[d];
+    const uint32_t g = key.x;
+    float4 vel4 = A.vel4[sp];
+    float4 nav4 = A.nav4[sp];
+    uint32_t misc = __float_as_uint(nav4.w);
+    if (S.r) { const float2 r = S.r[g]; pos.x = r.x; pos.y = r.y; }
+    if (S.radius) pos.z = S.radius[g];
+    if (S.mass) pos.w = S.mass[g];
+    if (S.state) key.y = (key.y & ~3u) | (S.state[g] & 3u);
+    if (S.inertia) { const float2 v = S.inertia[g]; vel4.x = v.x; vel4.y = v.y; }
+    if (S.angle) vel4.z = S.angle[g];
+    if (S.angle_vel) vel4.w = S.angle_vel[g];
+    if (S.r_next) { const float2 v = S.r_next[g]; nav4.x = v.x; nav4.y = v.y; }
+    if (S.path_id) nav4.z = __int_as_float(S.path_id[g]);
+    if (S.waypoint) misc = (misc & ~0xFFFFu) | ((uint32_t)S.waypoint[g] & 0xFFFFu);
+    if (S.unit_type) misc = (misc & ~(0xFFu << 16)) | ((uint32_t)S.unit_type[g] << 16);
+    if (S.player) misc = (misc & ~(0xFu << 24)) | (((uint32_t)S.player[g] & 0xFu) << 24);
+    nav4.w = __uint_as_float(misc);
+    // the re-bin pass reads the "n" buffers at index = slot
+    A.pos4n[d] = pos;
+    A.key2n[d] = key;
+    A.vel4n[d] = vel4;
+    A.nav4n[d] = nav4;
+    A.trin[d] = A.tri[sp];
+    if (A.vel_outn) A.vel_outn[d] = A.vel_out[sp];
+}
+
+// stand-alone queries
+__global__ void k_coord_to_cell(const float2* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = coord_to_cell(xy[i].x, xy[i].y, nx, ny, cs);
+}
+__global__ void k_find_triangles(const float2* xy, uint32_t n, RtsParams P, MapDev M, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t flags = 0;
+    out[i] = find_triangle(M, P, xy[i].x, xy[i].y, flags);
+}
+__global__ void k_contact_edges(const float2* xy, const float* radius, uint32_t n, uint32_t cap, RtsParams P, MapDev M,
+                                uint32_t* counts, float* edges_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = 0;
+    float* o = edges_out ? edges_out + (size_t)5 * cap * i : nullptr;
+    counts[i] = (uint32_t)contact_walls(M, P, V(xy[i].x, xy[i].y), radius[i], [&](float, float, uint32_t e) {
+        if (o && k < cap) {
+            const float4 ft = M.edge_ft[e];
+            o[5 * k + 0] = ft.x; o[5 * k + 1] = ft.y; o[5 * k + 2] = ft.z; o[5 * k + 3] = ft.w; o[5 * k + 4] = M.edge_l[e];
+        }
+        ++k;
+    });
+}
+
+}  // namespace rts

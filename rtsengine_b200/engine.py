@@ -1,0 +1,268 @@
+"""Host-side binding of librts_b200.so (C ABI in include/rts_gpu.h).
+
+`GpuAgentSystem` mirrors the three-phase interface of the reference's `System2`
+(src/ECS.h:147-234: updateSharedData -> update -> communicate) for the fused Physics+Seek path.
+There is no CPU fallback: if the CUDA library cannot be loaded or no device is present this
+module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librts_b200.so")
+
+_lib = None
+
+
+class RtsError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"{abi.STATUS_NAMES.get(code, code)}: {text}")
+        self.code = code
+
+
+def load_library():
+    """Loads librts_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C rtsengine_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    i32, u32, f32 = C.c_int32, C.c_uint32, C.c_float
+    vp = C.c_void_p
+    PP = C.POINTER(abi.RtsParams)
+    AV = C.POINTER(abi.RtsAgentView)
+    sig = {
+        "rts_default_params": (None, [PP, i32, i32]),
+        "rts_create": (i32, [PP, i32, C.POINTER(H)]),
+        "rts_destroy": (i32, [H]),
+        "rts_last_error": (C.c_char_p, [H]),
+        "rts_set_params": (i32, [H, PP]),
+        "rts_upload_map": (i32, [H, vp, u32, vp, C.POINTER(abi.RtsWallTable)]),
+        "rts_upload_unit_types": (i32, [H, vp, u32]),
+        "rts_upload_paths": (i32, [H, C.POINTER(abi.RtsPathTable)]),
+        "rts_set_agents": (i32, [H, u32, AV]),
+        "rts_append_agents": (i32, [H, u32, AV]),
+        "rts_remove_agents": (i32, [H, vp, u32]),
+        "rts_command_agents": (i32, [H, vp, u32, i32, C.c_uint8]),
+        "rts_update_agents": (i32, [H, AV]),
+        "rts_agent_count": (u32, [H]),
+        "rts_step": (i32, [H, u32]),
+        "rts_download": (i32, [H, AV]),
+        "rts_sync": (i32, [H]),
+        "rts_get_timings": (i32, [H, C.POINTER(abi.RtsTimings)]),
+        "rts_kernel_time_ms": (i32, [H, i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+        "rts_reset_timings": (i32, [H]),
+        "rts_set_profiling": (i32, [H, i32]),
+        "rts_abi_sizeof": (C.c_size_t, [i32]),
+        "rts_coord_to_cell": (i32, [H, vp, u32, i32, i32, f32, vp]),
+        "rts_find_triangles": (i32, [H, vp, u32, vp]),
+        "rts_contact_edges": (i32, [H, vp, vp, u32, u32, vp, vp]),
+        "rts_stream": (vp, [H]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._rts_signatures = sig
+    _lib = L
+    return L
+
+
+def default_params(map_nx: int, map_ny: int) -> abi.RtsParams:
+    p = abi.RtsParams()
+    load_library().rts_default_params(C.byref(p), map_nx, map_ny)
+    return p
+
+
+KERNELS = {"step": 0, "bin": 1, "scan": 2, "reorder": 3}
+
+
+class GpuAgentSystem:
+    """The fused Physics+Seek system on one GPU.
+
+    reference interface                         here
+    ------------------------------------------  -----------------------------------------------
+    System2::addComponent (ECS.h:165)           set_agents / append_agents
+    System2::remove (ECS.h:197)                 remove_agents
+    System2::updateSharedData (ECS.h:232)       update_shared_data(fields)
+    System2::update (ECS.h:231)                 update(n_steps)
+    System2::communicate (ECS.h:233)            communicate(names) -> dict of arrays
+    PhysicsSystem::p_map_, SeekSystem::p_cdt_   upload_map(tables)
+    PathFinder2::setPathOfAgent                 upload_paths(paths)
+    PhysicsSystem::force_multipliers            params / set_params
+    """
+
+    def __init__(self, params: abi.RtsParams | None = None, map_cells=(512, 512), device: int = 0):
+        self.L = load_library()
+        self.params = params if params is not None else default_params(*map_cells)
+        self.h = C.c_void_p()
+        rc = self.L.rts_create(C.byref(self.params), device, C.byref(self.h))
+        if rc != 0:
+            text = self.L.rts_last_error(self.h).decode() if self.h else "no CUDA device (there is no CPU fallback)"
+            if self.h:
+                self.L.rts_destroy(self.h)
+                self.h = C.c_void_p()
+            raise RtsError(rc, text)
+        self._keep: list = []
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RtsError(rc, self.L.rts_last_error(self.h).decode())
+
+    # -- tables -----------------------------------------------------------------------------
+    def set_params(self, params: abi.RtsParams):
+        self._chk(self.L.rts_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def upload_map(self, tables: dict):
+        keep: list = []
+        tris = abi.triangles_array(tables["tri_verts"], tables["tri_nbrs"], tables.get("tri_constrained"))
+        c2t = np.ascontiguousarray(tables["cell2tri"], np.uint32)
+        if c2t.size != self.params.tri_nx * self.params.tri_ny:
+            raise ValueError("cell2tri does not match the triangle grid of the params")
+        walls = abi.wall_table(tables, keep)
+        self._chk(self.L.rts_upload_map(self.h, tris.ctypes.data, len(tris), c2t.ctypes.data, C.byref(walls)))
+
+    def upload_unit_types(self, types: np.ndarray):
+        types = np.ascontiguousarray(types, abi.UNIT_DTYPE)
+        self._chk(self.L.rts_upload_unit_types(self.h, types.ctypes.data, len(types)))
+
+    def upload_paths(self, paths: dict):
+        keep: list = []
+        t = abi.path_table(paths, keep)
+        self._chk(self.L.rts_upload_paths(self.h, C.byref(t)))
+
+    # -- agents -----------------------------------------------------------------------------
+    def set_agents(self, agents: dict):
+        n = len(agents["r"])
+        keep: list = []
+        v = abi.agent_view({k: a for k, a in agents.items() if k not in abi.DOWNLOAD_ONLY}, n, keep)
+        self._chk(self.L.rts_set_agents(self.h, n, C.byref(v)))
+
+    def append_agents(self, agents: dict):
+        n = len(agents["r"])
+        keep: list = []
+        v = abi.agent_view({k: a for k, a in agents.items() if k not in abi.DOWNLOAD_ONLY}, n, keep)
+        self._chk(self.L.rts_append_agents(self.h, n, C.byref(v)))
+
+    def remove_agents(self, indices):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        self._chk(self.L.rts_remove_agents(self.h, idx.ctypes.data, len(idx)))
+
+    def command_agents(self, indices, path_id: int, state: int = abi.MOVING):
+        idx = np.ascontiguousarray(indices, np.uint32)
+        self._chk(self.L.rts_command_agents(self.h, idx.ctypes.data, len(idx), path_id, state))
+
+    @property
+    def n(self) -> int:
+        return self.L.rts_agent_count(self.h)
+
+    # -- the three System2 phases -------------------------------------------------------------
+    def update_shared_data(self, fields: dict):
+        keep: list = []
+        v = abi.agent_view({k: a for k, a in fields.items() if k not in abi.DOWNLOAD_ONLY}, self.n, keep)
+        self._chk(self.L.rts_update_agents(self.h, C.byref(v)))
+
+    def update(self, n_steps: int = 1, sync: bool = False):
+        self._chk(self.L.rts_step(self.h, n_steps))
+        if sync:
+            self.sync()
+
+    step = update
+
+    def communicate(self, names=("r", "vel", "inertia", "angle", "angle_vel", "state"), out: dict | None = None) -> dict:
+        n = self.n
+        arrays = out if out is not None else abi.alloc_agent_arrays(n, set(names))
+        keep: list = []
+        v = abi.agent_view({k: arrays[k] for k in names}, n, keep)
+        for k, a in zip(names, keep):
+            if a is not arrays[k]:
+                raise ValueError(f"output array {k!r} must be C-contiguous with the ABI dtype")
+        self._chk(self.L.rts_download(self.h, C.byref(v)))
+        return arrays
+
+    download = communicate
+
+    def sync(self):
+        self._chk(self.L.rts_sync(self.h))
+
+    # -- raw-pointer variants for pinned host memory (bench end-to-end leg) -------------------------
+    def update_shared_data_ptrs(self, ptrs: dict):
+        v = abi.RtsAgentView()
+        for k, p in ptrs.items():
+            setattr(v, k, p)
+        self._chk(self.L.rts_update_agents(self.h, C.byref(v)))
+
+    def communicate_ptrs(self, ptrs: dict):
+        v = abi.RtsAgentView()
+        for k, p in ptrs.items():
+            setattr(v, k, p)
+        self._chk(self.L.rts_download(self.h, C.byref(v)))
+
+    # -- measurement ------------------------------------------------------------------------
+    def set_profiling(self, on: bool):
+        self._chk(self.L.rts_set_profiling(self.h, 1 if on else 0))
+
+    def reset_timings(self):
+        self._chk(self.L.rts_reset_timings(self.h))
+
+    def timings(self) -> abi.RtsTimings:
+        t = abi.RtsTimings()
+        self._chk(self.L.rts_get_timings(self.h, C.byref(t)))
+        return t
+
+    def kernel_time_ms(self, which="step"):
+        ms = C.c_double()
+        cnt = C.c_uint64()
+        self._chk(self.L.rts_kernel_time_ms(self.h, KERNELS[which], C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    # -- stand-alone queries ------------------------------------------------------------------
+    def coord_to_cell(self, xy, nx, ny, cs):
+        xy = np.ascontiguousarray(xy, np.float32)
+        out = np.zeros(len(xy), np.uint32)
+        self._chk(self.L.rts_coord_to_cell(self.h, xy.ctypes.data, len(xy), nx, ny, cs, out.ctypes.data))
+        return out
+
+    def find_triangles(self, xy):
+        xy = np.ascontiguousarray(xy, np.float32)
+        out = np.zeros(len(xy), np.uint32)
+        self._chk(self.L.rts_find_triangles(self.h, xy.ctypes.data, len(xy), out.ctypes.data))
+        return out
+
+    def contact_edges(self, xy, radius, cap=8):
+        xy = np.ascontiguousarray(xy, np.float32)
+        radius = np.ascontiguousarray(radius, np.float32)
+        n = len(xy)
+        counts = np.zeros(n, np.uint32)
+        out = np.zeros((n, cap, 5), np.float32)
+        self._chk(self.L.rts_contact_edges(self.h, xy.ctypes.data, radius.ctypes.data, n, cap, counts.ctypes.data,
+                                           out.ctypes.data))
+        return counts, out

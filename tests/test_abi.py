@@ -1,0 +1,54 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/rts_gpu.h declares, its struct
+layouts match the ctypes mirror, and it refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from rtsengine_b200 import abi, engine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "rts_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    names = declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(cuda_lib, n), f"{n} is declared in include/rts_gpu.h but not exported by librts_b200.so"
+    # and the binding covers all of them
+    assert set(names) <= set(cuda_lib._rts_signatures), set(names) - set(cuda_lib._rts_signatures)
+
+
+def test_struct_layouts_match(cuda_lib):
+    for which, st in enumerate([abi.RtsParams, abi.RtsTriangle, abi.RtsEdge, abi.RtsWallTable, abi.RtsPathTable,
+                                abi.RtsUnitType, abi.RtsAgentView, abi.RtsTimings]):
+        assert cuda_lib.rts_abi_sizeof(which) == C.sizeof(st), st.__name__
+    assert abi.TRI_DTYPE.itemsize == C.sizeof(abi.RtsTriangle)
+    assert abi.EDGE_DTYPE.itemsize == C.sizeof(abi.RtsEdge)
+    assert abi.UNIT_DTYPE.itemsize == C.sizeof(abi.RtsUnitType)
+
+
+def test_default_params_follow_the_reference(cuda_lib):
+    p = engine.default_params(512, 512)
+    # NeighbourSearcherContext.cpp:70-71 with box 2560, cell 60 -> 43; main.cpp:50 -> 64 cells of 40
+    assert (p.ns_nx, p.ns_ny, p.ns_cell_size, p.r_max2) == (43, 43, 60.0, 30.0)
+    assert (p.tri_nx, p.tri_ny, p.tri_cell_size) == (64, 64, 40.0)
+    # UI.cpp:124-131
+    assert [round(x, 6) for x in (p.mul_push, p.mul_repulse, p.mul_scatter, p.mul_decay, p.mul_velocity)] == [0.1, 1.0, 0.1, 1.0, 2.0]
+    p2 = engine.default_params(1024, 1024)
+    assert (p2.ns_nx, p2.tri_nx) == (86, 128)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback(cuda_lib):
+    with pytest.raises(engine.RtsError) as e:
+        engine.GpuAgentSystem(map_cells=(512, 512))
+    assert e.value.code == abi.RTS_E_CUDA

@@ -1,0 +1,234 @@
+"""GPU: the CUDA path, called through the C ABI, against (1) fixtures recorded from the verbatim
+reference and (2) the CPU oracle on seeded inputs.  Everything is compared bit for bit: integer
+indices exactly, and floats too, because the kernels keep the reference's operation and summation
+order (--fmad=false, IEEE div/sqrt).  The 1e-5 vector-norm tolerance of SURVEY §8d is asserted as well."""
+import numpy as np
+import pytest
+
+from oracle import port
+from rtsengine_b200 import abi, engine
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5   # BASELINE.json north_star: single-step positions / velocities within 1e-5 relative
+
+
+def make_system(tables, paths=None, map_cells=(512, 512), **kw):
+    p = engine.default_params(*map_cells)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    g = engine.GpuAgentSystem(p)
+    g.upload_map(tables)
+    if paths is not None:
+        g.upload_paths(paths)
+    return g
+
+
+def test_known_answer_triangle_finder():
+    k = H.load("kat.npz")          # src/Tests/test_triangulation.cc:97-115
+    with make_system(H.tables_of(k, "tf_")) as g:
+        assert int(g.find_triangles(np.array([[54.0, 54.0]], np.float32))[0]) == 4
+
+
+def test_point_queries_match_reference_fixtures():
+    q = H.load("queries_small.npz")
+    fx = H.load("frame_small.npz")
+    with make_system(H.tables_of(fx)) as g:
+        H.assert_same_bits(g.find_triangles(q["tri_pts"]), q["tri_expected"], "findTriangle")
+        cnt, edges = g.contact_edges(q["wall_pts"], q["wall_radius"], cap=q["wall_edges"].shape[1])
+        H.assert_same_bits(cnt, q["wall_counts"], "calcContactEdgesO count")
+        H.assert_same_bits(edges, q["wall_edges"], "calcContactEdgesO edges")
+        for nx, cs in ((43, 60.0), (86, 30.0), (512, 5.0), (64, 40.0)):
+            H.assert_same_bits(g.coord_to_cell(q["cell_pts"], nx, nx, cs), q[f"cell_{nx}_{int(cs)}"].astype(np.uint32),
+                               f"coordToCell {nx}x{cs}")
+
+
+@pytest.mark.parametrize("name", ["frame_small.npz", "frame_dense.npz"])
+def test_frames_match_reference_fixtures(name):
+    fx = H.load(name)
+    tables = H.tables_of(fx)
+    prev = None
+    with make_system(tables) as g:
+        for s in range(len(fx["x_r"])):
+            a, paths = H.frame_agents(fx, s, prev)
+            g.upload_paths(paths)
+            g.set_agents(a)
+            g.update(1)
+            out = g.communicate(("r", "vel", "inertia", "angle", "angle_vel", "state", "tri_idx", "ns_cell", "map_cell",
+                                 "r_next", "waypoint", "flags"))
+            for k in ("r", "vel", "inertia"):
+                assert H.rel_err(out[k], fx["x_" + k][s]).max() <= TOL, (name, s, k)
+                H.assert_same_bits(out[k], fx["x_" + k][s], f"{name} frame {s} {k}")
+            for k in ("angle", "angle_vel"):
+                H.assert_same_bits(out[k], fx["x_" + k][s], f"{name} frame {s} {k}")
+            H.assert_same_bits(out["tri_idx"], fx["x_tri"][s], f"{name} frame {s} tri")
+            H.assert_same_bits(out["state"], fx["x_state"][s], f"{name} frame {s} state")
+            H.assert_same_bits(out["ns_cell"], port.coord_to_cell(out["r"], 43, 43, 60.0), "ns cell")
+            H.assert_same_bits(out["map_cell"], port.coord_to_cell(out["r"], 512, 512, 5.0), "map cell")
+            prev = out
+
+
+def random_world(seed, n, tables, lo, hi, moving=0.6):
+    rng = np.random.default_rng(seed)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = rng.uniform(lo, hi, (n, 2))
+    a["inertia"][:] = rng.normal(0, 5, (n, 2))
+    a["angle"][:] = rng.uniform(-200, 200, n)
+    a["angle_vel"][:] = rng.uniform(-5, 5, n)
+    big = rng.random(n) < 0.2
+    a["radius"][:] = np.where(big, 5.0, 3.0)
+    a["mass"][:] = np.where(big, 50.0, 1.0)
+    a["unit_type"][:] = big
+    a["player"][:] = rng.integers(0, 2, n)
+    a["state"][:] = np.where(rng.random(n) < moving, abi.MOVING, abi.STANDING)
+    # 8 hand-made paths of 3-5 waypoints with portals across the way
+    n_paths = 8
+    off = [0]
+    wps, pos, ends = [], [], []
+    for p in range(n_paths):
+        k = int(rng.integers(3, 6))
+        pts = rng.uniform(lo, hi, (k, 2)).astype(np.float32)
+        for j in range(k):
+            d = rng.normal(size=2)
+            d /= np.linalg.norm(d)
+            L = float(rng.uniform(0, 40)) if j < k - 1 else 0.0
+            frm = pts[j] - d * L / 2
+            wps.append(pts[j])
+            pos.append([frm[0], frm[1], d[0], d[1], L])
+        ends.append(pts[-1])
+        off.append(off[-1] + k)
+    paths = {"offsets": np.array(off, np.uint32), "waypoints": np.array(wps, np.float32),
+             "portals": np.array(pos, np.float32), "path_end": np.array(ends, np.float32)}
+    a["path_id"][:] = np.where(a["state"] == abi.MOVING, rng.integers(0, n_paths, n), -1)
+    a["waypoint"][:] = rng.integers(0, 3, n)
+    a["r_next"][:] = np.nan
+    return a, paths
+
+
+@pytest.mark.parametrize("n,lo,hi,seed", [(20000, 100.0, 900.0, 1), (50000, 150.0, 700.0, 2), (3000, 300.0, 420.0, 3)])
+def test_multi_step_matches_oracle(n, lo, hi, seed):
+    """seeded random crowd (the last case is ~0.2 agents/unit²: > NBR_CAP neighbours, selection path)"""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(seed, n, tables, lo, hi)
+    P = port.default_params(512, 512)
+    ow = port.OracleWorld(P, tables, paths)
+    ref = {k: v.copy() for k, v in a.items()}
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "tri_idx", "ns_cell", "map_cell", "r_next", "waypoint", "flags")
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        for s in range(4):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            finite = np.isfinite(ref["r"]).all(1)
+            assert finite.mean() > 0.99
+            for k in names:
+                H.assert_same_bits(out[k][finite], ref[k][finite], f"step {s} {k}")
+            assert H.rel_err(out["r"][finite], ref["r"][finite]).max() <= TOL
+
+
+def test_graph_replay_equals_single_steps():
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(5, 30000, tables, 100.0, 1000.0)
+    with make_system(tables, paths) as g1, make_system(tables, paths) as g2:
+        g1.set_agents(a)
+        g2.set_agents(a)
+        g1.update(7)                 # graph of 2 frames x3 + 1 plain
+        for _ in range(7):
+            g2.update(1)
+        o1 = g1.communicate(("r", "inertia", "tri_idx", "waypoint"))
+        o2 = g2.communicate(("r", "inertia", "tri_idx", "waypoint"))
+        for k in o1:
+            H.assert_same_bits(o1[k], o2[k], k)
+
+
+def test_update_shared_data_roundtrip_and_population_edits():
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(9, 5000, tables, 100.0, 1000.0)
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        out = g.communicate(("r", "inertia", "angle", "state", "radius", "mass", "path_id", "waypoint", "gid"))
+        H.assert_same_bits(out["r"], a["r"], "download returns caller order")
+        H.assert_same_bits(out["gid"], np.arange(5000, dtype=np.uint32), "gid = component index")
+        # System2::updateSharedData: overwrite positions/state, everything else stays
+        r2 = a["r"][::-1].copy()
+        g.update_shared_data({"r": r2})
+        out2 = g.communicate(("r", "inertia", "path_id"))
+        H.assert_same_bits(out2["r"], r2, "positions replaced")
+        H.assert_same_bits(out2["inertia"], a["inertia"], "inertia kept")
+        # System2::remove is swap-with-last
+        g.remove_agents([10, 0])
+        assert g.n == 4998
+        out3 = g.communicate(("r", "mass"))
+        exp = r2.copy()
+        exp[10] = exp[4999]
+        exp[0] = exp[4998]
+        H.assert_same_bits(out3["r"], exp[:4998], "swap-with-last removal")
+        # System2::addComponent appends
+        extra = {k: v[:7].copy() for k, v in a.items() if k not in abi.DOWNLOAD_ONLY}
+        g.append_agents(extra)
+        assert g.n == 5005
+        out4 = g.communicate(("r", "mass"))
+        H.assert_same_bits(out4["r"][4998:], a["r"][:7], "appended at the end")
+        H.assert_same_bits(out4["r"][:4998], exp[:4998], "old agents keep their index")
+
+
+def test_empty_population_and_errors():
+    fx = H.load("frame_small.npz")
+    with make_system(H.tables_of(fx)) as g:
+        g.set_agents({"r": np.zeros((0, 2), np.float32)})
+        g.update(3)
+        assert g.n == 0
+        bad = dict(H.tables_of(fx))
+        bad["cell2tri"] = bad["cell2tri"].copy()
+        bad["cell2tri"][5] = 10 ** 8
+        with pytest.raises(engine.RtsError) as e:
+            g.upload_map(bad)
+        assert e.value.code == abi.RTS_E_ARG
+    p = engine.default_params(512, 512)
+    with engine.GpuAgentSystem(p) as g:
+        g.set_agents({"r": np.ones((4, 2), np.float32)})
+        with pytest.raises(engine.RtsError) as e:
+            g.update(1)                         # no map uploaded
+        assert e.value.code == abi.RTS_E_STATE
+
+
+def test_full_size_properties_1m():
+    """BASELINE config 3 size (1M agents, 1024² map): properties that do not need the oracle at full size,
+    plus an oracle check on a 2 % sample of agents re-simulated with all their neighbours."""
+    fx = H.load("map_c3.npz")
+    tables = H.tables_of(fx)
+    from rtsengine_b200 import scenario
+    a, paths = scenario.config3_agents(fx, n=1_000_000, seed=1236)
+    p = engine.default_params(1024, 1024)
+    with engine.GpuAgentSystem(p) as g:
+        g.upload_map(tables)
+        g.upload_paths(paths)
+        g.set_agents(a)
+        before = g.communicate(("r", "gid"))
+        H.assert_same_bits(before["r"], a["r"], "upload/download is the identity")
+        g.update(1)
+        out = g.communicate(("r", "vel", "inertia", "tri_idx", "ns_cell", "map_cell", "state", "flags"))
+        assert np.isfinite(out["r"]).all()
+        # integration identity r' = r + v*dt, bit for bit (ECS.cpp:110)
+        H.assert_same_bits(out["r"], a["r"] + out["vel"] * np.float32(p.dt), "r' = r + v dt")
+        # indices are pure functions of the new position
+        H.assert_same_bits(out["ns_cell"], port.coord_to_cell(out["r"], p.ns_nx, p.ns_ny, 60.0), "ns cell")
+        H.assert_same_bits(out["map_cell"], port.coord_to_cell(out["r"], 1024, 1024, 5.0), "map cell")
+        ow = port.OracleWorld(port.default_params(1024, 1024), tables, paths)
+        H.assert_same_bits(out["tri_idx"], ow.find_triangles(out["r"]), "triangle index of every agent")
+        assert (out["flags"] & abi.FLAG_WALK_FAILED).sum() == 0
+        # sample: a 400x400 window, agents further than 6 units from its border have all neighbours inside
+        lo, hi = 2000.0, 2400.0
+        inside = ((a["r"] >= lo) & (a["r"] < hi)).all(1)
+        idx = np.nonzero(inside)[0]
+        sub = {k: np.ascontiguousarray(v[idx]) for k, v in a.items()}
+        ow.step(sub)
+        core = ((a["r"][idx] >= lo + 6) & (a["r"][idx] < hi - 6)).all(1)
+        assert core.sum() > 3000
+        for k in ("r", "vel", "inertia", "tri_idx"):
+            H.assert_same_bits(out[k][idx][core], sub[k][core], f"1M sample {k}")
