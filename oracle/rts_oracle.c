@@ -108,7 +108,15 @@ static inline int lines_intersect(iv2 v11, iv2 v12, iv2 v21, iv2 v22) { /* Trian
 static inline int nxt(int i) { return i == 2 ? 0 : i + 1; }
 static inline int prv(int i) { return i == 0 ? 2 : i - 1; }
 
+static long g_walk_brute = 0, g_walk_hops = 0, g_walk_calls = 0;
+void rts_oracle_walk_stats(long* out, int reset) {
+    out[0] = g_walk_calls; out[1] = g_walk_hops; out[2] = g_walk_brute;
+    if (reset) g_walk_calls = g_walk_hops = g_walk_brute = 0;
+}
+
 static uint32_t brute_force(iv2 q, const RtsTriangle* tris, uint32_t n_tris) {
+#pragma omp atomic
+    g_walk_brute++;
     for (uint32_t i = 0; i < n_tris; ++i)
         if (in_triangle(q, &tris[i])) return i;
     return 0xFFFFFFFFu;

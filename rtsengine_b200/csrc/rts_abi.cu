@@ -1,7 +1,9 @@
 // C ABI of librts_b200.so (include/rts_gpu.h): context, table uploads, step scheduling, downloads.
 // Host code is plain C++; nothing here falls back to the CPU — without a CUDA device every entry point
 // that computes returns RTS_E_CUDA.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -208,7 +210,10 @@ int32_t launch_scan_reorder(RtsContext* h) {
     k_scan_final<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, nullptr);
     timer_end(h, KT_SCAN);
     timer_begin(h, KT_REORDER);
-    if (h->n) k_reorder<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->F, h->A);
+    if (h->n) {
+        if (h->M.coords_fit_i32) k_reorder<false><<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+        else k_reorder<true><<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+    }
     timer_end(h, KT_REORDER);
     h->launches += 3;
     swap_prev_order(h);
@@ -455,11 +460,44 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
         CU(cudaMemcpyAsync(d_ft, ft.data(), ft.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(d_el, el.data(), el.size() * 4, cudaMemcpyHostToDevice, h->stream));
     }
+    // conservative wall pre-filter bitmap (see may_touch_wall)
+    const float filter_r = 8.0f;
+    const int32_t bx = (int32_t)std::ceil(P.map_nx * P.map_cell_size / WALL_BLOCK) + 1;
+    const int32_t by = (int32_t)std::ceil(P.map_ny * P.map_cell_size / WALL_BLOCK) + 1;
+    std::vector<uint32_t> bits(((size_t)bx * by + 31) / 32, 0u);
+    for (size_t e = 0; e < ft.size(); ++e) {
+        const float x0 = ft[e].x, y0 = ft[e].y, x1 = x0 + ft[e].z * el[e], y1 = y0 + ft[e].w * el[e];
+        const float reach = filter_r + 1.0f;
+        const int ix0 = std::max(0, (int)std::floor((std::min(x0, x1) - reach) / WALL_BLOCK));
+        const int ix1 = std::min(bx - 1, (int)std::floor((std::max(x0, x1) + reach) / WALL_BLOCK));
+        const int iy0 = std::max(0, (int)std::floor((std::min(y0, y1) - reach) / WALL_BLOCK));
+        const int iy1 = std::min(by - 1, (int)std::floor((std::max(y0, y1) + reach) / WALL_BLOCK));
+        for (int iy = iy0; iy <= iy1; ++iy)
+            for (int ix = ix0; ix <= ix1; ++ix) {
+                const size_t b = (size_t)iy * bx + ix;
+                bits[b >> 5] |= 1u << (b & 31);
+            }
+    }
+    uint32_t* d_bits;
+    if ((rc = dev_alloc(h, &d_bits, bits.size(), h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    // int32 triangle walk is exact iff no product can overflow: |coord| <= 16383 (see tri_sign)
+    int32_t cmax = 0;
+    for (uint32_t t = 0; t < n_tris; ++t)
+        for (int k = 0; k < 3; ++k) cmax = std::max(cmax, std::max(std::abs(tris[t].vx[k]), std::abs(tris[t].vy[k])));
     CU(cudaStreamSynchronize(h->stream));
     M.tris = d_tris; M.n_tris = n_tris; M.cell2tri = d_c2t;
     M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
+    M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r;
+    M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
     h->map_ready = true;
     h->drop_graphs();
+    if (h->n) {   // agents uploaded before the map: give them their triangle index now
+        Staging none{};
+        k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, none, h->A);
+        if ((rc = rebin(h)) != RTS_OK) return rc;
+        CU(cudaStreamSynchronize(h->stream));
+    }
     return RTS_OK;
 }
 

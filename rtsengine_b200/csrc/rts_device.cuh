@@ -32,7 +32,14 @@ struct MapDev {
     const RtsUnitType* __restrict__ unit_types;
     uint32_t n_types;
     const float* __restrict__ acos_table;   // AcosTable<1000>, built on the host (src/core.h:115-124)
+    // conservative wall pre-filter: one bit per block of WALL_BLOCK map units, set if any wall lies within
+    // wall_filter_radius (+1) of the block; agents with a larger radius always run the full query
+    const uint32_t* __restrict__ wall_bits;
+    int32_t wall_bx, wall_by;
+    float wall_filter_radius;
+    int32_t coords_fit_i32;   // 1: every triangle-walk product fits int32 (the reference's own arithmetic)
 };
+constexpr float WALL_BLOCK = 20.f;
 
 struct v2 {
     float x, y;
@@ -78,33 +85,38 @@ __device__ __forceinline__ float table_angle(const float* __restrict__ table, v2
 struct iv2 {
     int32_t x, y;
 };
-// sign(), Triangulation.h:73-76: integer arithmetic then ->float. 64-bit products: identical to the
-// reference's int32 wherever that does not overflow (it would on 8192² maps, where it is UB).
+// sign(), Triangulation.h:73-76: integer arithmetic, then ->float.  WIDE = false is the reference's own int32
+// arithmetic (used when the map is small enough that nothing overflows); WIDE = true forms the products in 64 bits,
+// identical wherever int32 does not overflow (on 8192² maps the reference overflows, which is UB there).
+template <bool WIDE>
 __device__ __forceinline__ float tri_sign(iv2 p1, iv2 p2, iv2 p3) {
-    return (float)((int64_t)(p1.x - p3.x) * (p2.y - p3.y) - (int64_t)(p2.x - p3.x) * (p1.y - p3.y));
+    if (WIDE) return (float)((int64_t)(p1.x - p3.x) * (p2.y - p3.y) - (int64_t)(p2.x - p3.x) * (p1.y - p3.y));
+    return (float)((p1.x - p3.x) * (p2.y - p3.y) - (p2.x - p3.x) * (p1.y - p3.y));
 }
+template <bool WIDE>
 __device__ __forceinline__ bool in_triangle(iv2 q, iv2 a, iv2 b, iv2 c) {  // isInTriangle, Triangulation.h:83-96
-    const float d1 = tri_sign(q, a, b), d2 = tri_sign(q, b, c), d3 = tri_sign(q, c, a);
+    const float d1 = tri_sign<WIDE>(q, a, b), d2 = tri_sign<WIDE>(q, b, c), d3 = tri_sign<WIDE>(q, c, a);
     const bool has_neg = (d1 < 0) || (d2 < 0) || (d3 < 0);
     const bool has_pos = (d1 > 0) || (d2 > 0) || (d3 > 0);
     return !(has_neg && has_pos);
 }
-__device__ __forceinline__ float idot(iv2 a, iv2 b) { return (float)((int64_t)a.x * b.x + (int64_t)a.y * b.y); }
+template <bool WIDE>
+__device__ __forceinline__ float idot(iv2 a, iv2 b) {  // dot<Vertex>, core.h:99
+    if (WIDE) return (float)((int64_t)a.x * b.x + (int64_t)a.y * b.y);
+    return (float)(a.x * b.x + a.y * b.y);
+}
+template <bool WIDE>
 __device__ __forceinline__ bool lines_intersect(iv2 v11, iv2 v12, iv2 v21, iv2 v22) {  // Triangulation.cpp:1805-1818
     const iv2 dr{v21.x - v11.x, v21.y - v11.y};
     const iv2 t1{v12.x - v11.x, v12.y - v11.y};
     const iv2 t2{v22.x - v21.x, v22.y - v21.y};
     const iv2 n1{t1.y, -t1.x};
     const iv2 n2{t2.y, -t2.x};
-    const float alpha1 = +idot(dr, n2) / idot(t1, n2);
-    const float alpha2 = -idot(dr, n1) / idot(t2, n1);
+    const float alpha1 = +idot<WIDE>(dr, n2) / idot<WIDE>(t1, n2);
+    const float alpha2 = -idot<WIDE>(dr, n1) / idot<WIDE>(t2, n1);
     return alpha1 >= 0 && alpha1 <= 1 && alpha2 >= 0 && alpha2 <= 1;
 }
 
-struct TriRec {
-    iv2 v[3];
-    uint32_t nb[3];
-};
 __device__ __forceinline__ void load_tri_verts(const MapDev& M, uint32_t t, iv2& a, iv2& b, iv2& c, int4& w1) {
     const int4 w0 = __ldg(M.tris + 3 * (size_t)t);
     w1 = __ldg(M.tris + 3 * (size_t)t + 1);
@@ -113,54 +125,88 @@ __device__ __forceinline__ void load_tri_verts(const MapDev& M, uint32_t t, iv2&
     c = iv2{w1.x, w1.y};
 }
 
-__device__ __noinline__ uint32_t tri_brute_force(const MapDev& M, iv2 q) {  // Triangulation.cpp:1503-1510, 1539-1546
-    for (uint32_t i = 0; i < M.n_tris; ++i) {
-        iv2 a, b, c;
-        int4 w1;
-        load_tri_verts(M, i, a, b, c, w1);
-        if (in_triangle(q, a, b, c)) return i;
-    }
-    return 0xFFFFFFFFu;
-}
+constexpr uint32_t TRI_NONE = 0xFFFFFFFFu;
+constexpr uint32_t TRI_NEED_SCAN = 0xFFFFFFFEu;   // the reference falls back to its linear scan here
 
-__device__ __forceinline__ uint32_t find_triangle(const MapDev& M, const RtsParams& P, float fx, float fy, uint32_t& flags) {
-    const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
+// Walk part of findTriangle. Returns the triangle, TRI_NEED_SCAN where the reference would scan all triangles
+// (Triangulation.cpp:1503-1510, 1539-1546; done warp-cooperatively by the caller), or TRI_NONE + flag on failure.
+template <bool WIDE>
+__device__ __forceinline__ uint32_t find_triangle_walk(const MapDev& M, const RtsParams& P, iv2 q, uint32_t& flags) {
     const uint32_t cell = coord_to_cell((float)q.x, (float)q.y, P.tri_nx, P.tri_ny, P.tri_cell_size);
     uint32_t t = __ldg(M.cell2tri + cell);
-    if (t == 0xFFFFFFFFu) return tri_brute_force(M, q);
+    if (t == TRI_NONE) return TRI_NEED_SCAN;
     iv2 a, b, c;
     int4 w1;
     load_tri_verts(M, t, a, b, c, w1);
-    if (in_triangle(q, a, b, c)) return t;
+    if (in_triangle<WIDE>(q, a, b, c)) return t;
     iv2 vc;
     {
         const iv2 g{(a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3};  // integer division, :1524
-        if (lines_intersect(g, q, a, b)) { t = (uint32_t)w1.z; vc = a; }
-        else if (lines_intersect(g, q, b, c)) { t = (uint32_t)w1.w; vc = b; }
-        else if (lines_intersect(g, q, c, a)) { t = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x; vc = c; }
-        else t = 0xFFFFFFFFu;
+        if (lines_intersect<WIDE>(g, q, a, b)) { t = (uint32_t)w1.z; vc = a; }
+        else if (lines_intersect<WIDE>(g, q, b, c)) { t = (uint32_t)w1.w; vc = b; }
+        else if (lines_intersect<WIDE>(g, q, c, a)) { t = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x; vc = c; }
+        else t = TRI_NONE;
     }
-    if (t == 0xFFFFFFFFu) return tri_brute_force(M, q);
+    if (t == TRI_NONE) return TRI_NEED_SCAN;
     const uint32_t hop_limit = 4 * M.n_tris + 16;
     for (uint32_t hops = 0;; ++hops) {  // fan walk around vc, :1548-1563
         load_tri_verts(M, t, a, b, c, w1);
-        if (in_triangle(q, a, b, c)) return t;
+        if (in_triangle<WIDE>(q, a, b, c)) return t;
         int k = -1;
         if (a.x == vc.x && a.y == vc.y) k = 0;
         else if (b.x == vc.x && b.y == vc.y) k = 1;
         else if (c.x == vc.x && c.y == vc.y) k = 2;
         if (k < 0 || hops >= hop_limit) {  // the reference would index out of bounds / never return: report instead
             flags |= RTS_FLAG_WALK_FAILED;
-            return 0xFFFFFFFFu;
+            return TRI_NONE;
         }
         const uint32_t n2 = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x;
-        const uint32_t nb[3] = {(uint32_t)w1.z, (uint32_t)w1.w, n2};
-        const iv2 vs[3] = {a, b, c};
+        const uint32_t nb0 = (uint32_t)w1.z, nb1 = (uint32_t)w1.w;
         const int kn = (k == 2) ? 0 : k + 1, kp = (k == 0) ? 2 : k - 1;
-        if (lines_intersect(vc, q, vs[kn], vs[kp])) { t = nb[kn]; vc = vs[kn]; }
-        else t = nb[k];
-        if (t == 0xFFFFFFFFu) { flags |= RTS_FLAG_WALK_FAILED; return t; }
+        const iv2 vn = (kn == 0) ? a : (kn == 1) ? b : c;
+        const iv2 vp = (kp == 0) ? a : (kp == 1) ? b : c;
+        if (lines_intersect<WIDE>(vc, q, vn, vp)) { t = (kn == 0) ? nb0 : (kn == 1) ? nb1 : n2; vc = vn; }
+        else t = (k == 0) ? nb0 : (k == 1) ? nb1 : n2;
+        if (t == TRI_NONE) { flags |= RTS_FLAG_WALK_FAILED; return t; }
     }
+}
+
+// findTriangle for the lanes of one warp. `want` says whether this lane has a query; every lane of `mask` must call.
+// The rare linear scans are served by the whole warp: 32 triangles per iteration, lowest index wins.
+template <bool WIDE>
+__device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const RtsParams& P, bool want, float fx, float fy,
+                                                       uint32_t& flags, unsigned mask) {
+    const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
+    uint32_t t = TRI_NONE;
+    if (want) t = find_triangle_walk<WIDE>(M, P, q, flags);
+    unsigned need = __ballot_sync(mask, want && t == TRI_NEED_SCAN);
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t n_lanes = (uint32_t)__popc(mask);                       // lanes that take part (exited lanes cannot)
+    const uint32_t my = (uint32_t)__popc(mask & ((1u << lane) - 1u));      // rank of this lane among them
+    while (need) {
+        const int src = __ffs(need) - 1;
+        const iv2 qq{__shfl_sync(mask, q.x, src), __shfl_sync(mask, q.y, src)};
+        uint32_t found = TRI_NONE;
+        for (uint32_t base = 0; base < M.n_tris; base += n_lanes) {
+            const uint32_t i = base + my;
+            bool hit = false;
+            if (i < M.n_tris) {
+                iv2 a, b, c;
+                int4 w1;
+                load_tri_verts(M, i, a, b, c, w1);
+                hit = in_triangle<WIDE>(qq, a, b, c);
+            }
+            const unsigned hits = __ballot_sync(mask, hit);
+            if (hits) {   // lowest triangle index = lowest participating lane that hit
+                const int first = __ffs(hits) - 1;
+                found = base + (uint32_t)__popc(mask & ((1u << first) - 1u));
+                break;
+            }
+        }
+        if ((int)lane == src) t = found;
+        need &= need - 1;
+    }
+    return t;
 }
 
 // ---- Edges::calcContactEdgesO + isTouchingEdge, src/Edges.cpp:245-296, 128-143 ----------------------
@@ -222,6 +268,16 @@ __device__ __forceinline__ int contact_walls(const MapDev& M, const RtsParams& P
         }
     }
     return count;
+}
+
+// Conservative pre-filter of the wall query: false only if no wall can touch a circle of `radius` at r
+// (a contact needs dist(r, segment) <= radius; the bitmap marks every block within wall_filter_radius+1 of a wall).
+__device__ __forceinline__ bool may_touch_wall(const MapDev& M, v2 r, float radius) {
+    if (!M.wall_bits || !(radius <= M.wall_filter_radius)) return true;
+    const float fx = r.x * (1.f / WALL_BLOCK), fy = r.y * (1.f / WALL_BLOCK);
+    if (!(fx >= 0.f && fy >= 0.f && fx < (float)M.wall_bx && fy < (float)M.wall_by)) return true;   // outside the map (or NaN)
+    const uint32_t b = (uint32_t)(int)fy * (uint32_t)M.wall_bx + (uint32_t)(int)fx;
+    return (__ldg(M.wall_bits + (b >> 5)) >> (b & 31u)) & 1u;
 }
 
 // PhysicsSystem::avoidWall body for one wall, src/Systems/PhysicsSystem.cpp:146-158

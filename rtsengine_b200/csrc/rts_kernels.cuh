@@ -18,9 +18,15 @@ constexpr int STEP_BLOCK = 128;   // threads per CTA of k_step
 constexpr int NBR_CAP = 24;       // neighbours kept sorted in shared memory per agent; more -> selection path
 constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
 
-// key2.y = ns_cell << 3 | ghost << 2 | state
-__device__ __forceinline__ uint32_t pack_cs(uint32_t ns_cell, uint32_t ghost, uint32_t state) {
-    return (ns_cell << 3) | (ghost << 2) | (state & 3u);
+// key2.y = cy << 16 | cx << 3 | ghost << 2 | state, (cx, cy) = 2-D coordinates of the physics-grid cell (13 bits each)
+__device__ __forceinline__ uint32_t pack_cs(uint32_t cx, uint32_t cy, uint32_t ghost, uint32_t state) {
+    return (cy << 16) | (cx << 3) | (ghost << 2) | (state & 3u);
+}
+__device__ __forceinline__ int cs_cx(uint32_t y) { return (int)((y >> 3) & 0x1FFFu); }
+__device__ __forceinline__ int cs_cy(uint32_t y) { return (int)(y >> 16); }
+// Grid::coordToCell on the physics grid, kept as 2-D coordinates (cell index = cx + cy * ns_nx)
+__device__ __forceinline__ uint32_t ns_pack(const RtsParams& P, float x, float y, uint32_t ghost, uint32_t state) {
+    return pack_cs(axis_cell(x, P.ns_cell_size, P.ns_nx), axis_cell(y, P.ns_cell_size, P.ns_ny), ghost, state);
 }
 // nav4.w bits: waypoint 0..15 | unit_type 16..23 | player 24..27 | flags 28..31
 __device__ __forceinline__ uint32_t pack_misc(uint32_t wp, uint32_t type, uint32_t player, uint32_t flags) {
@@ -57,7 +63,7 @@ __device__ __forceinline__ uint32_t warp_aggregated_rank(uint32_t* count, uint32
 struct AgentArrays {
     // neighbour record, CURRENT cell order
     float4* pos4;   // {x, y, radius, mass}
-    uint2* key2;    // {gid, ns_cell<<3 | ghost<<2 | state}
+    uint2* key2;    // {gid, cy<<16 | cx<<3 | ghost<<2 | state}
     uint32_t* src;  // slot -> index into the previous-order arrays below
     // previous-order arrays (outputs of the last step / the upload), read through src[]
     float4* vel4;   // {inertia.x, inertia.y, angle, angle_vel}
@@ -81,8 +87,7 @@ __global__ void k_bin(uint32_t n, RtsParams P, FineGrid F, AgentArrays A) {
     if (p >= n) return;
     const float4 pos = A.pos4n[p];
     uint2 k = A.key2n[p];
-    const uint32_t ns = coord_to_cell(pos.x, pos.y, P.ns_nx, P.ns_ny, P.ns_cell_size);
-    k.y = pack_cs(ns, (k.y >> 2) & 1u, k.y & 3u);
+    k.y = ns_pack(P, pos.x, pos.y, (k.y >> 2) & 1u, k.y & 3u);
     A.key2n[p] = k;
     int fx, fy;
     fine_coords(F, pos.x, pos.y, fx, fy);
@@ -172,15 +177,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
     }
 }
 
-__global__ void k_reorder(uint32_t n, FineGrid F, AgentArrays A) {
+// Counting-sort scatter of the neighbour record into the new cell order + the triangle walk
+// (Triangulation::findTriangle) of the new position.  Low register count, so the walk's dependent table loads
+// are hidden by occupancy instead of stalling the fat frame kernel.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_reorder(uint32_t n, RtsParams P, MapDev M, FineGrid F, AgentArrays A) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned mask = __ballot_sync(0xffffffffu, p < n);
     if (p >= n) return;
     const uint2 cr = A.cellrank[p];
-    if (cr.x == INVALID_CELL) return;  // dropped (ghost / migrated away)
-    const uint32_t d = F.start[cr.x] + cr.y;
-    A.pos4[d] = A.pos4n[p];
-    A.key2[d] = A.key2n[p];
-    A.src[d] = p;
+    const bool live = cr.x != INVALID_CELL;   // ghosts / migrated agents are dropped
+    float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 key = make_uint2(0u, 0u);
+    if (live) {
+        pos = A.pos4n[p];
+        key = A.key2n[p];
+        const uint32_t d = F.start[cr.x] + cr.y;
+        A.pos4[d] = pos;
+        A.key2[d] = key;
+        A.src[d] = p;
+    }
+    const bool want = live && M.n_tris != 0 && (P.walk_all || (key.y & 3u) == RTS_MOVING);   // no map uploaded yet: no walk
+    uint32_t flags = 0;
+    uint32_t t;
+    // the int32 walk needs |q| <= 16383 as well as the table bound checked at upload
+    const bool small = fabsf(pos.x) <= 16383.f && fabsf(pos.y) <= 16383.f;
+    if (!WIDE && __all_sync(mask, small || !want)) t = find_triangle_warp<false>(M, P, want, pos.x, pos.y, flags, mask);
+    else t = find_triangle_warp<true>(M, P, want, pos.x, pos.y, flags, mask);
+    if (want) {
+        A.trin[p] = t;
+        if (flags) {
+            float4 nav = A.nav4n[p];
+            nav.w = __uint_as_float(__float_as_uint(nav.w) | (flags << 28));
+            A.nav4n[p] = nav;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -188,8 +219,7 @@ __global__ void k_reorder(uint32_t n, FineGrid F, AgentArrays A) {
 // neighbouring cells and the neighbour records come out of L1).
 template <bool KEEP_VEL>
 __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, MapDev M, FineGrid F, AgentArrays A) {
-    __shared__ uint32_t s_key[NBR_CAP][STEP_BLOCK];
-    __shared__ uint32_t s_q[NBR_CAP][STEP_BLOCK];
+    __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, slot} of the NBR_CAP smallest keys seen, ascending
     const uint32_t p = blockIdx.x * STEP_BLOCK + threadIdx.x;
     const unsigned valid = __ballot_sync(0xffffffffu, p < n);
     if (p >= n) return;
@@ -208,8 +238,7 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
         A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
         return;
     }
-    const uint32_t ns_i = mykey.y >> 3;
-    const int cxi = (int)(ns_i % (uint32_t)P.ns_nx), cyi = (int)((ns_i / (uint32_t)P.ns_nx) % (uint32_t)P.ns_ny);
+    const int cxi = cs_cx(mykey.y), cyi = cs_cy(mykey.y);
 
     const float4 vel4 = A.vel4[sp];
     const float4 nav4 = A.nav4[sp];
@@ -232,9 +261,8 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
                 const v2 dr = V(o.x, o.y) - r;
                 if (norm2(dr) < P.r_max2 && q != p) {
                     const uint2 ok = __ldg(A.key2 + q);
-                    const uint32_t ns_j = ok.y >> 3;
-                    const int dxc = (int)(ns_j % (uint32_t)P.ns_nx) - cxi;
-                    const int dyc = (int)((ns_j / (uint32_t)P.ns_nx) % (uint32_t)P.ns_ny) - cyi;
+                    const int dxc = cs_cx(ok.y) - cxi;
+                    const int dyc = cs_cy(ok.y) - cyi;
                     // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
                     const int idx = (dxc + 1) * 3 + (dyc + 1);
                     const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
@@ -270,33 +298,39 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
         }
     };
 
-    int cnt = 0;
+    // Pass structure: one scan keeps the NBR_CAP smallest keys above `floor_key`, sorted, in shared memory; they are
+    // accumulated in order; crowds with more neighbours than NBR_CAP take further scans (floor_key = last key used).
+    int cnt = 0, kept = 0;
     for_each_neighbour([&](uint32_t key, uint32_t q) {
-        if (cnt < NBR_CAP) {
-            int pos = cnt;
-            while (pos > 0 && s_key[pos - 1][tid] > key) {
-                s_key[pos][tid] = s_key[pos - 1][tid];
-                s_q[pos][tid] = s_q[pos - 1][tid];
+        ++cnt;
+        int pos;
+        if (kept < NBR_CAP) pos = kept++;
+        else if (key < s_kq[NBR_CAP - 1][tid].x) pos = NBR_CAP - 1;
+        else return;
+        while (pos > 0 && s_kq[pos - 1][tid].x > key) {
+            s_kq[pos][tid] = s_kq[pos - 1][tid];
+            --pos;
+        }
+        s_kq[pos][tid] = make_uint2(key, q);
+    });
+    for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+    for (int done = kept; done < cnt;) {   // dense crowd: more passes
+        const uint32_t floor_key = s_kq[kept - 1][tid].x;
+        kept = 0;
+        for_each_neighbour([&](uint32_t key, uint32_t q) {
+            if (key <= floor_key) return;
+            int pos;
+            if (kept < NBR_CAP) pos = kept++;
+            else if (key < s_kq[NBR_CAP - 1][tid].x) pos = NBR_CAP - 1;
+            else return;
+            while (pos > 0 && s_kq[pos - 1][tid].x > key) {
+                s_kq[pos][tid] = s_kq[pos - 1][tid];
                 --pos;
             }
-            s_key[pos][tid] = key;
-            s_q[pos][tid] = q;
-        }
-        ++cnt;
-    });
-    if (cnt <= NBR_CAP) {
-        for (int k = 0; k < cnt; ++k) accumulate(s_q[k][tid]);
-    } else {
-        // dense crowd: selection in key order, no storage (O(cnt * candidates), rare)
-        uint32_t last_key = 0;
-        for (int k = 0; k < cnt; ++k) {
-            uint32_t best_key = 0xFFFFFFFFu, best_q = 0;
-            for_each_neighbour([&](uint32_t key, uint32_t q) {
-                if ((k == 0 || key > last_key) && key < best_key) { best_key = key; best_q = q; }
-            });
-            accumulate(best_q);
-            last_key = best_key;
-        }
+            s_kq[pos][tid] = make_uint2(key, q);
+        });
+        for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+        done += kept;
     }
 
     // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116
@@ -318,7 +352,9 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
     inertia = inertia - inertia * decay;
 
     // ---- P4: wall pass #1, PhysicsSystem.cpp:130-162
-    const int n_walls = contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, vp, inertia); });
+    int n_walls = 0;
+    if (may_touch_wall(M, r, radius))
+        n_walls = contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, vp, inertia); });
 
     // ---- S1: SeekSystem::update per-agent body, SeekSystem.cpp:76-111
     v2 vs = V(0.f, 0.f);
@@ -387,18 +423,14 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
     const v2 r_new = r + v * P.dt;
     angle = angle + angle_vel;
 
-    // ---- K7: triangle walk on the new position
-    uint32_t tri;
-    if (P.walk_all || state_i == RTS_MOVING) tri = find_triangle(M, P, r_new.x, r_new.y, flags);
-    else tri = A.tri[sp];
+    // ---- K7 (triangle walk on the new position) runs in k_reorder; agents that are not walked keep their index
+    if (!(P.walk_all || state_i == RTS_MOVING)) A.trin[p] = A.tri[sp];
 
     // ---- write the new record at this slot; bin it for the next order
-    const uint32_t ns_new = coord_to_cell(r_new.x, r_new.y, P.ns_nx, P.ns_ny, P.ns_cell_size);
     A.pos4n[p] = make_float4(r_new.x, r_new.y, radius, mass_i);
-    A.key2n[p] = make_uint2(gid, pack_cs(ns_new, 0u, (uint32_t)state_i));
+    A.key2n[p] = make_uint2(gid, ns_pack(P, r_new.x, r_new.y, 0u, (uint32_t)state_i));
     A.vel4n[p] = make_float4(inertia.x, inertia.y, angle, angle_vel);
     A.nav4n[p] = make_float4(r_next.x, r_next.y, nav4.z, __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
-    A.trin[p] = tri;
     if (KEEP_VEL) A.vel_outn[p] = make_float2(v.x, v.y);
     int nfx, nfy;
     fine_coords(F, r_new.x, r_new.y, nfx, nfy);
@@ -440,7 +472,7 @@ __global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int 
     if (S.r_next) S.r_next[o] = make_float2(nav4.x, nav4.y);
     if (S.gid) S.gid[o] = key.x;
     if (S.tri_idx) S.tri_idx[o] = A.tri[sp];
-    if (S.ns_cell) S.ns_cell[o] = key.y >> 3;
+    if (S.ns_cell) S.ns_cell[o] = (uint32_t)cs_cx(key.y) + (uint32_t)cs_cy(key.y) * (uint32_t)P.ns_nx;
     if (S.map_cell) S.map_cell[o] = coord_to_cell(pos.x, pos.y, P.map_nx, P.map_ny, P.map_cell_size);
     if (S.flags) {
         S.flags[o] = (misc >> 28) & 0xFu;
@@ -456,7 +488,7 @@ __global__ void k_ingest(uint32_t n, uint32_t first, Staging S, AgentArrays A) {
     const float2 r = S.r[i];
     A.pos4n[d] = make_float4(r.x, r.y, S.radius ? S.radius[i] : 3.f, S.mass ? S.mass[i] : 1.f);
     const uint32_t state = S.state ? S.state[i] : (uint32_t)RTS_STANDING;
-    A.key2n[d] = make_uint2(S.gid ? S.gid[i] : d, pack_cs(0u, 0u, state));
+    A.key2n[d] = make_uint2(S.gid ? S.gid[i] : d, pack_cs(0u, 0u, 0u, state));
     const float2 in = S.inertia ? S.inertia[i] : make_float2(0.f, 0.f);
     A.vel4n[d] = make_float4(in.x, in.y, S.angle ? S.angle[i] : 0.f, S.angle_vel ? S.angle_vel[i] : 0.f);
     const float qnan = __uint_as_float(0x7FC00000u);
@@ -510,9 +542,13 @@ __global__ void k_coord_to_cell(const float2* xy, uint32_t n, int32_t nx, int32_
 }
 __global__ void k_find_triangles(const float2* xy, uint32_t n, RtsParams P, MapDev M, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned mask = __ballot_sync(0xffffffffu, i < n);
     if (i >= n) return;
     uint32_t flags = 0;
-    out[i] = find_triangle(M, P, xy[i].x, xy[i].y, flags);
+    const float2 q = xy[i];
+    const bool small = M.coords_fit_i32 && fabsf(q.x) <= 16383.f && fabsf(q.y) <= 16383.f;
+    if (__all_sync(mask, small)) out[i] = find_triangle_warp<false>(M, P, true, q.x, q.y, flags, mask);
+    else out[i] = find_triangle_warp<true>(M, P, true, q.x, q.y, flags, mask);
 }
 __global__ void k_contact_edges(const float2* xy, const float* radius, uint32_t n, uint32_t cap, RtsParams P, MapDev M,
                                 uint32_t* counts, float* edges_out) {

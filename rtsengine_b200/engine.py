@@ -201,10 +201,11 @@ class GpuAgentSystem:
         n = self.n
         arrays = out if out is not None else abi.alloc_agent_arrays(n, set(names))
         keep: list = []
-        v = abi.agent_view({k: arrays[k] for k in names}, n, keep)
-        for k, a in zip(names, keep):
-            if a is not arrays[k]:
+        dtypes = {name: dt for name, dt, _ in abi.AGENT_FIELDS}
+        for k in names:
+            if arrays[k].dtype != dtypes[k] or not arrays[k].flags.c_contiguous:
                 raise ValueError(f"output array {k!r} must be C-contiguous with the ABI dtype")
+        v = abi.agent_view({k: arrays[k] for k in names}, n, keep)
         self._chk(self.L.rts_download(self.h, C.byref(v)))
         return arrays
 

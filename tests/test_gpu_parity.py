@@ -227,6 +227,7 @@ def test_full_size_properties_1m():
         inside = ((a["r"] >= lo) & (a["r"] < hi)).all(1)
         idx = np.nonzero(inside)[0]
         sub = {k: np.ascontiguousarray(v[idx]) for k, v in a.items()}
+        sub.update(abi.alloc_agent_arrays(len(idx), abi.DOWNLOAD_ONLY))
         ow.step(sub)
         core = ((a["r"][idx] >= lo + 6) & (a["r"][idx] < hi - 6)).all(1)
         assert core.sum() > 3000
