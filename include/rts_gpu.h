@@ -194,7 +194,8 @@ uint32_t rts_agent_count(RtsHandle h);
 /* replaces: PhysicsSystem::update + SeekSystem::update + communicate + avoidWall + integration
    (ECS.cpp:65-113), n_steps frames, asynchronous on the handle's stream */
 int32_t rts_step(RtsHandle h, uint32_t n_steps);
-/* replaces: System2::communicate → SharedData (ECS.h:136-145); synchronises */
+/* replaces: System2::communicate → SharedData (ECS.h:136-145); synchronises.  Arrays hold rts_agent_count() entries
+   (for a slab handle: call rts_sync first, the count then includes ghost slots, which come back with gid 0xFFFFFFFF) */
 int32_t rts_download(RtsHandle h, const RtsAgentView* out);
 int32_t rts_sync(RtsHandle h);
 int32_t rts_get_timings(RtsHandle h, RtsTimings* out);
@@ -217,6 +218,28 @@ int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* o
    of them in visit order (5 floats each) */
 int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uint32_t n, uint32_t cap,
                           uint32_t* counts, float* edges_out);
+
+/* ---- multi-GPU: spatial slab decomposition, one handle (one process, one GPU) per y-slab -----------------------
+   The reference has no distributed path; this is the north-star extension.  A handle created with
+   params.slab_row_lo/hi owns the physics-grid rows [lo, hi).  Every frame the frame kernel packs (a) agents whose
+   new position left the slab (full record, "migrants") and (b) agents within the interaction range of a slab
+   boundary (neighbour record only, "halo") into fixed-capacity device buffers; neighbours exchange them with
+   ncclSend/ncclRecv over NVLink on the handle's stream; arrivals are appended before the counting sort.
+   Agents carry global ids (RtsAgentView.gid, required) so that the summation order — hence every bit of the
+   result — is independent of the number of slabs. */
+int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t cap_migrants, uint32_t cap_halo);
+/* NCCL bootstrap: rank 0 creates the 128-byte ncclUniqueId, the host distributes it (torch.distributed, MPI, a file),
+   every rank calls rts_comm_init.  libnccl.so.2 is resolved with dlopen at this point, not at load time. */
+int32_t rts_comm_unique_id(void* out128);
+int32_t rts_comm_init(RtsHandle h, const void* id128);
+/* after rts_set_agents on every rank: exchange the halo bands once so the first frame sees its ghosts */
+int32_t rts_halo_refresh(RtsHandle h);
+/* split-phase variants for a host that moves the buffers itself (and for emulating two ranks on one device):
+   rts_step_begin | rts_halo_begin  ->  move send buffers to the neighbours' receive buffers  ->  rts_step_end */
+int32_t rts_step_begin(RtsHandle h);
+int32_t rts_halo_begin(RtsHandle h);
+int32_t rts_step_end(RtsHandle h);
+int32_t rts_slab_exchange_local(RtsHandle lower, RtsHandle upper);
 
 /* raw CUDA stream of the handle (cudaStream_t as void*), so a host that owns device buffers can order work after it */
 void* rts_stream(RtsHandle h);

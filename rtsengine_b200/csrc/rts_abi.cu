@@ -10,6 +10,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is resolved with dlopen when rts_comm_init is called
+
 #include "rts_kernels.cuh"
 
 using namespace rts;
@@ -63,6 +66,26 @@ struct RtsContext {
     uint32_t graph_n[2] = {0, 0};
     int parity = 0;
     bool use_graph = true;
+    // ---- slab decomposition (multi-GPU) ----
+    bool multi = false;
+    SlabDev SL{};
+    uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
+    std::vector<void*> slab_allocs;
+    size_t ex_bytes = 0;              // bytes of one exchange buffer (header + migrant + halo segments)
+    void* ex_send[2] = {nullptr, nullptr};
+    void* ex_recv[2] = {nullptr, nullptr};
+    uint32_t* n_dev = nullptr;
+    // NCCL, resolved at run time
+    void* nccl_lib = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    decltype(&ncclCommInitRank) p_ncclCommInitRank = nullptr;
+    decltype(&ncclCommDestroy) p_ncclCommDestroy = nullptr;
+    decltype(&ncclSend) p_ncclSend = nullptr;
+    decltype(&ncclRecv) p_ncclRecv = nullptr;
+    decltype(&ncclGroupStart) p_ncclGroupStart = nullptr;
+    decltype(&ncclGroupEnd) p_ncclGroupEnd = nullptr;
+    decltype(&ncclGetErrorString) p_ncclGetErrorString = nullptr;
 
     void drop_graphs() {
         for (auto& g : graph2)
@@ -146,6 +169,7 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     AL(pos4n, float4) AL(key2n, uint2) AL(vel4n, float4) AL(nav4n, float4) AL(trin, uint32_t) AL(cellrank, uint2)
     if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
 #undef AL
+    A.n_dev = h->n_dev;
     h->cap = cap;
     h->drop_graphs();
     return RTS_OK;
@@ -207,12 +231,13 @@ int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t nb = blocks_for(h->F.n_cells, SCAN_TILE);
     timer_begin(h, KT_SCAN);
     k_scan_partial<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F);
-    k_scan_final<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, nullptr);
+    k_scan_final<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
     timer_end(h, KT_SCAN);
     timer_begin(h, KT_REORDER);
-    if (h->n) {
-        if (h->M.coords_fit_i32) k_reorder<false><<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
-        else k_reorder<true><<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+    const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
+    if (n_slots) {
+        if (h->M.coords_fit_i32) k_reorder<false><<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->P, h->M, h->F, h->A);
+        else k_reorder<true><<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->P, h->M, h->F, h->A);
     }
     timer_end(h, KT_REORDER);
     h->launches += 3;
@@ -220,18 +245,72 @@ int32_t launch_scan_reorder(RtsContext* h) {
     return RTS_OK;
 }
 
-int32_t launch_frame(RtsContext* h) {
+void launch_step_kernel(RtsContext* h) {
+    const uint32_t nb = h->multi ? h->cap_main : h->n;
     timer_begin(h, KT_STEP);
-    if (h->n) {
-        if (h->keep_vel) k_step<true><<<blocks_for(h->n, STEP_BLOCK), STEP_BLOCK, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
-        else k_step<false><<<blocks_for(h->n, STEP_BLOCK), STEP_BLOCK, 0, h->stream>>>(h->n, h->P, h->M, h->F, h->A);
+    if (nb) {
+        const dim3 grid(blocks_for(nb, STEP_BLOCK));
+        if (h->multi) {
+            if (h->keep_vel) k_step<true, true><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
+            else k_step<false, true><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
+        } else {
+            if (h->keep_vel) k_step<true, false><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
+            else k_step<false, false><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
+        }
     }
     timer_end(h, KT_STEP);
     h->launches += 1;
+}
+
+// slabs: first half of a frame — zero the send headers, run the frame kernel (which packs migrants + halo)
+int32_t frame_begin(RtsContext* h) {
+    if (h->multi)
+        for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(h->ex_send[d], 0, 16, h->stream));
+    launch_step_kernel(h);
+    return RTS_OK;
+}
+
+// slabs: second half — append what arrived, then scan + reorder
+int32_t frame_end(RtsContext* h) {
+    if (h->multi) {
+        const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
+        for (int d = 0; d < 2; ++d) {
+            const uint32_t base = h->cap_main + (uint32_t)d * per_dir;
+            k_ingest_remote<<<blocks_for(per_dir, 256), 256, 0, h->stream>>>(base, h->SL.recv[d], h->SL.cap_mig, h->SL.cap_halo, h->F, h->A);
+        }
+        h->launches += 2;
+    }
     return launch_scan_reorder(h);
 }
 
+// neighbour exchange over NCCL: send[0] goes to rank-1 and lands in its recv[1]; send[1] goes to rank+1's recv[0]
+int32_t exchange_nccl(RtsContext* h) {
+    if (!h->comm) return h->fail(RTS_E_STATE, "exchange", "rts_comm_init has not been called");
+    ncclResult_t r = h->p_ncclGroupStart();
+    for (int d = 0; d < 2 && r == ncclSuccess; ++d) {
+        if (!h->SL.has[d]) continue;
+        const int peer = h->rank + (d == 0 ? -1 : 1);
+        r = h->p_ncclSend(h->ex_send[d], h->ex_bytes, ncclUint8, peer, h->comm, h->stream);
+        if (r == ncclSuccess) r = h->p_ncclRecv(h->ex_recv[d], h->ex_bytes, ncclUint8, peer, h->comm, h->stream);
+    }
+    const ncclResult_t r2 = h->p_ncclGroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclSend/ncclRecv", h->p_ncclGetErrorString(r));
+    return RTS_OK;
+}
+
+int32_t launch_frame(RtsContext* h) {
+    int32_t rc = frame_begin(h);
+    if (rc != RTS_OK) return rc;
+    if (h->multi && h->nranks > 1 && (rc = exchange_nccl(h)) != RTS_OK) return rc;
+    return frame_end(h);
+}
+
 int32_t rebin(RtsContext* h) {  // the "n" buffers hold the population in arbitrary order -> cell order
+    if (h->multi) {   // every slot that k_bin does not fill is marked unused (0xFF.. = INVALID_CELL)
+        const uint32_t n_slots = h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo);
+        CU(cudaMemsetAsync(h->A.cellrank, 0xFF, sizeof(uint2) * (size_t)n_slots, h->stream));
+    }
     timer_begin(h, KT_BIN);
     if (h->n) k_bin<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->P, h->F, h->A);
     timer_end(h, KT_BIN);
@@ -330,6 +409,8 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     }
     rc = setup_fine_grid(h);
     if (rc != RTS_OK) return rc;
+    CU(cudaMalloc(&h->n_dev, 16));
+    CU(cudaMemsetAsync(h->n_dev, 0, 16, h->stream));
     // default unit types (UnitTypes.txt has two; dynamics constants are the component defaults) and an empty path table
     RtsUnitType ut[2];
     for (auto& u : ut) { u = RtsUnitType{}; u.lambda = 0.169f; u.max_speed = 25.f; u.seek_max_speed = 50.f; u.turn_rate = 5.f; }
@@ -358,7 +439,9 @@ int32_t rts_destroy(RtsHandle h) {
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
-    free_all(h->agent_allocs); free_all(h->staging_allocs);
+    free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
+    if (h->comm && h->p_ncclCommDestroy) h->p_ncclCommDestroy(h->comm);
+    if (h->n_dev) cudaFree(h->n_dev);
     if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); }
     if (h->scratch) cudaFree(h->scratch);
     for (auto& t : h->kt) {
@@ -570,7 +653,15 @@ int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     int32_t rc;
-    if (n > h->cap || h->cap == 0) {
+    if (h->multi) {
+        if (n && !agents->gid) return h->fail(RTS_E_ARG, "rts_set_agents", "a slab handle needs global ids (RtsAgentView.gid)");
+        const uint32_t extra = 2 * (h->SL.cap_mig + h->SL.cap_halo);
+        const uint32_t want_main = n + n / 4 + 4096;
+        if (want_main > h->cap_main || h->cap < h->cap_main + extra) {
+            h->cap_main = want_main;
+            if ((rc = alloc_agents(h, h->cap_main + extra)) != RTS_OK) return rc;
+        }
+    } else if (n > h->cap || h->cap == 0) {
         const uint32_t cap = std::max<uint32_t>(n + n / 8 + 1024, 1024);
         if ((rc = alloc_agents(h, cap)) != RTS_OK) return rc;
     }
@@ -666,7 +757,7 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
-    if (h->use_graph && !h->profiling && n_steps >= 2) {
+    if (h->use_graph && !h->profiling && !h->multi && n_steps >= 2) {
         const int par = h->parity;
         if (!h->graph2[par] || h->graph_n[par] != h->n) {
             int32_t rc = build_graph(h);
@@ -677,7 +768,10 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
             h->launches += 8;
         }
     }
-    for (; done < n_steps; ++done) launch_frame(h);
+    for (; done < n_steps; ++done) {
+        const int32_t rc = launch_frame(h);
+        if (rc != RTS_OK) return rc;
+    }
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaGetLastError());
     h->steps += n_steps;
@@ -690,6 +784,14 @@ int32_t rts_sync(RtsHandle h) {
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     timer_collect(h);
+    if (h->multi) {
+        uint32_t n_live = 0, hdr[2][4];
+        CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));
+        for (int d = 0; d < 2; ++d) CU(cudaMemcpy(hdr[d], h->ex_send[d], 16, cudaMemcpyDeviceToHost));
+        h->n = n_live;
+        if (hdr[0][2] || hdr[1][2]) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
+        if (n_live > h->cap_main) return h->fail(RTS_E_CAPACITY, "slab", "population outgrew the slot capacity of this handle");
+    }
     return RTS_OK;
 }
 
@@ -703,6 +805,10 @@ int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     WANT(r) WANT(vel) WANT(inertia) WANT(angle) WANT(angle_vel) WANT(radius) WANT(mass) WANT(state) WANT(player)
     WANT(unit_type) WANT(path_id) WANT(waypoint) WANT(r_next) WANT(gid) WANT(tri_idx) WANT(ns_cell) WANT(map_cell) WANT(flags)
 #undef WANT
+    if (h->multi) {
+        rc = rts_sync(h);
+        if (rc != RTS_OK) return rc;
+    }
     const uint32_t n = h->n;
     if (n) k_gather<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, h->P, h->A, S, h->gid_is_index ? 1 : 0, out->flags ? 1 : 0);
     h->launches += 1;
@@ -866,6 +972,133 @@ int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uin
     if (d_edges) CU(cudaMemcpyAsync(edges_out, d_edges, (size_t)n * cap * 20, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+// ---- slab decomposition ---------------------------------------------------------------------------
+int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t cap_migrants, uint32_t cap_halo) {
+    if (!h) return RTS_E_ARG;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad rank");
+    if (h->n) return h->fail(RTS_E_STATE, "rts_slab_configure", "configure the slab before uploading agents");
+    const RtsParams& P = h->P;
+    if (P.slab_row_lo < 0 || P.slab_row_hi > P.ns_ny || P.slab_row_lo >= P.slab_row_hi) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad slab rows in the params");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    free_all(h->slab_allocs);
+    cap_migrants = (cap_migrants + 3u) & ~3u;
+    cap_halo = (cap_halo + 3u) & ~3u;
+    SlabDev SL{};
+    SL.row_lo = P.slab_row_lo; SL.row_hi = P.slab_row_hi;
+    SL.y_lo = P.slab_row_lo * P.ns_cell_size; SL.y_hi = P.slab_row_hi * P.ns_cell_size;
+    SL.halo = std::sqrt(P.r_max2) * 1.05f + 0.25f;
+    SL.has[0] = P.slab_row_lo > 0; SL.has[1] = P.slab_row_hi < P.ns_ny;
+    SL.cap_mig = cap_migrants; SL.cap_halo = cap_halo;
+    // one buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
+    const size_t bytes = 16 + (size_t)cap_migrants * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8);
+    auto carve = [&](void* base, ExBuf& B) {
+        char* p = static_cast<char*>(base);
+        B.hdr = reinterpret_cast<uint32_t*>(p); p += 16;
+        B.m_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
+        B.m_vel4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
+        B.m_nav4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
+        B.h_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_halo * 16;
+        B.m_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_migrants * 8;
+        B.h_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_halo * 8;
+        B.m_velout = reinterpret_cast<float2*>(p); p += (size_t)cap_migrants * 8;
+        B.m_tri = reinterpret_cast<uint32_t*>(p);
+    };
+    for (int d = 0; d < 2; ++d) {
+        char* a; char* b;
+        int32_t rc;
+        if ((rc = dev_alloc<char>(h, &a, bytes, h->slab_allocs)) != RTS_OK) return rc;
+        if ((rc = dev_alloc<char>(h, &b, bytes, h->slab_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(a, 0, bytes, h->stream));
+        CU(cudaMemsetAsync(b, 0, bytes, h->stream));
+        h->ex_send[d] = a; h->ex_recv[d] = b;
+        carve(a, SL.send[d]);
+        carve(b, SL.recv[d]);
+    }
+    h->ex_bytes = bytes;
+    h->SL = SL;
+    h->multi = true;
+    h->rank = rank; h->nranks = nranks;
+    h->drop_graphs();
+    CU(cudaStreamSynchronize(h->stream));
+    return setup_fine_grid(h);
+}
+
+int32_t rts_comm_unique_id(void* out128) {
+    if (!out128) return RTS_E_ARG;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return RTS_E_NCCL;
+    auto fn = reinterpret_cast<decltype(&ncclGetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    if (!fn) return RTS_E_NCCL;
+    ncclUniqueId id;
+    if (fn(&id) != ncclSuccess) return RTS_E_NCCL;
+    std::memcpy(out128, &id, sizeof(id));
+    return RTS_OK;
+}
+
+int32_t rts_comm_init(RtsHandle h, const void* id128) {
+    if (!h || !id128) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_comm_init", "rts_slab_configure first");
+    CU(cudaSetDevice(h->device));
+    h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h->nccl_lib) return h->fail(RTS_E_NCCL, "dlopen(libnccl.so.2)", dlerror());
+#define SYM(name)                                                                              \
+    h->p_##name = reinterpret_cast<decltype(&name)>(dlsym(h->nccl_lib, #name));                 \
+    if (!h->p_##name) return h->fail(RTS_E_NCCL, "dlsym", #name);
+    SYM(ncclCommInitRank) SYM(ncclCommDestroy) SYM(ncclSend) SYM(ncclRecv) SYM(ncclGroupStart) SYM(ncclGroupEnd) SYM(ncclGetErrorString)
+#undef SYM
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    const ncclResult_t r = h->p_ncclCommInitRank(&h->comm, h->nranks, id, h->rank);
+    if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclCommInitRank", h->p_ncclGetErrorString(r));
+    return RTS_OK;
+}
+
+// first half of a frame (frame kernel + packing of migrants / halo) — the caller moves the buffers, then rts_step_end
+int32_t rts_step_begin(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_step_begin", "not a slab handle");
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_step_begin", "rts_upload_map has not been called");
+    CU(cudaSetDevice(h->device));
+    const int32_t rc = frame_begin(h);
+    h->steps += 1;
+    return rc;
+}
+int32_t rts_step_end(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_step_end", "not a slab handle");
+    CU(cudaSetDevice(h->device));
+    return frame_end(h);
+}
+// packs the halo bands of the current state without stepping (after an upload); finish with rts_step_end
+int32_t rts_halo_begin(RtsHandle h) {
+    if (!h) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_halo_begin", "not a slab handle");
+    CU(cudaSetDevice(h->device));
+    for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(h->ex_send[d], 0, 16, h->stream));
+    if (h->cap_main) k_halo_seed<<<blocks_for(h->cap_main, 256), 256, 0, h->stream>>>(h->cap_main, h->P, h->F, h->A, h->SL);
+    h->launches += 1;
+    return RTS_OK;
+}
+// rts_halo_begin + NCCL exchange + rts_step_end
+int32_t rts_halo_refresh(RtsHandle h) {
+    int32_t rc = rts_halo_begin(h);
+    if (rc != RTS_OK) return rc;
+    if (h->nranks > 1 && (rc = exchange_nccl(h)) != RTS_OK) return rc;
+    return frame_end(h);
+}
+// single-device emulation of two neighbouring ranks (tests): lower.send[up] -> upper.recv[down] and back
+int32_t rts_slab_exchange_local(RtsHandle lower, RtsHandle upper) {
+    if (!lower || !upper) return RTS_E_ARG;
+    RtsHandle h = lower;
+    if (!lower->multi || !upper->multi || lower->ex_bytes != upper->ex_bytes) return h->fail(RTS_E_STATE, "rts_slab_exchange_local", "handles are not matching slabs");
+    CU(cudaStreamSynchronize(lower->stream));
+    CU(cudaStreamSynchronize(upper->stream));
+    CU(cudaMemcpy(upper->ex_recv[0], lower->ex_send[1], lower->ex_bytes, cudaMemcpyDeviceToDevice));
+    CU(cudaMemcpy(lower->ex_recv[1], upper->ex_send[0], lower->ex_bytes, cudaMemcpyDeviceToDevice));
     return RTS_OK;
 }
 

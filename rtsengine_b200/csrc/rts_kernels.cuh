@@ -60,7 +60,29 @@ __device__ __forceinline__ uint32_t warp_aggregated_rank(uint32_t* count, uint32
     return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
 
+// ---- multi-GPU slab decomposition: exchange buffers of one direction (0 = towards lower rows, 1 = higher) ----
+struct ExBuf {
+    uint32_t* hdr;      // [0] migrants, [1] halo records, [2] overflow flag, [3] unused
+    float4* m_pos4;     // migrants: the full per-agent record
+    uint2* m_key2;
+    float4* m_vel4;
+    float4* m_nav4;
+    uint32_t* m_tri;
+    float2* m_velout;
+    float4* h_pos4;     // halo: the neighbour record only
+    uint2* h_key2;
+};
+struct SlabDev {
+    int32_t row_lo, row_hi;   // physics-grid rows owned: [row_lo, row_hi)
+    float y_lo, y_hi;         // = row * ns_cell_size
+    float halo;               // agents this close to a boundary are mirrored on the neighbour (>= sqrt(r_max2))
+    int32_t has[2];           // neighbour present in direction 0 / 1
+    uint32_t cap_mig, cap_halo;
+    ExBuf send[2], recv[2];
+};
+
 struct AgentArrays {
+    uint32_t* n_dev;  // live slots of the CURRENT order (owned agents + ghosts); written by the scan
     // neighbour record, CURRENT cell order
     float4* pos4;   // {x, y, radius, mass}
     uint2* key2;    // {gid, cy<<16 | cx<<3 | ghost<<2 | state}
@@ -214,15 +236,96 @@ __global__ void __launch_bounds__(256) k_reorder(uint32_t n, RtsParams P, MapDev
     }
 }
 
+// Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
+// frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
+__global__ void k_ingest_remote(uint32_t base, ExBuf B, uint32_t cap_mig, uint32_t cap_halo, FineGrid F, AgentArrays A) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cap_mig + cap_halo) return;
+    const uint32_t slot = base + i;
+    const bool is_mig = i < cap_mig;
+    const uint32_t k = is_mig ? i : i - cap_mig;
+    const uint32_t cnt = is_mig ? min(B.hdr[0], cap_mig) : min(B.hdr[1], cap_halo);
+    if (k >= cnt) {
+        A.cellrank[slot] = make_uint2(INVALID_CELL, 0u);
+        return;
+    }
+    float4 pos;
+    if (is_mig) {
+        pos = B.m_pos4[k];
+        A.pos4n[slot] = pos;
+        A.key2n[slot] = B.m_key2[k];
+        A.vel4n[slot] = B.m_vel4[k];
+        A.nav4n[slot] = B.m_nav4[k];
+        A.trin[slot] = B.m_tri[k];
+        if (A.vel_outn) A.vel_outn[slot] = B.m_velout[k];
+    } else {
+        pos = B.h_pos4[k];
+        A.pos4n[slot] = pos;
+        A.key2n[slot] = B.h_key2[k];   // ghost bit set by the sender
+        A.vel4n[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        A.nav4n[slot] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+        A.trin[slot] = 0xFFFFFFFFu;
+        if (A.vel_outn) A.vel_outn[slot] = make_float2(0.f, 0.f);
+    }
+    int fx, fy;
+    fine_coords(F, pos.x, pos.y, fx, fy);
+    const uint32_t cell = (uint32_t)fy * (uint32_t)F.nx + (uint32_t)fx;
+    A.cellrank[slot] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
+}
+
+// Slab exchange without a frame (after an upload): current state -> "n" buffers (ghosts dropped), halo bands packed.
+__global__ void k_halo_seed(uint32_t n_bound, RtsParams P, FineGrid F, AgentArrays A, SlabDev SL) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *A.n_dev;
+    const unsigned valid = __ballot_sync(0xffffffffu, p < n);
+    if (p >= n) {
+        if (p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
+        return;
+    }
+    const float4 pos = A.pos4[p];
+    const uint2 key = A.key2[p];
+    const bool ghost = (key.y >> 2) & 1u;
+    const unsigned active = __ballot_sync(valid, !ghost);
+    if (ghost) {
+        A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
+        return;
+    }
+    const uint32_t sp = A.src[p];
+    A.pos4n[p] = pos;
+    A.key2n[p] = key;
+    A.vel4n[p] = A.vel4[sp];
+    A.nav4n[p] = A.nav4[sp];
+    A.trin[p] = A.tri[sp];
+    if (A.vel_outn) A.vel_outn[p] = A.vel_out[sp];
+    if (SL.has[0] && pos.y < SL.y_lo + SL.halo) {
+        const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
+        if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos; SL.send[0].h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        else SL.send[0].hdr[2] = 1u;
+    }
+    if (SL.has[1] && pos.y >= SL.y_hi - SL.halo) {
+        const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
+        if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos; SL.send[1].h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        else SL.send[1].hdr[2] = 1u;
+    }
+    int fx, fy;
+    fine_coords(F, pos.x, pos.y, fx, fy);
+    const uint32_t cell = (uint32_t)fy * (uint32_t)F.nx + (uint32_t)fx;
+    A.cellrank[p] = make_uint2(cell, warp_aggregated_rank(F.count, cell, active));
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
-template <bool KEEP_VEL>
-__global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, MapDev M, FineGrid F, AgentArrays A) {
+template <bool KEEP_VEL, bool MULTI>
+__global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
     __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, slot} of the NBR_CAP smallest keys seen, ascending
     const uint32_t p = blockIdx.x * STEP_BLOCK + threadIdx.x;
+    const uint32_t n = MULTI ? *A.n_dev : n_bound;   // slabs: the population changes every frame, the count lives on the device
     const unsigned valid = __ballot_sync(0xffffffffu, p < n);
-    if (p >= n) return;
+    if (p >= n) {
+        if (MULTI && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
+        return;
+    }
     const int tid = threadIdx.x;
 
     const float4 me = A.pos4[p];
@@ -427,10 +530,45 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n, RtsParams P, Ma
     if (!(P.walk_all || state_i == RTS_MOVING)) A.trin[p] = A.tri[sp];
 
     // ---- write the new record at this slot; bin it for the next order
-    A.pos4n[p] = make_float4(r_new.x, r_new.y, radius, mass_i);
-    A.key2n[p] = make_uint2(gid, ns_pack(P, r_new.x, r_new.y, 0u, (uint32_t)state_i));
-    A.vel4n[p] = make_float4(inertia.x, inertia.y, angle, angle_vel);
-    A.nav4n[p] = make_float4(r_next.x, r_next.y, nav4.z, __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
+    const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
+    const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, P.ns_ny);
+    uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_i);
+    const float4 vel_new = make_float4(inertia.x, inertia.y, angle, angle_vel);
+    const float4 nav_new = make_float4(r_next.x, r_next.y, nav4.z, __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
+    if (MULTI) {
+        // ownership follows the physics-grid row of the new position (integer, identical on every rank)
+        const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
+        if (dir >= 0 && SL.has[dir]) {
+            // migrate: full record to the neighbour; the local copy stays one more frame as a ghost (it is within
+            // one frame's travel of the boundary, i.e. inside the halo band of this slab)
+            const ExBuf& B = SL.send[dir];
+            const uint32_t k = atomicAdd(B.hdr + 0, 1u);
+            if (k < SL.cap_mig) {
+                B.m_pos4[k] = pos_new;
+                B.m_key2[k] = make_uint2(gid, cs_new);
+                B.m_vel4[k] = vel_new;
+                B.m_nav4[k] = nav_new;
+                B.m_tri[k] = 0xFFFFFFFFu;   // walked by the receiver's reorder pass
+                B.m_velout[k] = make_float2(v.x, v.y);
+            } else B.hdr[2] = 1u;
+            cs_new |= 4u;
+        } else {
+            if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
+                const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
+                if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos_new; SL.send[0].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                else SL.send[0].hdr[2] = 1u;
+            }
+            if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
+                const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
+                if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos_new; SL.send[1].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                else SL.send[1].hdr[2] = 1u;
+            }
+        }
+    }
+    A.pos4n[p] = pos_new;
+    A.key2n[p] = make_uint2(gid, cs_new);
+    A.vel4n[p] = vel_new;
+    A.nav4n[p] = nav_new;
     if (KEEP_VEL) A.vel_outn[p] = make_float2(v.x, v.y);
     int nfx, nfy;
     fine_coords(F, r_new.x, r_new.y, nfx, nfy);
@@ -457,6 +595,10 @@ __global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int 
     const float4 nav4 = A.nav4[sp];
     const uint32_t misc = __float_as_uint(nav4.w);
     const uint32_t o = by_gid ? key.x : d;
+    if ((key.y >> 2) & 1u) {   // ghost (halo copy owned by the neighbour slab): not part of this handle's population
+        if (S.gid) S.gid[o] = 0xFFFFFFFFu;
+        return;
+    }
     if (S.r) S.r[o] = make_float2(pos.x, pos.y);
     if (S.vel) S.vel[o] = A.vel_out ? A.vel_out[sp] : make_float2(0.f, 0.f);
     if (S.inertia) S.inertia[o] = make_float2(vel4.x, vel4.y);

@@ -67,6 +67,14 @@ def load_library():
         "rts_find_triangles": (i32, [H, vp, u32, vp]),
         "rts_contact_edges": (i32, [H, vp, vp, u32, u32, vp, vp]),
         "rts_stream": (vp, [H]),
+        "rts_slab_configure": (i32, [H, i32, i32, u32, u32]),
+        "rts_comm_unique_id": (i32, [vp]),
+        "rts_comm_init": (i32, [H, vp]),
+        "rts_halo_refresh": (i32, [H]),
+        "rts_step_begin": (i32, [H]),
+        "rts_halo_begin": (i32, [H]),
+        "rts_step_end": (i32, [H]),
+        "rts_slab_exchange_local": (i32, [H, H]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -198,6 +206,7 @@ class GpuAgentSystem:
     step = update
 
     def communicate(self, names=("r", "vel", "inertia", "angle", "angle_vel", "state"), out: dict | None = None) -> dict:
+        self.sync()   # a slab handle's population (owned + ghosts) changes every frame: refresh the count first
         n = self.n
         arrays = out if out is not None else abi.alloc_agent_arrays(n, set(names))
         keep: list = []

@@ -120,3 +120,136 @@ def config1_agents(n: int = 2000, seed: int = 1234):
     paths = {"offsets": np.array([0, 1], np.uint32), "waypoints": np.array([[2000.0, 2000.0]], np.float32),
              "portals": np.zeros((1, 5), np.float32), "path_end": np.array([[2000.0, 2000.0]], np.float32)}
     return a, paths
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Large maps: tx x ty copies of a tile map.  Each tile keeps its complete reference-built CDT (super-triangle
+# included), shifted to the tile's origin; the cell->triangle cache is tile aligned (5120 = 128 x 40), so
+# Triangulation::findTriangle for a point of tile T starts in T's table and never leaves it.  The wall
+# tables are rebuilt for the big MapGrid with the reference's line-index rules (EdgesFinder1D.cpp:231-236) and
+# per-line sort keys (MapGrid.cpp:1277-1303).
+# ---------------------------------------------------------------------------------------------------------
+def tile_map(fx: dict, tx: int, ty: int) -> dict:
+    nx_t, ny_t = (int(v) for v in fx["n_cells"])
+    nx, ny = nx_t * tx, ny_t * ty
+    W_t, H_t = nx_t * 5, ny_t * 5
+    n_tri = len(fx["tri_verts"])
+    tgx, tgy = nx_t // 8, ny_t // 8                      # triangle cache cells per tile
+    # Global triangle order: the inner triangles (all vertices inside the tile square) of every tile first, then the
+    # outer ones (super-triangle region).  findTriangle's rare linear-scan fallback returns the lowest index that
+    # contains the query; with this order it finds the triangle of the query's own tile, as on the single tile.
+    tv = fx["tri_verts"].reshape(n_tri, 3, 2)
+    inner = ((tv[:, :, 0] >= 0) & (tv[:, :, 0] <= W_t) & (tv[:, :, 1] >= 0) & (tv[:, :, 1] <= H_t)).all(1)
+    n_in = int(inner.sum())
+    n_tiles = tx * ty
+    rank_in = np.cumsum(inner) - 1
+    rank_out = np.cumsum(~inner) - 1
+
+    def gindex(t):   # local triangle index -> global index, tile t
+        return np.where(inner, t * n_in + rank_in, n_tiles * n_in + t * (n_tri - n_in) + rank_out).astype(np.int64)
+
+    tri_global = np.zeros((n_tiles * n_tri, 6), np.int32)
+    nbr_global = np.zeros((n_tiles * n_tri, 3), np.uint32)
+    con_global = np.zeros((n_tiles * n_tri, 3), np.uint8)
+    verts, nbrs, cons = [], [], []
+    c2t = np.zeros((tgy * ty, tgx * tx), np.uint32)      # [row(y), col(x)]: cell = x + y * (tgx*tx)
+    tile_c2t = fx["cell2tri"].reshape(tgy, tgx)
+    edges = {o: [] for o in range(4)}
+    lines = {o: [] for o in range(4)}
+    blds = []
+    poff, pw, pp, pe, ps = [0], [], [], [], []
+    for j in range(ty):
+        for i in range(tx):
+            t = j * tx + i
+            off = np.array([i * W_t, j * H_t], np.int32)
+            gi = gindex(t)
+            tri_global[gi] = (tv + off).reshape(n_tri, 6)
+            nb = fx["tri_nbrs"].astype(np.int64)
+            nbr_global[gi] = np.where(nb == 0xFFFFFFFF, 0xFFFFFFFF, gi[np.minimum(nb, n_tri - 1)]).astype(np.uint32)
+            con_global[gi] = fx["tri_constrained"]
+            blk = tile_c2t.astype(np.int64)
+            c2t[j * tgy:(j + 1) * tgy, i * tgx:(i + 1) * tgx] = np.where(blk == 0xFFFFFFFF, 0xFFFFFFFF, gi[np.minimum(blk, n_tri - 1)]).astype(np.uint32)
+            ox, oy = i * nx_t, j * ny_t
+            for o in range(4):
+                e = fx[f"edges{o}"].copy()
+                lo = fx[f"line_off{o}"]
+                local_line = np.repeat(np.arange(len(lo) - 1), np.diff(lo))
+                e[:, 0] += off[0]
+                e[:, 1] += off[1]
+                if o == 0:
+                    gl = local_line + oy
+                elif o == 2:
+                    gl = local_line + ox
+                elif o == 1:
+                    gl = local_line - (ny_t - 1) + ox - oy + (ny - 1)
+                else:
+                    gl = local_line + ox + oy
+                edges[o].append(e)
+                lines[o].append(gl)
+            b = fx["buildings"].copy()
+            b[:, 0] += ox
+            b[:, 1] += oy
+            blds.append(b)
+            if "path_offsets" in fx:
+                po = fx["path_offsets"]
+                poff.extend((po[1:].astype(np.int64) + poff[-1]).tolist())
+                pw.append(fx["path_waypoints"] + off.astype(np.float32))
+                q = fx["path_portals"].copy()
+                q[:, 0] += off[0]
+                q[:, 1] += off[1]
+                pp.append(q)
+                pe.append(fx["path_end"] + off.astype(np.float32))
+                ps.append(fx["path_start"] + off.astype(np.float32))
+    out = {"tri_verts": tri_global, "tri_nbrs": nbr_global,
+           "tri_constrained": con_global, "cell2tri": c2t.reshape(-1), "n_cells": np.array([nx, ny], np.int32),
+           "tile_tri_index": np.stack([gindex(t) for t in range(n_tiles)]).astype(np.uint32),
+           "buildings": np.concatenate(blds), "tiles": np.array([tx, ty], np.int32), "tile_cells": np.array([nx_t, ny_t], np.int32)}
+    n_lines = [ny + 1, nx + ny + 1, nx + 1, nx + ny + 1]
+    for o in range(4):
+        e = np.concatenate(edges[o])
+        gl = np.concatenate(lines[o])
+        if o == 0:
+            key = np.minimum(e[:, 0], e[:, 0] + e[:, 2] * e[:, 4])   # min(from.x, to().x)
+        elif o == 2:
+            key = e[:, 1]                                            # from.y
+        else:
+            key = e[:, 0]                                            # from.x
+        order = np.lexsort((key, gl))
+        e, gl = e[order], gl[order]
+        cnt = np.bincount(gl, minlength=n_lines[o])
+        out[f"edges{o}"] = np.ascontiguousarray(e, np.float32)
+        out[f"line_off{o}"] = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
+    if pw:
+        out.update(path_offsets=np.array(poff, np.uint32), path_waypoints=np.concatenate(pw).astype(np.float32),
+                   path_portals=np.concatenate(pp).astype(np.float32), path_end=np.concatenate(pe).astype(np.float32),
+                   path_start=np.concatenate(ps).astype(np.float32))
+    return out
+
+
+def tiled_agents(fx_tile: dict, tx: int, ty: int, n_per_tile: int, seed: int = 1237, groups_per_tile_side: int = 8):
+    """config-3 style population on every tile of a tile_map(fx_tile, tx, ty): n_per_tile agents per tile, all MOVING,
+    one command group per block (groups_per_tile_side² blocks per tile; 2 gives the 256 groups of config 4 on 8x8 tiles)."""
+    nx_t = int(fx_tile["n_cells"][0])
+    W_t = nx_t * 5.0
+    n_paths_tile = len(fx_tile["path_end"])
+    side = int(round(np.sqrt(n_paths_tile)))
+    parts = []
+    for j in range(ty):
+        for i in range(tx):
+            t = j * tx + i
+            rng = np.random.default_rng(seed + 7919 * t)
+            a = _blank(n_per_tile)
+            r = free_positions(fx_tile, n_per_tile, rng)
+            a["angle"][:] = rng.uniform(-180, 180, n_per_tile)
+            gs = groups_per_tile_side
+            bx = np.minimum((r[:, 0] // (W_t / gs)).astype(np.int64), gs - 1)
+            by = np.minimum((r[:, 1] // (W_t / gs)).astype(np.int64), gs - 1)
+            # path of the 8x8 block nearest the centre of the group's block
+            px = np.minimum(((bx + 0.5) * side / gs).astype(np.int64), side - 1)
+            py = np.minimum(((by + 0.5) * side / gs).astype(np.int64), side - 1)
+            a["path_id"][:] = t * n_paths_tile + px + side * py
+            a["waypoint"][:] = 1
+            a["state"][:] = abi.MOVING
+            a["r"][:] = r + np.array([i * W_t, j * W_t], np.float32)
+            parts.append(a)
+    return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
