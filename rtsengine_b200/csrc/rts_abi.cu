@@ -32,7 +32,7 @@ struct KernelTimer {  // per-kind CUDA-event timing of launches on the handle's 
     uint64_t launches = 0;
 };
 
-enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_COUNT = 4 };
+enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_EXCHANGE = 4, KT_INGEST = 5, KT_COUNT = 6 };
 
 }  // namespace
 
@@ -274,10 +274,12 @@ int32_t frame_begin(RtsContext* h) {
 int32_t frame_end(RtsContext* h) {
     if (h->multi) {
         const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
+        timer_begin(h, KT_INGEST);
         for (int d = 0; d < 2; ++d) {
             const uint32_t base = h->cap_main + (uint32_t)d * per_dir;
             k_ingest_remote<<<blocks_for(per_dir, 256), 256, 0, h->stream>>>(base, h->SL.recv[d], h->SL.cap_mig, h->SL.cap_halo, h->F, h->A);
         }
+        timer_end(h, KT_INGEST);
         h->launches += 2;
     }
     return launch_scan_reorder(h);
@@ -286,6 +288,7 @@ int32_t frame_end(RtsContext* h) {
 // neighbour exchange over NCCL: send[0] goes to rank-1 and lands in its recv[1]; send[1] goes to rank+1's recv[0]
 int32_t exchange_nccl(RtsContext* h) {
     if (!h->comm) return h->fail(RTS_E_STATE, "exchange", "rts_comm_init has not been called");
+    timer_begin(h, KT_EXCHANGE);
     ncclResult_t r = h->p_ncclGroupStart();
     for (int d = 0; d < 2 && r == ncclSuccess; ++d) {
         if (!h->SL.has[d]) continue;
@@ -295,6 +298,7 @@ int32_t exchange_nccl(RtsContext* h) {
     }
     const ncclResult_t r2 = h->p_ncclGroupEnd();
     if (r == ncclSuccess) r = r2;
+    timer_end(h, KT_EXCHANGE);
     if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclSend/ncclRecv", h->p_ncclGetErrorString(r));
     return RTS_OK;
 }
@@ -564,6 +568,43 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     uint32_t* d_bits;
     if ((rc = dev_alloc(h, &d_bits, bits.size(), h->table_allocs)) != RTS_OK) return rc;
     CU(cudaMemcpyAsync(d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    // scan lists for findTriangle's linear-scan fallback (see MapDev)
+    std::vector<uint32_t> scan_off(n_tri_cells + 1, 0u), scan_list, scan_large;
+    {
+        auto cell_range = [&](int32_t lo, int32_t hi, int32_t n, int& c0, int& c1) {
+            c0 = (int)std::floor((float)lo / P.tri_cell_size);
+            c1 = (int)std::floor((float)hi / P.tri_cell_size);
+            c0 = std::max(c0, 0);
+            c1 = std::min(c1, n - 1);
+        };
+        std::vector<int> bx0(n_tris), bx1(n_tris), by0(n_tris), by1(n_tris);
+        std::vector<uint8_t> large(n_tris, 0);
+        for (uint32_t t = 0; t < n_tris; ++t) {
+            const RtsTriangle& T = tris[t];
+            cell_range(std::min({T.vx[0], T.vx[1], T.vx[2]}), std::max({T.vx[0], T.vx[1], T.vx[2]}), P.tri_nx, bx0[t], bx1[t]);
+            cell_range(std::min({T.vy[0], T.vy[1], T.vy[2]}), std::max({T.vy[0], T.vy[1], T.vy[2]}), P.tri_ny, by0[t], by1[t]);
+            if (bx0[t] > bx1[t] || by0[t] > by1[t]) continue;   // entirely outside the grid
+            const uint64_t cells = (uint64_t)(bx1[t] - bx0[t] + 1) * (uint64_t)(by1[t] - by0[t] + 1);
+            if (cells > SCAN_LARGE_CELLS) { large[t] = 1; scan_large.push_back(t); continue; }
+            for (int y = by0[t]; y <= by1[t]; ++y)
+                for (int x = bx0[t]; x <= bx1[t]; ++x) scan_off[(size_t)y * P.tri_nx + x + 1]++;
+        }
+        for (size_t c = 0; c < n_tri_cells; ++c) scan_off[c + 1] += scan_off[c];
+        scan_list.resize(scan_off[n_tri_cells]);
+        std::vector<uint32_t> fill(scan_off.begin(), scan_off.end() - 1);
+        for (uint32_t t = 0; t < n_tris; ++t) {   // ascending t => every cell list is ascending
+            if (large[t] || bx0[t] > bx1[t] || by0[t] > by1[t]) continue;
+            for (int y = by0[t]; y <= by1[t]; ++y)
+                for (int x = bx0[t]; x <= bx1[t]; ++x) scan_list[fill[(size_t)y * P.tri_nx + x]++] = t;
+        }
+    }
+    uint32_t *d_soff, *d_slist, *d_slarge;
+    if ((rc = dev_alloc(h, &d_soff, scan_off.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_slist, scan_list.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_slarge, scan_large.size(), h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_soff, scan_off.data(), scan_off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!scan_list.empty()) CU(cudaMemcpyAsync(d_slist, scan_list.data(), scan_list.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (!scan_large.empty()) CU(cudaMemcpyAsync(d_slarge, scan_large.data(), scan_large.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // int32 triangle walk is exact iff no product can overflow: |coord| <= 16383 (see tri_sign)
     int32_t cmax = 0;
     for (uint32_t t = 0; t < n_tris; ++t)
@@ -573,6 +614,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
     M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r;
     M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
+    M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
     h->map_ready = true;
     h->drop_graphs();
     if (h->n) {   // agents uploaded before the map: give them their triangle index now

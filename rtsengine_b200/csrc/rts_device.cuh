@@ -38,7 +38,15 @@ struct MapDev {
     int32_t wall_bx, wall_by;
     float wall_filter_radius;
     int32_t coords_fit_i32;   // 1: every triangle-walk product fits int32 (the reference's own arithmetic)
+    // acceleration of findTriangle's linear-scan fallback (lowest triangle index containing q): per cache cell the
+    // ascending list of "small" triangles whose bounding box touches the cell, plus one ascending list of the few
+    // "large" triangles (bounding box over SCAN_LARGE_CELLS cells)
+    const uint32_t* __restrict__ scan_off;
+    const uint32_t* __restrict__ scan_list;
+    const uint32_t* __restrict__ scan_large;
+    uint32_t n_scan_large;
 };
+constexpr uint32_t SCAN_LARGE_CELLS = 1024;
 constexpr float WALL_BLOCK = 20.f;
 
 struct v2 {
@@ -179,7 +187,32 @@ __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const Rt
     const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
     uint32_t t = TRI_NONE;
     if (want) t = find_triangle_walk<WIDE>(M, P, q, flags);
-    unsigned need = __ballot_sync(mask, want && t == TRI_NEED_SCAN);
+    if (want && t == TRI_NEED_SCAN && M.scan_off) {
+        // the reference scans every triangle in index order; a triangle that contains q has q inside its bounding box,
+        // so only the triangles listed for q's cache cell (and the large ones) can be the answer
+        const float cxf = floorf((float)q.x / P.tri_cell_size), cyf = floorf((float)q.y / P.tri_cell_size);
+        if (cxf >= 0.f && cyf >= 0.f && cxf < (float)P.tri_nx && cyf < (float)P.tri_ny) {
+            const uint32_t cell = (uint32_t)cxf + (uint32_t)cyf * (uint32_t)P.tri_nx;
+            uint32_t best = TRI_NONE;
+            for (uint32_t k = __ldg(M.scan_off + cell), e = __ldg(M.scan_off + cell + 1); k < e; ++k) {
+                const uint32_t i = __ldg(M.scan_list + k);
+                iv2 a, b, c;
+                int4 w1;
+                load_tri_verts(M, i, a, b, c, w1);
+                if (in_triangle<WIDE>(q, a, b, c)) { best = i; break; }
+            }
+            for (uint32_t k = 0; k < M.n_scan_large; ++k) {
+                const uint32_t i = __ldg(M.scan_large + k);
+                if (i >= best) break;
+                iv2 a, b, c;
+                int4 w1;
+                load_tri_verts(M, i, a, b, c, w1);
+                if (in_triangle<WIDE>(q, a, b, c)) { best = i; break; }
+            }
+            t = best;
+        }
+    }
+    unsigned need = __ballot_sync(mask, want && t == TRI_NEED_SCAN);   // outside the cache grid: scan everything
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t n_lanes = (uint32_t)__popc(mask);                       // lanes that take part (exited lanes cannot)
     const uint32_t my = (uint32_t)__popc(mask & ((1u << lane) - 1u));      // rank of this lane among them

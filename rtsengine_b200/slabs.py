@@ -242,7 +242,11 @@ def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     agents["gid"] = np.arange(n_total, dtype=np.uint32)
     bounds = partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
     parts = split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
-    sr = SlabRank(base, bounds, rank, local)
+    # exchange capacities from the density: agents in a halo band / crossing a boundary per frame, with a wide margin
+    per_unit_height = per_gpu / (fx["tile_cells"][1] * 5.0)
+    cap_halo = int(max(4096, 6 * per_unit_height * halo_width(base.r_max2)))
+    cap_mig = int(max(1024, 6 * per_unit_height * 2.0))
+    sr = SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
     uid = [make_unique_id(sr.g.L) if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sr.init_comm(uid[0])

@@ -1,0 +1,45 @@
+"""Per-rank timing of the slab path (diagnostic). torchrun --nproc-per-node N tools/slab_trace.py [agents_per_gpu] [frames] [cap_halo] [cap_mig]"""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from rtsengine_b200 import engine, scenario, slabs
+
+per_gpu = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+cap_halo = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 17
+cap_mig = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 15
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+tile = scenario.load_map("map_c3.npz")
+fx = scenario.tile_map(tile, 1, world)
+nx, ny = (int(v) for v in fx["n_cells"])
+base = engine.default_params(nx, ny)
+agents = scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
+agents["gid"] = np.arange(per_gpu * world, dtype=np.uint32)
+bounds = slabs.partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
+parts = slabs.split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
+sr = slabs.SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
+uid = [slabs.make_unique_id(sr.g.L) if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+sr.init_comm(uid[0])
+sr.g.upload_map(scenario.tables_of(fx)); sr.g.upload_paths(scenario.paths_of(fx)); sr.g.set_agents(parts[rank]); sr.halo_refresh()
+sr.g.update(10, sync=True)
+res = {}
+for mode in ("profiled", "plain", "profiled2"):
+    sr.g.set_profiling(mode.startswith("profiled"))
+    dist.barrier(); torch.cuda.synchronize()
+    sr.g.reset_timings()
+    t0 = time.perf_counter()
+    sr.g.update(frames); t1 = time.perf_counter()
+    sr.g.sync(); t2 = time.perf_counter()
+    res[mode] = {"enqueue_ms_per_frame": 1e3 * (t1 - t0) / frames, "wall_ms_per_frame": 1e3 * (t2 - t0) / frames,
+                 "dev_ms_per_frame": sr.g.timings().last_step_ms / frames}
+    if mode.startswith("profiled"):
+        res[mode]["kernels"] = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in ("step", "scan", "reorder", "exchange", "ingest")}
+own = sr.owned(("r",))
+res["owned"] = len(own["gid"]); res["rank"] = rank
+for r in range(world):
+    dist.barrier()
+    if r == rank: print(json.dumps(res), flush=True)
+sr.close(); dist.destroy_process_group()
