@@ -206,7 +206,11 @@ int32_t setup_fine_grid(RtsContext* h) {
     F.row0 = (int32_t)(y_lo / cs);
     F.ny = (int32_t)(y_hi / cs) + 2 - F.row0;
     F.n_cells = (uint32_t)F.nx * (uint32_t)F.ny;
-    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); }
+    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); cudaFree(h->F.status); cudaFree(h->F.ticket); }
+    CU(cudaMalloc(&F.status, sizeof(unsigned long long) * (blocks_for(F.n_cells, SCAN_TILE) + 1)));
+    CU(cudaMalloc(&F.ticket, 16));
+    CU(cudaMemsetAsync(F.status, 0, sizeof(unsigned long long) * (blocks_for(F.n_cells, SCAN_TILE) + 1), h->stream));
+    CU(cudaMemsetAsync(F.ticket, 0, 16, h->stream));
     CU(cudaMalloc(&F.count, sizeof(uint32_t) * F.n_cells));
     CU(cudaMalloc(&F.start, sizeof(uint32_t) * (F.n_cells + 1)));
     CU(cudaMalloc(&F.partial, sizeof(uint32_t) * (blocks_for(F.n_cells, SCAN_TILE) + 1)));
@@ -230,8 +234,7 @@ void swap_prev_order(RtsContext* h) {
 int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t nb = blocks_for(h->F.n_cells, SCAN_TILE);
     timer_begin(h, KT_SCAN);
-    k_scan_partial<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F);
-    k_scan_final<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
+    k_scan_onepass<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
     timer_end(h, KT_SCAN);
     timer_begin(h, KT_REORDER);
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
@@ -240,7 +243,7 @@ int32_t launch_scan_reorder(RtsContext* h) {
         else k_reorder<true><<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->P, h->M, h->F, h->A);
     }
     timer_end(h, KT_REORDER);
-    h->launches += 3;
+    h->launches += 2;
     swap_prev_order(h);
     return RTS_OK;
 }
@@ -446,7 +449,7 @@ int32_t rts_destroy(RtsHandle h) {
     free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
     if (h->comm && h->p_ncclCommDestroy) h->p_ncclCommDestroy(h->comm);
     if (h->n_dev) cudaFree(h->n_dev);
-    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); }
+    if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); cudaFree(h->F.status); cudaFree(h->F.ticket); }
     if (h->scratch) cudaFree(h->scratch);
     for (auto& t : h->kt) {
         for (auto e : t.beg) cudaEventDestroy(e);
@@ -807,7 +810,7 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
         }
         for (; done + 2 <= n_steps; done += 2) {
             CU(cudaGraphLaunch(h->graph2[par], h->stream));
-            h->launches += 8;
+            h->launches += 6;
         }
     }
     for (; done < n_steps; ++done) {

@@ -15,7 +15,8 @@
 namespace rts {
 
 constexpr int STEP_BLOCK = 128;   // threads per CTA of k_step
-constexpr int NBR_CAP = 24;       // neighbours kept sorted in shared memory per agent; more -> selection path
+constexpr int NBR_CAP = 24;       // neighbours kept sorted in shared memory per agent
+constexpr int SPILL_CAP = 104;    // further neighbours parked unsorted in local memory before re-scanning is needed
 constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
 
 // key2.y = cy << 16 | cx << 3 | ghost << 2 | state, (cx, cy) = 2-D coordinates of the physics-grid cell (13 bits each)
@@ -40,7 +41,9 @@ struct FineGrid {
     uint32_t n_cells;   // nx * ny
     uint32_t* count;    // [n_cells]   agents per fine cell for the NEXT order (atomics), zeroed by the scan
     uint32_t* start;    // [n_cells+1] first slot of each fine cell in the CURRENT order
-    uint32_t* partial;  // scan scratch
+    uint32_t* partial;  // scan scratch (two-kernel scan)
+    unsigned long long* status;   // one-pass scan: per tile {flag<<32 | value}
+    uint32_t* ticket;             // [0] next tile to hand out, [1] epoch of the flags (bumped by the last tile)
 };
 
 __device__ __forceinline__ void fine_coords(const FineGrid& F, float x, float y, int& fx, int& fy) {
@@ -118,9 +121,9 @@ __global__ void k_bin(uint32_t n, RtsParams P, FineGrid F, AgentArrays A) {
     A.cellrank[p] = make_uint2(cell, rank);
 }
 
-// ---- scan: 4096 cells per CTA (512 threads x 8) ----
-constexpr int SCAN_THREADS = 512;
-constexpr int SCAN_ITEMS = 8;
+// ---- scan: 1024 cells per CTA (256 threads x 4) ----
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem) {
@@ -137,6 +140,79 @@ __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem)
     t = smem[0];
     __syncthreads();
     return t;
+}
+
+// One-pass exclusive scan of the cell counts (decoupled look-back): tiles are handed out by an atomic ticket, so a tile
+// only ever waits for tiles that already started; flags carry an epoch, so nothing is reset between launches (the
+// kernel is replayed from a CUDA graph with frozen arguments).
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint32_t* n_out) {
+    __shared__ uint32_t smem[32];
+    __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile, s_prefix, s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = *((volatile uint32_t*)(F.ticket + 1));
+        s_tile = atomicAdd(F.ticket, 1u);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile, epoch = s_epoch;
+    const uint32_t n_tiles = (F.n_cells + SCAN_TILE - 1) / SCAN_TILE;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < F.n_cells) ? F.count[base + i] : 0u;
+        s += v[i];
+    }
+    const uint32_t aggregate = block_reduce_sum(s, smem);
+    // publish this tile's sum, then add up the sums of all earlier tiles (they all hold a ticket, so they will publish);
+    // every thread polls a strided share of them, so the wait is one round trip, not a chain
+    const uint32_t flag_now = epoch + 1u;   // epoch starts at 0 and status words at 0: flag 0 never matches
+    if (threadIdx.x == 0) atomicExch(F.status + tile, ((unsigned long long)flag_now << 32) | aggregate);
+    uint32_t before = 0;
+    for (uint32_t j = threadIdx.x; j < tile; j += SCAN_THREADS) {
+        unsigned long long wv;
+        do { wv = atomicAdd(F.status + j, 0ull); } while ((uint32_t)(wv >> 32) != flag_now);
+        before += (uint32_t)wv;
+    }
+    before = block_reduce_sum(before, smem);
+    if (threadIdx.x == 0) s_prefix = before;
+    // exclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = (lane < SCAN_THREADS / 32) ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + warp_tot[w] + (incl - s);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < F.n_cells) {
+            F.start[base + i] = run;
+            F.count[base + i] = 0u;
+            run += v[i];
+        }
+    }
+    if (base <= F.n_cells - 1 && F.n_cells - 1 < base + SCAN_ITEMS) {   // owner of the last cell closes the CSR
+        F.start[F.n_cells] = run;
+        if (n_out) *n_out = run;
+    }
+    if (tile == n_tiles - 1 && threadIdx.x == 0) {   // every tile has read the epoch and taken its ticket by now
+        F.ticket[0] = 0u;
+        F.ticket[1] = epoch + 1u;
+    }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partial(FineGrid F) {
@@ -355,21 +431,42 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
     const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
     const int ylo = max(fy - 1, 0), yhi = min(fy + 1, F.ny - 1);
 
-    auto for_each_neighbour = [&](auto&& fn) {
-        for (int yy = ylo; yy <= yhi; ++yy) {
+    // slot ranges of the three fine rows (each row's 3 cells are contiguous in slot order); loaded up front
+    uint32_t row_qb[3], row_qe[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int yy = fy - 1 + k;
+        if (yy >= ylo && yy <= yhi) {
             const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
-            const uint32_t qb = __ldg(F.start + rowbase + xlo), qe = __ldg(F.start + rowbase + xhi + 1);
-            for (uint32_t q = qb; q < qe; ++q) {
-                const float4 o = __ldg(A.pos4 + q);
-                const v2 dr = V(o.x, o.y) - r;
-                if (norm2(dr) < P.r_max2 && q != p) {
-                    const uint2 ok = __ldg(A.key2 + q);
-                    const int dxc = cs_cx(ok.y) - cxi;
-                    const int dyc = cs_cy(ok.y) - cyi;
-                    // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
-                    const int idx = (dxc + 1) * 3 + (dyc + 1);
-                    const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
-                    fn((rank << 28) | ok.x, q);
+            row_qb[k] = __ldg(F.start + rowbase + xlo);
+            row_qe[k] = __ldg(F.start + rowbase + xhi + 1);
+        } else {
+            row_qb[k] = 0u;
+            row_qe[k] = 0u;
+        }
+    }
+    auto for_each_neighbour = [&](auto&& fn) {
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t qe = row_qe[k];
+#pragma unroll 1
+            for (uint32_t q0 = row_qb[k]; q0 < qe; q0 += 4) {
+                float4 o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) o[u] = __ldg(A.pos4 + min(q0 + u, qe - 1u));   // 4 independent loads in flight
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t q = q0 + u;
+                    const v2 dr = V(o[u].x, o[u].y) - r;
+                    if (q < qe && norm2(dr) < P.r_max2 && q != p) {
+                        const uint2 ok = __ldg(A.key2 + q);
+                        const int dxc = cs_cx(ok.y) - cxi;
+                        const int dyc = cs_cy(ok.y) - cyi;
+                        // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
+                        const int idx = (dxc + 1) * 3 + (dyc + 1);
+                        const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
+                        fn((rank << 28) | ok.x, q);
+                    }
                 }
             }
         }
@@ -401,39 +498,58 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
         }
     };
 
-    // Pass structure: one scan keeps the NBR_CAP smallest keys above `floor_key`, sorted, in shared memory; they are
-    // accumulated in order; crowds with more neighbours than NBR_CAP take further scans (floor_key = last key used).
-    int cnt = 0, kept = 0;
-    for_each_neighbour([&](uint32_t key, uint32_t q) {
-        ++cnt;
+    // Ordering: ONE scan of the candidates. The NBR_CAP smallest keys are kept sorted in shared memory; whatever does not
+    // fit (pushed out, or larger than everything kept) goes unsorted to a per-thread spill list in local memory. The kept
+    // keys are accumulated in order; then the spill — all of it larger than what was just used — is filtered through the
+    // same bounded insertion, NBR_CAP at a time, without touching the candidates again. Crowds beyond NBR_CAP+SPILL_CAP
+    // neighbours fall back to re-scanning the candidates above the last used key.
+    uint2 spill[SPILL_CAP];
+    int cnt = 0, kept = 0, n_spill = 0;
+    bool spill_lost = false;
+    auto offer = [&](uint2 e, bool to_spill) {   // bounded sorted insertion; the loser goes to the spill list
         int pos;
         if (kept < NBR_CAP) pos = kept++;
-        else if (key < s_kq[NBR_CAP - 1][tid].x) pos = NBR_CAP - 1;
-        else return;
-        while (pos > 0 && s_kq[pos - 1][tid].x > key) {
+        else {
+            uint2 out = e;
+            if (e.x < s_kq[NBR_CAP - 1][tid].x) { out = s_kq[NBR_CAP - 1][tid]; pos = NBR_CAP - 1; }
+            else pos = -1;
+            if (to_spill) {
+                if (n_spill < SPILL_CAP) spill[n_spill++] = out;
+                else spill_lost = true;
+            }
+            if (pos < 0) return;
+        }
+        while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
             s_kq[pos][tid] = s_kq[pos - 1][tid];
             --pos;
         }
-        s_kq[pos][tid] = make_uint2(key, q);
+        s_kq[pos][tid] = e;
+    };
+    for_each_neighbour([&](uint32_t key, uint32_t q) {
+        ++cnt;
+        offer(make_uint2(key, q), true);
     });
     for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-    for (int done = kept; done < cnt;) {   // dense crowd: more passes
-        const uint32_t floor_key = s_kq[kept - 1][tid].x;
-        kept = 0;
-        for_each_neighbour([&](uint32_t key, uint32_t q) {
-            if (key <= floor_key) return;
-            int pos;
-            if (kept < NBR_CAP) pos = kept++;
-            else if (key < s_kq[NBR_CAP - 1][tid].x) pos = NBR_CAP - 1;
-            else return;
-            while (pos > 0 && s_kq[pos - 1][tid].x > key) {
-                s_kq[pos][tid] = s_kq[pos - 1][tid];
-                --pos;
-            }
-            s_kq[pos][tid] = make_uint2(key, q);
-        });
-        for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-        done += kept;
+    int done = kept;
+    if (!spill_lost) {
+        while (n_spill > 0) {   // rounds over the spill only
+            const int m = n_spill;
+            n_spill = 0;
+            kept = 0;
+            for (int k = 0; k < m; ++k) offer(spill[k], true);   // losers are re-appended at indices < k: in-place compaction
+            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+            done += kept;
+        }
+    } else {
+        while (done < cnt) {    // very dense crowd: re-scan the candidates above the last key used
+            const uint32_t floor_key = s_kq[kept - 1][tid].x;
+            kept = 0;
+            for_each_neighbour([&](uint32_t key, uint32_t q) {
+                if (key > floor_key) offer(make_uint2(key, q), false);
+            });
+            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+            done += kept;
+        }
     }
 
     // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116

@@ -71,20 +71,31 @@ def _blank(n: int) -> dict:
     return a
 
 
+def path_of_position(fx: dict, r: np.ndarray) -> np.ndarray:
+    """index of the funnel path an agent at r follows: its command group is the block of the side x side block grid it
+    stands in, and inside the group the path planned from its sub-block (one path per start region, as
+    PathFinder2::issuePaths2 buckets a group by start triangle, PathFinder2.cpp:541-606)"""
+    nx = int(fx["n_cells"][0]) if "tile_cells" not in fx else int(fx["tile_cells"][0])
+    side, sub = (int(v) for v in fx["path_grid"])
+    W = nx * 5.0
+    bw = W / side
+    sw = bw / sub
+    bx = np.minimum((r[:, 0] // bw).astype(np.int64), side - 1)
+    by = np.minimum((r[:, 1] // bw).astype(np.int64), side - 1)
+    si = np.minimum(((r[:, 0] - bx * bw) // sw).astype(np.int64), sub - 1)
+    sj = np.minimum(((r[:, 1] - by * bw) // sw).astype(np.int64), sub - 1)
+    return ((bx + side * by) * sub * sub + sj * sub + si).astype(np.int32)
+
+
 def config3_agents(fx: dict, n: int = 1_000_000, seed: int = 1236):
-    """BASELINE config 3: n agents over the whole 1024² map, radius 3 / mass 1, all MOVING, one command group per
-    block of the 8x8 block grid, each following its group's precomputed funnel path (waypoint 0 is the path's
-    start point, so agents begin at waypoint 1 as PathFinder2::setPathOfAgent does, PathFinder2.cpp:338)."""
+    """BASELINE config 3: n agents over the whole 1024² map, radius 3 / mass 1, all MOVING in 64 command groups (8x8
+    blocks, one destination each) that follow precomputed funnel paths (waypoint 0 is the path's start point, so
+    agents begin at waypoint 1 as PathFinder2::setPathOfAgent does, PathFinder2.cpp:338)."""
     rng = np.random.default_rng(seed)
     a = _blank(n)
     a["r"][:] = free_positions(fx, n, rng)
     a["angle"][:] = rng.uniform(-180, 180, n)
-    nx = int(fx["n_cells"][0])
-    n_groups = len(fx["path_end"])
-    side = int(round(np.sqrt(n_groups)))
-    block = nx * 5.0 / side
-    g = np.minimum((a["r"][:, 0] // block).astype(np.int64), side - 1) + side * np.minimum((a["r"][:, 1] // block).astype(np.int64), side - 1)
-    a["path_id"][:] = g
+    a["path_id"][:] = path_of_position(fx, a["r"])
     a["waypoint"][:] = 1
     a["state"][:] = abi.MOVING
     return a, paths_of(fx)
@@ -104,7 +115,11 @@ def config2_agents(fx: dict, n: int = 100_000, seed: int = 1235):
     a["player"][:] = rng.integers(0, 2, n)
     moving = rng.random(n) < 0.5
     a["state"][:] = np.where(moving, abi.MOVING, abi.STANDING)
-    a["path_id"][:] = np.where(moving, rng.integers(0, 16, n) * 4, -1)
+    n_paths = len(fx["path_end"])
+    sub2 = int(fx["path_grid"][1]) ** 2
+    # 16 of the 64 destinations; an agent takes the path of that group planned from a random start region
+    a["path_id"][:] = np.where(moving, (rng.integers(0, 16, n) * 4) * sub2 + rng.integers(0, sub2, n), -1)
+    assert a["path_id"].max() < n_paths
     a["waypoint"][:] = 1
     return a, paths_of(fx)
 
@@ -222,17 +237,16 @@ def tile_map(fx: dict, tx: int, ty: int) -> dict:
     if pw:
         out.update(path_offsets=np.array(poff, np.uint32), path_waypoints=np.concatenate(pw).astype(np.float32),
                    path_portals=np.concatenate(pp).astype(np.float32), path_end=np.concatenate(pe).astype(np.float32),
-                   path_start=np.concatenate(ps).astype(np.float32))
+                   path_start=np.concatenate(ps).astype(np.float32), path_grid=fx["path_grid"])
     return out
 
 
-def tiled_agents(fx_tile: dict, tx: int, ty: int, n_per_tile: int, seed: int = 1237, groups_per_tile_side: int = 8):
-    """config-3 style population on every tile of a tile_map(fx_tile, tx, ty): n_per_tile agents per tile, all MOVING,
-    one command group per block (groups_per_tile_side² blocks per tile; 2 gives the 256 groups of config 4 on 8x8 tiles)."""
+def tiled_agents(fx_tile: dict, tx: int, ty: int, n_per_tile: int, seed: int = 1237):
+    """config-3 population on every tile of a tile_map(fx_tile, tx, ty): n_per_tile agents per tile, all MOVING along
+    the funnel path of their start region inside their own tile."""
     nx_t = int(fx_tile["n_cells"][0])
     W_t = nx_t * 5.0
     n_paths_tile = len(fx_tile["path_end"])
-    side = int(round(np.sqrt(n_paths_tile)))
     parts = []
     for j in range(ty):
         for i in range(tx):
@@ -241,13 +255,7 @@ def tiled_agents(fx_tile: dict, tx: int, ty: int, n_per_tile: int, seed: int = 1
             a = _blank(n_per_tile)
             r = free_positions(fx_tile, n_per_tile, rng)
             a["angle"][:] = rng.uniform(-180, 180, n_per_tile)
-            gs = groups_per_tile_side
-            bx = np.minimum((r[:, 0] // (W_t / gs)).astype(np.int64), gs - 1)
-            by = np.minimum((r[:, 1] // (W_t / gs)).astype(np.int64), gs - 1)
-            # path of the 8x8 block nearest the centre of the group's block
-            px = np.minimum(((bx + 0.5) * side / gs).astype(np.int64), side - 1)
-            py = np.minimum(((by + 0.5) * side / gs).astype(np.int64), side - 1)
-            a["path_id"][:] = t * n_paths_tile + px + side * py
+            a["path_id"][:] = t * n_paths_tile + path_of_position(fx_tile, r)
             a["waypoint"][:] = 1
             a["state"][:] = abi.MOVING
             a["r"][:] = r + np.array([i * W_t, j * W_t], np.float32)

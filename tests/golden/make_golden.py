@@ -101,9 +101,11 @@ def free_point_near(occ, x, y, rng):
     raise RuntimeError("no free point")
 
 
-def make_map_c3(cells=1024, n_buildings=200, n_groups=64, seed=7, name="map_c3.npz"):
-    """BASELINE configs 2/3: 1024² cells, 200 octagonal buildings, and one funnel path per command group
-    (8x8 blocks of the map, block centre -> random target) planned by the reference's PathFinder2."""
+def make_map_c3(cells=1024, n_buildings=200, n_groups=64, sub=8, seed=7, name="map_c3.npz"):
+    """BASELINE configs 2/3: 1024² cells, 200 octagonal buildings, 64 command groups (8x8 blocks of the map, one random
+    target per group).  As PathFinder2::issuePaths2 plans one funnel path per start triangle of a group
+    (PathFinder2.cpp:541-606), every group gets one path per sub-block (sub x sub per block) from the sub-block centre
+    to the group's target, planned by the reference's PathFinder2: n_groups * sub² paths."""
     rng = np.random.default_rng(seed)
     w = refh.RefWorld(cells, cells)
     blds, occ = place_buildings(w, n_buildings, rng, 12, cells - 12, (cells, cells))
@@ -112,32 +114,52 @@ def make_map_c3(cells=1024, n_buildings=200, n_groups=64, seed=7, name="map_c3.n
     tables = w.tables()
     W = cells * 5.0
     side = int(round(np.sqrt(n_groups)))
-    off, wps, pos, ends, starts = [0], [], [], [], []
+    bw = W / side
+    sw = bw / sub
+    off, wps, pos, ends, starts, group_of = [0], [], [], [], [], []
+    targets = []
     for g in range(n_groups):
         bx, by = g % side, g // side
-        sx, sy = free_point_near(occ, (bx + 0.5) * W / side, (by + 0.5) * W / side, rng)
+        cx, cy = (bx + 0.5) * bw, (by + 0.5) * bw
         while True:
             ex, ey = free_point_near(occ, rng.uniform(0.1 * W, 0.9 * W), rng.uniform(0.1 * W, 0.9 * W), rng)
-            if np.hypot(ex - sx, ey - sy) <= 0.3 * W:
-                continue
-            try:
-                path, portals = w.plan_path(sx, sy, ex, ey, 3.0)
+            if np.hypot(ex - cx, ey - cy) > 0.3 * W:
                 break
-            except RuntimeError as e:   # the reference's funnel occasionally runs away (bad_alloc under the rlimit below)
-                print("planner failed for group", g, (sx, sy, ex, ey), e, "- drawing another target")
-        if len(path) >= 2 and (path[-1] == path[-2]).all():      # setPathOfAgent drops a doubled end, PathFinder2.cpp:333-336
-            path, portals = path[:-1], portals[:-1]
-        assert len(path) >= 2 and np.isfinite(path).all() and np.isfinite(portals).all(), (g, path)
-        wps.append(path)
-        pos.append(portals)
-        ends.append([ex, ey])
-        starts.append([sx, sy])
-        off.append(off[-1] + len(path))
+        targets.append((ex, ey))
+    fails = 0
+    for g in range(n_groups):
+        bx, by = g % side, g // side
+        ex, ey = targets[g]
+        for sj in range(sub):
+            for si in range(sub):
+                sx0, sy0 = bx * bw + (si + 0.5) * sw, by * bw + (sj + 0.5) * sw
+                path = None
+                for attempt in range(8):
+                    sx, sy = free_point_near(occ, sx0 + (rng.uniform(-10, 10) if attempt else 0.0), sy0 + (rng.uniform(-10, 10) if attempt else 0.0), rng)
+                    try:
+                        path, portals = w.plan_path(sx, sy, ex, ey, 3.0)
+                        break
+                    except RuntimeError:   # the reference's funnel occasionally runs away (bad_alloc under the rlimit set in main)
+                        fails += 1
+                if path is None:            # give this sub-block a straight leg to the target
+                    path = np.array([[sx, sy], [ex, ey]], np.float32)
+                    portals = np.zeros((2, 5), np.float32)
+                if len(path) >= 3 and (path[-1] == path[-2]).all():   # setPathOfAgent drops a doubled end, PathFinder2.cpp:333-336
+                    path, portals = path[:-1], portals[:-1]
+                assert len(path) >= 2 and np.isfinite(path).all() and np.isfinite(portals).all(), (g, path)
+                wps.append(path)
+                pos.append(portals)
+                ends.append([ex, ey])
+                starts.append([sx, sy])
+                group_of.append(g)
+                off.append(off[-1] + len(path))
     np.savez_compressed(os.path.join(OUT, name), **tables, buildings=blds,
                         path_offsets=np.array(off, np.uint32), path_waypoints=np.concatenate(wps).astype(np.float32),
                         path_portals=np.concatenate(pos).astype(np.float32), path_end=np.array(ends, np.float32),
-                        path_start=np.array(starts, np.float32))
-    print(name, "triangles", len(tables["tri_verts"]), "waypoints", off[-1], "max/path", max(np.diff(off)))
+                        path_start=np.array(starts, np.float32), path_group=np.array(group_of, np.int32),
+                        path_grid=np.array([side, sub], np.int32))
+    print(name, "triangles", len(tables["tri_verts"]), "paths", len(ends), "waypoints", off[-1], "max/path", max(np.diff(off)),
+          "planner failures", fails)
     w.close()
 
 

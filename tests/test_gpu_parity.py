@@ -106,9 +106,11 @@ def random_world(seed, n, tables, lo, hi, moving=0.6):
     return a, paths
 
 
-@pytest.mark.parametrize("n,lo,hi,seed", [(20000, 100.0, 900.0, 1), (50000, 150.0, 700.0, 2), (3000, 300.0, 420.0, 3)])
+@pytest.mark.parametrize("n,lo,hi,seed", [(20000, 100.0, 900.0, 1), (50000, 150.0, 700.0, 2), (3000, 300.0, 420.0, 3),
+                                          (4000, 500.0, 560.0, 4), (2500, 610.0, 640.0, 5)])
 def test_multi_step_matches_oracle(n, lo, hi, seed):
-    """seeded random crowd (the last case is ~0.2 agents/unit²: > NBR_CAP neighbours, selection path)"""
+    """seeded random crowds. Densities: 0.03, 0.17, 0.2 agents/unit², then 1.1 (≈100 neighbours: shared-memory list +
+    local-memory spill) and 2.8 (≈260 neighbours: beyond the spill, candidates are re-scanned)"""
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
     a, paths = random_world(seed, n, tables, lo, hi)
@@ -175,6 +177,45 @@ def test_update_shared_data_roundtrip_and_population_edits():
         out4 = g.communicate(("r", "mass"))
         H.assert_same_bits(out4["r"][4998:], a["r"][:7], "appended at the end")
         H.assert_same_bits(out4["r"][:4998], exp[:4998], "old agents keep their index")
+
+
+def test_agents_outside_the_map_and_coincident_agents():
+    """Grid::coordToCell wraps out-of-range positions modulo the grid (size_t arithmetic, Grid.cpp:18-24); coincident
+    agents give NaN forces in the reference (0/0). Neither may crash, and both must match the oracle."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(11, 4000, tables, 200.0, 800.0)
+    a["r"][:50] = np.random.default_rng(0).uniform(-300, 0, (50, 2))          # negative coordinates
+    a["r"][50:100] = np.random.default_rng(1).uniform(2560, 3000, (50, 2))     # beyond the 512² map
+    a["r"][100:104] = a["r"][104:108]                                          # coincident pairs -> NaN
+    ref = {k: v.copy() for k, v in a.items()}
+    ow = port.OracleWorld(port.default_params(512, 512), tables, paths)
+    names = ("r", "vel", "inertia", "state", "ns_cell", "map_cell", "waypoint")
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        for s in range(3):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            sane = np.isfinite(ref["r"]).all(1) & (np.abs(ref["r"]) < 1e6).all(1)
+            assert (~np.isfinite(ref["r"]).all(1)).sum() >= 8          # the NaN pairs really are NaN in the oracle
+            assert (np.isfinite(out["r"]).all(1) == np.isfinite(ref["r"]).all(1)).all()
+            for k in names:
+                H.assert_same_bits(out[k][sane], ref[k][sane], f"step {s} {k}")
+
+
+def test_single_agent():
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(12, 1, tables, 400.0, 500.0)
+    ref = {k: v.copy() for k, v in a.items()}
+    port.OracleWorld(port.default_params(512, 512), tables, paths).step(ref, 5)
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        g.update(5)
+        out = g.communicate(("r", "inertia", "tri_idx"))
+        for k in out:
+            H.assert_same_bits(out[k], ref[k], k)
 
 
 def test_empty_population_and_errors():

@@ -22,6 +22,8 @@ for s in range(0, total, every):
     c = (r[:, 0] // 6).astype(np.int64) * 4096 + (r[:, 1] // 6).astype(np.int64)
     cnt = np.bincount(c[(c >= 0)])
     cnt = cnt[cnt > 0]
-    print(json.dumps({"frame": s + every, "k_step_ms": round(ms["step"], 4), "scan_ms": round(ms["scan"], 4), "reorder_ms": round(ms["reorder"], 4),
+    cc = (r[:, 0] // 60).astype(np.int64) * 4096 + (r[:, 1] // 60).astype(np.int64)
+    ccnt = np.bincount(cc[cc >= 0])
+    print(json.dumps({"frame": s + every, "max_per_ns_cell": int(ccnt.max()), "k_step_ms": round(ms["step"], 4), "scan_ms": round(ms["scan"], 4), "reorder_ms": round(ms["reorder"], 4),
                       "max_per_cell": int(cnt.max()), "p999": float(np.percentile(cnt, 99.9)), "mean_occ": float(cnt.mean()),
                       "nan": int(np.isnan(r).any(1).sum()), "wp_mean": float(out["waypoint"].mean())}), flush=True)
