@@ -68,7 +68,11 @@ typedef struct RtsParams {
     /* SeekSystemSettings, src/Settings.cpp:53-56 (used by the arrival rule) */
     float finish_angle, finish_radius, finish_n_steps, finish_cone_len;
     /* behaviour switches */
-    uint32_t enable_arrival; /* 0: finalizeSeek is skipped (single-step parity mode); 1: two-phase arrival rule */
+    uint32_t enable_arrival; /* 0: SeekSystem::finalizeSeek is skipped; 1: arrival rule with frame-start snapshot semantics:
+                                a MOVING agent on its last leg within 2*radius + sqrt(finished_area(group)/pi) of path_end stops
+                                and stops its same-group neighbours of the seek neighbour list within finish_radius
+                                (SeekSystem.cpp:235-275, CommandGroupManager.h:141-177); the reference runs this inside its serial
+                                per-agent loop, here every agent sees the group areas and neighbour states of the frame start */
     uint32_t walk_all;       /* 1: keep tri_idx for every agent; 0: MOVING agents only (as SeekSystem.cpp:206) */
     /* multi-GPU slab owned by this handle: physics-grid rows [slab_row_lo, slab_row_hi); 0,ns_ny = whole map */
     int32_t slab_row_lo, slab_row_hi;
@@ -114,6 +118,8 @@ typedef struct RtsPathTable {
     const float* waypoints;   /* 2 floats per waypoint */
     const RtsEdge* portals;   /* one per waypoint */
     const float* path_end;    /* 2 floats per path: the commanded destination (PathFinderComponent::path_end) */
+    const int32_t* group;     /* command group of each path (CommandGroupManager2::entity2command_group); NULL: group = path */
+    uint32_t n_groups;        /* number of command groups (ignored when group is NULL) */
 } RtsPathTable;
 
 /* per-unit-type constants (UnitTypes.txt + component defaults, Components.h:84-119) */
@@ -190,6 +196,9 @@ int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int
    fields of every agent from caller-order arrays (the ECS blackboard), then re-bin */
 int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields);
 uint32_t rts_agent_count(RtsHandle h);
+/* CommandGroupManager2::group2finished_surface_area_ (CommandGroupManager.h:133): read / overwrite, n = number of groups */
+int32_t rts_get_finished_area(RtsHandle h, float* out, uint32_t n);
+int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n);
 
 /* replaces: PhysicsSystem::update + SeekSystem::update + communicate + avoidWall + integration
    (ECS.cpp:65-113), n_steps frames, asynchronous on the handle's stream */

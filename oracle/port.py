@@ -34,7 +34,7 @@ def load(fast=False):
     L.rts_oracle_default_params.argtypes = [C.POINTER(abi.RtsParams), C.c_int32, C.c_int32]
     L.rts_oracle_default_params.restype = None
     L.rts_oracle_step.argtypes = [C.POINTER(abi.RtsParams), vp, C.c_uint32, vp, C.POINTER(abi.RtsWallTable), vp,
-                                  C.c_uint32, C.POINTER(abi.RtsPathTable), C.c_uint32, C.POINTER(abi.RtsAgentView), vp]
+                                  C.c_uint32, C.POINTER(abi.RtsPathTable), C.c_uint32, C.POINTER(abi.RtsAgentView), vp, vp]
     L.rts_oracle_step.restype = C.c_int32
     L.rts_oracle_coord_to_cell.argtypes = [vp, C.c_uint32, C.c_int32, C.c_int32, C.c_float, vp]
     L.rts_oracle_find_triangles.argtypes = [C.POINTER(abi.RtsParams), vp, C.c_uint32, vp, vp, C.c_uint32, vp]
@@ -69,6 +69,7 @@ class OracleWorld:
             paths = {"offsets": np.zeros(1, np.uint32), "waypoints": np.zeros((0, 2), np.float32),
                      "portals": np.zeros((0, 5), np.float32), "path_end": np.zeros((0, 2), np.float32)}
         self.paths = abi.path_table(paths, self._keep)
+        self.fin_area = np.zeros(max(int(self.paths.n_groups), 1), np.float32)   # group2finished_surface_area_
 
     def step(self, agents: dict, n_steps=1, ghost=None):
         """agents: dict of numpy arrays (see abi.AGENT_FIELDS); updated in place."""
@@ -87,7 +88,7 @@ class OracleWorld:
             rc = self.L.rts_oracle_step(C.byref(self.params), self.tris.ctypes.data, len(self.tris),
                                         self.cell2tri.ctypes.data, C.byref(self.walls), self.unit_types.ctypes.data,
                                         len(self.unit_types), C.byref(self.paths), n, C.byref(view),
-                                        None if g is None else g.ctypes.data)
+                                        None if g is None else g.ctypes.data, self.fin_area.ctypes.data)
             if rc != 0:
                 raise RuntimeError(f"oracle step failed: {rc}")
 

@@ -280,7 +280,7 @@ static void build_grid(const RtsParams* P, uint32_t n, const float* r, ns_grid* 
  */
 int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
                         const RtsWallTable* W, const RtsUnitType* types, uint32_t n_types, const RtsPathTable* paths,
-                        uint32_t n, RtsAgentView* a, const uint8_t* ghost) {
+                        uint32_t n, RtsAgentView* a, const uint8_t* ghost, float* fin_area) {
     acos_init();
     (void)n_types;
     ns_grid g;
@@ -293,6 +293,55 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
     uint8_t* s0 = (uint8_t*)malloc(n ? n : 1);
     memcpy(r0, a->r, sizeof(float) * 2 * n);
     memcpy(s0, a->state, n);
+
+    /* ---- arrival (SeekSystem::finalizeSeek, SeekSystem.cpp:235-275) with frame-start snapshot semantics: see
+       RtsParams.enable_arrival. stop[i] = agent i stops this frame. The cone rule (neighboursInFrontReachedEnd, :153-179)
+       needs STANDING agents that are still members of the group; stopSeeking always removes an agent from its group
+       (:136-144, CommandGroupManager.h:141-161), so it never fires and is not evaluated. */
+    uint8_t* stop = (uint8_t*)calloc(n ? n : 1, 1);
+    if (P->enable_arrival && fin_area && a->path_id) {
+        const float area_unit = (float)3.14159265358979323846 * P->rhard * P->rhard; /* M_PIf * RHARD * RHARD */
+        for (uint32_t i = 0; i < n; ++i) {
+            if (ghost && ghost[i]) continue;
+            const int32_t pid = a->path_id[i];
+            if (s0[i] != RTS_MOVING || pid < 0) continue;
+            const uint32_t p0 = paths->offsets[pid], last = paths->offsets[pid + 1] - 1;
+            const uint32_t wpi = a->waypoint ? (uint32_t)a->waypoint[i] : 0u;
+            const uint32_t w0 = p0 + wpi < last ? p0 + wpi : last;
+            v2 r_next = V(a->r_next[2 * i], a->r_next[2 * i + 1]);
+            if (r_next.x != r_next.x) r_next = V(paths->waypoints[2 * w0], paths->waypoints[2 * w0 + 1]);
+            const v2 path_end = V(paths->path_end[2 * pid], paths->path_end[2 * pid + 1]);
+            if (!vequal(path_end, r_next)) continue;                          /* SeekSystem.cpp:106 */
+            const int32_t g_i = paths->group ? paths->group[pid] : pid;
+            const v2 r = V(r0[2 * i], r0[2 * i + 1]);
+            const float finish_radius = sqrtf(fin_area[g_i] / (float)3.14159265358979323846);
+            const float dist_to_end = sqrtf(vdist2(path_end, r));
+            if (!(dist_to_end < 2 * a->radius[i] + finish_radius)) continue; /* :258 */
+            stop[i] = 1;
+            const uint32_t ci = cell_of[i];
+            const int cx = (int)(ci % (uint32_t)P->ns_nx), cy = (int)((ci / (uint32_t)P->ns_nx) % (uint32_t)P->ns_ny);
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy) {
+                    if (cx + dx < 0 || cx + dx >= P->ns_nx || cy + dy < 0 || cy + dy >= P->ns_ny) continue;
+                    const uint32_t cj = (uint32_t)(cx + dx) + (uint32_t)(cy + dy) * (uint32_t)P->ns_nx;
+                    for (uint32_t k = g.cell_start[cj]; k < g.cell_start[cj + 1]; ++k) {
+                        const uint32_t j = g.cell_items[k];
+                        if (j == i || (ghost && ghost[j]) || s0[j] != RTS_MOVING) continue;
+                        const int32_t pj = a->path_id[j];
+                        if (pj < 0 || (paths->group ? paths->group[pj] : pj) != g_i) continue;
+                        const v2 dr = vsub(V(r0[2 * j], r0[2 * j + 1]), r);
+                        const float rr = a->radius[i] + a->radius[j];
+                        if (!(vnorm2(dr) < 10.f * rr * rr)) continue;         /* seek neighbour list, Strategy.cpp:109-111 */
+                        if (sqrtf(vnorm2(vsub(r, V(r0[2 * j], r0[2 * j + 1])))) < P->finish_radius) stop[j] = 1; /* :266-270 */
+                    }
+                }
+        }
+        for (uint32_t i = 0; i < n; ++i)
+            if (stop[i]) {
+                const int32_t pid = a->path_id[i];
+                fin_area[paths->group ? paths->group[pid] : pid] += area_unit; /* CommandGroupManager.h:150 */
+            }
+    }
 
     int32_t rc = RTS_OK;
 #pragma omp parallel for schedule(dynamic, 256)
@@ -370,7 +419,13 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
         int state = state_i;
         int32_t wp = a->waypoint ? a->waypoint[i] : 0;
         v2 r_next = V(a->r_next[2 * i], a->r_next[2 * i + 1]);
-        const int32_t pid = a->path_id ? a->path_id[i] : -1;
+        int32_t pid = a->path_id ? a->path_id[i] : -1;
+        if (stop[i]) { /* stopSeeking, SeekSystem.cpp:136-144: no seek velocity this frame, out of the group */
+            state = RTS_STANDING;
+            angle_vel = 0;
+            pid = -1;
+            a->path_id[i] = -1;
+        }
         if (state == RTS_MOVING && pid >= 0) {
             const uint32_t p0 = paths->offsets[pid], p1 = paths->offsets[pid + 1];
             const uint32_t last = p1 - 1;
@@ -448,7 +503,7 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
         if (a->map_cell) a->map_cell[i] = (uint32_t)coord_to_cell(r_new.x, r_new.y, P->map_nx, P->map_ny, P->map_cell_size);
         if (a->flags) a->flags[i] = flags;
     }
-    free(r0); free(s0); free(cell_of); free(g.cell_start); free(g.cell_items);
+    free(r0); free(s0); free(cell_of); free(g.cell_start); free(g.cell_items); free(stop);
     return rc;
 }
 

@@ -59,7 +59,7 @@ class RtsWallTable(C.Structure):
 
 class RtsPathTable(C.Structure):
     _fields_ = [("n_paths", C.c_uint32), ("offsets", C.c_void_p), ("waypoints", C.c_void_p), ("portals", C.c_void_p),
-                ("path_end", C.c_void_p)]
+                ("path_end", C.c_void_p), ("group", C.c_void_p), ("n_groups", C.c_uint32)]
 
 
 class RtsUnitType(C.Structure):
@@ -161,6 +161,17 @@ def path_table(paths: dict, keep: list) -> RtsPathTable:
     t = RtsPathTable()
     t.n_paths = len(off) - 1
     t.offsets, t.waypoints, t.portals, t.path_end = off.ctypes.data, wp.ctypes.data, po.ctypes.data, pe.ctypes.data
+    grp = paths.get("group")
+    if grp is not None and len(grp):
+        grp = np.ascontiguousarray(grp, np.int32)
+        if len(grp) != t.n_paths:
+            raise ValueError("path table: one group id per path")
+        keep.append(grp)
+        t.group = grp.ctypes.data
+        t.n_groups = int(grp.max()) + 1
+    else:
+        t.group = None
+        t.n_groups = t.n_paths
     return t
 
 

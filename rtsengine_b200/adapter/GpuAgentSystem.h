@@ -22,6 +22,7 @@
 // becomes std::runtime_error, the reference's own error convention (NeighbourSearcherContext.cpp:46).
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -44,6 +45,9 @@ struct GpuSeekSlot : System2 {
     GpuPhysicsSlot* physics = nullptr;   // same component order as this slot (both filled by ECSystem::initializeEntity)
     bool population_dirty = true;        // set after addComponent / remove
     bool paths_dirty = true;             // set after the planner rewrote windows (PathFinder2::setPathOfAgent)
+    // command group of each component (CommandGroupManager2::entity2command_group, CommandGroupManager.h:130); the host
+    // copies it here after addGroup / removeFromGroup. Empty: every agent is its own group (no arrival cascade).
+    std::vector<int32_t> command_group;
 
     GpuSeekSlot(ComponentID id, const RtsParams& params, int device = 0) : System2(id) {
         check(rts_create(&params, device, &h), "rts_create");
@@ -170,7 +174,16 @@ private:
             path_id[i] = c.state == MoveState::MOVING ? (int32_t)i : -1;
         }
         off[n] = 2 * n;
-        RtsPathTable t{n, off.data(), wp.data(), portals.data(), end.data()};
+        RtsPathTable t{n, off.data(), wp.data(), portals.data(), end.data(), nullptr, 0};
+        std::vector<int32_t> grp;
+        if (command_group.size() == n) {   // groups -1 (no command) get ids of their own behind the real ones
+            int32_t ng = 0;
+            for (auto g : command_group) ng = std::max(ng, g + 1);
+            grp.resize(n);
+            for (uint32_t i = 0; i < n; ++i) grp[i] = command_group[i] >= 0 ? command_group[i] : ng++;
+            t.group = grp.data();
+            t.n_groups = (uint32_t)ng;
+        }
         check(rts_upload_paths(h, &t), "rts_upload_paths");
         RtsAgentView v{};
         v.path_id = path_id.data(); v.waypoint = waypoint.data(); v.r_next = r_next.data();

@@ -168,7 +168,9 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     AL(pos4, float4) AL(key2, uint2) AL(src, uint32_t) AL(vel4, float4) AL(nav4, float4) AL(tri, uint32_t)
     AL(pos4n, float4) AL(key2n, uint2) AL(vel4n, float4) AL(nav4n, float4) AL(trin, uint32_t) AL(cellrank, uint2)
     if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
+    AL(stop_req, uint32_t)
 #undef AL
+    CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
     A.n_dev = h->n_dev;
     h->cap = cap;
     h->drop_graphs();
@@ -250,6 +252,11 @@ int32_t launch_scan_reorder(RtsContext* h) {
 
 void launch_step_kernel(RtsContext* h) {
     const uint32_t nb = h->multi ? h->cap_main : h->n;
+    if (h->P.enable_arrival && nb && h->M.n_groups) {
+        k_area_sync<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M);
+        k_arrive<<<blocks_for(nb, 256), 256, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->multi ? 1 : 0);
+        h->launches += 2;
+    }
     timer_begin(h, KT_STEP);
     if (nb) {
         const dim3 grid(blocks_for(nb, STEP_BLOCK));
@@ -661,6 +668,18 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
         if (paths->offsets[p + 1] <= paths->offsets[p]) return h->fail(RTS_E_ARG, "rts_upload_paths", "every path needs at least one waypoint");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    const uint32_t ng = paths->group ? paths->n_groups : np;
+    std::vector<int32_t> grp(std::max<uint32_t>(np, 1), 0);
+    for (uint32_t p = 0; p < np; ++p) {
+        grp[p] = paths->group ? paths->group[p] : (int32_t)p;
+        if (grp[p] < 0 || (uint32_t)grp[p] >= ng) return h->fail(RTS_E_ARG, "rts_upload_paths", "group id out of range");
+    }
+    // finished areas survive a re-upload with the same number of groups (the planner rewrites windows every few frames)
+    std::vector<float> keep_area;
+    if (h->M.n_groups == ng && ng && h->M.area_acc) {
+        keep_area.resize(ng);
+        CU(cudaMemcpy(keep_area.data(), h->M.area_acc, sizeof(float) * ng, cudaMemcpyDeviceToHost));
+    }
     free_all(h->path_allocs);
     std::vector<float4> wp(2 * (size_t)nw);
     for (uint32_t k = 0; k < nw; ++k) {
@@ -668,8 +687,18 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
         wp[2 * k] = make_float4(paths->waypoints[2 * k], paths->waypoints[2 * k + 1], e.from_x, e.from_y);
         wp[2 * k + 1] = make_float4(e.t_x, e.t_y, e.l, 0.f);
     }
-    uint32_t* d_off; float4* d_wp; float2* d_end;
+    uint32_t* d_off; float4* d_wp; float2* d_end; int32_t* d_grp; float *d_ar, *d_aa;
     int32_t rc;
+    if ((rc = dev_alloc(h, &d_grp, np, h->path_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_ar, ng, h->path_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_aa, ng, h->path_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int32_t) * std::max<uint32_t>(np, 1), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(d_ar, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
+    CU(cudaMemsetAsync(d_aa, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
+    if (!keep_area.empty()) {
+        CU(cudaMemcpyAsync(d_ar, keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(d_aa, keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
+    }
     if ((rc = dev_alloc(h, &d_off, np + 1, h->path_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_wp, wp.size(), h->path_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_end, np, h->path_allocs)) != RTS_OK) return rc;
@@ -678,6 +707,7 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
     if (np) CU(cudaMemcpyAsync(d_end, paths->path_end, 8 * (size_t)np, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np;
+    h->M.path_group = d_grp; h->M.n_groups = ng; h->M.area_read = d_ar; h->M.area_acc = d_aa;
     h->drop_graphs();
     return RTS_OK;
 }
@@ -779,6 +809,27 @@ int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields) {
 }
 
 uint32_t rts_agent_count(RtsHandle h) { return h ? h->n : 0; }
+
+int32_t rts_get_finished_area(RtsHandle h, float* out, uint32_t n) {
+    if (!h || !out) return RTS_E_ARG;
+    if (n > h->M.n_groups) return h->fail(RTS_E_ARG, "rts_get_finished_area", "more groups requested than uploaded");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (n) CU(cudaMemcpy(out, h->M.area_acc, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return RTS_OK;
+}
+
+int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n) {
+    if (!h || !area) return RTS_E_ARG;
+    if (n > h->M.n_groups) return h->fail(RTS_E_ARG, "rts_set_finished_area", "more groups than uploaded");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (n) {
+        CU(cudaMemcpy(h->M.area_acc, area, sizeof(float) * n, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->M.area_read, area, sizeof(float) * n, cudaMemcpyHostToDevice));
+    }
+    return RTS_OK;
+}
 
 static int32_t build_graph(RtsContext* h) {
     const int par = h->parity;

@@ -29,6 +29,10 @@ struct MapDev {
     const float4* __restrict__ waypoints;
     const float2* __restrict__ path_end;
     uint32_t n_paths;
+    const int32_t* __restrict__ path_group;   // command group of each path
+    uint32_t n_groups;
+    float* area_read;    // CommandGroupManager2::group2finished_surface_area_, value at the start of the frame
+    float* area_acc;     // ... accumulating this frame's stops
     const RtsUnitType* __restrict__ unit_types;
     uint32_t n_types;
     const float* __restrict__ acos_table;   // AcosTable<1000>, built on the host (src/core.h:115-124)

@@ -103,6 +103,7 @@ struct AgentArrays {
     uint32_t* trin;
     float2* vel_outn;
     uint2* cellrank;  // {next fine cell, rank inside it}
+    uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -389,6 +390,64 @@ __global__ void k_halo_seed(uint32_t n_bound, RtsParams P, FineGrid F, AgentArra
     A.cellrank[p] = make_uint2(cell, warp_aggregated_rank(F.count, cell, active));
 }
 
+// Arrival rule (SeekSystem::finalizeSeek, SeekSystem.cpp:235-275) with frame-start snapshot semantics; runs before the
+// frame kernel. A MOVING agent on its last leg (r_next == path_end) that is within 2*radius + sqrt(area/pi) of path_end
+// stops, and stops the same-group members of its seek neighbour list (|dr|^2 < 10 (ri+rj)^2, Strategy.cpp:109-111) that
+// are within finish_radius. Every stop adds pi*RHARD^2 to the group's finished area exactly once (atomicExch claim); the
+// increments are all equal, so the float sum does not depend on their order.
+__global__ void k_area_sync(MapDev M) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < M.n_groups) M.area_read[g] = M.area_acc[g];
+}
+
+__global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, int multi) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = multi ? *A.n_dev : n_bound;
+    if (p >= n) return;
+    const uint2 key = A.key2[p];
+    if ((key.y & 3u) != RTS_MOVING || ((key.y >> 2) & 1u)) return;
+    const float4 nav4 = A.nav4[A.src[p]];
+    const int32_t pid = __float_as_int(nav4.z);
+    if (pid < 0) return;
+    const uint32_t p0 = __ldg(M.path_off + pid), last = __ldg(M.path_off + pid + 1) - 1;
+    const uint32_t w0 = min(p0 + (__float_as_uint(nav4.w) & 0xFFFFu), last);
+    v2 r_next = V(nav4.x, nav4.y);
+    if (r_next.x != r_next.x) { const float4 wa = __ldg(M.waypoints + 2 * (size_t)w0); r_next = V(wa.x, wa.y); }
+    const float2 pe = __ldg(M.path_end + pid);
+    const v2 path_end = V(pe.x, pe.y);
+    if (!vequal(path_end, r_next)) return;
+    const int32_t g_i = __ldg(M.path_group + pid);
+    const float4 me = A.pos4[p];
+    const v2 r = V(me.x, me.y);
+    const float finish_radius = sqrtf(M.area_read[g_i] / 3.14159265358979323846f);
+    const float dist_to_end = sqrtf(dist2(path_end, r));
+    if (!(dist_to_end < 2 * me.z + finish_radius)) return;
+    const float area_unit = 3.14159265358979323846f * P.rhard * P.rhard;
+    if (atomicExch(A.stop_req + p, 1u) == 0u) atomicAdd(M.area_acc + g_i, area_unit);
+    // neighbours: every fine cell that can hold an agent within finish_radius
+    int fx, fy;
+    fine_coords(F, r.x, r.y, fx, fy);
+    const int reach = (int)ceilf(P.finish_radius * F.inv_cs);
+    const int xlo = max(fx - reach, 0), xhi = min(fx + reach, F.nx - 1);
+    for (int yy = max(fy - reach, 0); yy <= min(fy + reach, F.ny - 1); ++yy) {
+        const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
+        const uint32_t qb = __ldg(F.start + rowbase + xlo), qe = __ldg(F.start + rowbase + xhi + 1);
+        for (uint32_t q = qb; q < qe; ++q) {
+            if (q == p) continue;
+            const float4 o = A.pos4[q];
+            const v2 dr = V(o.x, o.y) - r;
+            const float rr = me.z + o.z;
+            if (!(norm2(dr) < 10.f * rr * rr)) continue;
+            if (!(sqrtf(norm2(r - V(o.x, o.y))) < P.finish_radius)) continue;
+            const uint2 ok = A.key2[q];
+            if ((ok.y & 3u) != RTS_MOVING || ((ok.y >> 2) & 1u)) continue;
+            const int32_t pj = __float_as_int(A.nav4[A.src[q]].z);
+            if (pj < 0 || __ldg(M.path_group + pj) != g_i) continue;
+            if (atomicExch(A.stop_req + q, 1u) == 0u) atomicAdd(M.area_acc + g_i, area_unit);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
@@ -581,8 +640,15 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
     uint32_t wp = misc & 0xFFFFu;
     uint32_t flags = (misc >> 28) & 0xFu;
     v2 r_next = V(nav4.x, nav4.y);
-    const int32_t pid = __float_as_int(nav4.z);
-    if (state_i == RTS_MOVING && pid >= 0) {
+    int32_t pid = __float_as_int(nav4.z);
+    int state_out = state_i;
+    if (P.enable_arrival && A.stop_req[p]) {   // stopSeeking, SeekSystem.cpp:136-144: no seek velocity, out of the group
+        A.stop_req[p] = 0u;
+        state_out = RTS_STANDING;
+        angle_vel = 0.f;
+        pid = -1;
+    }
+    if (state_out == RTS_MOVING && pid >= 0) {
         const uint32_t p0 = __ldg(M.path_off + pid), p1 = __ldg(M.path_off + pid + 1);
         const uint32_t last = p1 - 1;
         const uint32_t w0 = min(p0 + wp, last);
@@ -643,14 +709,14 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
     angle = angle + angle_vel;
 
     // ---- K7 (triangle walk on the new position) runs in k_reorder; agents that are not walked keep their index
-    if (!(P.walk_all || state_i == RTS_MOVING)) A.trin[p] = A.tri[sp];
+    if (!(P.walk_all || state_out == RTS_MOVING)) A.trin[p] = A.tri[sp];
 
     // ---- write the new record at this slot; bin it for the next order
     const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
     const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, P.ns_ny);
-    uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_i);
+    uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_out);
     const float4 vel_new = make_float4(inertia.x, inertia.y, angle, angle_vel);
-    const float4 nav_new = make_float4(r_next.x, r_next.y, nav4.z, __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
+    const float4 nav_new = make_float4(r_next.x, r_next.y, __int_as_float(pid), __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
     if (MULTI) {
         // ownership follows the physics-grid row of the new position (integer, identical on every rank)
         const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);

@@ -55,6 +55,8 @@ def load_library():
         "rts_command_agents": (i32, [H, vp, u32, i32, C.c_uint8]),
         "rts_update_agents": (i32, [H, AV]),
         "rts_agent_count": (u32, [H]),
+        "rts_get_finished_area": (i32, [H, vp, u32]),
+        "rts_set_finished_area": (i32, [H, vp, u32]),
         "rts_step": (i32, [H, u32]),
         "rts_download": (i32, [H, AV]),
         "rts_sync": (i32, [H]),
@@ -187,6 +189,11 @@ class GpuAgentSystem:
     def command_agents(self, indices, path_id: int, state: int = abi.MOVING):
         idx = np.ascontiguousarray(indices, np.uint32)
         self._chk(self.L.rts_command_agents(self.h, idx.ctypes.data, len(idx), path_id, state))
+
+    def finished_area(self, n_groups: int) -> np.ndarray:
+        out = np.zeros(n_groups, np.float32)
+        self._chk(self.L.rts_get_finished_area(self.h, out.ctypes.data, n_groups))
+        return out
 
     @property
     def n(self) -> int:

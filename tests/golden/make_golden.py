@@ -251,7 +251,13 @@ def main():
                         r0=s0["r"], inertia0=s0["inertia"], angle0=s0["angle"], angle_vel0=s0["angle_vel"],
                         **{"x_" + k: v for k, v in rec.items()})
     w.close()
-    make_map_c3()
+    # ---- empty 512² map (BASELINE config 1) -----------------------------------------------------------
+    w = refh.RefWorld(512, 512)
+    w.finalize_map()
+    np.savez_compressed(os.path.join(OUT, "map_empty.npz"), **w.tables(), buildings=np.zeros((0, 4), np.int32))
+    w.close()
+    if "--with-c3" in sys.argv:      # ~8 minutes: 4096 planner queries, a few of which run away until the rlimit stops them
+        make_map_c3()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

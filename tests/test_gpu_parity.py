@@ -274,3 +274,40 @@ def test_full_size_properties_1m():
         assert core.sum() > 3000
         for k in ("r", "vel", "inertia", "tri_idx"):
             H.assert_same_bits(out[k][idx][core], sub[k][core], f"1M sample {k}")
+
+
+def test_arrival_rule_matches_oracle_and_tracks_the_reference_cascade():
+    """SeekSystem::finalizeSeek (SeekSystem.cpp:235-275) with frame-start snapshot semantics: GPU == oracle bit for bit
+    over the whole arrival of a 1 500-agent group (BASELINE config 1 geometry, shortened). The oracle's rule itself is
+    compared with the verbatim reference's serial cascade in tests/test_oracle_vs_ref.py."""
+    fx = H.load("map_empty.npz")
+    tables = H.tables_of(fx)
+    n = 1500
+    rng = np.random.default_rng(5)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = rng.uniform(700, 1000, (n, 2))
+    a["radius"][:] = 3
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = rng.integers(0, 2, n)          # two groups, two destinations
+    a["r_next"][:] = np.nan
+    paths = {"offsets": np.array([0, 1, 2], np.uint32), "waypoints": np.array([[1100.0, 1100.0], [1150.0, 800.0]], np.float32),
+             "portals": np.zeros((2, 5), np.float32), "path_end": np.array([[1100.0, 1100.0], [1150.0, 800.0]], np.float32),
+             "group": np.array([0, 1], np.int32)}
+    P = port.default_params(512, 512)
+    P.enable_arrival = 1
+    ow = port.OracleWorld(P, tables, paths)
+    ref = {k: v.copy() for k, v in a.items()}
+    with make_system(tables, paths, enable_arrival=1) as g:
+        g.set_agents(a)
+        standing = []
+        for chunk in range(10):
+            ow.step(ref, 60)
+            g.update(60)
+            out = g.communicate(("r", "inertia", "state", "path_id", "angle_vel"))
+            for k in out:
+                H.assert_same_bits(out[k], ref[k], f"frame {60 * (chunk + 1)} {k}")
+            H.assert_same_bits(g.finished_area(2), ow.fin_area, "finished area per group")
+            standing.append(int((out["state"] == abi.STANDING).sum()))
+        assert standing[0] == 0 and standing[-1] > 0.9 * n and sorted(standing) == standing
+        assert (out["path_id"][out["state"] == abi.STANDING] == -1).all()

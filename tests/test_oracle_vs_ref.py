@@ -1,0 +1,101 @@
+"""CPU, only where oracle/_ref (the verbatim reference build) exists: live comparisons of the C oracle with the
+reference's own compiled systems, beyond the committed fixtures."""
+import numpy as np
+import pytest
+
+from oracle import port, refh
+from rtsengine_b200 import abi
+from tests import helpers as H
+
+pytestmark = pytest.mark.skipif(not refh.available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def test_frames_bit_exact_against_live_reference():
+    rng = np.random.default_rng(3)
+    w = refh.RefWorld(512, 512)
+    occ = np.zeros((512, 512), bool)
+    k = 0
+    while k < 30:
+        cx, cy = (int(v) for v in rng.integers(30, 200, 2))
+        if occ[cx - 7:cx + 7, cy - 7:cy + 7].any():
+            continue
+        assert w.add_building(cx, cy, 8, 8, 1) == 0
+        occ[cx - 5:cx + 5, cy - 5:cy + 5] = True
+        k += 1
+    w.finalize_map()
+    n = 1200
+    pos = []
+    while len(pos) < n:
+        p = rng.uniform(150, 700, 2).astype(np.float32)
+        if not occ[int(p[0] // 5), int(p[1] // 5)]:
+            pos.append(p)
+    radius = np.where(rng.random(n) < 0.3, 5.0, 3.0).astype(np.float32)
+    mass = np.where(radius > 4, 50.0, 1.0).astype(np.float32)
+    for i in range(n):
+        w.add_agent(float(pos[i][0]), float(pos[i][1]), 0.0, float(radius[i]), float(mass[i]), 0, 1)
+    w.issue_paths(np.arange(0, n, 2, dtype=np.int32), 1100.0, 1000.0)
+    w.plan_now()
+    tables = w.tables()
+    P = port.default_params(512, 512)
+    s = w.state()
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = s["r"]
+    a["radius"][:] = radius
+    a["mass"][:] = mass
+    for f in range(150):
+        w.plan_now()
+        win = w.seek_window()
+        st = w.state()["state"]
+        a["state"][:] = st
+        a["path_id"][:] = np.where(st == abi.MOVING, np.arange(n), -1)
+        a["waypoint"][:] = 0
+        a["r_next"][:] = win[:, 0:2]
+        port.OracleWorld(P, tables, H.windows_to_paths(win)).step(a)
+        w.step(1)
+        s = w.state()
+        for k in ("r", "vel", "inertia", "angle", "angle_vel"):
+            H.assert_same_bits(a[k], s[k], f"frame {f} {k}")
+        H.assert_same_bits(a["tri_idx"], w.find_triangles(s["r"]), f"frame {f} tri")
+
+
+def test_snapshot_arrival_rule_tracks_the_serial_cascade():
+    """f2: the oracle's frame-start-snapshot arrival rule against the reference's order-dependent finalizeSeek cascade
+    (SeekSystem.cpp:235-275): identical until the first stop, then the same blob within a few percent."""
+    n = 1200
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(300, 650, (n, 2)).astype(np.float32)
+    w = refh.RefWorld(512, 512)
+    w.finalize_map()
+    for p in pos:
+        w.add_agent(float(p[0]), float(p[1]))
+    target = (900.0, 900.0)
+    w.issue_paths(np.arange(n, dtype=np.int32), *target)
+    w.plan_now()
+    P = port.default_params(512, 512)
+    P.enable_arrival = 1
+    paths = {"offsets": np.array([0, 1], np.uint32), "waypoints": np.array([target], np.float32),
+             "portals": np.zeros((1, 5), np.float32), "path_end": np.array([target], np.float32)}
+    ow = port.OracleWorld(P, w.tables(), paths)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = pos
+    a["radius"][:] = 3
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["r_next"][:] = np.nan
+    first_ref = first_or = None
+    for f in range(0, 1300, 50):
+        w.step(50)
+        ow.step(a, 50)
+        s = w.state()
+        n_ref, n_or = int((s["state"] == 1).sum()), int((a["state"] == 1).sum())
+        if n_ref == 0 and n_or == 0:
+            H.assert_same_bits(a["r"], s["r"], f"frame {f + 50}: identical before the first arrival")
+        first_ref = first_ref or (f if n_ref else None)
+        first_or = first_or or (f if n_or else None)
+        assert abs(n_ref - n_or) <= 0.05 * n + 5, (f, n_ref, n_or)
+    assert first_ref == first_or
+    assert n_ref > 0.97 * n and n_or > 0.97 * n
+    d_ref = np.linalg.norm(s["r"] - np.array(target), axis=1)
+    d_or = np.linalg.norm(a["r"] - np.array(target), axis=1)
+    assert abs(d_ref.mean() - d_or.mean()) < 0.03 * d_ref.mean()
+    assert abs(ow.fin_area[0] - n_or * np.float32(np.pi) * 9) < 1.0
