@@ -68,6 +68,7 @@ struct RtsContext {
     bool use_graph = true;
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
+    bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
     std::vector<void*> slab_allocs;
@@ -260,13 +261,19 @@ void launch_step_kernel(RtsContext* h) {
     timer_begin(h, KT_STEP);
     if (nb) {
         const dim3 grid(blocks_for(nb, STEP_BLOCK));
-        if (h->multi) {
-            if (h->keep_vel) k_step<true, true><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
-            else k_step<false, true><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
-        } else {
-            if (h->keep_vel) k_step<true, false><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
-            else k_step<false, false><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL);
+#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL)
+        const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->staged ? 1 : 0);
+        switch (variant) {
+            case 0: LAUNCH_STEP(false, false, false); break;
+            case 1: LAUNCH_STEP(false, false, true); break;
+            case 2: LAUNCH_STEP(false, true, false); break;
+            case 3: LAUNCH_STEP(false, true, true); break;
+            case 4: LAUNCH_STEP(true, false, false); break;
+            case 5: LAUNCH_STEP(true, false, true); break;
+            case 6: LAUNCH_STEP(true, true, false); break;
+            default: LAUNCH_STEP(true, true, true); break;
         }
+#undef LAUNCH_STEP
     }
     timer_end(h, KT_STEP);
     h->launches += 1;
@@ -414,6 +421,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->keep_vel = params->reserved[0] == 0;   // reserved[0] = 1 drops the per-step velocity output
     if (params->reserved[1]) std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float));
     h->use_graph = params->reserved[2] == 0;
+    h->staged = params->reserved[3] != 0;
     *out = h;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {

@@ -15,7 +15,18 @@
 namespace rts {
 
 constexpr int STEP_BLOCK = 128;   // threads per CTA of k_step
-constexpr int NBR_CAP = 24;       // neighbours kept sorted in shared memory per agent
+#ifndef RTS_STEP_MIN_BLOCKS
+#define RTS_STEP_MIN_BLOCKS 8
+#endif
+constexpr int STEP_MIN_BLOCKS = RTS_STEP_MIN_BLOCKS;
+#ifndef RTS_NBR_CAP
+#define RTS_NBR_CAP 16
+#endif
+constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memory per agent
+#ifndef RTS_STAGE_CAP
+#define RTS_STAGE_CAP 640
+#endif
+constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in shared memory (typically ~400)
 constexpr int SPILL_CAP = 104;    // further neighbours parked unsorted in local memory before re-scanning is needed
 constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
 
@@ -451,31 +462,101 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
 // ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
-template <bool KEEP_VEL, bool MULTI>
-__global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
-    __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, slot} of the NBR_CAP smallest keys seen, ascending
-    const uint32_t p = blockIdx.x * STEP_BLOCK + threadIdx.x;
+template <bool KEEP_VEL, bool MULTI, bool STAGED>
+__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+    __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
+    // neighbour records of every fine cell this CTA's agents can see, staged once (coalesced) instead of being fetched
+    // ~9 times each by individual lanes. The CTA's 128 slots lie in one fine row (3 row segments) or straddle two
+    // (6 segments); anything else, or more than STAGE_CAP records, falls back to reading global memory.
+    __shared__ float4 s_pos[STAGED ? STAGE_CAP : 1];
+    __shared__ uint2 s_key[STAGED ? STAGE_CAP : 1];
+    __shared__ uint32_t s_seg_gb[6], s_seg_off[6];
+    __shared__ int s_first[2], s_last[2], s_mode, s_total;
+
+    const int tid = threadIdx.x;
+    const uint32_t block0 = blockIdx.x * STEP_BLOCK;
+    const uint32_t p = block0 + tid;
     const uint32_t n = MULTI ? *A.n_dev : n_bound;   // slabs: the population changes every frame, the count lives on the device
-    const unsigned valid = __ballot_sync(0xffffffffu, p < n);
-    if (p >= n) {
+    const bool in_range = p < n;
+    const unsigned valid = __ballot_sync(0xffffffffu, in_range);
+
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 mykey = make_uint2(0u, 4u);
+    if (in_range) {
+        me = A.pos4[p];
+        mykey = A.key2[p];
+    }
+    const v2 r = V(me.x, me.y);
+    const bool ghost = (mykey.y >> 2) & 1u;
+    const unsigned active = __ballot_sync(valid, !ghost);  // lanes that reach the re-bin at the end
+    int fx, fy;
+    fine_coords(F, r.x, r.y, fx, fy);
+
+    // ---- stage the candidate window of the CTA
+    if (STAGED && block0 < n) {
+        const uint32_t last_valid = min(n, block0 + STEP_BLOCK) - 1u;
+        if (p == block0) { s_first[0] = fx; s_first[1] = fy; }
+        if (p == last_valid) { s_last[0] = fx; s_last[1] = fy; }
+    }
+    if (STAGED) __syncthreads();
+    if (STAGED && tid < 32) {
+        uint32_t gb = 0, len = 0;
+        int mode = 0;
+        if (block0 < n) {
+            const int fx0 = s_first[0], fy0 = s_first[1], fx1 = s_last[0], fy1 = s_last[1];
+            mode = (fy1 == fy0) ? 1 : ((fy1 == fy0 + 1) ? 2 : 0);
+            if (tid < 6 && mode) {
+                int row, x0, x1;
+                if (mode == 1) { row = (tid < 3) ? fy0 - 1 + tid : -1; x0 = fx0 - 1; x1 = fx1 + 1; }
+                else if (tid < 3) { row = fy0 - 1 + tid; x0 = fx0 - 1; x1 = F.nx - 1; }
+                else { row = fy1 - 1 + (tid - 3); x0 = 0; x1 = fx1 + 1; }
+                x0 = max(x0, 0);
+                x1 = min(x1, F.nx - 1);
+                if (row >= 0 && row < F.ny) {
+                    const uint32_t rowbase = (uint32_t)row * (uint32_t)F.nx;
+                    gb = __ldg(F.start + rowbase + x0);
+                    len = __ldg(F.start + rowbase + x1 + 1) - gb;
+                }
+            }
+        }
+        uint32_t incl = len;   // prefix over the 6 segment lengths
+        for (int o = 1; o < 8; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (tid >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 5);
+        if (tid < 6) { s_seg_gb[tid] = gb; s_seg_off[tid] = incl - len; }
+        if (tid == 0) { s_mode = (total <= (uint32_t)STAGE_CAP) ? mode : 0; s_total = (int)total; }
+    }
+    if (STAGED) __syncthreads();
+    const int mode = STAGED ? s_mode : 0;
+    if (STAGED && mode) {
+        const int total = s_total;
+        for (int i = tid; i < total; i += STEP_BLOCK) {
+            int sg = 0;
+#pragma unroll
+            for (int k = 1; k < 6; ++k) sg += ((uint32_t)i >= s_seg_off[k]) ? 1 : 0;   // offsets are non-decreasing
+            // empty trailing segments share the last offset; the last segment whose offset is <= i and that is non-empty
+            // is found because an empty segment k has off[k] == off[k+1] and i >= off[k+1] moves past it
+            const uint32_t q = s_seg_gb[sg] + ((uint32_t)i - s_seg_off[sg]);
+            s_pos[i] = A.pos4[q];
+            s_key[i] = A.key2[q];
+        }
+    }
+    if (STAGED) __syncthreads();
+
+    if (!in_range) {
         if (MULTI && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
         return;
     }
-    const int tid = threadIdx.x;
-
-    const float4 me = A.pos4[p];
-    const uint2 mykey = A.key2[p];
-    const uint32_t sp = A.src[p];
-    const v2 r = V(me.x, me.y);
-    const float radius = me.z, mass_i = me.w;
-    const uint32_t gid = mykey.x;
-    const int state_i = (int)(mykey.y & 3u);
-    const bool ghost = (mykey.y >> 2) & 1u;
-    const unsigned active = __ballot_sync(valid, !ghost);  // lanes that reach the re-bin at the end
     if (ghost) {  // halo copy: neighbour only, dropped from the next order
         A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
         return;
     }
+    const uint32_t sp = A.src[p];
+    const float radius = me.z, mass_i = me.w;
+    const uint32_t gid = mykey.x;
+    const int state_i = (int)(mykey.y & 3u);
     const int cxi = cs_cx(mykey.y), cyi = cs_cy(mykey.y);
 
     const float4 vel4 = A.vel4[sp];
@@ -485,26 +566,30 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
 
     // ---- P1: neighbour pass (Strategy.cpp:10-68) over the 3x3 fine cells; accepted neighbours are kept
     //      sorted by (reference visit rank of their 60-unit cell, gid) = the reference's visit order
-    int fx, fy;
-    fine_coords(F, r.x, r.y, fx, fy);
     const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
     const int ylo = max(fy - 1, 0), yhi = min(fy + 1, F.ny - 1);
 
-    // slot ranges of the three fine rows (each row's 3 cells are contiguous in slot order); loaded up front
+    // candidate index ranges of the three fine rows (each row's 3 cells are contiguous in slot order). Candidates are
+    // addressed through generic pointers: the staged copy in shared memory, or the global arrays (fallback)
+    const float4* cand_pos = mode ? s_pos : A.pos4;
+    const uint2* cand_key = mode ? s_key : A.key2;
+    const int seg0 = (mode == 2 && fy != s_first[1]) ? 3 : 0;
     uint32_t row_qb[3], row_qe[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int yy = fy - 1 + k;
         if (yy >= ylo && yy <= yhi) {
             const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
-            row_qb[k] = __ldg(F.start + rowbase + xlo);
-            row_qe[k] = __ldg(F.start + rowbase + xhi + 1);
+            const uint32_t shift = mode ? s_seg_off[seg0 + k] - s_seg_gb[seg0 + k] : 0u;   // global slot -> staged index
+            row_qb[k] = __ldg(F.start + rowbase + xlo) + shift;
+            row_qe[k] = __ldg(F.start + rowbase + xhi + 1) + shift;
         } else {
             row_qb[k] = 0u;
             row_qe[k] = 0u;
         }
     }
-    auto for_each_neighbour = [&](auto&& fn) {
+    const uint32_t self_idx = p + (mode ? s_seg_off[seg0 + 1] - s_seg_gb[seg0 + 1] : 0u);
+    auto for_each_accepted = [&](auto&& fn) {   // candidates within the interaction range, in slot order
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
             const uint32_t qe = row_qe[k];
@@ -512,23 +597,25 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
             for (uint32_t q0 = row_qb[k]; q0 < qe; q0 += 4) {
                 float4 o[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) o[u] = __ldg(A.pos4 + min(q0 + u, qe - 1u));   // 4 independent loads in flight
+                for (int u = 0; u < 4; ++u) o[u] = cand_pos[min(q0 + u, qe - 1u)];   // 4 independent loads in flight
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t q = q0 + u;
                     const v2 dr = V(o[u].x, o[u].y) - r;
-                    if (q < qe && norm2(dr) < P.r_max2 && q != p) {
-                        const uint2 ok = __ldg(A.key2 + q);
-                        const int dxc = cs_cx(ok.y) - cxi;
-                        const int dyc = cs_cy(ok.y) - cyi;
-                        // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
-                        const int idx = (dxc + 1) * 3 + (dyc + 1);
-                        const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
-                        fn((rank << 28) | ok.x, q);
-                    }
+                    if (q < qe && norm2(dr) < P.r_max2 && q != self_idx) fn(q);
                 }
             }
         }
+    };
+    // ordering key of a neighbour: (visit rank of its 60-unit cell, gid)
+    auto key_of = [&](uint32_t q) -> uint32_t {
+        const uint2 ok = cand_key[q];
+        const int dxc = cs_cx(ok.y) - cxi;
+        const int dyc = cs_cy(ok.y) - cyi;
+        // calcNearestCells order (Grid.cpp:103-118): dx outer, dy inner, centre appended last (Strategy.cpp:34)
+        const int idx = (dxc + 1) * 3 + (dyc + 1);
+        const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
+        return (rank << 28) | ok.x;
     };
 
     v2 repulsion = V(0.f, 0.f), push = V(0.f, 0.f), scatter = V(0.f, 0.f), dr_nn = V(0.f, 0.f);
@@ -536,8 +623,8 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
     const float rscatter2 = P.rscatter * P.rscatter;
     // applyForces loop body, PhysicsSystem.cpp:69-102
     auto accumulate = [&](uint32_t q) {
-        const float4 o = __ldg(A.pos4 + q);
-        const int state_j = (int)(__ldg(A.key2 + q).y & 3u);
+        const float4 o = cand_pos[q];
+        const int state_j = (int)(cand_key[q].y & 3u);
         const v2 dr = V(o.x, o.y) - r;
         const float r_collision = o.z + radius;
         const float mass_j = o.w;
@@ -557,57 +644,77 @@ __global__ void __launch_bounds__(STEP_BLOCK) k_step(uint32_t n_bound, RtsParams
         }
     };
 
-    // Ordering: ONE scan of the candidates. The NBR_CAP smallest keys are kept sorted in shared memory; whatever does not
-    // fit (pushed out, or larger than everything kept) goes unsorted to a per-thread spill list in local memory. The kept
-    // keys are accumulated in order; then the spill — all of it larger than what was just used — is filtered through the
-    // same bounded insertion, NBR_CAP at a time, without touching the candidates again. Crowds beyond NBR_CAP+SPILL_CAP
-    // neighbours fall back to re-scanning the candidates above the last used key.
-    uint2 spill[SPILL_CAP];
-    int cnt = 0, kept = 0, n_spill = 0;
-    bool spill_lost = false;
-    auto offer = [&](uint2 e, bool to_spill) {   // bounded sorted insertion; the loser goes to the spill list
-        int pos;
-        if (kept < NBR_CAP) pos = kept++;
-        else {
-            uint2 out = e;
-            if (e.x < s_kq[NBR_CAP - 1][tid].x) { out = s_kq[NBR_CAP - 1][tid]; pos = NBR_CAP - 1; }
-            else pos = -1;
-            if (to_spill) {
-                if (n_spill < SPILL_CAP) spill[n_spill++] = out;
-                else spill_lost = true;
-            }
-            if (pos < 0) return;
-        }
-        while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
-            s_kq[pos][tid] = s_kq[pos - 1][tid];
-            --pos;
-        }
-        s_kq[pos][tid] = e;
-    };
-    for_each_neighbour([&](uint32_t key, uint32_t q) {
+    // Ordering. Common case (at most NBR_CAP neighbours): the scan only appends the accepted candidates to the shared
+    // memory list; keys are fetched and the list is insertion-sorted afterwards, when every lane of the warp is doing the
+    // same thing (sorting inside the scan ran with ~3 of 32 lanes active).
+    int cnt = 0;
+    for_each_accepted([&](uint32_t q) {
+        if (cnt < NBR_CAP) s_kq[cnt][tid].y = q;
         ++cnt;
-        offer(make_uint2(key, q), true);
     });
-    for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-    int done = kept;
-    if (!spill_lost) {
-        while (n_spill > 0) {   // rounds over the spill only
-            const int m = n_spill;
-            n_spill = 0;
-            kept = 0;
-            for (int k = 0; k < m; ++k) offer(spill[k], true);   // losers are re-appended at indices < k: in-place compaction
-            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-            done += kept;
+    if (cnt <= NBR_CAP) {
+        for (int k = 0; k < cnt; ++k) s_kq[k][tid].x = key_of(s_kq[k][tid].y);
+        for (int k = 1; k < cnt; ++k) {
+            const uint2 e = s_kq[k][tid];
+            int pos = k;
+            while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
+                s_kq[pos][tid] = s_kq[pos - 1][tid];
+                --pos;
+            }
+            s_kq[pos][tid] = e;
         }
+        for (int k = 0; k < cnt; ++k) accumulate(s_kq[k][tid].y);
     } else {
-        while (done < cnt) {    // very dense crowd: re-scan the candidates above the last key used
-            const uint32_t floor_key = s_kq[kept - 1][tid].x;
-            kept = 0;
-            for_each_neighbour([&](uint32_t key, uint32_t q) {
-                if (key > floor_key) offer(make_uint2(key, q), false);
-            });
-            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-            done += kept;
+        // Dense crowd: ONE more scan. The NBR_CAP smallest keys are kept sorted in shared memory; whatever does not fit
+        // (pushed out, or larger than everything kept) goes unsorted to a per-thread spill list in local memory. The kept
+        // keys are accumulated in order; then the spill — all of it larger than what was just used — is filtered through
+        // the same bounded insertion, NBR_CAP at a time, without touching the candidates again. Crowds beyond
+        // NBR_CAP+SPILL_CAP neighbours fall back to re-scanning the candidates above the last used key.
+        uint2 spill[SPILL_CAP];
+        int kept = 0, n_spill = 0;
+        bool spill_lost = false;
+        auto offer = [&](uint2 e, bool to_spill) {   // bounded sorted insertion; the loser goes to the spill list
+            int pos;
+            if (kept < NBR_CAP) pos = kept++;
+            else {
+                uint2 out = e;
+                if (e.x < s_kq[NBR_CAP - 1][tid].x) { out = s_kq[NBR_CAP - 1][tid]; pos = NBR_CAP - 1; }
+                else pos = -1;
+                if (to_spill) {
+                    if (n_spill < SPILL_CAP) spill[n_spill++] = out;
+                    else spill_lost = true;
+                }
+                if (pos < 0) return;
+            }
+            while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
+                s_kq[pos][tid] = s_kq[pos - 1][tid];
+                --pos;
+            }
+            s_kq[pos][tid] = e;
+        };
+        for_each_accepted([&](uint32_t q) { offer(make_uint2(key_of(q), q), true); });
+        for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+        int done = kept;
+        if (!spill_lost) {
+            while (n_spill > 0) {   // rounds over the spill only
+                const int m = n_spill;
+                n_spill = 0;
+                kept = 0;
+                for (int k = 0; k < m; ++k) offer(spill[k], true);   // losers are re-appended at indices < k: in-place compaction
+                for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+                done += kept;
+            }
+        } else {
+            while (done < cnt) {    // very dense crowd: re-scan the candidates above the last key used
+                const uint32_t floor_key = s_kq[kept - 1][tid].x;
+                kept = 0;
+                for_each_accepted([&](uint32_t q) {
+                    const uint32_t key = key_of(q);
+                    if (key > floor_key) offer(make_uint2(key, q), false);
+                });
+                for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+                done += kept;
+            }
         }
     }
 
