@@ -79,7 +79,8 @@ typedef struct RtsParams {
     /* tuning words, 0 = default: [0] 1 = do not keep the per-step merged velocity (RtsAgentView.vel reads 0)
        [1] fine gather-cell size as float bits (default 6.0, clamped to >= 1.05*sqrt(r_max2))
        [2] 1 = launch kernels one by one instead of replaying a CUDA graph of two frames
-       [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower) */
+       [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower)
+       [4] 1 = run the triangle walk on the main stream instead of overlapping it with the next frame on a second stream */
     uint32_t reserved[6];
 } RtsParams;
 

@@ -497,8 +497,11 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
         a->state[i] = (uint8_t)state;
         if (a->waypoint) a->waypoint[i] = wp;
         a->r_next[2 * i] = r_next.x; a->r_next[2 * i + 1] = r_next.y;
-        if (a->tri_idx && (P->walk_all || state == RTS_MOVING))
+        if (a->tri_idx && (P->walk_all || state == RTS_MOVING)) {
             a->tri_idx[i] = find_triangle(P, tris, n_tris, cell2tri, r_new.x, r_new.y, &flags);
+            if (a->tri_idx[i] == 0xFFFFFFFFu) flags |= RTS_FLAG_WALK_FAILED;   /* no containing triangle at all */
+            else flags &= ~(uint32_t)RTS_FLAG_WALK_FAILED;
+        }
         if (a->ns_cell) a->ns_cell[i] = (uint32_t)coord_to_cell(r_new.x, r_new.y, P->ns_nx, P->ns_ny, P->ns_cell_size);
         if (a->map_cell) a->map_cell[i] = (uint32_t)coord_to_cell(r_new.x, r_new.y, P->map_nx, P->map_ny, P->map_cell_size);
         if (a->flags) a->flags[i] = flags;

@@ -32,7 +32,7 @@ struct KernelTimer {  // per-kind CUDA-event timing of launches on the handle's 
     uint64_t launches = 0;
 };
 
-enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_EXCHANGE = 4, KT_INGEST = 5, KT_COUNT = 6 };
+enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_EXCHANGE = 4, KT_INGEST = 5, KT_WALK = 6, KT_COUNT = 7 };
 
 }  // namespace
 
@@ -58,16 +58,22 @@ struct RtsContext {
     size_t scratch_bytes = 0;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // the triangle walk runs on a second stream, overlapping the next frame kernel
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr;
+    bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
     uint64_t launches = 0, steps = 0;
     // step graph (two frames: the previous-order buffers ping-pong)
     cudaGraphExec_t graph2[2] = {nullptr, nullptr};   // one per ping-pong parity
     uint32_t graph_n[2] = {0, 0};
+    uint64_t graph_launches = 0;
     int parity = 0;
     bool use_graph = true;
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
+    bool overlap_walk = true;         // triangle walk on the side stream (reserved[4] = 1 turns it off)
     bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
@@ -173,6 +179,7 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
 #undef AL
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
     A.n_dev = h->n_dev;
+    A.n_tris_dev_hint = h->map_ready ? h->M.n_tris : 0u;
     h->cap = cap;
     h->drop_graphs();
     return RTS_OK;
@@ -234,20 +241,48 @@ void swap_prev_order(RtsContext* h) {
 }
 
 // scan of the counts + scatter into the new order; the "n" buffers become the previous-order arrays
+// main stream waits for the walk still running on the side stream (before anything overwrites pos4/key2/src/tri)
+int32_t join_walk(RtsContext* h) {
+    if (h->walk_pending) {
+        CU(cudaStreamWaitEvent(h->stream, h->ev_walk, 0));
+        h->walk_pending = false;
+    }
+    return RTS_OK;
+}
+
 int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t nb = blocks_for(h->F.n_cells, SCAN_TILE);
     timer_begin(h, KT_SCAN);
     k_scan_onepass<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
     timer_end(h, KT_SCAN);
+    int32_t rc = join_walk(h);   // the previous walk reads what the scatter is about to overwrite
+    if (rc != RTS_OK) return rc;
     timer_begin(h, KT_REORDER);
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
-    if (n_slots) {
-        if (h->M.coords_fit_i32) k_reorder<false><<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->P, h->M, h->F, h->A);
-        else k_reorder<true><<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->P, h->M, h->F, h->A);
-    }
+    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A);
     timer_end(h, KT_REORDER);
     h->launches += 2;
     swap_prev_order(h);
+    // triangle walk of the new order. With walk_all the next frame kernel never touches `tri`, so the walk goes to the
+    // side stream and overlaps it; otherwise (agents that are not walked copy their index) it stays on the main stream.
+    const uint32_t n_walk = h->multi ? h->cap_main : h->n;
+    if (n_walk && h->map_ready) {
+        const bool side = h->P.walk_all != 0 && h->overlap_walk && !h->profiling;
+        cudaStream_t st = side ? h->stream2 : h->stream;
+        if (side) {
+            CU(cudaEventRecord(h->ev_scatter, h->stream));
+            CU(cudaStreamWaitEvent(h->stream2, h->ev_scatter, 0));
+        }
+        timer_begin(h, KT_WALK);
+        if (h->M.coords_fit_i32) k_walk<false><<<blocks_for(n_walk, 256), 256, 0, st>>>(n_walk, h->P, h->M, h->A, h->multi ? 1 : 0);
+        else k_walk<true><<<blocks_for(n_walk, 256), 256, 0, st>>>(n_walk, h->P, h->M, h->A, h->multi ? 1 : 0);
+        timer_end(h, KT_WALK);
+        if (side) {
+            CU(cudaEventRecord(h->ev_walk, h->stream2));
+            h->walk_pending = true;
+        }
+        h->launches += 1;
+    }
     return RTS_OK;
 }
 
@@ -422,8 +457,12 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     if (params->reserved[1]) std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float));
     h->use_graph = params->reserved[2] == 0;
     h->staged = params->reserved[3] != 0;
+    h->overlap_walk = params->reserved[4] == 0;
     *out = h;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         *out = nullptr;
         delete h;
@@ -458,6 +497,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
 int32_t rts_destroy(RtsHandle h) {
     if (!h) return RTS_E_ARG;
     cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream2);
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
@@ -471,6 +511,8 @@ int32_t rts_destroy(RtsHandle h) {
         for (auto e : t.end) cudaEventDestroy(e);
     }
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_scatter); cudaEventDestroy(h->ev_walk);
+    cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
     return RTS_OK;
@@ -483,6 +525,7 @@ int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
     int32_t rc = check_params(h, params);
     if (rc != RTS_OK) return rc;
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     const bool regrid = params->map_nx != h->P.map_nx || params->map_ny != h->P.map_ny || params->r_max2 != h->P.r_max2 ||
                         params->map_cell_size != h->P.map_cell_size || params->slab_row_lo != h->P.slab_row_lo ||
                         params->slab_row_hi != h->P.slab_row_hi || params->ns_cell_size != h->P.ns_cell_size;
@@ -505,6 +548,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     if (!h) return RTS_E_ARG;
     if (!tris || !n_tris || !cell2tri || !walls) return h->fail(RTS_E_ARG, "rts_upload_map", "null table");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
     free_all(h->table_allocs);
     h->map_ready = false;
@@ -632,6 +676,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
     M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r;
     M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
+    h->A.n_tris_dev_hint = n_tris;
     M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
     h->map_ready = true;
     h->drop_graphs();
@@ -648,6 +693,7 @@ int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_
     if (!h) return RTS_E_ARG;
     if (!types || n_types == 0 || n_types > 256) return h->fail(RTS_E_ARG, "rts_upload_unit_types", "need 1..256 types");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
     RtsUnitType* d;
     void* old = const_cast<RtsUnitType*>(h->M.unit_types);
@@ -675,6 +721,7 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
     for (uint32_t p = 0; p < np; ++p)
         if (paths->offsets[p + 1] <= paths->offsets[p]) return h->fail(RTS_E_ARG, "rts_upload_paths", "every path needs at least one waypoint");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
     const uint32_t ng = paths->group ? paths->n_groups : np;
     std::vector<int32_t> grp(std::max<uint32_t>(np, 1), 0);
@@ -734,6 +781,7 @@ int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
     if (n && (!agents || !agents->r)) return h->fail(RTS_E_ARG, "rts_set_agents", "positions are required");
     if (n >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_set_agents", "more than 2^28 agents");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
     int32_t rc;
     if (h->multi) {
@@ -774,6 +822,7 @@ int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents) {
     if (h->gid_is_index && agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses component indices as gid");
     if (!h->gid_is_index && !agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses explicit gids");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     int32_t rc;
     if (h->n + m > h->cap) {
         // grow: keep the old arrays alive while the state is copied across
@@ -808,6 +857,7 @@ int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields) {
     if (!h || !fields) return RTS_E_ARG;
     if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_update_agents", "needs component-index gids");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     Staging S;
     int32_t rc = stage_in(h, fields, h->n, &S);
     if (rc != RTS_OK) return rc;
@@ -839,16 +889,23 @@ int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n) {
     return RTS_OK;
 }
 
+constexpr uint32_t GRAPH_FRAMES = 8;   // even (the previous-order buffers ping-pong); more frames = more walks overlapped
+
 static int32_t build_graph(RtsContext* h) {
     const int par = h->parity;
     if (h->graph2[par]) { cudaGraphExecDestroy(h->graph2[par]); h->graph2[par] = nullptr; }
+    int32_t rc = join_walk(h);
+    if (rc != RTS_OK) return rc;
     cudaGraph_t g = nullptr;
     const uint64_t launches0 = h->launches;
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    launch_frame(h);
-    launch_frame(h);   // two frames restore the ping-pong pointers
-    CU(cudaStreamEndCapture(h->stream, &g));
+    for (uint32_t f = 0; f < GRAPH_FRAMES && rc == RTS_OK; ++f) rc = launch_frame(h);
+    if (rc == RTS_OK) rc = join_walk(h);   // the side stream must rejoin before the capture ends
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+    h->graph_launches = h->launches - launches0;
     h->launches = launches0;
+    if (rc != RTS_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (ce != cudaSuccess) return h->fail(RTS_E_CUDA, "cudaStreamEndCapture", cudaGetErrorString(ce));
     CU(cudaGraphInstantiate(&h->graph2[par], g, 0));
     cudaGraphDestroy(g);
     h->graph_n[par] = h->n;
@@ -861,15 +918,17 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
-    if (h->use_graph && !h->profiling && !h->multi && n_steps >= 2) {
+    if (h->use_graph && !h->profiling && !h->multi && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
         if (!h->graph2[par] || h->graph_n[par] != h->n) {
             int32_t rc = build_graph(h);
             if (rc != RTS_OK) return rc;
         }
-        for (; done + 2 <= n_steps; done += 2) {
+        int32_t rc = join_walk(h);
+        if (rc != RTS_OK) return rc;
+        for (; done + GRAPH_FRAMES <= n_steps; done += GRAPH_FRAMES) {
             CU(cudaGraphLaunch(h->graph2[par], h->stream));
-            h->launches += 6;
+            h->launches += h->graph_launches;
         }
     }
     for (; done < n_steps; ++done) {
@@ -885,6 +944,10 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
 int32_t rts_sync(RtsHandle h) {
     if (!h) return RTS_E_ARG;
     CU(cudaSetDevice(h->device));
+    {
+        const int32_t rcj = join_walk(h);
+        if (rcj != RTS_OK) return rcj;
+    }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     timer_collect(h);
@@ -902,6 +965,7 @@ int32_t rts_sync(RtsHandle h) {
 int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     if (!h || !out) return RTS_E_ARG;
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     int32_t rc = alloc_staging(h, h->cap);
     if (rc != RTS_OK) return rc;
     Staging S = h->S;
@@ -1182,6 +1246,7 @@ int32_t rts_halo_begin(RtsHandle h) {
     if (!h) return RTS_E_ARG;
     if (!h->multi) return h->fail(RTS_E_STATE, "rts_halo_begin", "not a slab handle");
     CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(h->ex_send[d], 0, 16, h->stream));
     if (h->cap_main) k_halo_seed<<<blocks_for(h->cap_main, 256), 256, 0, h->stream>>>(h->cap_main, h->P, h->F, h->A, h->SL);
     h->launches += 1;

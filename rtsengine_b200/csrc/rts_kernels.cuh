@@ -3,7 +3,8 @@
 //
 //   k_bin      : fine-cell id + slot rank of freshly uploaded agents (warp-aggregated atomics)
 //   k_scan_*   : exclusive scan of the per-cell counts -> cell_start
-//   k_reorder  : counting-sort scatter of the neighbour record {pos4,key2} into cell order, builds src[]
+//   k_scatter  : counting-sort scatter of the neighbour record {pos4,key2} into cell order, builds src[]
+//   k_walk     : triangle walk of the new positions (second stream, overlaps the next frame kernel)
 //   k_step     : the fused frame — neighbour gather, boids forces, clamp/decay, wall pass, seek, merge,
 //                wall pass, integrate, triangle walk, re-bin of the new position
 //   k_gather   : slot order -> caller order for rts_download
@@ -115,6 +116,7 @@ struct AgentArrays {
     float2* vel_outn;
     uint2* cellrank;  // {next fine cell, rank inside it}
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
+    uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,41 +289,39 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
     }
 }
 
-// Counting-sort scatter of the neighbour record into the new cell order + the triangle walk
-// (Triangulation::findTriangle) of the new position.  Low register count, so the walk's dependent table loads
-// are hidden by occupancy instead of stalling the fat frame kernel.
-template <bool WIDE>
-__global__ void __launch_bounds__(256) k_reorder(uint32_t n, RtsParams P, MapDev M, FineGrid F, AgentArrays A) {
+// Counting-sort scatter of the neighbour record into the new cell order; builds src[].
+__global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned mask = __ballot_sync(0xffffffffu, p < n);
     if (p >= n) return;
     const uint2 cr = A.cellrank[p];
-    const bool live = cr.x != INVALID_CELL;   // ghosts / migrated agents are dropped
-    float4 pos = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint2 key = make_uint2(0u, 0u);
-    if (live) {
-        pos = A.pos4n[p];
-        key = A.key2n[p];
-        const uint32_t d = F.start[cr.x] + cr.y;
-        A.pos4[d] = pos;
-        A.key2[d] = key;
-        A.src[d] = p;
-    }
-    const bool want = live && M.n_tris != 0 && (P.walk_all || (key.y & 3u) == RTS_MOVING);   // no map uploaded yet: no walk
+    if (cr.x == INVALID_CELL) return;   // ghosts / migrated agents / unused slots are dropped
+    const uint32_t d = F.start[cr.x] + cr.y;
+    A.pos4[d] = A.pos4n[p];
+    A.key2[d] = A.key2n[p];
+    A.src[d] = p;
+}
+
+// The triangle walk (Triangulation::findTriangle) of the new positions, one thread per slot of the NEW order, writing
+// the previous-order `tri` array the next frame carries along. It only reads what the next frame kernel also only
+// reads (pos4, key2, src), so it runs on a second stream concurrently with the next frame kernel; its low register
+// count lets its warps fill the issue slots the divergent frame kernel leaves idle. A failed walk stores 0xFFFFFFFF.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_walk(uint32_t n_bound, RtsParams P, MapDev M, AgentArrays A, int multi) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = multi ? *A.n_dev : n_bound;
+    const unsigned mask = __ballot_sync(0xffffffffu, d < n);
+    if (d >= n) return;
+    const float4 pos = A.pos4[d];
+    const uint2 key = A.key2[d];
+    const bool ghost = (key.y >> 2) & 1u;
+    const bool want = !ghost && M.n_tris != 0 && (P.walk_all || (key.y & 3u) == RTS_MOVING);   // no map uploaded yet: no walk
     uint32_t flags = 0;
     uint32_t t;
     // the int32 walk needs |q| <= 16383 as well as the table bound checked at upload
     const bool small = fabsf(pos.x) <= 16383.f && fabsf(pos.y) <= 16383.f;
     if (!WIDE && __all_sync(mask, small || !want)) t = find_triangle_warp<false>(M, P, want, pos.x, pos.y, flags, mask);
     else t = find_triangle_warp<true>(M, P, want, pos.x, pos.y, flags, mask);
-    if (want) {
-        A.trin[p] = t;
-        if (flags) {
-            float4 nav = A.nav4n[p];
-            nav.w = __uint_as_float(__float_as_uint(nav.w) | (flags << 28));
-            A.nav4n[p] = nav;
-        }
-    }
+    if (want) A.tri[A.src[d]] = t;
 }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     const v2 r_new = r + v * P.dt;
     angle = angle + angle_vel;
 
-    // ---- K7 (triangle walk on the new position) runs in k_reorder; agents that are not walked keep their index
+    // ---- K7 (triangle walk on the new position) runs in k_walk; agents that are not walked keep their index
     if (!(P.walk_all || state_out == RTS_MOVING)) A.trin[p] = A.tri[sp];
 
     // ---- write the new record at this slot; bin it for the next order
@@ -906,7 +906,8 @@ __global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int 
     if (S.ns_cell) S.ns_cell[o] = (uint32_t)cs_cx(key.y) + (uint32_t)cs_cy(key.y) * (uint32_t)P.ns_nx;
     if (S.map_cell) S.map_cell[o] = coord_to_cell(pos.x, pos.y, P.map_nx, P.map_ny, P.map_cell_size);
     if (S.flags) {
-        S.flags[o] = (misc >> 28) & 0xFu;
+        const bool walked = P.walk_all || (key.y & 3u) == RTS_MOVING;
+        S.flags[o] = ((misc >> 28) & 0xFu) | ((walked && A.tri[sp] == 0xFFFFFFFFu && A.n_tris_dev_hint) ? (uint32_t)RTS_FLAG_WALK_FAILED : 0u);
         if (clear_replan) A.nav4[sp].w = __uint_as_float(misc & ~((uint32_t)RTS_FLAG_REPLAN << 28));
     }
 }
