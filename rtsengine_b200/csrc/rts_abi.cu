@@ -217,15 +217,16 @@ int32_t setup_fine_grid(RtsContext* h) {
     F.ny = (int32_t)(y_hi / cs) + 2 - F.row0;
     F.n_cells = (uint32_t)F.nx * (uint32_t)F.ny;
     if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); cudaFree(h->F.status); cudaFree(h->F.ticket); }
-    CU(cudaMalloc(&F.status, sizeof(unsigned long long) * (blocks_for(F.n_cells, SCAN_TILE) + 1)));
+    CU(cudaMalloc(&F.status, sizeof(unsigned long long) * (blocks_for(F.n_cells + 8, SCAN_TILE) + 1)));
     CU(cudaMalloc(&F.ticket, 16));
-    CU(cudaMemsetAsync(F.status, 0, sizeof(unsigned long long) * (blocks_for(F.n_cells, SCAN_TILE) + 1), h->stream));
+    CU(cudaMemsetAsync(F.status, 0, sizeof(unsigned long long) * (blocks_for(F.n_cells + 8, SCAN_TILE) + 1), h->stream));
     CU(cudaMemsetAsync(F.ticket, 0, 16, h->stream));
-    CU(cudaMalloc(&F.count, sizeof(uint32_t) * F.n_cells));
-    CU(cudaMalloc(&F.start, sizeof(uint32_t) * (F.n_cells + 1)));
+    const size_t n_pad = ((size_t)F.n_cells + 1 + 7) & ~(size_t)7;   // see k_scan_onepass
+    CU(cudaMalloc(&F.count, sizeof(uint32_t) * n_pad));
+    CU(cudaMalloc(&F.start, sizeof(uint32_t) * n_pad));
     CU(cudaMalloc(&F.partial, sizeof(uint32_t) * (blocks_for(F.n_cells, SCAN_TILE) + 1)));
-    CU(cudaMemsetAsync(F.count, 0, sizeof(uint32_t) * F.n_cells, h->stream));
-    CU(cudaMemsetAsync(F.start, 0, sizeof(uint32_t) * (F.n_cells + 1), h->stream));
+    CU(cudaMemsetAsync(F.count, 0, sizeof(uint32_t) * n_pad, h->stream));
+    CU(cudaMemsetAsync(F.start, 0, sizeof(uint32_t) * n_pad, h->stream));
     h->F = F;
     h->drop_graphs();
     return RTS_OK;
@@ -251,7 +252,7 @@ int32_t join_walk(RtsContext* h) {
 }
 
 int32_t launch_scan_reorder(RtsContext* h) {
-    const uint32_t nb = blocks_for(h->F.n_cells, SCAN_TILE);
+    const uint32_t nb = blocks_for(((h->F.n_cells + 1u + 7u) & ~7u), SCAN_TILE);
     timer_begin(h, KT_SCAN);
     k_scan_onepass<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
     timer_end(h, KT_SCAN);

@@ -135,9 +135,9 @@ __global__ void k_bin(uint32_t n, RtsParams P, FineGrid F, AgentArrays A) {
     A.cellrank[p] = make_uint2(cell, rank);
 }
 
-// ---- scan: 1024 cells per CTA (256 threads x 4) ----
+// ---- scan: 2048 cells per CTA (256 threads x 8) ----
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem) {
@@ -160,6 +160,7 @@ __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem)
 // only ever waits for tiles that already started; flags carry an epoch, so nothing is reset between launches (the
 // kernel is replayed from a CUDA graph with frozen arguments).
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint32_t* n_out) {
+    static_assert(SCAN_ITEMS == 8, "two uint4 per thread");
     __shared__ uint32_t smem[32];
     __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
     __shared__ uint32_t s_tile, s_prefix, s_epoch;
@@ -169,15 +170,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint3
     }
     __syncthreads();
     const uint32_t tile = s_tile, epoch = s_epoch;
-    const uint32_t n_tiles = (F.n_cells + SCAN_TILE - 1) / SCAN_TILE;
+    // count[] and start[] are padded to n_pad = a multiple of 8 >= n_cells + 1 (padding counts are 0), so every thread
+    // moves two aligned uint4 and start[n_cells] = total falls out of the scan
+    const uint32_t n_pad = (F.n_cells + 1u + 7u) & ~7u;
+    const uint32_t n_tiles = (n_pad + SCAN_TILE - 1) / SCAN_TILE;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
+    if (base < n_pad) {
+        const uint4 a = *reinterpret_cast<const uint4*>(F.count + base), b = *reinterpret_cast<const uint4*>(F.count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = 0u;
+    }
     uint32_t s = 0;
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        v[i] = (base + i < F.n_cells) ? F.count[base + i] : 0u;
-        s += v[i];
-    }
+    for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
     const uint32_t aggregate = block_reduce_sum(s, smem);
     // publish this tile's sum, then add up the sums of all earlier tiles (they all hold a ticket, so they will publish);
     // every thread polls a strided share of them, so the wait is one round trip, not a chain
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint3
     uint32_t before = 0;
     for (uint32_t j = threadIdx.x; j < tile; j += SCAN_THREADS) {
         unsigned long long wv;
-        do { wv = atomicAdd(F.status + j, 0ull); } while ((uint32_t)(wv >> 32) != flag_now);
+        do { wv = *((volatile unsigned long long*)(F.status + j)); } while ((uint32_t)(wv >> 32) != flag_now);   // plain L2 reads
         before += (uint32_t)wv;
     }
     before = block_reduce_sum(before, smem);
@@ -211,17 +219,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint3
     }
     __syncthreads();
     uint32_t run = s_prefix + warp_tot[w] + (incl - s);
+    if (base < n_pad) {
+        uint32_t o[SCAN_ITEMS];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < F.n_cells) {
-            F.start[base + i] = run;
-            F.count[base + i] = 0u;
-            run += v[i];
-        }
-    }
-    if (base <= F.n_cells - 1 && F.n_cells - 1 < base + SCAN_ITEMS) {   // owner of the last cell closes the CSR
-        F.start[F.n_cells] = run;
-        if (n_out) *n_out = run;
+        for (int i = 0; i < SCAN_ITEMS; ++i) { o[i] = run; run += v[i]; }
+        *reinterpret_cast<uint4*>(F.start + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(F.start + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<uint4*>(F.count + base) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(F.count + base + 4) = make_uint4(0u, 0u, 0u, 0u);
+        if (n_out && base <= F.n_cells && F.n_cells < base + SCAN_ITEMS) *n_out = o[F.n_cells - base];   // = total
     }
     if (tile == n_tiles - 1 && threadIdx.x == 0) {   // every tile has read the epoch and taken its ticket by now
         F.ticket[0] = 0u;
@@ -647,14 +653,18 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     // Ordering. Common case (at most NBR_CAP neighbours): the scan only appends the accepted candidates to the shared
     // memory list; keys are fetched and the list is insertion-sorted afterwards, when every lane of the warp is doing the
     // same thing (sorting inside the scan ran with ~3 of 32 lanes active).
+    // Accepted candidates beyond NBR_CAP are parked (index only) in a per-thread list in local memory.
+    uint2 spill[SPILL_CAP];
     int cnt = 0;
     for_each_accepted([&](uint32_t q) {
         if (cnt < NBR_CAP) s_kq[cnt][tid].y = q;
+        else if (cnt - NBR_CAP < SPILL_CAP) spill[cnt - NBR_CAP].y = q;
         ++cnt;
     });
-    if (cnt <= NBR_CAP) {
-        for (int k = 0; k < cnt; ++k) s_kq[k][tid].x = key_of(s_kq[k][tid].y);
-        for (int k = 1; k < cnt; ++k) {
+    {   // keys + insertion sort of the shared-memory part, every lane in step
+        const int m = min(cnt, NBR_CAP);
+        for (int k = 0; k < m; ++k) s_kq[k][tid].x = key_of(s_kq[k][tid].y);
+        for (int k = 1; k < m; ++k) {
             const uint2 e = s_kq[k][tid];
             int pos = k;
             while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
@@ -663,16 +673,15 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
             }
             s_kq[pos][tid] = e;
         }
+    }
+    if (cnt <= NBR_CAP) {
         for (int k = 0; k < cnt; ++k) accumulate(s_kq[k][tid].y);
     } else {
-        // Dense crowd: ONE more scan. The NBR_CAP smallest keys are kept sorted in shared memory; whatever does not fit
-        // (pushed out, or larger than everything kept) goes unsorted to a per-thread spill list in local memory. The kept
-        // keys are accumulated in order; then the spill — all of it larger than what was just used — is filtered through
-        // the same bounded insertion, NBR_CAP at a time, without touching the candidates again. Crowds beyond
-        // NBR_CAP+SPILL_CAP neighbours fall back to re-scanning the candidates above the last used key.
-        uint2 spill[SPILL_CAP];
-        int kept = 0, n_spill = 0;
-        bool spill_lost = false;
+        // Dense crowd. Shared memory keeps the NBR_CAP smallest keys, sorted; an entry that does not fit (pushed out, or
+        // larger than everything kept) goes back to the spill list. The kept keys are accumulated in order; then the
+        // spill — all of it larger than what was just used — is filtered through the same bounded insertion, NBR_CAP at
+        // a time. Only crowds beyond NBR_CAP+SPILL_CAP neighbours re-scan the candidates (above the last used key).
+        int kept = NBR_CAP, n_spill = 0;
         auto offer = [&](uint2 e, bool to_spill) {   // bounded sorted insertion; the loser goes to the spill list
             int pos;
             if (kept < NBR_CAP) pos = kept++;
@@ -680,10 +689,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
                 uint2 out = e;
                 if (e.x < s_kq[NBR_CAP - 1][tid].x) { out = s_kq[NBR_CAP - 1][tid]; pos = NBR_CAP - 1; }
                 else pos = -1;
-                if (to_spill) {
-                    if (n_spill < SPILL_CAP) spill[n_spill++] = out;
-                    else spill_lost = true;
-                }
+                if (to_spill) spill[n_spill++] = out;   // n_spill never overtakes the read index: in-place compaction
                 if (pos < 0) return;
             }
             while (pos > 0 && s_kq[pos - 1][tid].x > e.x) {
@@ -692,20 +698,28 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
             }
             s_kq[pos][tid] = e;
         };
-        for_each_accepted([&](uint32_t q) { offer(make_uint2(key_of(q), q), true); });
-        for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-        int done = kept;
-        if (!spill_lost) {
+        if (cnt <= NBR_CAP + SPILL_CAP) {
+            const int m0 = cnt - NBR_CAP;
+            for (int k = 0; k < m0; ++k) {
+                const uint32_t q = spill[k].y;
+                offer(make_uint2(key_of(q), q), true);
+            }
+            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
             while (n_spill > 0) {   // rounds over the spill only
                 const int m = n_spill;
                 n_spill = 0;
                 kept = 0;
-                for (int k = 0; k < m; ++k) offer(spill[k], true);   // losers are re-appended at indices < k: in-place compaction
+                for (int k = 0; k < m; ++k) offer(spill[k], true);
                 for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
-                done += kept;
             }
         } else {
-            while (done < cnt) {    // very dense crowd: re-scan the candidates above the last key used
+            // very dense crowd: the sorted list holds the NBR_CAP smallest of the FIRST NBR_CAP accepted only; rebuild it
+            // over all candidates, then keep re-scanning above the last key used
+            kept = 0;
+            for_each_accepted([&](uint32_t q) { offer(make_uint2(key_of(q), q), false); });
+            for (int k = 0; k < kept; ++k) accumulate(s_kq[k][tid].y);
+            int done = kept;
+            while (done < cnt) {
                 const uint32_t floor_key = s_kq[kept - 1][tid].x;
                 kept = 0;
                 for_each_accepted([&](uint32_t q) {
