@@ -117,6 +117,16 @@ __device__ __forceinline__ float idot(iv2 a, iv2 b) {  // dot<Vertex>, core.h:99
     if (WIDE) return (float)((int64_t)a.x * b.x + (int64_t)a.y * b.y);
     return (float)(a.x * b.x + a.y * b.y);
 }
+// RN(N / D) in [0, 1] for finite floats N, D — decided without dividing, exactly:
+//   D == 0          -> the quotient is +-inf or NaN: false
+//   N == 0          -> +-0: true
+//   opposite signs  -> negative (no underflow: |N| >= 1 here... any nonzero finite quotient keeps its sign): false
+//   same signs      -> RN(q) <= 1  <=>  q <= 1 + 2^-24 (the tie rounds to even = 1). |N| <= |D| gives q <= 1. |N| > |D|
+//                      means |N| >= |D| + ulp(|D|), and ulp(|D|)/|D| > 2^-24 strictly (|D| < 2^(e+1)), so q > 1 + 2^-24.
+//   Hence the quotient is in [0,1]  <=>  D != 0 and (N == 0 or (sign N == sign D and |N| <= |D|)).
+__device__ __forceinline__ bool quotient_in_unit_interval(float N, float D) {
+    return (D > 0.f && N >= 0.f && N <= D) || (D < 0.f && N <= 0.f && N >= D);
+}
 template <bool WIDE>
 __device__ __forceinline__ bool lines_intersect(iv2 v11, iv2 v12, iv2 v21, iv2 v22) {  // Triangulation.cpp:1805-1818
     const iv2 dr{v21.x - v11.x, v21.y - v11.y};
@@ -124,9 +134,11 @@ __device__ __forceinline__ bool lines_intersect(iv2 v11, iv2 v12, iv2 v21, iv2 v
     const iv2 t2{v22.x - v21.x, v22.y - v21.y};
     const iv2 n1{t1.y, -t1.x};
     const iv2 n2{t2.y, -t2.x};
-    const float alpha1 = +idot<WIDE>(dr, n2) / idot<WIDE>(t1, n2);
-    const float alpha2 = -idot<WIDE>(dr, n1) / idot<WIDE>(t2, n1);
-    return alpha1 >= 0 && alpha1 <= 1 && alpha2 >= 0 && alpha2 <= 1;
+    // alpha1 = +dot(dr,n2)/dot(t1,n2), alpha2 = -dot(dr,n1)/dot(t2,n1), both required in [0,1]; the dots are integers
+    // converted to float as in the reference (dot<Vertex> returns float, core.h:99), the two IEEE divisions are replaced
+    // by the equivalent comparisons above
+    return quotient_in_unit_interval(+idot<WIDE>(dr, n2), idot<WIDE>(t1, n2)) &&
+           quotient_in_unit_interval(-idot<WIDE>(dr, n1), idot<WIDE>(t2, n1));
 }
 
 __device__ __forceinline__ void load_tri_verts(const MapDev& M, uint32_t t, iv2& a, iv2& b, iv2& c, int4& w1) {
