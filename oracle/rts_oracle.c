@@ -109,6 +109,7 @@ static inline int nxt(int i) { return i == 2 ? 0 : i + 1; }
 static inline int prv(int i) { return i == 0 ? 2 : i - 1; }
 
 static long g_walk_brute = 0, g_walk_hops = 0, g_walk_calls = 0;
+static _Thread_local uint32_t g_last_hops = 0;
 void rts_oracle_walk_stats(long* out, int reset) {
     out[0] = g_walk_calls; out[1] = g_walk_hops; out[2] = g_walk_brute;
     if (reset) g_walk_calls = g_walk_hops = g_walk_brute = 0;
@@ -141,7 +142,9 @@ static uint32_t find_triangle(const RtsParams* P, const RtsTriangle* tris, uint3
     }
     if (t == 0xFFFFFFFFu) return brute_force(q, tris, n_tris); /* :1539-1546 */
     uint32_t hops = 0;
+    g_last_hops = 0;
     while (!in_triangle(q, &tris[t])) { /* fan walk, :1548-1563 */
+        g_last_hops++;
         const RtsTriangle* T = &tris[t];
         int k = -1;
         if (T->vx[0] == vc.x && T->vy[0] == vc.y) k = 0;
@@ -159,6 +162,9 @@ static uint32_t find_triangle(const RtsParams* P, const RtsTriangle* tris, uint3
     return t;
 }
 
+/* diagnostic: fan-walk hops per query point (serial) */
+void rts_oracle_walk_hops(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
+                          const float* xy, uint32_t n, uint32_t* hops_out);
 void rts_oracle_find_triangles(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
                                const float* xy, uint32_t n, uint32_t* out) {
 #pragma omp parallel for schedule(static)
@@ -554,3 +560,12 @@ void rts_oracle_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
 }
 
 int rts_oracle_threads(void) { return omp_get_max_threads(); }
+
+void rts_oracle_walk_hops(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
+                          const float* xy, uint32_t n, uint32_t* hops_out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        g_last_hops = 0;
+        (void)find_triangle(P, tris, n_tris, cell2tri, xy[2 * i], xy[2 * i + 1], 0);
+        hops_out[i] = g_last_hops;
+    }
+}
