@@ -919,6 +919,7 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
+    // (not for slab handles: capturing ncclSend/ncclRecv into the graph measured slower than launching frame by frame)
     if (h->use_graph && !h->profiling && !h->multi && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
         if (!h->graph2[par] || h->graph_n[par] != h->n) {
