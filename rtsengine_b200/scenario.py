@@ -41,13 +41,13 @@ def occupancy(fx: dict, margin_cells: int = 1) -> np.ndarray:
     return occ
 
 
-def free_positions(fx: dict, n: int, rng: np.random.Generator, lo=None, hi=None) -> np.ndarray:
+def free_positions(fx: dict, n: int, rng: np.random.Generator, lo=None, hi=None, margin_cells: int = 1) -> np.ndarray:
     """uniform over free space by rejection with a one-cell margin (radius+1 <= 6 units for the largest unit type)"""
     nx, ny = (int(v) for v in fx["n_cells"])
     W, Hh = nx * 5.0, ny * 5.0
     lo = np.array([8.0, 8.0]) if lo is None else np.asarray(lo, float)
     hi = np.array([W - 8.0, Hh - 8.0]) if hi is None else np.asarray(hi, float)
-    occ = occupancy(fx)
+    occ = occupancy(fx, margin_cells)
     out = np.empty((n, 2), np.float32)
     filled = 0
     while filled < n:
@@ -106,7 +106,7 @@ def config2_agents(fx: dict, n: int = 100_000, seed: int = 1235):
     UnitTypes.txt, 50 % MOVING in 16 command groups."""
     rng = np.random.default_rng(seed)
     a = _blank(n)
-    a["r"][:] = free_positions(fx, n, rng)
+    a["r"][:] = free_positions(fx, n, rng, margin_cells=0)      # right up to the walls: some agents start in contact
     a["angle"][:] = rng.uniform(-180, 180, n)
     big = rng.random(n) < 0.2
     a["radius"][:] = np.where(big, 5.0, 3.0)

@@ -311,3 +311,87 @@ def test_arrival_rule_matches_oracle_and_tracks_the_reference_cascade():
             standing.append(int((out["state"] == abi.STANDING).sum()))
         assert standing[0] == 0 and standing[-1] > 0.9 * n and sorted(standing) == standing
         assert (out["path_id"][out["state"] == abi.STANDING] == -1).all()
+
+
+def test_baseline_config1_1000_frames():
+    """BASELINE configs[0]: 2 000 agents, boids + seek on an empty 512x512 map, 1 000 frames — bit-exact vs the oracle at
+    the end (the verbatim reference runs the same case in bench.py --impl reference / tests/test_oracle_vs_ref.py)."""
+    from rtsengine_b200 import scenario
+    fx = H.load("map_empty.npz")
+    tables = H.tables_of(fx)
+    a0, paths = scenario.config1_agents()
+    a = abi.alloc_agent_arrays(len(a0["r"]), set(H.ALL_FIELDS))
+    for k, v in a0.items():
+        a[k][:] = v
+    ref = {k: v.copy() for k, v in a.items()}
+    ow = port.OracleWorld(port.default_params(512, 512), tables, paths)
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        for chunk in range(4):
+            ow.step(ref, 250)
+            g.update(250)
+            out = g.communicate(("r", "inertia", "angle", "angle_vel", "tri_idx", "ns_cell"))
+            for k in out:
+                H.assert_same_bits(out[k], ref[k], f"frame {250 * (chunk + 1)} {k}")
+    assert np.isfinite(ref["r"]).all() and np.linalg.norm(ref["r"] - a0["r"], axis=1).min() > 500   # they all travelled
+
+
+def test_baseline_config2_100k_mixed_units():
+    """BASELINE configs[1]: 100k agents, unit mix of UnitTypes.txt (radius 3 / mass 1 and radius 5 / mass 50), 1024x1024
+    map with 200 buildings, half of them MOVING in 16 groups — 5 frames bit-exact vs the oracle, every agent."""
+    from rtsengine_b200 import scenario
+    fx = H.load("map_c3.npz")
+    tables = H.tables_of(fx)
+    a0, paths = scenario.config2_agents(fx, n=100_000)
+    a = abi.alloc_agent_arrays(len(a0["r"]), set(H.ALL_FIELDS))
+    for k, v in a0.items():
+        a[k][:] = v
+    ref = {k: v.copy() for k, v in a.items()}
+    ow = port.OracleWorld(port.default_params(1024, 1024), tables, paths)
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "tri_idx", "ns_cell", "map_cell", "r_next", "waypoint", "flags")
+    with make_system(tables, paths, map_cells=(1024, 1024)) as g:
+        g.set_agents(a)
+        for s in range(5):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(out[k], ref[k], f"frame {s} {k}")
+    walls = port.OracleWorld(port.default_params(1024, 1024), tables, paths).contact_edges(a0["r"], a0["radius"])[0]
+    assert (walls > 0).sum() > 50          # the case has agents in contact with building walls
+
+
+def test_baseline_config4_map_tiles_wide_arithmetic():
+    """BASELINE configs[3] geometry at reduced population: an 8x8-tile map (8192x8192 cells, 12 800 buildings, coordinates
+    up to 40 960 so the triangle walk takes the 64-bit product path), 2M agents, 2 frames: integration identity, cell and
+    triangle indices of every agent vs the oracle, and a re-simulated window bit-exact."""
+    from rtsengine_b200 import scenario
+    tile = H.load("map_c3.npz")
+    fx = scenario.tile_map(tile, 8, 8)
+    tables = scenario.tables_of(fx)
+    paths = scenario.paths_of(fx)
+    a0 = scenario.tiled_agents(tile, 8, 8, 2_000_000 // 64, seed=1237)
+    n = len(a0["r"])
+    p = engine.default_params(8192, 8192)
+    assert (p.ns_nx, p.tri_nx) == (683, 1024)
+    with engine.GpuAgentSystem(p) as g:
+        g.upload_map(tables)
+        g.upload_paths(paths)
+        g.set_agents(a0)
+        g.update(1)
+        out = g.communicate(("r", "vel", "inertia", "tri_idx", "ns_cell", "map_cell", "flags"))
+        assert np.isfinite(out["r"]).all()
+        H.assert_same_bits(out["r"], a0["r"] + out["vel"] * np.float32(p.dt), "r' = r + v dt")
+        H.assert_same_bits(out["ns_cell"], port.coord_to_cell(out["r"], p.ns_nx, p.ns_ny, 60.0), "ns cell")
+        H.assert_same_bits(out["map_cell"], port.coord_to_cell(out["r"], 8192, 8192, 5.0), "map cell")
+        ow = port.OracleWorld(port.default_params(8192, 8192), tables, paths)
+        H.assert_same_bits(out["tri_idx"], ow.find_triangles(out["r"]), "triangle index of every agent")
+        lo, hi = np.array([30000.0, 36000.0]), np.array([31200.0, 37200.0])      # far corner: large coordinates
+        idx = np.nonzero(((a0["r"] >= lo) & (a0["r"] < hi)).all(1))[0]
+        sub = {k: np.ascontiguousarray(v[idx]) for k, v in a0.items()}
+        sub.update(abi.alloc_agent_arrays(len(idx), abi.DOWNLOAD_ONLY))
+        ow.step(sub)
+        core = ((a0["r"][idx] >= lo + 6) & (a0["r"][idx] < hi - 6)).all(1)
+        assert core.sum() > 500
+        for k in ("r", "vel", "inertia", "tri_idx"):
+            H.assert_same_bits(out[k][idx][core], sub[k][core], f"window {k}")
