@@ -632,7 +632,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     if ((rc = dev_alloc(h, &d_bits, bits.size(), h->table_allocs)) != RTS_OK) return rc;
     CU(cudaMemcpyAsync(d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // scan lists for findTriangle's linear-scan fallback (see MapDev)
-    std::vector<uint32_t> scan_off(n_tri_cells + 1, 0u), scan_list, scan_large;
+    std::vector<uint32_t> scan_off(n_tri_cells + 1, 0u), scan_list, scan_large, scan_outer;
     {
         auto cell_range = [&](int32_t lo, int32_t hi, int32_t n, int& c0, int& c1) {
             c0 = (int)std::floor((float)lo / P.tri_cell_size);
@@ -644,6 +644,12 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
         std::vector<uint8_t> large(n_tris, 0);
         for (uint32_t t = 0; t < n_tris; ++t) {
             const RtsTriangle& T = tris[t];
+            {
+                const float gw = P.tri_nx * P.tri_cell_size, gh = P.tri_ny * P.tri_cell_size;
+                const int32_t xmin = std::min({T.vx[0], T.vx[1], T.vx[2]}), xmax = std::max({T.vx[0], T.vx[1], T.vx[2]});
+                const int32_t ymin = std::min({T.vy[0], T.vy[1], T.vy[2]}), ymax = std::max({T.vy[0], T.vy[1], T.vy[2]});
+                if (xmin < 0 || ymin < 0 || (float)xmax > gw || (float)ymax > gh) scan_outer.push_back(t);
+            }
             cell_range(std::min({T.vx[0], T.vx[1], T.vx[2]}), std::max({T.vx[0], T.vx[1], T.vx[2]}), P.tri_nx, bx0[t], bx1[t]);
             cell_range(std::min({T.vy[0], T.vy[1], T.vy[2]}), std::max({T.vy[0], T.vy[1], T.vy[2]}), P.tri_ny, by0[t], by1[t]);
             if (bx0[t] > bx1[t] || by0[t] > by1[t]) continue;   // entirely outside the grid
@@ -661,7 +667,9 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
                 for (int x = bx0[t]; x <= bx1[t]; ++x) scan_list[fill[(size_t)y * P.tri_nx + x]++] = t;
         }
     }
-    uint32_t *d_soff, *d_slist, *d_slarge;
+    uint32_t *d_soff, *d_slist, *d_slarge, *d_souter;
+    if ((rc = dev_alloc(h, &d_souter, scan_outer.size(), h->table_allocs)) != RTS_OK) return rc;
+    if (!scan_outer.empty()) CU(cudaMemcpyAsync(d_souter, scan_outer.data(), scan_outer.size() * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = dev_alloc(h, &d_soff, scan_off.size(), h->table_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_slist, scan_list.size(), h->table_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_slarge, scan_large.size(), h->table_allocs)) != RTS_OK) return rc;
@@ -679,6 +687,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
     h->A.n_tris_dev_hint = n_tris;
     M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
+    M.scan_outer = d_souter; M.n_scan_outer = (uint32_t)scan_outer.size();
     h->map_ready = true;
     h->drop_graphs();
     if (h->n) {   // agents uploaded before the map: give them their triangle index now

@@ -49,6 +49,8 @@ struct MapDev {
     const uint32_t* __restrict__ scan_list;
     const uint32_t* __restrict__ scan_large;
     uint32_t n_scan_large;
+    const uint32_t* __restrict__ scan_outer;   // triangles reaching beyond the cache grid (the super-triangle fan)
+    uint32_t n_scan_outer;
 };
 constexpr uint32_t SCAN_LARGE_CELLS = 1024;
 constexpr float WALL_BLOCK = 20.f;
@@ -174,6 +176,7 @@ __device__ __forceinline__ uint32_t find_triangle_walk(const MapDev& M, const Rt
     if (t == TRI_NONE) return TRI_NEED_SCAN;
     const uint32_t hop_limit = 4 * M.n_tris + 16;
     for (uint32_t hops = 0;; ++hops) {  // fan walk around vc, :1548-1563
+        const int4 w2 = __ldg(M.tris + 3 * (size_t)t + 2);   // issued with the two vertex words: one round trip per hop
         load_tri_verts(M, t, a, b, c, w1);
         if (in_triangle<WIDE>(q, a, b, c)) return t;
         int k = -1;
@@ -184,7 +187,7 @@ __device__ __forceinline__ uint32_t find_triangle_walk(const MapDev& M, const Rt
             flags |= RTS_FLAG_WALK_FAILED;
             return TRI_NONE;
         }
-        const uint32_t n2 = (uint32_t)__ldg(M.tris + 3 * (size_t)t + 2).x;
+        const uint32_t n2 = (uint32_t)w2.x;
         const uint32_t nb0 = (uint32_t)w1.z, nb1 = (uint32_t)w1.w;
         const int kn = (k == 2) ? 0 : k + 1, kp = (k == 0) ? 2 : k - 1;
         const iv2 vn = (kn == 0) ? a : (kn == 1) ? b : c;
@@ -202,7 +205,25 @@ __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const Rt
                                                        uint32_t& flags, unsigned mask) {
     const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
     uint32_t t = TRI_NONE;
-    if (want) t = find_triangle_walk<WIDE>(M, P, q, flags);
+    bool done = false;
+    if (want && M.scan_off) {
+        // A query outside the cache grid (an agent pushed over the map edge: the reference has no outer wall) gets its
+        // start triangle from a cell index wrapped modulo the grid (Grid.cpp:18-24), i.e. from the far side of the map,
+        // and the walk needs 100+ hops. Out there only the few triangles of the super-triangle fan exist. If the
+        // query lies STRICTLY inside one of them, that triangle is the only one containing it, so every walk ends there.
+        const float cxf = floorf((float)q.x / P.tri_cell_size), cyf = floorf((float)q.y / P.tri_cell_size);
+        if (!(cxf >= 0.f && cyf >= 0.f && cxf < (float)P.tri_nx && cyf < (float)P.tri_ny)) {
+            for (uint32_t k = 0; k < M.n_scan_outer && !done; ++k) {
+                const uint32_t i = __ldg(M.scan_outer + k);
+                iv2 a, b, c;
+                int4 w1;
+                load_tri_verts(M, i, a, b, c, w1);
+                const float d1 = tri_sign<WIDE>(q, a, b), d2 = tri_sign<WIDE>(q, b, c), d3 = tri_sign<WIDE>(q, c, a);
+                if ((d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0)) { t = i; done = true; }
+            }
+        }
+    }
+    if (want && !done) t = find_triangle_walk<WIDE>(M, P, q, flags);
     if (want && t == TRI_NEED_SCAN && M.scan_off) {
         // the reference scans every triangle in index order; a triangle that contains q has q inside its bounding box,
         // so only the triangles listed for q's cache cell (and the large ones) can be the answer
