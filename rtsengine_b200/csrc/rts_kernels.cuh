@@ -465,6 +465,212 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
     }
 }
 
+// Per-neighbour force terms of applyForces (PhysicsSystem.cpp:69-102): computed for one neighbour, then added to the
+// running sums in the reference's visit order. Split in two so that a warp can compute the terms of many neighbours in
+// parallel and still add them up in order (k_step_dense).
+struct ForceSums {
+    v2 repulsion, push, dr_nn;
+    float n_neighbours;
+};
+struct ForceTerms {
+    v2 rep, push, dr;
+    uint32_t mask;   // bit 0: repulsion term present, bit 1: push term, bit 2: scatter contribution
+};
+__device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float mass_i, int state_i, float4 o, int state_j, float rscatter2) {
+    ForceTerms t;
+    t.mask = 0u;
+    t.rep = V(0.f, 0.f);
+    t.push = V(0.f, 0.f);
+    const v2 dr = V(o.x, o.y) - r;
+    t.dr = dr;
+    const float r_collision = o.z + radius;
+    const float mass_j = o.w;
+    const float r_collision_sq = r_collision * r_collision;
+    const float d_surfs = norm2(dr);
+    const float x = r_collision_sq / d_surfs;
+    if (x > 0.8f) {
+        const float m3 = 3.f * x * x * x;
+        const float mag = (m3 < 50000.0f) ? m3 : 50000.0f;
+        t.rep = (((-dr) / norm(dr)) * mag * mass_j) / (mass_i + mass_j);
+        t.mask |= 1u;
+    }
+    if (state_j == RTS_MOVING && state_i == RTS_STANDING && x > 0.75f) {
+        t.push = ((-dr) * x * mass_j) / (mass_i + mass_j);
+        t.mask |= 2u;
+    }
+    if (state_j == RTS_MOVING && x > r_collision_sq / rscatter2) t.mask |= 4u;
+    return t;
+}
+__device__ __forceinline__ void add_terms(ForceSums& S, v2 rep, v2 push, v2 dr, uint32_t mask) {
+    if (mask & 1u) S.repulsion = S.repulsion + rep;
+    if (mask & 2u) S.push = S.push + push;
+    if (mask & 4u) {
+        S.dr_nn = S.dr_nn + dr;
+        S.n_neighbours += 1.f;
+    }
+}
+
+// Everything of the frame after the neighbour sums: scatter term, clamp, decay, wall pass, seek, merge, wall pass,
+// integration, migration / halo packing, and the write of the new record at slot p. Returns the fine cell of the new
+// position (the caller ranks it).
+template <bool KEEP_VEL, bool MULTI>
+__device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4 me, uint2 mykey, float4 vel4, float4 nav4, const ForceSums& sums,
+                                                 const RtsParams& P, const MapDev& M, const FineGrid& F, const AgentArrays& A, const SlabDev& SL) {
+    const v2 r = V(me.x, me.y);
+    const float radius = me.z, mass_i = me.w;
+    const uint32_t gid = mykey.x;
+    const int state_i = (int)(mykey.y & 3u);
+    const uint32_t misc = __float_as_uint(nav4.w);
+    const RtsUnitType ut = M.unit_types[(misc >> 16) & 0xFFu];
+    v2 repulsion = sums.repulsion, push = sums.push, dr_nn = sums.dr_nn, scatter = V(0.f, 0.f);
+    const float n_neighbours = sums.n_neighbours;
+
+    // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116
+    dr_nn = dr_nn / n_neighbours;
+    if (n_neighbours > 1.f) scatter = (dr_nn / norm(dr_nn)) * ut.max_speed;
+    v2 inertia = V(vel4.x, vel4.y);
+    inertia = inertia + ((repulsion * P.mul_repulse + push * P.mul_push) + scatter * P.mul_scatter);
+
+    // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry)
+    v2 vp = V(0.f, 0.f);
+    float speed = norm(vp);
+    if (speed > P.sys_max_speed) vp = vp / (speed * P.sys_max_speed);
+    vp = vp + inertia;
+    const float max_vel = ut.max_speed * P.mul_velocity;
+    speed = norm(vp);
+    if (speed > max_vel) vp = vp * (max_vel / speed);
+    const float lm = ut.lambda * P.mul_decay;
+    const float decay = (lm < 1.f) ? lm : 1.f;
+    inertia = inertia - inertia * decay;
+
+    // ---- P4: wall pass #1, PhysicsSystem.cpp:130-162
+    int n_walls = 0;
+    if (may_touch_wall(M, r, radius))
+        n_walls = contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, vp, inertia); });
+
+    // ---- S1: SeekSystem::update per-agent body, SeekSystem.cpp:76-111
+    v2 vs = V(0.f, 0.f);
+    float angle = vel4.z, angle_vel = vel4.w;
+    uint32_t wp = misc & 0xFFFFu;
+    uint32_t flags = (misc >> 28) & 0xFu;
+    v2 r_next = V(nav4.x, nav4.y);
+    int32_t pid = __float_as_int(nav4.z);
+    int state_out = state_i;
+    if (P.enable_arrival && A.stop_req[p]) {   // stopSeeking, SeekSystem.cpp:136-144: no seek velocity, out of the group
+        A.stop_req[p] = 0u;
+        state_out = RTS_STANDING;
+        angle_vel = 0.f;
+        pid = -1;
+    }
+    if (state_out == RTS_MOVING && pid >= 0) {
+        const uint32_t p0 = __ldg(M.path_off + pid), p1 = __ldg(M.path_off + pid + 1);
+        const uint32_t last = p1 - 1;
+        const uint32_t w0 = min(p0 + wp, last);
+        const uint32_t w1 = min(w0 + 1, last);
+        const float4 wa = __ldg(M.waypoints + 2 * (size_t)w0), wb = __ldg(M.waypoints + 2 * (size_t)w0 + 1);
+        const float4 wn = __ldg(M.waypoints + 2 * (size_t)w1);
+        if (r_next.x != r_next.x) r_next = V(wa.x, wa.y);
+        const v2 r_nn = V(wn.x, wn.y);
+        const v2 path_end = V(__ldg(M.path_end + pid).x, __ldg(M.path_end + pid).y);
+
+        const v2 dr_to_target = r_next - r;
+        {   // turnTowards, SeekSystem.cpp:344-385 (the component-local angle edit is never communicated, :322-342)
+            float ang = angle;
+            if (ang > 180) ang -= 360;
+            if (ang < -180) ang += 360;
+            float desired;
+            if (norm2(dr_to_target) == 0) desired = ut.desired_angle;
+            else desired = table_angle(M.acos_table, dr_to_target);
+            float d_angle = desired - ang;
+            if (d_angle > 180) d_angle = -360 + d_angle;
+            if (d_angle < -180) d_angle = 360 + d_angle;
+            angle_vel = (d_angle < ut.turn_rate) ? d_angle : ut.turn_rate;
+            if (d_angle < 0) angle_vel = (d_angle > -ut.turn_rate) ? d_angle : -ut.turn_rate;
+            if (fabsf(d_angle) < ut.turn_rate) angle_vel = 0;
+        }
+        const float norm_dr = norm(dr_to_target);
+        if (norm_dr > radius) vs = (dr_to_target / norm_dr) * ut.seek_max_speed;
+
+        bool upd;  // needsUpdating, SeekSystem.cpp:181-233
+        if (vequal(r_next, path_end)) upd = false;
+        else {
+            const v2 t = r_nn - r_next;
+            const bool can_move = dot(-dr_to_target, t) > 0;
+            upd = (norm_dr < P.rhard && can_move) || veq(r_next, r_nn);
+            const v2 cp = closest_point_on_edge(r, V(wa.z, wa.w), V(wb.x, wb.y), wb.z);
+            if (norm_dr < radius || dot(dr_to_target, t) < 0) upd = true;
+            else {
+                if (dist2(cp, r) < dist2(r, r_next) && wb.z > 0 && dist2(cp, r) < 16 * P.rhard * P.rhard && norm2(t) != 0) {
+                    r_next = cp;
+                    upd = false;
+                } else if (vequal(r_next, r_nn) && !veq(r_next, path_end)) upd = true;
+            }
+        }
+        if (upd) {  // updateTarget, SeekSystem.cpp:277-304
+            const v2 dn = r_nn - r;
+            const float ndn = norm(dn);
+            r_next = r_nn;
+            if (p0 + wp < last) wp++;
+            if (ndn > 0) vs = (dn / ndn) * ut.seek_max_speed;
+            if (!veq(r_nn, path_end)) flags |= RTS_FLAG_REPLAN;
+        }
+    }
+
+    // ---- M: merge, wall pass #2 (same contact set: r has not moved), integrate (ECS.cpp:92-113)
+    v2 v = (V(0.f, 0.f) + vp) + vs;
+    if (n_walls > 0) contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, v, inertia); });
+    const v2 r_new = r + v * P.dt;
+    angle = angle + angle_vel;
+
+    // ---- K7 (triangle walk on the new position) runs in k_walk; agents that are not walked keep their index
+    if (!(P.walk_all || state_out == RTS_MOVING)) A.trin[p] = A.tri[sp];
+
+    // ---- write the new record at this slot; bin it for the next order
+    const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
+    const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, P.ns_ny);
+    uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_out);
+    const float4 vel_new = make_float4(inertia.x, inertia.y, angle, angle_vel);
+    const float4 nav_new = make_float4(r_next.x, r_next.y, __int_as_float(pid), __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
+    if (MULTI) {
+        // ownership follows the physics-grid row of the new position (integer, identical on every rank)
+        const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
+        if (dir >= 0 && SL.has[dir]) {
+            // migrate: full record to the neighbour; the local copy stays one more frame as a ghost (it is within
+            // one frame's travel of the boundary, i.e. inside the halo band of this slab)
+            const ExBuf& B = SL.send[dir];
+            const uint32_t k = atomicAdd(B.hdr + 0, 1u);
+            if (k < SL.cap_mig) {
+                B.m_pos4[k] = pos_new;
+                B.m_key2[k] = make_uint2(gid, cs_new);
+                B.m_vel4[k] = vel_new;
+                B.m_nav4[k] = nav_new;
+                B.m_tri[k] = 0xFFFFFFFFu;   // walked by the receiver's reorder pass
+                B.m_velout[k] = make_float2(v.x, v.y);
+            } else B.hdr[2] = 1u;
+            cs_new |= 4u;
+        } else {
+            if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
+                const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
+                if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos_new; SL.send[0].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                else SL.send[0].hdr[2] = 1u;
+            }
+            if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
+                const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
+                if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos_new; SL.send[1].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                else SL.send[1].hdr[2] = 1u;
+            }
+        }
+    }
+    A.pos4n[p] = pos_new;
+    A.key2n[p] = make_uint2(gid, cs_new);
+    A.vel4n[p] = vel_new;
+    A.nav4n[p] = nav_new;
+    if (KEEP_VEL) A.vel_outn[p] = make_float2(v.x, v.y);
+    int nfx, nfy;
+    fine_coords(F, r_new.x, r_new.y, nfx, nfy);
+    return (uint32_t)nfy * (uint32_t)F.nx + (uint32_t)nfx;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
@@ -624,35 +830,14 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         return (rank << 28) | ok.x;
     };
 
-    v2 repulsion = V(0.f, 0.f), push = V(0.f, 0.f), scatter = V(0.f, 0.f), dr_nn = V(0.f, 0.f);
-    float n_neighbours = 0.f;
+    ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
     const float rscatter2 = P.rscatter * P.rscatter;
     // applyForces loop body, PhysicsSystem.cpp:69-102
     auto accumulate = [&](uint32_t q) {
-        const float4 o = cand_pos[q];
-        const int state_j = (int)(cand_key[q].y & 3u);
-        const v2 dr = V(o.x, o.y) - r;
-        const float r_collision = o.z + radius;
-        const float mass_j = o.w;
-        const float r_collision_sq = r_collision * r_collision;
-        const float d_surfs = norm2(dr);
-        const float x = r_collision_sq / d_surfs;
-        if (x > 0.8f) {
-            const float m3 = 3.f * x * x * x;
-            const float mag = (m3 < 50000.0f) ? m3 : 50000.0f;
-            repulsion = repulsion + (((-dr) / norm(dr)) * mag * mass_j) / (mass_i + mass_j);
-        }
-        if (state_j == RTS_MOVING && state_i == RTS_STANDING && x > 0.75f)
-            push = push + ((-dr) * x * mass_j) / (mass_i + mass_j);
-        if (state_j == RTS_MOVING && x > r_collision_sq / rscatter2) {
-            dr_nn = dr_nn + dr;
-            n_neighbours += 1.f;
-        }
+        const ForceTerms t = neighbour_terms(r, radius, mass_i, state_i, cand_pos[q], (int)(cand_key[q].y & 3u), rscatter2);
+        add_terms(acc, t.rep, t.push, t.dr, t.mask);
     };
 
-    // Ordering. Common case (at most NBR_CAP neighbours): the scan only appends the accepted candidates to the shared
-    // memory list; keys are fetched and the list is insertion-sorted afterwards, when every lane of the warp is doing the
-    // same thing (sorting inside the scan ran with ~3 of 32 lanes active).
     // Accepted candidates beyond NBR_CAP are parked (index only) in a per-thread list in local memory.
     uint2 spill[SPILL_CAP];
     int cnt = 0;
@@ -732,150 +917,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         }
     }
 
-    // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116
-    dr_nn = dr_nn / n_neighbours;
-    if (n_neighbours > 1.f) scatter = (dr_nn / norm(dr_nn)) * ut.max_speed;
-    v2 inertia = V(vel4.x, vel4.y);
-    inertia = inertia + ((repulsion * P.mul_repulse + push * P.mul_push) + scatter * P.mul_scatter);
-
-    // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry)
-    v2 vp = V(0.f, 0.f);
-    float speed = norm(vp);
-    if (speed > P.sys_max_speed) vp = vp / (speed * P.sys_max_speed);
-    vp = vp + inertia;
-    const float max_vel = ut.max_speed * P.mul_velocity;
-    speed = norm(vp);
-    if (speed > max_vel) vp = vp * (max_vel / speed);
-    const float lm = ut.lambda * P.mul_decay;
-    const float decay = (lm < 1.f) ? lm : 1.f;
-    inertia = inertia - inertia * decay;
-
-    // ---- P4: wall pass #1, PhysicsSystem.cpp:130-162
-    int n_walls = 0;
-    if (may_touch_wall(M, r, radius))
-        n_walls = contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, vp, inertia); });
-
-    // ---- S1: SeekSystem::update per-agent body, SeekSystem.cpp:76-111
-    v2 vs = V(0.f, 0.f);
-    float angle = vel4.z, angle_vel = vel4.w;
-    uint32_t wp = misc & 0xFFFFu;
-    uint32_t flags = (misc >> 28) & 0xFu;
-    v2 r_next = V(nav4.x, nav4.y);
-    int32_t pid = __float_as_int(nav4.z);
-    int state_out = state_i;
-    if (P.enable_arrival && A.stop_req[p]) {   // stopSeeking, SeekSystem.cpp:136-144: no seek velocity, out of the group
-        A.stop_req[p] = 0u;
-        state_out = RTS_STANDING;
-        angle_vel = 0.f;
-        pid = -1;
-    }
-    if (state_out == RTS_MOVING && pid >= 0) {
-        const uint32_t p0 = __ldg(M.path_off + pid), p1 = __ldg(M.path_off + pid + 1);
-        const uint32_t last = p1 - 1;
-        const uint32_t w0 = min(p0 + wp, last);
-        const uint32_t w1 = min(w0 + 1, last);
-        const float4 wa = __ldg(M.waypoints + 2 * (size_t)w0), wb = __ldg(M.waypoints + 2 * (size_t)w0 + 1);
-        const float4 wn = __ldg(M.waypoints + 2 * (size_t)w1);
-        if (r_next.x != r_next.x) r_next = V(wa.x, wa.y);
-        const v2 r_nn = V(wn.x, wn.y);
-        const v2 path_end = V(__ldg(M.path_end + pid).x, __ldg(M.path_end + pid).y);
-
-        const v2 dr_to_target = r_next - r;
-        {   // turnTowards, SeekSystem.cpp:344-385 (the component-local angle edit is never communicated, :322-342)
-            float ang = angle;
-            if (ang > 180) ang -= 360;
-            if (ang < -180) ang += 360;
-            float desired;
-            if (norm2(dr_to_target) == 0) desired = ut.desired_angle;
-            else desired = table_angle(M.acos_table, dr_to_target);
-            float d_angle = desired - ang;
-            if (d_angle > 180) d_angle = -360 + d_angle;
-            if (d_angle < -180) d_angle = 360 + d_angle;
-            angle_vel = (d_angle < ut.turn_rate) ? d_angle : ut.turn_rate;
-            if (d_angle < 0) angle_vel = (d_angle > -ut.turn_rate) ? d_angle : -ut.turn_rate;
-            if (fabsf(d_angle) < ut.turn_rate) angle_vel = 0;
-        }
-        const float norm_dr = norm(dr_to_target);
-        if (norm_dr > radius) vs = (dr_to_target / norm_dr) * ut.seek_max_speed;
-
-        bool upd;  // needsUpdating, SeekSystem.cpp:181-233
-        if (vequal(r_next, path_end)) upd = false;
-        else {
-            const v2 t = r_nn - r_next;
-            const bool can_move = dot(-dr_to_target, t) > 0;
-            upd = (norm_dr < P.rhard && can_move) || veq(r_next, r_nn);
-            const v2 cp = closest_point_on_edge(r, V(wa.z, wa.w), V(wb.x, wb.y), wb.z);
-            if (norm_dr < radius || dot(dr_to_target, t) < 0) upd = true;
-            else {
-                if (dist2(cp, r) < dist2(r, r_next) && wb.z > 0 && dist2(cp, r) < 16 * P.rhard * P.rhard && norm2(t) != 0) {
-                    r_next = cp;
-                    upd = false;
-                } else if (vequal(r_next, r_nn) && !veq(r_next, path_end)) upd = true;
-            }
-        }
-        if (upd) {  // updateTarget, SeekSystem.cpp:277-304
-            const v2 dn = r_nn - r;
-            const float ndn = norm(dn);
-            r_next = r_nn;
-            if (p0 + wp < last) wp++;
-            if (ndn > 0) vs = (dn / ndn) * ut.seek_max_speed;
-            if (!veq(r_nn, path_end)) flags |= RTS_FLAG_REPLAN;
-        }
-    }
-
-    // ---- M: merge, wall pass #2 (same contact set: r has not moved), integrate (ECS.cpp:92-113)
-    v2 v = (V(0.f, 0.f) + vp) + vs;
-    if (n_walls > 0) contact_walls(M, P, r, radius, [&](float tx, float ty, uint32_t) { avoid_one(tx, ty, v, inertia); });
-    const v2 r_new = r + v * P.dt;
-    angle = angle + angle_vel;
-
-    // ---- K7 (triangle walk on the new position) runs in k_walk; agents that are not walked keep their index
-    if (!(P.walk_all || state_out == RTS_MOVING)) A.trin[p] = A.tri[sp];
-
-    // ---- write the new record at this slot; bin it for the next order
-    const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
-    const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, P.ns_ny);
-    uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_out);
-    const float4 vel_new = make_float4(inertia.x, inertia.y, angle, angle_vel);
-    const float4 nav_new = make_float4(r_next.x, r_next.y, __int_as_float(pid), __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
-    if (MULTI) {
-        // ownership follows the physics-grid row of the new position (integer, identical on every rank)
-        const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
-        if (dir >= 0 && SL.has[dir]) {
-            // migrate: full record to the neighbour; the local copy stays one more frame as a ghost (it is within
-            // one frame's travel of the boundary, i.e. inside the halo band of this slab)
-            const ExBuf& B = SL.send[dir];
-            const uint32_t k = atomicAdd(B.hdr + 0, 1u);
-            if (k < SL.cap_mig) {
-                B.m_pos4[k] = pos_new;
-                B.m_key2[k] = make_uint2(gid, cs_new);
-                B.m_vel4[k] = vel_new;
-                B.m_nav4[k] = nav_new;
-                B.m_tri[k] = 0xFFFFFFFFu;   // walked by the receiver's reorder pass
-                B.m_velout[k] = make_float2(v.x, v.y);
-            } else B.hdr[2] = 1u;
-            cs_new |= 4u;
-        } else {
-            if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
-                const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
-                if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos_new; SL.send[0].h_key2[k] = make_uint2(gid, cs_new | 4u); }
-                else SL.send[0].hdr[2] = 1u;
-            }
-            if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
-                const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
-                if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos_new; SL.send[1].h_key2[k] = make_uint2(gid, cs_new | 4u); }
-                else SL.send[1].hdr[2] = 1u;
-            }
-        }
-    }
-    A.pos4n[p] = pos_new;
-    A.key2n[p] = make_uint2(gid, cs_new);
-    A.vel4n[p] = vel_new;
-    A.nav4n[p] = nav_new;
-    if (KEEP_VEL) A.vel_outn[p] = make_float2(v.x, v.y);
-    int nfx, nfy;
-    fine_coords(F, r_new.x, r_new.y, nfx, nfy);
-    const uint32_t cell = (uint32_t)nfy * (uint32_t)F.nx + (uint32_t)nfx;
+    const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
     A.cellrank[p] = make_uint2(cell, rank);
 }
