@@ -176,7 +176,14 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     AL(pos4n, float4) AL(key2n, uint2) AL(vel4n, float4) AL(nav4n, float4) AL(trin, uint32_t) AL(cellrank, uint2)
     if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
     AL(stop_req, uint32_t)
+    AL(dense_q, uint32_t)
 #undef AL
+    {
+        uint32_t* dn = nullptr;
+        if ((rc = dev_alloc<uint32_t>(h, &dn, 4, h->agent_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(dn, 0, 16, h->stream));
+        A.dense_n = dn;
+    }
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
     A.n_dev = h->n_dev;
     A.n_tris_dev_hint = h->map_ready ? h->M.n_tris : 0u;
@@ -310,6 +317,15 @@ void launch_step_kernel(RtsContext* h) {
             default: LAUNCH_STEP(true, true, true); break;
         }
 #undef LAUNCH_STEP
+        if (USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
+            const dim3 dgrid(148 * 4);
+            const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
+            if (dv == 0) k_step_dense<false, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
+            else if (dv == 1) k_step_dense<false, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
+            else if (dv == 2) k_step_dense<true, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
+            else k_step_dense<true, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
+            h->launches += 1;
+        }
     }
     timer_end(h, KT_STEP);
     h->launches += 1;

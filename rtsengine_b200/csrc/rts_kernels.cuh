@@ -15,6 +15,10 @@
 
 namespace rts {
 
+#ifndef RTS_USE_DENSE_KERNEL
+#define RTS_USE_DENSE_KERNEL 1
+#endif
+constexpr bool USE_DENSE_KERNEL = RTS_USE_DENSE_KERNEL != 0;
 constexpr int STEP_BLOCK = 128;   // threads per CTA of k_step
 #ifndef RTS_STEP_MIN_BLOCKS
 #define RTS_STEP_MIN_BLOCKS 8
@@ -28,6 +32,11 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 #define RTS_STAGE_CAP 640
 #endif
 constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in shared memory (typically ~400)
+#ifndef RTS_DENSE_MIN
+#define RTS_DENSE_MIN 32
+#endif
+constexpr int DENSE_MIN = RTS_DENSE_MIN;   // agents with more neighbours than this are handed to k_step_dense (one warp each)
+constexpr int DENSE_MAX = 512;             // ... up to this many (the reference itself gives up at 500, Strategy.cpp:62-65)
 constexpr int SPILL_CAP = 104;    // further neighbours parked unsorted in local memory before re-scanning is needed
 constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
 
@@ -70,7 +79,7 @@ __device__ __forceinline__ uint32_t warp_aggregated_rank(uint32_t* count, uint32
     const unsigned peers = __match_any_sync(active, cell);
     const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if ((int)lane == leader) base = atomicAdd(count + cell, (uint32_t)__popc(peers));
+    if ((int)lane == leader && cell != 0xFFFFFFFFu) base = atomicAdd(count + cell, (uint32_t)__popc(peers));   // 0xFFFFFFFF: not binned here
     base = __shfl_sync(peers, base, leader);
     return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
 }
@@ -116,6 +125,8 @@ struct AgentArrays {
     float2* vel_outn;
     uint2* cellrank;  // {next fine cell, rank inside it}
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
+    uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
+    uint32_t* dense_n;   // their number (reset by k_scatter)
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
@@ -298,6 +309,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) *A.dense_n = 0u;        // the dense queue of this frame has been consumed
     if (p >= n) return;
     const uint2 cr = A.cellrank[p];
     if (cr.x == INVALID_CELL) return;   // ghosts / migrated agents / unused slots are dropped
@@ -846,6 +858,14 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         else if (cnt - NBR_CAP < SPILL_CAP) spill[cnt - NBR_CAP].y = q;
         ++cnt;
     });
+    // A crowded agent (DENSE_MIN < neighbours <= DENSE_MAX) would keep this thread busy for tens of thousands of
+    // instructions while the rest of its warp idles, and the slowest such thread sets the duration of the whole kernel.
+    // It is queued for k_step_dense instead, where a warp shares the scan, the sort and the force terms of ONE agent.
+    const bool to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
+    uint32_t cell = INVALID_CELL;
+    if (to_dense) {
+        A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
+    } else {
     {   // keys + insertion sort of the shared-memory part, every lane in step
         const int m = min(cnt, NBR_CAP);
         for (int k = 0; k < m; ++k) s_kq[k][tid].x = key_of(s_kq[k][tid].y);
@@ -917,9 +937,107 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         }
     }
 
-    const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
+    cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
+    }
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
-    A.cellrank[p] = make_uint2(cell, rank);
+    if (!to_dense) A.cellrank[p] = make_uint2(cell, rank);
+}
+
+// One warp per crowded agent (see k_step): the 32 lanes scan the candidates together, sort the accepted neighbours by
+// (visit rank, gid) with a bitonic sort in shared memory, compute the force terms of 32 neighbours at a time, and add
+// them up in order (every lane redundantly, through shuffles); lane 0 then finishes the frame for the agent.
+template <bool KEEP_VEL, bool MULTI>
+__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+    __shared__ uint2 s_list[4][DENSE_MAX];
+    const unsigned lane = threadIdx.x & 31u;
+    const int w = threadIdx.x >> 5;
+    const uint32_t n_warps = gridDim.x * 4u;
+    const uint32_t qn = *A.dense_n;
+    uint2* list = s_list[w];
+    const float rscatter2 = P.rscatter * P.rscatter;
+    for (uint32_t qi = blockIdx.x * 4u + (uint32_t)w; qi < qn; qi += n_warps) {
+        const uint32_t p = A.dense_q[qi];
+        const float4 me = A.pos4[p];
+        const uint2 mykey = A.key2[p];
+        const uint32_t sp = A.src[p];
+        const v2 r = V(me.x, me.y);
+        const int state_i = (int)(mykey.y & 3u);
+        const int cxi = cs_cx(mykey.y), cyi = cs_cy(mykey.y);
+        int fx, fy;
+        fine_coords(F, r.x, r.y, fx, fy);
+        const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
+        // ---- scan: lanes stride over the three row ranges; accepted neighbours are appended with their keys
+        uint32_t cnt = 0;
+        for (int k = 0; k < 3; ++k) {
+            const int yy = fy - 1 + k;
+            if (yy < 0 || yy >= F.ny) continue;
+            const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
+            const uint32_t qb = __ldg(F.start + rowbase + xlo), qe = __ldg(F.start + rowbase + xhi + 1);
+            for (uint32_t q0 = qb; q0 < qe; q0 += 32u) {
+                const uint32_t q = q0 + lane;
+                bool accept = false;
+                uint32_t key = 0;
+                if (q < qe) {
+                    const float4 o = __ldg(A.pos4 + q);
+                    const v2 dr = V(o.x, o.y) - r;
+                    if (norm2(dr) < P.r_max2 && q != p) {
+                        accept = true;
+                        const uint2 ok = __ldg(A.key2 + q);
+                        const int idx = (cs_cx(ok.y) - cxi + 1) * 3 + (cs_cy(ok.y) - cyi + 1);
+                        const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
+                        key = (rank << 28) | ok.x;
+                    }
+                }
+                const unsigned hits = __ballot_sync(0xffffffffu, accept);
+                const uint32_t pos = cnt + (uint32_t)__popc(hits & ((1u << lane) - 1u));
+                if (accept && pos < (uint32_t)DENSE_MAX) list[pos] = make_uint2(key, q);
+                cnt += (uint32_t)__popc(hits);
+            }
+        }
+        cnt = min(cnt, (uint32_t)DENSE_MAX);   // k_step queued this agent with the same count, <= DENSE_MAX
+        // ---- bitonic sort of the list, padded to a power of two with maximal keys
+        uint32_t n2 = 32u;
+        while (n2 < cnt) n2 <<= 1;
+        for (uint32_t i = cnt + lane; i < n2; i += 32u) list[i] = make_uint2(0xFFFFFFFFu, 0u);
+        __syncwarp();
+        for (uint32_t kk = 2u; kk <= n2; kk <<= 1) {
+            for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
+                for (uint32_t i = lane; i < n2; i += 32u) {
+                    const uint32_t ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint2 a = list[i], b = list[ixj];
+                        const bool up = (i & kk) == 0u;
+                        if ((a.x > b.x) == up) { list[i] = b; list[ixj] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- force terms 32 neighbours at a time, added in key order
+        ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+        for (uint32_t base = 0; base < cnt; base += 32u) {
+            const uint32_t k = base + lane;
+            ForceTerms t;
+            t.mask = 0u; t.rep = V(0.f, 0.f); t.push = V(0.f, 0.f); t.dr = V(0.f, 0.f);
+            if (k < cnt) {
+                const uint32_t q = list[k].y;
+                t = neighbour_terms(r, me.z, me.w, state_i, __ldg(A.pos4 + q), (int)(__ldg(A.key2 + q).y & 3u), rscatter2);
+            }
+            const uint32_t m = min(32u, cnt - base);
+            for (uint32_t j = 0; j < m; ++j) {
+                const uint32_t mk = __shfl_sync(0xffffffffu, t.mask, j);
+                const v2 rep = V(__shfl_sync(0xffffffffu, t.rep.x, j), __shfl_sync(0xffffffffu, t.rep.y, j));
+                const v2 psh = V(__shfl_sync(0xffffffffu, t.push.x, j), __shfl_sync(0xffffffffu, t.push.y, j));
+                const v2 dr = V(__shfl_sync(0xffffffffu, t.dr.x, j), __shfl_sync(0xffffffffu, t.dr.y, j));
+                add_terms(acc, rep, psh, dr, mk);
+            }
+        }
+        if (lane == 0u) {
+            const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
+            A.cellrank[p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
