@@ -318,7 +318,7 @@ void launch_step_kernel(RtsContext* h) {
         }
 #undef LAUNCH_STEP
         if (USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
-            const dim3 dgrid(148 * 4);
+            const dim3 dgrid(148 * RTS_DENSE_GRID_PER_SM);
             const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
             if (dv == 0) k_step_dense<false, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
             else if (dv == 1) k_step_dense<false, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);

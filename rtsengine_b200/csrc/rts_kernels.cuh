@@ -33,7 +33,10 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 #endif
 constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in shared memory (typically ~400)
 #ifndef RTS_DENSE_MIN
-#define RTS_DENSE_MIN 32
+#define RTS_DENSE_MIN 24
+#endif
+#ifndef RTS_DENSE_GRID_PER_SM
+#define RTS_DENSE_GRID_PER_SM 8
 #endif
 constexpr int DENSE_MIN = RTS_DENSE_MIN;   // agents with more neighbours than this are handed to k_step_dense (one warp each)
 constexpr int DENSE_MAX = 512;             // ... up to this many (the reference itself gives up at 500, Strategy.cpp:62-65)
