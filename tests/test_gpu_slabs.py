@@ -65,3 +65,44 @@ def test_two_slabs_equal_one_domain(n, lo, hi, frames):
         finally:
             for sr in ranks:
                 sr.close()
+
+
+def test_exchange_capacity_overflow_is_reported():
+    """fixed-capacity halo / migrant buffers: an overflow must surface as RTS_E_CAPACITY, never as silent loss"""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    n = 20000
+    a, paths = random_world(22, n, tables, 100.0, 1100.0)
+    base = engine.default_params(512, 512)
+    bounds = slabs.partition_rows(a["r"][:, 1], base.ns_ny, base.ns_cell_size, 2)
+    a2 = dict(a)
+    a2["gid"] = np.arange(n, dtype=np.uint32)
+    parts = slabs.split_agents(a2, bounds, base.ns_cell_size, base.ns_ny)
+    ranks = [slabs.SlabRank(base, bounds, r, 0, cap_migrants=4, cap_halo=8) for r in range(2)]   # far too small
+    L = ranks[0].g.L
+    try:
+        for r, sr in enumerate(ranks):
+            sr.g.upload_map(tables)
+            sr.g.upload_paths(paths)
+            sr.g.set_agents(parts[r])
+        for sr in ranks:
+            sr.g._chk(L.rts_halo_begin(sr.g.h))
+        with pytest.raises(engine.RtsError) as e:
+            for sr in ranks:
+                sr.g.sync()
+        assert e.value.code == abi.RTS_E_CAPACITY
+    finally:
+        for sr in ranks:
+            sr.close()
+
+
+def test_slab_handle_requires_global_ids():
+    fx = H.load("frame_small.npz")
+    base = engine.default_params(512, 512)
+    sr = slabs.SlabRank(base, [0, 20, 43], 0, 0, cap_migrants=64, cap_halo=64)
+    try:
+        with pytest.raises(engine.RtsError) as e:
+            sr.g.set_agents({"r": np.ones((10, 2), np.float32)})
+        assert e.value.code == abi.RTS_E_ARG
+    finally:
+        sr.close()

@@ -1,0 +1,68 @@
+"""CPU: host-side logic that needs no device — ABI struct helpers, scenario generators, map tiling."""
+import numpy as np
+import pytest
+
+from oracle import port
+from rtsengine_b200 import abi, scenario
+from tests import helpers as H
+
+
+def test_agent_view_checks_shapes_and_dtypes():
+    keep = []
+    v = abi.agent_view({"r": np.zeros((5, 2), np.float32), "state": np.ones(5, np.uint8)}, 5, keep)
+    assert v.r and v.state and not v.inertia
+    with pytest.raises(ValueError):
+        abi.agent_view({"r": np.zeros((4, 2), np.float32)}, 5, [])
+    t = abi.triangles_array(np.arange(12).reshape(2, 6), np.array([[1, 2, 0xFFFFFFFF], [0, 0xFFFFFFFF, 0xFFFFFFFF]]))
+    assert t["vx"].tolist() == [[0, 2, 4], [6, 8, 10]] and t["vy"].tolist() == [[1, 3, 5], [7, 9, 11]]
+    with pytest.raises(ValueError):
+        abi.path_table({"offsets": np.array([0, 2], np.uint32), "waypoints": np.zeros((1, 2)), "portals": np.zeros((2, 5)),
+                        "path_end": np.zeros((1, 2))}, [])
+    pt = abi.path_table({"offsets": np.array([0, 1, 3], np.uint32), "waypoints": np.zeros((3, 2)), "portals": np.zeros((3, 5)),
+                         "path_end": np.zeros((2, 2)), "group": np.array([4, 4])}, [])
+    assert (pt.n_paths, pt.n_groups) == (2, 5)
+
+
+def test_config3_population_and_paths():
+    fx = scenario.load_map("map_c3.npz")
+    a, paths = scenario.config3_agents(fx, n=50_000, seed=3)
+    assert len(paths["path_end"]) == 4096 and paths["offsets"][-1] == len(paths["waypoints"])
+    assert a["path_id"].min() >= 0 and a["path_id"].max() < 4096 and (a["state"] == abi.MOVING).all()
+    # nobody spawns inside a building (one-cell margin), everybody inside the map
+    occ = scenario.occupancy(fx, 0)
+    assert not occ[(a["r"][:, 0] // 5).astype(int), (a["r"][:, 1] // 5).astype(int)].any()
+    assert (a["r"] > 0).all() and (a["r"] < 5120).all()
+    # an agent follows the path planned from its own start region, towards its group's destination
+    pid = a["path_id"]
+    start = fx["path_start"][pid]
+    assert np.linalg.norm(start - a["r"], axis=1).max() < 80 * np.sqrt(2) + 60
+    side, sub = (int(v) for v in fx["path_grid"])
+    assert (fx["path_group"][pid] == pid // (sub * sub)).all()
+    # every path ends at its destination and has finite portals
+    last = paths["offsets"][1:] - 1
+    assert np.allclose(paths["waypoints"][last], paths["path_end"])
+    assert np.isfinite(paths["portals"]).all()
+
+
+def test_tiled_map_is_the_tile_map_shifted():
+    """a 2x3 tiling of the config-3 map must answer point queries like the single tile (oracle as the checker)"""
+    tile = scenario.load_map("map_c3.npz")
+    big = scenario.tile_map(tile, 2, 3)
+    assert big["n_cells"].tolist() == [2048, 3072]
+    assert [len(big[f"line_off{o}"]) - 1 for o in range(4)] == [3073, 5121, 2049, 5121]      # Edges.cpp:6-19
+    ow_big = port.OracleWorld(port.default_params(2048, 3072), scenario.tables_of(big))
+    ow_one = port.OracleWorld(port.default_params(1024, 1024), scenario.tables_of(tile))
+    rng = np.random.default_rng(0)
+    local = rng.uniform(5, 5115, (20000, 2)).astype(np.float32)
+    bl = tile["buildings"]
+    near = np.concatenate([rng.uniform([5 * (cx - n / 2) - 6, 5 * (cy - m / 2) - 6], [5 * (cx + n / 2) + 6, 5 * (cy + m / 2) + 6], (20, 2))
+                           for cx, cy, n, m in bl]).astype(np.float32)
+    rad = np.where(rng.random(len(near)) < 0.5, 3.0, 5.0).astype(np.float32)
+    c1, e1 = ow_one.contact_edges(near, rad)
+    assert (c1 > 0).sum() > 200
+    for t, (i, j) in enumerate([(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]):
+        off = np.array([5120.0 * i, 5120.0 * j], np.float32)
+        H.assert_same_bits(ow_big.find_triangles(local + off), big["tile_tri_index"][t][ow_one.find_triangles(local)], f"tile {t} triangles")
+        cb, eb = ow_big.contact_edges(near + off, rad)
+        H.assert_same_bits(cb, c1, f"tile {t} wall contact counts")
+        H.assert_same_bits(eb[..., 2:], e1[..., 2:], f"tile {t} wall tangents / lengths")
