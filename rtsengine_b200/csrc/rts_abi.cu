@@ -267,7 +267,7 @@ int32_t launch_scan_reorder(RtsContext* h) {
     if (rc != RTS_OK) return rc;
     timer_begin(h, KT_REORDER);
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
-    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A);
+    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0);
     timer_end(h, KT_REORDER);
     h->launches += 2;
     swap_prev_order(h);
@@ -333,9 +333,7 @@ void launch_step_kernel(RtsContext* h) {
 
 // slabs: first half of a frame — zero the send headers, run the frame kernel (which packs migrants + halo)
 int32_t frame_begin(RtsContext* h) {
-    if (h->multi)
-        for (int d = 0; d < 2; ++d) CU(cudaMemsetAsync(h->ex_send[d], 0, 16, h->stream));
-    launch_step_kernel(h);
+    launch_step_kernel(h);   // slabs: the send headers were zeroed by the previous k_scatter (or rts_slab_configure)
     return RTS_OK;
 }
 
@@ -344,12 +342,9 @@ int32_t frame_end(RtsContext* h) {
     if (h->multi) {
         const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
         timer_begin(h, KT_INGEST);
-        for (int d = 0; d < 2; ++d) {
-            const uint32_t base = h->cap_main + (uint32_t)d * per_dir;
-            k_ingest_remote<<<blocks_for(per_dir, 256), 256, 0, h->stream>>>(base, h->SL.recv[d], h->SL.cap_mig, h->SL.cap_halo, h->F, h->A);
-        }
+        k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, h->stream>>>(h->cap_main, h->SL, h->F, h->A);
         timer_end(h, KT_INGEST);
-        h->launches += 2;
+        h->launches += 1;
     }
     return launch_scan_reorder(h);
 }
@@ -979,11 +974,11 @@ int32_t rts_sync(RtsHandle h) {
     CU(cudaGetLastError());
     timer_collect(h);
     if (h->multi) {
-        uint32_t n_live = 0, hdr[2][4];
+        uint32_t n_live = 0, overflow = 0;
         CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));
-        for (int d = 0; d < 2; ++d) CU(cudaMemcpy(hdr[d], h->ex_send[d], 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&overflow, h->SL.overflow, 4, cudaMemcpyDeviceToHost));
         h->n = n_live;
-        if (hdr[0][2] || hdr[1][2]) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
+        if (overflow) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
         if (n_live > h->cap_main) return h->fail(RTS_E_CAPACITY, "slab", "population outgrew the slot capacity of this handle");
     }
     return RTS_OK;
@@ -1212,6 +1207,13 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
         h->ex_send[d] = a; h->ex_recv[d] = b;
         carve(a, SL.send[d]);
         carve(b, SL.recv[d]);
+    }
+    {
+        uint32_t* ov = nullptr;
+        int32_t rc = dev_alloc<uint32_t>(h, &ov, 4, h->slab_allocs);
+        if (rc != RTS_OK) return rc;
+        CU(cudaMemsetAsync(ov, 0, 16, h->stream));
+        SL.overflow = ov;
     }
     h->ex_bytes = bytes;
     h->SL = SL;

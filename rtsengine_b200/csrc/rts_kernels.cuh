@@ -106,6 +106,7 @@ struct SlabDev {
     int32_t has[2];           // neighbour present in direction 0 / 1
     uint32_t cap_mig, cap_halo;
     ExBuf send[2], recv[2];
+    uint32_t* overflow;       // sticky: set when a migrant / halo record did not fit its buffer
 };
 
 struct AgentArrays {
@@ -310,9 +311,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 }
 
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
-__global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A) {
+__global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) *A.dense_n = 0u;        // the dense queue of this frame has been consumed
+    if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
+        SL.send[p >> 2].hdr[p & 3u] = 0u;
+    }
     if (p >= n) return;
     const uint2 cr = A.cellrank[p];
     if (cr.x == INVALID_CELL) return;   // ghosts / migrated agents / unused slots are dropped
@@ -347,10 +351,13 @@ __global__ void __launch_bounds__(256) k_walk(uint32_t n_bound, RtsParams P, Map
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
-__global__ void k_ingest_remote(uint32_t base, ExBuf B, uint32_t cap_mig, uint32_t cap_halo, FineGrid F, AgentArrays A) {
+__global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArrays A) {
+    const uint32_t cap_mig = SL.cap_mig, cap_halo = SL.cap_halo;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap_mig + cap_halo) return;
-    const uint32_t slot = base + i;
+    const int dir = (int)blockIdx.y;                       // both directions in one launch
+    const ExBuf& B = SL.recv[dir];
+    const uint32_t slot = base0 + (uint32_t)dir * (cap_mig + cap_halo) + i;
     const bool is_mig = i < cap_mig;
     const uint32_t k = is_mig ? i : i - cap_mig;
     const uint32_t cnt = is_mig ? min(B.hdr[0], cap_mig) : min(B.hdr[1], cap_halo);
@@ -409,12 +416,12 @@ __global__ void k_halo_seed(uint32_t n_bound, RtsParams P, FineGrid F, AgentArra
     if (SL.has[0] && pos.y < SL.y_lo + SL.halo) {
         const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
         if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos; SL.send[0].h_key2[k] = make_uint2(key.x, key.y | 4u); }
-        else SL.send[0].hdr[2] = 1u;
+        else *SL.overflow = 1u;
     }
     if (SL.has[1] && pos.y >= SL.y_hi - SL.halo) {
         const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
         if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos; SL.send[1].h_key2[k] = make_uint2(key.x, key.y | 4u); }
-        else SL.send[1].hdr[2] = 1u;
+        else *SL.overflow = 1u;
     }
     int fx, fy;
     fine_coords(F, pos.x, pos.y, fx, fy);
@@ -661,18 +668,18 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
                 B.m_nav4[k] = nav_new;
                 B.m_tri[k] = 0xFFFFFFFFu;   // walked by the receiver's reorder pass
                 B.m_velout[k] = make_float2(v.x, v.y);
-            } else B.hdr[2] = 1u;
+            } else *SL.overflow = 1u;
             cs_new |= 4u;
         } else {
             if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
                 if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos_new; SL.send[0].h_key2[k] = make_uint2(gid, cs_new | 4u); }
-                else SL.send[0].hdr[2] = 1u;
+                else *SL.overflow = 1u;
             }
             if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
                 if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos_new; SL.send[1].h_key2[k] = make_uint2(gid, cs_new | 4u); }
-                else SL.send[1].hdr[2] = 1u;
+                else *SL.overflow = 1u;
             }
         }
     }
