@@ -32,7 +32,7 @@ struct KernelTimer {  // per-kind CUDA-event timing of launches on the handle's 
     uint64_t launches = 0;
 };
 
-enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_EXCHANGE = 4, KT_INGEST = 5, KT_WALK = 6, KT_COUNT = 7 };
+enum { KT_STEP = 0, KT_BIN = 1, KT_SCAN = 2, KT_REORDER = 3, KT_EXCHANGE = 4, KT_INGEST = 5, KT_WALK = 6, KT_DENSE = 7, KT_COUNT = 8 };
 
 }  // namespace
 
@@ -318,12 +318,14 @@ void launch_step_kernel(RtsContext* h) {
         }
 #undef LAUNCH_STEP
         if (USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
+            timer_begin(h, KT_DENSE);
             const dim3 dgrid(148 * RTS_DENSE_GRID_PER_SM);
             const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
             if (dv == 0) k_step_dense<false, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
             else if (dv == 1) k_step_dense<false, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
             else if (dv == 2) k_step_dense<true, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
             else k_step_dense<true, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
+            timer_end(h, KT_DENSE);
             h->launches += 1;
         }
     }

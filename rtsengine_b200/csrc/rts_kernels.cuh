@@ -959,6 +959,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
 template <bool KEEP_VEL, bool MULTI>
 __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
     __shared__ uint2 s_list[4][DENSE_MAX];
+    __shared__ float s_terms[4][7][32];
+    __shared__ uint32_t s_mask[4][32];
     const unsigned lane = threadIdx.x & 31u;
     const int w = threadIdx.x >> 5;
     const uint32_t n_warps = gridDim.x * 4u;
@@ -1023,8 +1025,11 @@ __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineG
                 __syncwarp();
             }
         }
-        // ---- force terms 32 neighbours at a time, added in key order
-        ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+        // ---- force terms 32 neighbours at a time (one per lane), then added in key order. Only the additions have to be
+        //      sequential; the seven running sums (repulsion.xy, push.xy, dr_nn.xy, neighbour count) are independent of
+        //      one another, so lanes 0..6 each carry one of them through the chunk.
+        float run = 0.f;                                                 // this lane's running sum
+        const uint32_t my_bit = (lane < 2u) ? 1u : (lane < 4u) ? 2u : 4u;   // term mask bit that gates it
         for (uint32_t base = 0; base < cnt; base += 32u) {
             const uint32_t k = base + lane;
             ForceTerms t;
@@ -1033,15 +1038,25 @@ __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineG
                 const uint32_t q = list[k].y;
                 t = neighbour_terms(r, me.z, me.w, state_i, __ldg(A.pos4 + q), (int)(__ldg(A.key2 + q).y & 3u), rscatter2);
             }
-            const uint32_t m = min(32u, cnt - base);
-            for (uint32_t j = 0; j < m; ++j) {
-                const uint32_t mk = __shfl_sync(0xffffffffu, t.mask, j);
-                const v2 rep = V(__shfl_sync(0xffffffffu, t.rep.x, j), __shfl_sync(0xffffffffu, t.rep.y, j));
-                const v2 psh = V(__shfl_sync(0xffffffffu, t.push.x, j), __shfl_sync(0xffffffffu, t.push.y, j));
-                const v2 dr = V(__shfl_sync(0xffffffffu, t.dr.x, j), __shfl_sync(0xffffffffu, t.dr.y, j));
-                add_terms(acc, rep, psh, dr, mk);
+            float* tw = &s_terms[w][0][0];
+            tw[0 * 32 + lane] = t.rep.x; tw[1 * 32 + lane] = t.rep.y;
+            tw[2 * 32 + lane] = t.push.x; tw[3 * 32 + lane] = t.push.y;
+            tw[4 * 32 + lane] = t.dr.x; tw[5 * 32 + lane] = t.dr.y;
+            tw[6 * 32 + lane] = 1.f;
+            s_mask[w][lane] = t.mask;
+            __syncwarp();
+            if (lane < 7u) {
+                const uint32_t m = min(32u, cnt - base);
+                for (uint32_t j = 0; j < m; ++j)
+                    if (s_mask[w][j] & my_bit) run += tw[lane * 32u + j];
             }
+            __syncwarp();
         }
+        ForceSums acc;
+        acc.repulsion = V(__shfl_sync(0xffffffffu, run, 0), __shfl_sync(0xffffffffu, run, 1));
+        acc.push = V(__shfl_sync(0xffffffffu, run, 2), __shfl_sync(0xffffffffu, run, 3));
+        acc.dr_nn = V(__shfl_sync(0xffffffffu, run, 4), __shfl_sync(0xffffffffu, run, 5));
+        acc.n_neighbours = __shfl_sync(0xffffffffu, run, 6);
         if (lane == 0u) {
             const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
             A.cellrank[p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));

@@ -93,7 +93,7 @@ def default_params(map_nx: int, map_ny: int) -> abi.RtsParams:
     return p
 
 
-KERNELS = {"step": 0, "bin": 1, "scan": 2, "reorder": 3, "exchange": 4, "ingest": 5, "walk": 6}
+KERNELS = {"step": 0, "bin": 1, "scan": 2, "reorder": 3, "exchange": 4, "ingest": 5, "walk": 6, "dense": 7}
 
 
 class GpuAgentSystem:

@@ -15,7 +15,7 @@ g.set_profiling(True)
 for s in range(0, total, every):
     g.reset_timings()
     g.update(every, sync=True)
-    ms = {k: g.kernel_time_ms(k)[0] for k in ("step", "scan", "reorder", "walk")}
+    ms = {k: g.kernel_time_ms(k)[0] for k in ("step", "scan", "reorder", "walk", "dense")}
     out = g.communicate(("r", "waypoint", "flags"))
     r = out["r"]
     # density: agents per 6x6 cell, max and 99.9 percentile
@@ -24,6 +24,6 @@ for s in range(0, total, every):
     cnt = cnt[cnt > 0]
     cc = (r[:, 0] // 60).astype(np.int64) * 4096 + (r[:, 1] // 60).astype(np.int64)
     ccnt = np.bincount(cc[cc >= 0])
-    print(json.dumps({"frame": s + every, "max_per_ns_cell": int(ccnt.max()), "k_step_ms": round(ms["step"], 4), "scan_ms": round(ms["scan"], 4), "reorder_ms": round(ms["reorder"], 4), "walk_ms": round(ms["walk"], 4),
+    print(json.dumps({"frame": s + every, "max_per_ns_cell": int(ccnt.max()), "k_step_ms": round(ms["step"], 4), "scan_ms": round(ms["scan"], 4), "reorder_ms": round(ms["reorder"], 4), "walk_ms": round(ms["walk"], 4), "dense_ms": round(ms["dense"], 4),
                       "max_per_cell": int(cnt.max()), "p999": float(np.percentile(cnt, 99.9)), "mean_occ": float(cnt.mean()),
                       "nan": int(np.isnan(r).any(1).sum()), "wp_mean": float(out["waypoint"].mean())}), flush=True)
