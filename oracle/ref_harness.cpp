@@ -56,6 +56,20 @@ struct RefWorld {
 
 inline RefWorld* W(void* h) { return static_cast<RefWorld*>(h); }
 
+// PathFinder2::updatePaths starts up to hardware_concurrency()-1 workers and indexes 12-entry per-thread arrays with
+// the worker id (PathFinder2.h:161-162 N_MAX_THREADS, PathFinder2.cpp:90,132-137): on a host with more than 13 hardware
+// threads the reference writes out of bounds. The harness therefore feeds the pending groups to the reference's own
+// updatePaths at most 8 at a time (each group's path is independent of the others, so the result is the same).
+void plan_pending(RefWorld* w) {
+    auto& comps = static_cast<ComponentArray<PathFinderComponent>&>(*w->ss->p_comps_).components_;
+    std::remove_reference_t<decltype(w->pf->to_update_groups_)> all;
+    all.swap(w->pf->to_update_groups_);
+    for (size_t i = 0; i < all.size(); i += 8) {
+        w->pf->to_update_groups_.assign(all.begin() + i, all.begin() + std::min(i + 8, all.size()));
+        w->pf->updatePaths(comps, w->ss->entity2compvec_ind_, 5000);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -236,8 +250,7 @@ int refh_issue_paths(void* h, const int* ids, int n, float tx, float ty) {
 int refh_plan_now(void* h) {
     auto* w = W(h);
     try {
-        auto& comps = static_cast<ComponentArray<PathFinderComponent>&>(*w->ss->p_comps_).components_;
-        w->pf->updatePaths(comps, w->ss->entity2compvec_ind_, 5000);
+        plan_pending(w);
     } catch (std::exception& e) {
         w->last_error = e.what();
         return -1;
@@ -254,6 +267,7 @@ int refh_step(void* h, int n_steps) {
         for (int s = 0; s < n_steps; ++s) {
             w->ps->updateSharedData(shared, w->active);
             w->ss->updateSharedData(shared, w->active);
+            plan_pending(w);   // what SeekSystem::update does first (SeekSystem.cpp:65), in safe portions
             w->ps->update();
             w->ss->update();
             w->ps->communicate(shared);
