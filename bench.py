@@ -37,53 +37,96 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (the timed
+    region is tens of milliseconds, an `nvidia-smi -lms` child would not deliver its first row in time); nvidia-smi once
+    as the fallback when NVML cannot be loaded."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (sm_mhz, reasons bitmask)
         self.index = index
+        self.max_mhz = None
+        self.h = None
+        self.nv = None
+        self.stop = threading.Event()
+        self.t = None
+
+    def _open(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            self.h = nv.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.nv = nv
+
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            why = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.rows.append((sm, why))
+
+    def _poll(self):
+        while not self.stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                return
+            time.sleep(0.002)
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self._open()
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        if self.nv is not None:
             try:
-                self.proc.wait(timeout=2)
+                self._sample()          # the work is still in flight or has just ended: at least one row under load
             except Exception:
-                self.proc.kill()
+                pass
+            self.stop.set()
+            if self.t:
+                self.t.join(timeout=1)
+        else:
+            self._smi_once()
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            c = [x.strip() for x in out.split(",")]
+            why = 0
+            for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if c[2 + k].lower().startswith("active"):
+                    why |= self.REASONS[nm]
+            self.rows.append((float(c[0]), why))
+            self.max_mhz = float(c[1])
+        except Exception:
+            pass
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        reasons = sorted(nm for nm, bit in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def build_world(n_agents, seed=1236):

@@ -179,9 +179,16 @@ const char* rts_last_error(RtsHandle h);
 int32_t rts_set_params(RtsHandle h, const RtsParams* params);
 
 /* replaces: the tables PhysicsSystem::p_map_ (Edges*) and SeekSystem::p_cdt_ (Triangulation*) point at;
-   call again after Game::updateTriangulation (Game.cpp:38-48). cell2tri has tri_nx*tri_ny entries. */
+   call again after Game::updateTriangulation (Game.cpp:38-48). cell2tri has tri_nx*tri_ny entries; NULL = build the
+   cache on the device from the triangles (rts_build_cell_grid with last_found_tri = 0). */
 int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
                        const RtsWallTable* walls);
+/* replaces: Triangulation::updateCellGrid (Triangulation.cpp:1829-1864), the host loop that rebuilds cell2triangle_ind_
+   after every CDT change with one findTriangle(centre, from_last_found=true) per cache cell in zig-zag order. Rebuilds the
+   handle's cache from the uploaded triangles, bit-identical to the reference's table; last_found_tri is
+   Triangulation::last_found_tri_ind_ on entry (Triangulation.h:147; it only matters when the first cell centre lies on a
+   triangle edge). cell2tri_out (host, tri_nx*tri_ny entries) may be NULL. */
+int32_t rts_build_cell_grid(RtsHandle h, uint32_t last_found_tri, uint32_t* cell2tri_out);
 int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_types);
 /* replaces: PathFinder2::setPathOfAgent writing windows into PathFinderComponents (PathFinder2.cpp:326-380) */
 int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths);

@@ -43,6 +43,8 @@ def load(fast=False):
     L.rts_oracle_neighbours.argtypes = [C.POINTER(abi.RtsParams), C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
     L.rts_oracle_neighbours.restype = C.c_uint32
     L.rts_oracle_acos_table.argtypes = [vp]
+    L.rts_oracle_build_cell_grid.argtypes = [C.POINTER(abi.RtsParams), vp, C.c_uint32, C.c_uint32, vp]
+    L.rts_oracle_build_cell_grid.restype = None
     L.rts_oracle_threads.restype = C.c_int
     _libs[fast] = L
     return L
@@ -97,6 +99,13 @@ class OracleWorld:
         out = np.zeros(len(xy), np.uint32)
         self.L.rts_oracle_find_triangles(C.byref(self.params), self.tris.ctypes.data, len(self.tris),
                                          self.cell2tri.ctypes.data, xy.ctypes.data, len(xy), out.ctypes.data)
+        return out
+
+    def build_cell_grid(self, last_found=0):
+        """Triangulation::updateCellGrid restated: the cell -> triangle cache, built from the triangles alone"""
+        out = np.zeros(int(self.params.tri_nx) * int(self.params.tri_ny), np.uint32)
+        self.L.rts_oracle_build_cell_grid(C.byref(self.params), self.tris.ctypes.data, len(self.tris), last_found,
+                                          out.ctypes.data)
         return out
 
     def contact_edges(self, xy, radius, cap=8):

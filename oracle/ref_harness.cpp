@@ -197,6 +197,12 @@ int refh_finalize_map(void* h) {
 }
 // only the cell→triangle cache (no reduced graph): enough for findTriangle
 void refh_update_cell_grid(void* h) { W(h)->cdt->updateCellGrid(); }
+// the same with Triangulation::last_found_tri_ind_ (where the first cell's walk starts) set by the caller
+void refh_rebuild_cell_grid(void* h, int last_found) {
+    W(h)->cdt->last_found_tri_ind_ = last_found;
+    W(h)->cdt->updateCellGrid();
+}
+int refh_last_found(void* h) { return (int)W(h)->cdt->last_found_tri_ind_; }
 int refh_consistent(void* h) { return W(h)->cdt->triangulationIsConsistent() ? 1 : 0; }
 
 // UnitInitializer::initializeUnit (UnitInitializer.cpp:19-80): pc.mass/radius from the unit type, pfc.radius = pc.radius.

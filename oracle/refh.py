@@ -114,6 +114,17 @@ class RefWorld:
     def add_building(self, cx, cy, n=8, m=8, c=1):
         return self.L.refh_add_building(self.h, cx, cy, n, m, c)
 
+    def rebuild_cell_grid(self, last_found: int):
+        """Triangulation::updateCellGrid with last_found_tri_ind_ preset (the cache then appears in tables())"""
+        self.L.refh_rebuild_cell_grid.argtypes = [C.c_void_p, C.c_int]
+        self.L.refh_rebuild_cell_grid.restype = None
+        self.L.refh_rebuild_cell_grid(self.h, int(last_found))
+
+    def last_found(self) -> int:
+        self.L.refh_last_found.argtypes = [C.c_void_p]
+        self.L.refh_last_found.restype = C.c_int
+        return int(self.L.refh_last_found(self.h))
+
     def finalize_map(self):
         self._chk(self.L.refh_finalize_map(self.h))
 

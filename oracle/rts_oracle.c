@@ -123,12 +123,8 @@ static uint32_t brute_force(iv2 q, const RtsTriangle* tris, uint32_t n_tris) {
     return 0xFFFFFFFFu;
 }
 
-static uint32_t find_triangle(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
-                              float fx, float fy, uint32_t* flags) {
-    const iv2 q = {(int32_t)fx, (int32_t)fy}; /* static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590 */
-    const uint64_t cell = coord_to_cell((float)q.x, (float)q.y, P->tri_nx, P->tri_ny, P->tri_cell_size);
-    uint32_t t = cell2tri[cell];
-    if (t == 0xFFFFFFFFu) return brute_force(q, tris, n_tris); /* :1503-1510 */
+/* the part of findTriangle after the start triangle is chosen (:1512-1566) */
+static uint32_t walk_from(const RtsTriangle* tris, uint32_t n_tris, iv2 q, uint32_t t, uint32_t* flags) {
     if (in_triangle(q, &tris[t])) return t;
     iv2 vc;
     {
@@ -160,6 +156,37 @@ static uint32_t find_triangle(const RtsParams* P, const RtsTriangle* tris, uint3
         if (t == 0xFFFFFFFFu) { if (flags) *flags |= RTS_FLAG_WALK_FAILED; return t; }
     }
     return t;
+}
+
+static uint32_t find_triangle(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
+                              float fx, float fy, uint32_t* flags) {
+    const iv2 q = {(int32_t)fx, (int32_t)fy}; /* static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590 */
+    const uint64_t cell = coord_to_cell((float)q.x, (float)q.y, P->tri_nx, P->tri_ny, P->tri_cell_size);
+    const uint32_t t = cell2tri[cell];
+    if (t == 0xFFFFFFFFu) return brute_force(q, tris, n_tris); /* :1503-1510 */
+    return walk_from(tris, n_tris, q, t, flags);
+}
+
+/* Triangulation::updateCellGrid, Triangulation.cpp:1829-1864: the cache cells are visited in a zig-zag (row pairs
+   ascending / descending, a left-over last row descending) and each cell centre is located with
+   findTriangle(centre, from_last_found = true), i.e. the walk starts at the triangle found for the previous cell
+   (last_found_tri_ind_, which findTriangle leaves at the returned index, :1504-1566). `last_found` is that member's value
+   on entry; it matters only when the first centre lies on a triangle edge. */
+void rts_oracle_build_cell_grid(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, uint32_t last_found, uint32_t* out) {
+    const int nx = P->tri_nx, ny = P->tri_ny;
+    const float dx = P->tri_cell_size, dy = P->tri_cell_size;
+    uint32_t last = last_found;
+    for (int j = 0; j < ny; ++j) {
+        const int asc = (j % 2 == 0) && (j < ny - 1);
+        for (int k = 0; k < nx; ++k) {
+            const int i = asc ? k : nx - 1 - k;
+            const float cx = i * dx + dx / 2.f, cy = j * dy + dy / 2.f;
+            const iv2 q = {(int32_t)cx, (int32_t)cy};
+            uint32_t t = (last == 0xFFFFFFFFu) ? brute_force(q, tris, n_tris) : walk_from(tris, n_tris, q, last, 0);
+            out[(size_t)j * nx + i] = t;
+            if (t != 0xFFFFFFFFu) last = t;
+        }
+    }
 }
 
 /* diagnostic: fan-walk hops per query point (serial) */

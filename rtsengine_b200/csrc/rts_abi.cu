@@ -44,6 +44,7 @@ struct RtsContext {
     FineGrid F{};
     AgentArrays A{};
     uint32_t n = 0, cap = 0;
+    uint32_t* c2t_dev = nullptr;   // writable alias of M.cell2tri
     bool map_ready = false, gid_is_index = true, keep_vel = true, profiling = false;
     float fine_cs = 6.0f;
     std::string err;
@@ -558,9 +559,34 @@ int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
     return RTS_OK;
 }
 
+// Triangulation::updateCellGrid on the device (see k_cellgrid_classify): fills the handle's cell -> triangle cache from
+// the uploaded triangles
+int32_t build_cell_grid(RtsContext* h, uint32_t last_found) {
+    const uint32_t n_cells = (uint32_t)h->P.tri_nx * (uint32_t)h->P.tri_ny;
+    uint32_t* first = nullptr;
+    uint8_t* amb = nullptr;
+    CU(cudaMalloc(&first, sizeof(uint32_t) * (size_t)n_cells));
+    if (cudaMalloc(&amb, n_cells) != cudaSuccess) { cudaFree(first); return h->fail(RTS_E_CUDA, "build_cell_grid", "out of device memory"); }
+    const uint32_t nb = blocks_for(n_cells, 128);
+    if (h->M.coords_fit_i32) {
+        k_cellgrid_classify<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb);
+        k_cellgrid_resolve<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb);
+    } else {
+        k_cellgrid_classify<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb);
+        k_cellgrid_resolve<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb);
+    }
+    h->launches += 2;
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(first);
+    cudaFree(amb);
+    if (e != cudaSuccess) return h->fail(RTS_E_CUDA, "build_cell_grid", cudaGetErrorString(e));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
 int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri, const RtsWallTable* walls) {
     if (!h) return RTS_E_ARG;
-    if (!tris || !n_tris || !cell2tri || !walls) return h->fail(RTS_E_ARG, "rts_upload_map", "null table");
+    if (!tris || !n_tris || !walls) return h->fail(RTS_E_ARG, "rts_upload_map", "null table");
     CU(cudaSetDevice(h->device));
     { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
@@ -584,14 +610,14 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
         t4[3 * t + 2] = make_int4((int)T.neighbours[2], T.is_constrained[0] | (T.is_constrained[1] << 1) | (T.is_constrained[2] << 2) | (T.type << 8), 0, 0);
     }
     const size_t n_tri_cells = (size_t)P.tri_nx * P.tri_ny;
-    for (size_t c = 0; c < n_tri_cells; ++c)
+    for (size_t c = 0; cell2tri && c < n_tri_cells; ++c)
         if (cell2tri[c] != 0xFFFFFFFFu && cell2tri[c] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "cell2tri entry out of range");
     int4* d_tris; uint32_t* d_c2t;
     int32_t rc;
     if ((rc = dev_alloc(h, &d_tris, t4.size(), h->table_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_c2t, n_tri_cells, h->table_allocs)) != RTS_OK) return rc;
     CU(cudaMemcpyAsync(d_tris, t4.data(), t4.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(d_c2t, cell2tri, n_tri_cells * 4, cudaMemcpyHostToDevice, h->stream));
+    if (cell2tri) CU(cudaMemcpyAsync(d_c2t, cell2tri, n_tri_cells * 4, cudaMemcpyHostToDevice, h->stream));
     // walls -> one CSR
     std::vector<uint32_t> off;
     std::vector<float4> ft;
@@ -701,6 +727,8 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     h->A.n_tris_dev_hint = n_tris;
     M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
     M.scan_outer = d_souter; M.n_scan_outer = (uint32_t)scan_outer.size();
+    h->c2t_dev = d_c2t;
+    if (!cell2tri && (rc = build_cell_grid(h, 0u)) != RTS_OK) return rc;   // no host cache given: built here
     h->map_ready = true;
     h->drop_graphs();
     if (h->n) {   // agents uploaded before the map: give them their triangle index now
@@ -1140,6 +1168,19 @@ int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* o
     CU(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+int32_t rts_build_cell_grid(RtsHandle h, uint32_t last_found_tri, uint32_t* cell2tri_out) {
+    if (!h) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_build_cell_grid", "rts_upload_map has not been called");
+    CU(cudaSetDevice(h->device));
+    int32_t rc = join_walk(h);   // a walk of the previous frame may still be reading the cache
+    if (rc != RTS_OK) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    if ((rc = build_cell_grid(h, last_found_tri)) != RTS_OK) return rc;
+    if (cell2tri_out)
+        CU(cudaMemcpy(cell2tri_out, h->c2t_dev, sizeof(uint32_t) * (size_t)h->P.tri_nx * h->P.tri_ny, cudaMemcpyDeviceToHost));
     return RTS_OK;
 }
 

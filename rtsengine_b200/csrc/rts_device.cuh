@@ -157,9 +157,16 @@ constexpr uint32_t TRI_NEED_SCAN = 0xFFFFFFFEu;   // the reference falls back to
 // Walk part of findTriangle. Returns the triangle, TRI_NEED_SCAN where the reference would scan all triangles
 // (Triangulation.cpp:1503-1510, 1539-1546; done warp-cooperatively by the caller), or TRI_NONE + flag on failure.
 template <bool WIDE>
+__device__ __forceinline__ uint32_t find_triangle_from(const MapDev& M, iv2 q, uint32_t t, uint32_t& flags);
+template <bool WIDE>
 __device__ __forceinline__ uint32_t find_triangle_walk(const MapDev& M, const RtsParams& P, iv2 q, uint32_t& flags) {
     const uint32_t cell = coord_to_cell((float)q.x, (float)q.y, P.tri_nx, P.tri_ny, P.tri_cell_size);
-    uint32_t t = __ldg(M.cell2tri + cell);
+    return find_triangle_from<WIDE>(M, q, __ldg(M.cell2tri + cell), flags);
+}
+// ... from an explicit start triangle: the cache entry of q's cell (from_last_found == false, :1500-1511), or the
+// previously found triangle (from_last_found == true, used by updateCellGrid)
+template <bool WIDE>
+__device__ __forceinline__ uint32_t find_triangle_from(const MapDev& M, iv2 q, uint32_t t, uint32_t& flags) {
     if (t == TRI_NONE) return TRI_NEED_SCAN;
     iv2 a, b, c;
     int4 w1;

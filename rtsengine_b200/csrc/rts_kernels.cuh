@@ -1166,6 +1166,75 @@ __global__ void k_apply(uint32_t n, Staging S, AgentArrays A) {
     if (A.vel_outn) A.vel_outn[d] = A.vel_out[sp];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Triangulation::updateCellGrid (Triangulation.cpp:1829-1864) on the device. The reference visits the cache cells in a
+// zig-zag and locates each cell centre with findTriangle(centre, from_last_found = true): a serial chain, every walk
+// starting where the previous one ended. The chain only matters for centres that lie on a triangle edge or vertex:
+// a centre strictly inside a triangle (or on the outer boundary) is contained in exactly one triangle, and every
+// terminating walk — and the linear-scan fallback — ends there. So:
+//   k_cellgrid_classify  one thread per cell: all triangles containing the centre (inclusive test) among the ones whose
+//                        bounding box touches the cell (MapDev scan lists); one hit -> final answer, several -> ambiguous
+//   k_cellgrid_resolve   one thread per maximal run of ambiguous cells in zig-zag order: the reference's own walk from
+//                        the predecessor's triangle, cell after cell (runs are short: a wall lying on a centre line)
+__device__ __forceinline__ void zigzag_cell(uint32_t z, int nx, int ny, int& i, int& j) {
+    j = (int)(z / (uint32_t)nx);
+    const int k = (int)(z % (uint32_t)nx);
+    const bool asc = (j % 2 == 0) && (j < ny - 1);   // row pairs ascending / descending; a left-over last row descends
+    i = asc ? k : nx - 1 - k;
+}
+__device__ __forceinline__ iv2 cell_centre(int i, int j, float cs) {
+    const float cx = (float)i * cs + cs / 2.f, cy = (float)j * cs + cs / 2.f;   // Triangulation.cpp:1838
+    return iv2{(int32_t)cx, (int32_t)cy};
+}
+template <bool WIDE>
+__global__ void k_cellgrid_classify(RtsParams P, MapDev M, uint32_t* cell2tri, uint32_t* first_hit, uint8_t* ambiguous) {
+    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_cells = (uint32_t)P.tri_nx * (uint32_t)P.tri_ny;
+    if (z >= n_cells) return;
+    int i, j;
+    zigzag_cell(z, P.tri_nx, P.tri_ny, i, j);
+    const iv2 q = cell_centre(i, j, P.tri_cell_size);
+    const uint32_t cell = (uint32_t)j * (uint32_t)P.tri_nx + (uint32_t)i;
+    uint32_t first = TRI_NONE, hits = 0;
+    auto test = [&](uint32_t t) {
+        iv2 a, b, c;
+        int4 w1;
+        load_tri_verts(M, t, a, b, c, w1);
+        if (in_triangle<WIDE>(q, a, b, c)) {
+            first = min(first, t);
+            ++hits;
+        }
+    };
+    for (uint32_t k = __ldg(M.scan_off + cell), e = __ldg(M.scan_off + cell + 1); k < e; ++k) test(__ldg(M.scan_list + k));
+    for (uint32_t k = 0; k < M.n_scan_large; ++k) test(__ldg(M.scan_large + k));
+    cell2tri[cell] = first;
+    first_hit[z] = first;
+    ambiguous[z] = hits > 1 ? 1 : 0;
+}
+template <bool WIDE>
+__global__ void k_cellgrid_resolve(RtsParams P, MapDev M, uint32_t last_found, uint32_t* cell2tri, const uint32_t* first_hit,
+                                   const uint8_t* ambiguous) {
+    const uint32_t z0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_cells = (uint32_t)P.tri_nx * (uint32_t)P.tri_ny;
+    if (z0 >= n_cells || !ambiguous[z0] || (z0 > 0 && ambiguous[z0 - 1])) return;   // heads of ambiguous runs only
+    int i, j;
+    uint32_t prev = last_found;
+    if (z0 > 0) {   // the predecessor is unambiguous, its entry is final
+        zigzag_cell(z0 - 1, P.tri_nx, P.tri_ny, i, j);
+        prev = cell2tri[(uint32_t)j * (uint32_t)P.tri_nx + (uint32_t)i];
+    }
+    if (prev >= M.n_tris) prev = TRI_NONE;
+    for (uint32_t z = z0; z < n_cells && ambiguous[z]; ++z) {
+        zigzag_cell(z, P.tri_nx, P.tri_ny, i, j);
+        const iv2 q = cell_centre(i, j, P.tri_cell_size);
+        uint32_t flags = 0;
+        uint32_t t = find_triangle_from<WIDE>(M, q, prev, flags);
+        if (t == TRI_NEED_SCAN) t = first_hit[z];   // the reference's linear scan returns the lowest containing index
+        cell2tri[(uint32_t)j * (uint32_t)P.tri_nx + (uint32_t)i] = t;
+        if (t != TRI_NONE) prev = t;
+    }
+}
+
 // stand-alone queries
 __global__ void k_coord_to_cell(const float2* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

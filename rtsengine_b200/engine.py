@@ -67,6 +67,7 @@ def load_library():
         "rts_abi_sizeof": (C.c_size_t, [i32]),
         "rts_coord_to_cell": (i32, [H, vp, u32, i32, i32, f32, vp]),
         "rts_find_triangles": (i32, [H, vp, u32, vp]),
+        "rts_build_cell_grid": (i32, [H, u32, vp]),
         "rts_contact_edges": (i32, [H, vp, vp, u32, u32, vp, vp]),
         "rts_stream": (vp, [H]),
         "rts_slab_configure": (i32, [H, i32, i32, u32, u32]),
@@ -154,11 +155,20 @@ class GpuAgentSystem:
     def upload_map(self, tables: dict):
         keep: list = []
         tris = abi.triangles_array(tables["tri_verts"], tables["tri_nbrs"], tables.get("tri_constrained"))
-        c2t = np.ascontiguousarray(tables["cell2tri"], np.uint32)
-        if c2t.size != self.params.tri_nx * self.params.tri_ny:
-            raise ValueError("cell2tri does not match the triangle grid of the params")
+        c2t = tables.get("cell2tri")   # None: the cache is built on the device (Triangulation::updateCellGrid)
+        if c2t is not None:
+            c2t = np.ascontiguousarray(c2t, np.uint32)
+            if c2t.size != self.params.tri_nx * self.params.tri_ny:
+                raise ValueError("cell2tri does not match the triangle grid of the params")
         walls = abi.wall_table(tables, keep)
-        self._chk(self.L.rts_upload_map(self.h, tris.ctypes.data, len(tris), c2t.ctypes.data, C.byref(walls)))
+        self._chk(self.L.rts_upload_map(self.h, tris.ctypes.data, len(tris), None if c2t is None else c2t.ctypes.data,
+                                        C.byref(walls)))
+
+    def build_cell_grid(self, last_found=0) -> np.ndarray:
+        """Triangulation::updateCellGrid on the device; returns (and installs) the cell -> triangle cache"""
+        out = np.zeros(int(self.params.tri_nx) * int(self.params.tri_ny), np.uint32)
+        self._chk(self.L.rts_build_cell_grid(self.h, int(last_found), out.ctypes.data))
+        return out
 
     def upload_unit_types(self, types: np.ndarray):
         types = np.ascontiguousarray(types, abi.UNIT_DTYPE)

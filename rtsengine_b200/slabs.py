@@ -17,6 +17,7 @@ import ctypes as C
 import json
 import math
 import os
+import sys
 import time
 
 import numpy as np
@@ -277,6 +278,15 @@ def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     cnt = torch.tensor([len(own["gid"])], device="cuda", dtype=torch.int64)
     dist.all_reduce(cnt)
     barrier()
+    if os.environ.get("RTS_BENCH_RANK_TRACE"):   # diagnostic: per-rank kernel times of a further (serialised) 40 frames
+        sr.g.set_profiling(True)
+        sr.g.reset_timings()
+        sr.g.update(40, sync=True)
+        ms = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in engine.KERNELS}
+        print(json.dumps({"rank": rank, "dev_ms_per_frame": dev_ms / K, "owned": len(own["gid"]), "kernel_ms": ms}),
+              file=sys.stderr, flush=True)
+        sr.g.set_profiling(False)
+        barrier()
     if rank == 0:
         peak, peak_src = measured_peak()
         value = n_total * K / (max_ms * 1e-3)

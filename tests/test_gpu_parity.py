@@ -395,3 +395,37 @@ def test_baseline_config4_map_tiles_wide_arithmetic():
         assert core.sum() > 500
         for k in ("r", "vel", "inertia", "tri_idx"):
             H.assert_same_bits(out[k][idx][core], sub[k][core], f"window {k}")
+
+
+# ---- f3: Triangulation::updateCellGrid on the device ------------------------------------------------------------
+# (map_empty: the first cell centre (20,20) lies on the diagonal shared by triangles 2 and 4, the reference's
+#  last_found_tri_ind_ was 2 when it built the recorded table)
+@pytest.mark.parametrize("name,cells,last_found", [("frame_small.npz", (512, 512), 0), ("frame_dense.npz", (512, 512), 0),
+                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0)])
+def test_cell_grid_built_on_device_equals_the_reference_table(name, cells, last_found):
+    fx = H.load(name)
+    tables = H.tables_of(fx)
+    recorded = np.asarray(tables["cell2tri"], np.uint32)
+    without = {k: v for k, v in tables.items() if k != "cell2tri"}
+    p = engine.default_params(*cells)
+    with engine.GpuAgentSystem(p) as g:
+        g.upload_map(without)                                   # no host cache: built by the upload
+        built = g.build_cell_grid(last_found)
+        assert np.array_equal(built, recorded), np.nonzero(built != recorded)[0][:8]
+        ow = port.OracleWorld(port.default_params(*cells), tables)
+        assert np.array_equal(ow.build_cell_grid(last_found), recorded)
+        rng = np.random.default_rng(4)
+        pts = rng.uniform(-30, cells[0] * 5 + 30, (20000, 2)).astype(np.float32)
+        H.assert_same_bits(g.find_triangles(pts), ow.find_triangles(pts), "findTriangle over the device-built cache")
+
+
+def test_cell_grid_wide_arithmetic_on_a_tiled_map():
+    from rtsengine_b200 import scenario
+    fx = scenario.tile_map(scenario.load_map("map_c3.npz"), 1, 4)          # 1024 x 4096 cells: int64 products
+    tables = scenario.tables_of(fx)
+    nx, ny = (int(v) for v in fx["n_cells"])
+    ow = port.OracleWorld(port.default_params(nx, ny), tables)
+    with engine.GpuAgentSystem(engine.default_params(nx, ny)) as g:
+        g.upload_map({k: v for k, v in tables.items() if k != "cell2tri"})
+        for lf in (0, 17):
+            assert np.array_equal(g.build_cell_grid(lf), ow.build_cell_grid(lf))

@@ -85,3 +85,14 @@ def test_ghosts_are_neighbours_only():
     own = ghost == 0
     H.assert_same_bits(b["r"][own], ref["r"][own], "owned agents unaffected by ghost marking")
     H.assert_same_bits(b["r"][~own], a["r"][~own], "ghosts are not moved")
+
+
+@pytest.mark.parametrize("name,cells,last_found", [("frame_small.npz", (512, 512), 0), ("frame_dense.npz", (512, 512), 0),
+                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0)])
+def test_cell_grid_restatement_reproduces_recorded_tables(name, cells, last_found):
+    """Triangulation::updateCellGrid (Triangulation.cpp:1829-1864): the tables in the fixtures were written by the
+    reference itself; 95 / 2 / 64 / 196 of their cell centres lie on triangle edges or vertices, where the entry depends
+    on the zig-zag walk (map_empty: the reference's last_found_tri_ind_ was 2 when it built the table)."""
+    tables = H.tables_of(H.load(name))
+    ow = port.OracleWorld(port.default_params(*cells), tables)
+    assert np.array_equal(ow.build_cell_grid(last_found), np.asarray(tables["cell2tri"], np.uint32))

@@ -99,3 +99,32 @@ def test_snapshot_arrival_rule_tracks_the_serial_cascade():
     d_or = np.linalg.norm(a["r"] - np.array(target), axis=1)
     assert abs(d_ref.mean() - d_or.mean()) < 0.03 * d_ref.mean()
     assert abs(ow.fin_area[0] - n_or * np.float32(np.pi) * 9) < 1.0
+
+
+@pytest.mark.parametrize("seed,buildings", [(0, 0), (1, 12), (2, 45)])
+def test_cell_grid_restatement_matches_update_cell_grid(seed, buildings):
+    """f3: oracle build_cell_grid == Triangulation::updateCellGrid (Triangulation.cpp:1829-1864) on live CDTs, for every
+    possible start triangle of the first cell (buildings snapped to the 40-unit cache grid put many cell centres on
+    triangle edges, where the answer depends on the walk)."""
+    rng = np.random.default_rng(seed)
+    w = refh.RefWorld(512, 512)
+    occ = np.zeros((512, 512), bool)
+    k = 0
+    while k < buildings:
+        cx, cy = (int(v) for v in rng.integers(4, 60, 2) * 4)          # centres at multiples of 20 units
+        if occ[cx - 7:cx + 7, cy - 7:cy + 7].any():
+            continue
+        assert w.add_building(cx, cy, 8, 8, 1) == 0
+        occ[cx - 5:cx + 5, cy - 5:cy + 5] = True
+        k += 1
+    w.finalize_map()
+    P = port.default_params(512, 512)
+    tables = w.tables()
+    ow = port.OracleWorld(P, tables)
+    n_tris = len(tables["tri_verts"])
+    starts = range(n_tris) if n_tris < 20 else rng.integers(0, n_tris, 6)
+    for lf in starts:
+        w.rebuild_cell_grid(int(lf))
+        ref = np.asarray(w.tables()["cell2tri"], np.uint32)
+        got = ow.build_cell_grid(int(lf))
+        assert np.array_equal(got, ref), (int(lf), np.nonzero(got != ref)[0][:8])
