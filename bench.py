@@ -204,7 +204,7 @@ def run_gpu(args):
     g.set_profiling(True)
     g.reset_timings()
     g.update(K, sync=True)
-    kt = {k: g.kernel_time_ms(k) for k in ("step", "scan", "reorder", "walk")}
+    kt = {k: g.kernel_time_ms(k) for k in ("step", "dense", "scan", "reorder", "walk")}
     g.set_profiling(False)
     step_ms = kt["step"][0]
     peak, peak_src = measured_peak()

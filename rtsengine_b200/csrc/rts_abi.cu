@@ -60,8 +60,8 @@ struct RtsContext {
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // the triangle walk runs on a second stream, overlapping the next frame kernel
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;
+    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork = nullptr, ev_dense = nullptr;
     bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
@@ -75,6 +75,8 @@ struct RtsContext {
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
     bool overlap_walk = true;         // triangle walk on the side stream (reserved[4] = 1 turns it off)
+    bool overlap_dense = true;        // k_step_dense on a third stream next to k_step (reserved[5] = 1 turns it off)
+    int dense_side_ctas = 2;          // ... with this many CTAs per SM (reserved[5] = 2..6 overrides)
     bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
@@ -186,6 +188,7 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
         A.dense_n = dn;
     }
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
+    CU(cudaMemsetAsync(A.dense_q, 0xFF, sizeof(uint32_t) * (size_t)cap, h->stream));   // DENSE_EMPTY
     A.n_dev = h->n_dev;
     A.n_tris_dev_hint = h->map_ready ? h->M.n_tris : 0u;
     h->cap = cap;
@@ -302,9 +305,16 @@ void launch_step_kernel(RtsContext* h) {
         k_arrive<<<blocks_for(nb, 256), 256, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->multi ? 1 : 0);
         h->launches += 2;
     }
+    // k_step_dense goes to a third stream and consumes the queue of crowded agents while k_step is still producing it
+    // (see the kernel); with per-kernel timing on it runs after k_step on the main stream instead
+    const bool side = USE_DENSE_KERNEL && nb && h->overlap_dense && !h->profiling;
+    if (side) {
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
+    }
+    const dim3 grid(blocks_for(nb, STEP_BLOCK));
     timer_begin(h, KT_STEP);
     if (nb) {
-        const dim3 grid(blocks_for(nb, STEP_BLOCK));
 #define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL)
         const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->staged ? 1 : 0);
         switch (variant) {
@@ -318,19 +328,30 @@ void launch_step_kernel(RtsContext* h) {
             default: LAUNCH_STEP(true, true, true); break;
         }
 #undef LAUNCH_STEP
-        if (USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
-            timer_begin(h, KT_DENSE);
-            const dim3 dgrid(148 * RTS_DENSE_GRID_PER_SM);
-            const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
-            if (dv == 0) k_step_dense<false, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
-            else if (dv == 1) k_step_dense<false, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
-            else if (dv == 2) k_step_dense<true, false><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
-            else k_step_dense<true, true><<<dgrid, 128, 0, h->stream>>>(h->P, h->M, h->F, h->A, h->SL);
-            timer_end(h, KT_DENSE);
-            h->launches += 1;
-        }
     }
     timer_end(h, KT_STEP);
+    if (nb && USE_DENSE_KERNEL) {   // the crowded agents k_step queues, one warp each
+        timer_begin(h, KT_DENSE);
+        const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
+#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, h->A, h->SL, grid.x, h->cap)
+        for (int pass = side ? 0 : 1; pass < 2; ++pass) {
+            // pass 0, next to k_step: it must never be able to fill the machine (its warps wait for k_step), 2 CTAs per SM;
+            // pass 1, after k_step on the main stream: the full grid for what is left of the queue
+            const dim3 dgrid(148 * (pass == 0 ? h->dense_side_ctas : RTS_DENSE_GRID_PER_SM));
+            cudaStream_t st = pass == 0 ? h->stream3 : h->stream;
+            if (dv == 0) LAUNCH_DENSE(false, false);
+            else if (dv == 1) LAUNCH_DENSE(false, true);
+            else if (dv == 2) LAUNCH_DENSE(true, false);
+            else LAUNCH_DENSE(true, true);
+            h->launches += 1;
+        }
+#undef LAUNCH_DENSE
+        timer_end(h, KT_DENSE);
+        if (side) {
+            cudaEventRecord(h->ev_dense, h->stream3);
+            cudaStreamWaitEvent(h->stream, h->ev_dense, 0);
+        }
+    }
     h->launches += 1;
 }
 
@@ -473,9 +494,14 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->use_graph = params->reserved[2] == 0;
     h->staged = params->reserved[3] != 0;
     h->overlap_walk = params->reserved[4] == 0;
+    h->overlap_dense = params->reserved[5] != 1;
+    if (params->reserved[5] >= 2 && params->reserved[5] <= 6) h->dense_side_ctas = (int)params->reserved[5];
     *out = h;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_dense, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
@@ -513,6 +539,7 @@ int32_t rts_destroy(RtsHandle h) {
     if (!h) return RTS_E_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream2);
+    cudaStreamSynchronize(h->stream3);
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
@@ -527,7 +554,9 @@ int32_t rts_destroy(RtsHandle h) {
     }
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev_scatter); cudaEventDestroy(h->ev_walk);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_dense);
     cudaStreamDestroy(h->stream2);
+    cudaStreamDestroy(h->stream3);
     cudaStreamDestroy(h->stream);
     delete h;
     return RTS_OK;
@@ -1003,6 +1032,11 @@ int32_t rts_sync(RtsHandle h) {
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     timer_collect(h);
+    if (USE_DENSE_KERNEL && h->A.dense_n) {
+        uint32_t timed_out = 0;
+        CU(cudaMemcpy(&timed_out, h->A.dense_n + 3, 4, cudaMemcpyDeviceToHost));
+        if (timed_out) return h->fail(RTS_E_STATE, "k_step_dense", "gave up waiting for the frame kernel (agents were left unprocessed)");
+    }
     if (h->multi) {
         uint32_t n_live = 0, overflow = 0;
         CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));

@@ -130,7 +130,8 @@ struct AgentArrays {
     uint2* cellrank;  // {next fine cell, rank inside it}
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
     uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
-    uint32_t* dense_n;   // their number (reset by k_scatter)
+    uint32_t* dense_n;   // [0] their number, [1] k_step CTAs that have finished, [2] next queue position to consume (all reset by
+                         // k_scatter), [3] a consumer timed out
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) *A.dense_n = 0u;        // the dense queue of this frame has been consumed
+    if (p == 0) { A.dense_n[0] = 0u; A.dense_n[1] = 0u; A.dense_n[2] = 0u; }   // the dense queue of this frame has been consumed
     if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
         SL.send[p >> 2].hdr[p & 3u] = 0u;
     }
@@ -781,12 +782,9 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
 
     if (!in_range) {
         if (MULTI && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
-        return;
-    }
-    if (ghost) {  // halo copy: neighbour only, dropped from the next order
+    } else if (ghost) {  // halo copy: neighbour only, dropped from the next order
         A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
-        return;
-    }
+    } else {
     const uint32_t sp = A.src[p];
     const float radius = me.z, mass_i = me.w;
     const uint32_t gid = mykey.x;
@@ -874,7 +872,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     const bool to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
     uint32_t cell = INVALID_CELL;
     if (to_dense) {
-        A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
+        *((volatile uint32_t*)A.dense_q + atomicAdd(A.dense_n, 1u)) = p;
+        __threadfence();
     } else {
     {   // keys + insertion sort of the shared-memory part, every lane in step
         const int m = min(cnt, NBR_CAP);
@@ -951,24 +950,62 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     }
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
     if (!to_dense) A.cellrank[p] = make_uint2(cell, rank);
+    }
+    if (USE_DENSE_KERNEL) {   // k_step_dense may already be running (second stream): tell it when every queue entry is out
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(A.dense_n + 1, 1u);
+        }
+    }
 }
 
 // One warp per crowded agent (see k_step): the 32 lanes scan the candidates together, sort the accepted neighbours by
 // (visit rank, gid) with a bitonic sort in shared memory, compute the force terms of 32 neighbours at a time, and add
 // them up in order (every lane redundantly, through shuffles); lane 0 then finishes the frame for the agent.
+// The kernel is launched twice per frame. A small grid goes to another stream next to k_step and consumes the queue while
+// k_step is still filling it (its CTAs are dispatched when k_step has no CTA left to dispatch, i.e. into k_step's tail); a
+// full grid follows k_step on the main stream and helps with whatever is left. A warp claims the next queue position and
+// waits for the entry to appear, or for the count of finished k_step CTAs to reach `n_producers`, after which a missing
+// entry means the queue has ended. Entries are reset to DENSE_EMPTY by the consumer. The wait is bounded (DENSE_SPIN_LIMIT).
+constexpr uint32_t DENSE_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t DENSE_SPIN_LIMIT = 1u << 21;   // x ~0.25 us
 template <bool KEEP_VEL, bool MULTI>
-__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL, uint32_t n_producers,
+                                                    uint32_t q_cap) {
     __shared__ uint2 s_list[4][DENSE_MAX];
     __shared__ float s_terms[4][7][32];
     __shared__ uint32_t s_mask[4][32];
     const unsigned lane = threadIdx.x & 31u;
     const int w = threadIdx.x >> 5;
-    const uint32_t n_warps = gridDim.x * 4u;
-    const uint32_t qn = *A.dense_n;
     uint2* list = s_list[w];
     const float rscatter2 = P.rscatter * P.rscatter;
-    for (uint32_t qi = blockIdx.x * 4u + (uint32_t)w; qi < qn; qi += n_warps) {
-        const uint32_t p = A.dense_q[qi];
+    for (;;) {
+        uint32_t p = DENSE_EMPTY;
+        if (lane == 0u) {
+            volatile uint32_t* q = A.dense_q;
+            volatile uint32_t* ctr = A.dense_n;
+            // (once k_step has finished, a queue that has been claimed to its end needs no further claim)
+            const bool drained = ctr[1] >= n_producers && ctr[2] >= ctr[0];
+            const uint32_t qi = drained ? q_cap : atomicAdd(A.dense_n + 2, 1u);   // next unclaimed queue position
+            for (uint32_t spins = 0; qi < q_cap; ++spins) {
+                p = q[qi];
+                if (p != DENSE_EMPTY) break;
+                if (ctr[1] >= n_producers) {   // every producer has finished and published: the entry is there, or never will be
+                    __threadfence();
+                    p = q[qi];
+                    break;
+                }
+                if (spins > DENSE_SPIN_LIMIT) {   // never hang the device: flag it (reported by rts_sync) and give up
+                    ctr[3] = 1u;
+                    break;
+                }
+                __nanosleep(200);
+            }
+            if (p != DENSE_EMPTY) q[qi] = DENSE_EMPTY;
+        }
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p == DENSE_EMPTY) break;
         const float4 me = A.pos4[p];
         const uint2 mykey = A.key2[p];
         const uint32_t sp = A.src[p];

@@ -15,7 +15,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librts_b200.so")
+LIB_PATH = os.environ.get("RTS_B200_LIB") or os.path.join(_HERE, "librts_b200.so")   # override: A/B of build variants (tools/)
 
 _lib = None
 
