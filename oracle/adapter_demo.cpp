@@ -132,6 +132,7 @@ int main(int argc, char** argv) {
     }
     RefWorld& A = *W[0];
     RefWorld& B = *W[1];
+    long cell_grid_mismatches = 0;
 
     // ---- world B: the GPU slots in place of the CPU systems (what INTEGRATION.md §2 adds to ECSystem's constructor)
     RtsParams params;
@@ -148,6 +149,8 @@ int main(int argc, char** argv) {
     }
     if (gpu) seek->p_comps_ = std::make_shared<ComponentArray<PathFinderComponent>>();
     if (gpu) seek->physics = phys.get();
+    A.cdt->last_found_tri_ind_ = 0;
+    A.cdt->updateCellGrid();
     if (gpu) {   // Game::updateTriangulation hook: flatten Edges + CDT and upload
         auto& cdt = *B.cdt;
         std::vector<RtsTriangle> tris(cdt.triangles_.size());
@@ -171,7 +174,14 @@ int main(int argc, char** argv) {
             walls.line_offsets[o] = off[o].data();
             walls.n_lines[o] = (uint32_t)off[o].size() - 1;
         }
-        seek->uploadMap(tris.data(), (uint32_t)tris.size(), cdt.cell2triangle_ind_.data(), walls);
+        // the findTriangle cache: the host loop (Triangulation::updateCellGrid, above) in world A, the device builder in world B
+        seek->uploadMap(tris.data(), (uint32_t)tris.size(), nullptr, walls);
+        std::vector<uint32_t> built(cdt.cell2triangle_ind_.size());
+        if (rts_build_cell_grid(seek->h, 0u, built.data()) != RTS_OK) { printf("{\"error\": \"rts_build_cell_grid\"}\n"); return 2; }
+        for (size_t c = 0; c < built.size(); ++c) {
+            cell_grid_mismatches += built[c] != (uint32_t)A.cdt->cell2triangle_ind_[c];
+            cdt.cell2triangle_ind_[c] = (TriInd)built[c];   // world B's host planner reads the device-built table
+        }
     }
 
     // ---- units (UnitInitializer::initializeUnit): identical in both worlds
@@ -299,8 +309,8 @@ int main(int argc, char** argv) {
     }
     int moving = 0;
     for (int i = 0; i < n_agents; ++i) moving += A.shared->at(i).state == MoveState::MOVING;
-    printf("{\"agents\": %d, \"buildings\": %d, \"frames\": %d, \"compared\": %ld, \"mismatches\": %ld, \"first_bad_frame\": %d, "
+    printf("{\"agents\": %d, \"buildings\": %d, \"frames\": %d, \"cell_grid_mismatches\": %ld, \"compared\": %ld, \"mismatches\": %ld, \"first_bad_frame\": %d, "
            "\"replans\": %d, \"moving_at_end\": %d, \"cpu_ms_per_frame\": %.3f, \"gpu_adapter_ms_per_frame\": %.3f}\n",
-           n_agents, n_buildings, frames, compared, mismatches, first_bad_frame, replans, moving, 1e3 * t_cpu / frames, 1e3 * t_gpu / frames);
-    return mismatches ? 3 : 0;
+           n_agents, n_buildings, frames, cell_grid_mismatches, compared, mismatches, first_bad_frame, replans, moving, 1e3 * t_cpu / frames, 1e3 * t_gpu / frames);
+    return (mismatches || cell_grid_mismatches) ? 3 : 0;
 }

@@ -60,8 +60,12 @@ struct RtsContext {
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // the triangle walk runs on a second stream, overlapping the next frame kernel
-    cudaStream_t stream2 = nullptr, stream3 = nullptr;
-    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork = nullptr, ev_dense = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // walk / streamed dense kernel / slab edge rows + exchange
+    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork = nullptr, ev_dense = nullptr, ev_fork2 = nullptr, ev_comm = nullptr;
+    std::vector<RtsUnitType> types_host;
+    float max_type_speed = 100.f;     // max over unit types of the velocity clamp + seek speed, see set_edge_rows
+    bool frame_is_split = false;      // this frame's edge rows, exchange and ingest are on stream4 (see split_frame)
+    bool overlap_exchange = true;     // reserved[5] bit 3 (value 8) turns the split off
     bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
@@ -179,16 +183,16 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     AL(pos4n, float4) AL(key2n, uint2) AL(vel4n, float4) AL(nav4n, float4) AL(trin, uint32_t) AL(cellrank, uint2)
     if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
     AL(stop_req, uint32_t)
-    AL(dense_q, uint32_t)
 #undef AL
-    {
+    {   // two queues of crowded agents (whole population / interior, and the edge rows of a slab) + their counters
+        if ((rc = dev_alloc<uint32_t>(h, &A.dense_q, 2 * (size_t)cap, h->agent_allocs)) != RTS_OK) return rc;
         uint32_t* dn = nullptr;
-        if ((rc = dev_alloc<uint32_t>(h, &dn, 4, h->agent_allocs)) != RTS_OK) return rc;
-        CU(cudaMemsetAsync(dn, 0, 16, h->stream));
+        if ((rc = dev_alloc<uint32_t>(h, &dn, 8, h->agent_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(dn, 0, 32, h->stream));
         A.dense_n = dn;
     }
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
-    CU(cudaMemsetAsync(A.dense_q, 0xFF, sizeof(uint32_t) * (size_t)cap, h->stream));   // DENSE_EMPTY
+    CU(cudaMemsetAsync(A.dense_q, 0xFF, sizeof(uint32_t) * 2 * (size_t)cap, h->stream));   // DENSE_EMPTY
     A.n_dev = h->n_dev;
     A.n_tris_dev_hint = h->map_ready ? h->M.n_tris : 0u;
     h->cap = cap;
@@ -298,12 +302,62 @@ int32_t launch_scan_reorder(RtsContext* h) {
     return RTS_OK;
 }
 
+// Edge rows of a slab (SlabDev): the fine rows that reach into the halo band plus the farthest an agent can travel in one
+// frame (velocity clamp of the fastest unit type + its seek speed), with one more fine row of margin.
+void set_edge_rows(RtsContext* h) {
+    SlabDev& SL = h->SL;
+    const FineGrid& F = h->F;
+    const float max_travel = h->max_type_speed * std::fabs(h->P.dt);
+    const float reach = SL.halo + max_travel + 1.0f / F.inv_cs;
+    const int lo = (int)std::floor((SL.y_lo + reach) * F.inv_cs) - F.row0 + 1;
+    const int hi = (int)std::floor((SL.y_hi - reach) * F.inv_cs) - F.row0;
+    SL.edge_row_lo = std::min(std::max(lo, 0), F.ny);
+    SL.edge_row_hi = std::min(std::max(hi, SL.edge_row_lo), F.ny);
+    SL.interior_launch = 0;
+}
+
+// Does this frame split the frame kernel into the edge rows (comm stream, followed there by the exchange and the ingest)
+// and the interior (main stream)? Only slab handles with a neighbour; not while per-kernel timers are on.
+bool split_frame(const RtsContext* h) {
+    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->staged;
+}
+
 void launch_step_kernel(RtsContext* h) {
     const uint32_t nb = h->multi ? h->cap_main : h->n;
     if (h->P.enable_arrival && nb && h->M.n_groups) {
         k_area_sync<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M);
         k_arrive<<<blocks_for(nb, 256), 256, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->multi ? 1 : 0);
         h->launches += 2;
+    }
+    const dim3 grid(blocks_for(nb, STEP_BLOCK));
+    const bool split = nb && split_frame(h);
+    h->frame_is_split = split;
+    if (split) {   // |v| <= max_speed * mul_velocity (clamp, PhysicsSystem.cpp:34-37) + seek_max_speed (SeekSystem.cpp:92)
+        float vmax = 0.f;
+        for (const RtsUnitType& u : h->types_host) vmax = std::max(vmax, std::fabs(u.max_speed * h->P.mul_velocity) + std::fabs(u.seek_max_speed));
+        h->max_type_speed = vmax;
+        set_edge_rows(h);
+    }
+    const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
+#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq, grid.x, h->cap)
+    if (split) {
+        // edge rows first, on the comm stream: their own queue of crowded agents, drained right behind them
+        cudaEventRecord(h->ev_fork2, h->stream);
+        cudaStreamWaitEvent(h->stream4, h->ev_fork2, 0);
+        AgentArrays Aq = h->A;
+        Aq.dense_q = h->A.dense_q + h->cap;
+        Aq.dense_n = h->A.dense_n + 4;
+        const SlabDev SLq = h->SL;
+        if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+        else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+        h->launches += 1;
+        if (USE_DENSE_KERNEL) {
+            const dim3 dgrid(148 * 2);
+            cudaStream_t st = h->stream4;
+            if (dv == 1) LAUNCH_DENSE(false, true);
+            else LAUNCH_DENSE(true, true);
+            h->launches += 1;
+        }
     }
     // k_step_dense goes to a third stream and consumes the queue of crowded agents while k_step is still producing it
     // (see the kernel); with per-kernel timing on it runs after k_step on the main stream instead
@@ -312,10 +366,15 @@ void launch_step_kernel(RtsContext* h) {
         cudaEventRecord(h->ev_fork, h->stream);
         cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
     }
-    const dim3 grid(blocks_for(nb, STEP_BLOCK));
+    SlabDev SLq = h->SL;
+    SLq.interior_launch = split ? 1 : 0;
+    const AgentArrays& Aq = h->A;
     timer_begin(h, KT_STEP);
-    if (nb) {
-#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->SL)
+    if (split) {
+        if (h->keep_vel) k_step<true, true, false, 2><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq);
+        else k_step<false, true, false, 2><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq);
+    } else if (nb) {
+#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq)
         const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->staged ? 1 : 0);
         switch (variant) {
             case 0: LAUNCH_STEP(false, false, false); break;
@@ -332,8 +391,6 @@ void launch_step_kernel(RtsContext* h) {
     timer_end(h, KT_STEP);
     if (nb && USE_DENSE_KERNEL) {   // the crowded agents k_step queues, one warp each
         timer_begin(h, KT_DENSE);
-        const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
-#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, h->A, h->SL, grid.x, h->cap)
         for (int pass = side ? 0 : 1; pass < 2; ++pass) {
             // pass 0, next to k_step: it must never be able to fill the machine (its warps wait for k_step), 2 CTAs per SM;
             // pass 1, after k_step on the main stream: the full grid for what is left of the queue
@@ -345,30 +402,38 @@ void launch_step_kernel(RtsContext* h) {
             else LAUNCH_DENSE(true, true);
             h->launches += 1;
         }
-#undef LAUNCH_DENSE
         timer_end(h, KT_DENSE);
         if (side) {
             cudaEventRecord(h->ev_dense, h->stream3);
             cudaStreamWaitEvent(h->stream, h->ev_dense, 0);
         }
     }
+#undef LAUNCH_DENSE
     h->launches += 1;
 }
 
-// slabs: first half of a frame — zero the send headers, run the frame kernel (which packs migrants + halo)
+// slabs: first half of a frame — run the frame kernel (which packs migrants + halo)
 int32_t frame_begin(RtsContext* h) {
     launch_step_kernel(h);   // slabs: the send headers were zeroed by the previous k_scatter (or rts_slab_configure)
     return RTS_OK;
 }
+
+// the stream the exchange and the ingest of this frame go to
+cudaStream_t comm_stream(const RtsContext* h) { return h->frame_is_split ? h->stream4 : h->stream; }
 
 // slabs: second half — append what arrived, then scan + reorder
 int32_t frame_end(RtsContext* h) {
     if (h->multi) {
         const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
         timer_begin(h, KT_INGEST);
-        k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, h->stream>>>(h->cap_main, h->SL, h->F, h->A);
+        k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, comm_stream(h)>>>(h->cap_main, h->SL, h->F, h->A);
         timer_end(h, KT_INGEST);
         h->launches += 1;
+        if (h->frame_is_split) {   // the interior (main stream) and the edge rows + exchange + ingest (comm stream) meet here
+            cudaEventRecord(h->ev_comm, h->stream4);
+            cudaStreamWaitEvent(h->stream, h->ev_comm, 0);
+            h->frame_is_split = false;
+        }
     }
     return launch_scan_reorder(h);
 }
@@ -376,13 +441,14 @@ int32_t frame_end(RtsContext* h) {
 // neighbour exchange over NCCL: send[0] goes to rank-1 and lands in its recv[1]; send[1] goes to rank+1's recv[0]
 int32_t exchange_nccl(RtsContext* h) {
     if (!h->comm) return h->fail(RTS_E_STATE, "exchange", "rts_comm_init has not been called");
+    cudaStream_t st = comm_stream(h);
     timer_begin(h, KT_EXCHANGE);
     ncclResult_t r = h->p_ncclGroupStart();
     for (int d = 0; d < 2 && r == ncclSuccess; ++d) {
         if (!h->SL.has[d]) continue;
         const int peer = h->rank + (d == 0 ? -1 : 1);
-        r = h->p_ncclSend(h->ex_send[d], h->ex_bytes, ncclUint8, peer, h->comm, h->stream);
-        if (r == ncclSuccess) r = h->p_ncclRecv(h->ex_recv[d], h->ex_bytes, ncclUint8, peer, h->comm, h->stream);
+        r = h->p_ncclSend(h->ex_send[d], h->ex_bytes, ncclUint8, peer, h->comm, st);
+        if (r == ncclSuccess) r = h->p_ncclRecv(h->ex_recv[d], h->ex_bytes, ncclUint8, peer, h->comm, st);
     }
     const ncclResult_t r2 = h->p_ncclGroupEnd();
     if (r == ncclSuccess) r = r2;
@@ -494,12 +560,16 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->use_graph = params->reserved[2] == 0;
     h->staged = params->reserved[3] != 0;
     h->overlap_walk = params->reserved[4] == 0;
-    h->overlap_dense = params->reserved[5] != 1;
-    if (params->reserved[5] >= 2 && params->reserved[5] <= 6) h->dense_side_ctas = (int)params->reserved[5];
+    h->overlap_dense = (params->reserved[5] & 7u) != 1;
+    if ((params->reserved[5] & 7u) >= 2 && (params->reserved[5] & 7u) <= 6) h->dense_side_ctas = (int)(params->reserved[5] & 7u);
+    h->overlap_exchange = (params->reserved[5] & 8u) == 0;
     *out = h;
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_dense, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming) != cudaSuccess ||
@@ -540,6 +610,7 @@ int32_t rts_destroy(RtsHandle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream2);
     cudaStreamSynchronize(h->stream3);
+    cudaStreamSynchronize(h->stream4);
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
@@ -555,6 +626,8 @@ int32_t rts_destroy(RtsHandle h) {
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev_scatter); cudaEventDestroy(h->ev_walk);
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_dense);
+    cudaEventDestroy(h->ev_fork2); cudaEventDestroy(h->ev_comm);
+    cudaStreamDestroy(h->stream4);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream3);
     cudaStreamDestroy(h->stream);
@@ -784,6 +857,7 @@ int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_
     CU(cudaMemcpyAsync(d, full.data(), sizeof(RtsUnitType) * 256, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->M.unit_types = d; h->M.n_types = n_types;
+    h->types_host.assign(types, types + n_types);
     if (old) {
         for (auto it = h->type_allocs.begin(); it != h->type_allocs.end(); ++it)
             if (*it == old) { cudaFree(old); h->type_allocs.erase(it); break; }
@@ -1042,6 +1116,7 @@ int32_t rts_sync(RtsHandle h) {
         CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&overflow, h->SL.overflow, 4, cudaMemcpyDeviceToHost));
         h->n = n_live;
+        if (overflow == 2u) return h->fail(RTS_E_STATE, "slab exchange", "an agent outside the edge rows crossed into the halo band (moved farther in one frame than its unit type allows)");
         if (overflow) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
         if (n_live > h->cap_main) return h->fail(RTS_E_CAPACITY, "slab", "population outgrew the slot capacity of this handle");
     }
@@ -1260,6 +1335,7 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     SL.halo = std::sqrt(P.r_max2) * 1.05f + 0.25f;
     SL.has[0] = P.slab_row_lo > 0; SL.has[1] = P.slab_row_hi < P.ns_ny;
     SL.cap_mig = cap_migrants; SL.cap_halo = cap_halo;
+    set_edge_rows(h);
     // one buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
     const size_t bytes = 16 + (size_t)cap_migrants * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8);
     auto carve = [&](void* base, ExBuf& B) {
@@ -1372,6 +1448,8 @@ int32_t rts_slab_exchange_local(RtsHandle lower, RtsHandle upper) {
     if (!lower->multi || !upper->multi || lower->ex_bytes != upper->ex_bytes) return h->fail(RTS_E_STATE, "rts_slab_exchange_local", "handles are not matching slabs");
     CU(cudaStreamSynchronize(lower->stream));
     CU(cudaStreamSynchronize(upper->stream));
+    CU(cudaStreamSynchronize(lower->stream4));   // the edge rows (which fill the send buffers) may be on the comm stream
+    CU(cudaStreamSynchronize(upper->stream4));
     CU(cudaMemcpy(upper->ex_recv[0], lower->ex_send[1], lower->ex_bytes, cudaMemcpyDeviceToDevice));
     CU(cudaMemcpy(lower->ex_recv[1], upper->ex_send[0], lower->ex_bytes, cudaMemcpyDeviceToDevice));
     return RTS_OK;

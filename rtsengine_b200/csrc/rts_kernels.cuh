@@ -106,7 +106,12 @@ struct SlabDev {
     int32_t has[2];           // neighbour present in direction 0 / 1
     uint32_t cap_mig, cap_halo;
     ExBuf send[2], recv[2];
-    uint32_t* overflow;       // sticky: set when a migrant / halo record did not fit its buffer
+    uint32_t* overflow;       // sticky: 1 = a migrant / halo record did not fit its buffer, 2 = an agent outside the edge rows packed
+    // Edge rows (fine-grid rows relative to FineGrid::row0): slots of rows < edge_row_lo or >= edge_row_hi can send
+    // something to a neighbour this frame (halo band + one frame of travel). k_step<PHASE 1> steps exactly those, so that
+    // the exchange can start while k_step<PHASE 2> is still working on the interior.
+    int32_t edge_row_lo, edge_row_hi;
+    int32_t interior_launch;  // set in the copy handed to PHASE 2 launches: an agent that packs there was missed by PHASE 1
 };
 
 struct AgentArrays {
@@ -131,7 +136,7 @@ struct AgentArrays {
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
     uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
     uint32_t* dense_n;   // [0] their number, [1] k_step CTAs that have finished, [2] next queue position to consume (all reset by
-                         // k_scatter), [3] a consumer timed out
+                         // k_scatter), [3] a consumer timed out; [4..7] the same for the queue of a slab's edge-row launch
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
@@ -314,7 +319,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) { A.dense_n[0] = 0u; A.dense_n[1] = 0u; A.dense_n[2] = 0u; }   // the dense queue of this frame has been consumed
+    if (p == 0) {   // the dense queues of this frame (whole / interior, and the edge rows' own) have been consumed
+        A.dense_n[0] = 0u; A.dense_n[1] = 0u; A.dense_n[2] = 0u;
+        A.dense_n[4] = 0u; A.dense_n[5] = 0u; A.dense_n[6] = 0u;
+    }
     if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
         SL.send[p >> 2].hdr[p & 3u] = 0u;
     }
@@ -657,6 +665,9 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     if (MULTI) {
         // ownership follows the physics-grid row of the new position (integer, identical on every rank)
         const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
+        if (SL.interior_launch && ((dir >= 0 && SL.has[dir]) || (SL.has[0] && r_new.y < SL.y_lo + SL.halo) ||
+                                   (SL.has[1] && r_new.y >= SL.y_hi - SL.halo)))
+            *SL.overflow = 2u;   // the exchange of this frame is already under way: report (rts_sync), never drop silently
         if (dir >= 0 && SL.has[dir]) {
             // migrate: full record to the neighbour; the local copy stays one more frame as a ghost (it is within
             // one frame's travel of the boundary, i.e. inside the halo band of this slab)
@@ -697,7 +708,8 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
 // ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
-template <bool KEEP_VEL, bool MULTI, bool STAGED>
+// PHASE 0: every slot; PHASE 1: the edge rows of a slab only (see SlabDev), PHASE 2: everything else.
+template <bool KEEP_VEL, bool MULTI, bool STAGED, int PHASE = 0>
 __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
     __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
     // neighbour records of every fine cell this CTA's agents can see, staged once (coalesced) instead of being fetched
@@ -723,7 +735,13 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     }
     const v2 r = V(me.x, me.y);
     const bool ghost = (mykey.y >> 2) & 1u;
-    const unsigned active = __ballot_sync(valid, !ghost);  // lanes that reach the re-bin at the end
+    bool mine = true;   // does this launch step this slot?
+    if (PHASE != 0) {
+        const uint32_t a = SL.has[0] ? __ldg(F.start + (uint32_t)SL.edge_row_lo * (uint32_t)F.nx) : 0u;
+        const uint32_t b = SL.has[1] ? __ldg(F.start + (uint32_t)SL.edge_row_hi * (uint32_t)F.nx) : 0xFFFFFFFFu;
+        mine = (PHASE == 1) == (p < a || p >= b);
+    }
+    const unsigned active = __ballot_sync(valid, !ghost && mine);  // lanes that reach the re-bin at the end
     int fx, fy;
     fine_coords(F, r.x, r.y, fx, fy);
 
@@ -781,7 +799,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     if (STAGED) __syncthreads();
 
     if (!in_range) {
-        if (MULTI && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
+        if (MULTI && PHASE != 1 && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
+    } else if (!mine) {
     } else if (ghost) {  // halo copy: neighbour only, dropped from the next order
         A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
     } else {

@@ -33,6 +33,7 @@ def test_system2_adapter_matches_reference_systems(agents, buildings, frames, se
     assert line, out.stdout + out.stderr
     res = json.loads(line[-1])
     assert "error" not in res, res
+    assert res["cell_grid_mismatches"] == 0, res          # rts_build_cell_grid == Triangulation::updateCellGrid
     assert res["compared"] == agents * frames
     assert res["mismatches"] == 0, res
     assert res["moving_at_end"] > 0.5 * agents          # the move commands were still being followed

@@ -10,7 +10,8 @@ from tests.test_gpu_parity import random_world
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("n,lo,hi,frames", [(40000, 100.0, 1100.0, 12), (6000, 380.0, 620.0, 8)])
+# (the third case is a crowd of 1.4 agents per unit² cut by the slab boundary: the edge rows' own queue of crowded agents)
+@pytest.mark.parametrize("n,lo,hi,frames", [(40000, 100.0, 1100.0, 12), (6000, 380.0, 620.0, 8), (20000, 440.0, 560.0, 6)])
 def test_two_slabs_equal_one_domain(n, lo, hi, frames):
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
