@@ -60,12 +60,14 @@ struct RtsContext {
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // the triangle walk runs on a second stream, overlapping the next frame kernel
-    cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;   // walk / streamed dense kernel / slab edge rows + exchange
-    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork = nullptr, ev_dense = nullptr, ev_fork2 = nullptr, ev_comm = nullptr;
+    cudaStream_t stream2 = nullptr, stream4 = nullptr;   // walk / slab edge rows + exchange
+    cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork2 = nullptr, ev_comm = nullptr;
     std::vector<RtsUnitType> types_host;
     float max_type_speed = 100.f;     // max over unit types of the velocity clamp + seek speed, see set_edge_rows
+    bool ingest_done = false;         // k_ingest_remote of this frame has been launched
     bool frame_is_split = false;      // this frame's edge rows, exchange and ingest are on stream4 (see split_frame)
-    bool overlap_exchange = true;     // reserved[5] bit 3 (value 8) turns the split off
+    bool overlap_exchange = false;    // reserved[5] bit 3 (value 8) turns the split on: it measured 2 % slower at 2 GPUs (0.262 vs
+                                      // 0.257 ms per frame) than exchanging between the frame kernel and the scan, so it is opt-in
     bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
@@ -79,8 +81,6 @@ struct RtsContext {
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
     bool overlap_walk = true;         // triangle walk on the side stream (reserved[4] = 1 turns it off)
-    bool overlap_dense = true;        // k_step_dense on a third stream next to k_step (reserved[5] = 1 turns it off)
-    int dense_side_ctas = 2;          // ... with this many CTAs per SM (reserved[5] = 2..6 overrides)
     bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
@@ -192,7 +192,6 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
         A.dense_n = dn;
     }
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
-    CU(cudaMemsetAsync(A.dense_q, 0xFF, sizeof(uint32_t) * 2 * (size_t)cap, h->stream));   // DENSE_EMPTY
     A.n_dev = h->n_dev;
     A.n_tris_dev_hint = h->map_ready ? h->M.n_tris : 0u;
     h->cap = cap;
@@ -311,61 +310,65 @@ void set_edge_rows(RtsContext* h) {
     const float reach = SL.halo + max_travel + 1.0f / F.inv_cs;
     const int lo = (int)std::floor((SL.y_lo + reach) * F.inv_cs) - F.row0 + 1;
     const int hi = (int)std::floor((SL.y_hi - reach) * F.inv_cs) - F.row0;
-    SL.edge_row_lo = std::min(std::max(lo, 0), F.ny);
-    SL.edge_row_hi = std::min(std::max(hi, SL.edge_row_lo), F.ny);
+    SL.edge_row_lo = std::min(std::max(lo, 1), F.ny - 1);
+    SL.edge_row_hi = std::min(std::max(hi, SL.edge_row_lo), F.ny - 1);
     SL.interior_launch = 0;
+    // grid of the edge launch, per side: the edge rows hold ~3x the agents of the halo band (band + travel + one row +
+    // the ghosts below the boundary); the halo capacity already carries the caller's safety factor
+    SL.edge_blocks = std::min(blocks_for(2u * SL.cap_halo + SL.cap_mig, STEP_BLOCK), blocks_for(std::max(h->cap_main, 1u), STEP_BLOCK));
 }
 
 // Does this frame split the frame kernel into the edge rows (comm stream, followed there by the exchange and the ingest)
 // and the interior (main stream)? Only slab handles with a neighbour; not while per-kernel timers are on.
 bool split_frame(const RtsContext* h) {
-    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->staged;
+    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->staged && h->F.ny >= 4;
 }
 
-void launch_step_kernel(RtsContext* h) {
+#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq)
+
+// arrival kernels, then — slab handles with a neighbour — the edge rows on the comm stream (their own queue of crowded
+// agents is drained right behind them)
+void launch_step_edges(RtsContext* h) {
     const uint32_t nb = h->multi ? h->cap_main : h->n;
     if (h->P.enable_arrival && nb && h->M.n_groups) {
         k_area_sync<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M);
         k_arrive<<<blocks_for(nb, 256), 256, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->multi ? 1 : 0);
         h->launches += 2;
     }
-    const dim3 grid(blocks_for(nb, STEP_BLOCK));
     const bool split = nb && split_frame(h);
     h->frame_is_split = split;
-    if (split) {   // |v| <= max_speed * mul_velocity (clamp, PhysicsSystem.cpp:34-37) + seek_max_speed (SeekSystem.cpp:92)
+    if (!split) return;
+    {   // |v| <= max_speed * mul_velocity (clamp, PhysicsSystem.cpp:34-37) + seek_max_speed (SeekSystem.cpp:92)
         float vmax = 0.f;
         for (const RtsUnitType& u : h->types_host) vmax = std::max(vmax, std::fabs(u.max_speed * h->P.mul_velocity) + std::fabs(u.seek_max_speed));
         h->max_type_speed = vmax;
         set_edge_rows(h);
     }
-    const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
-#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq, grid.x, h->cap)
-    if (split) {
-        // edge rows first, on the comm stream: their own queue of crowded agents, drained right behind them
-        cudaEventRecord(h->ev_fork2, h->stream);
-        cudaStreamWaitEvent(h->stream4, h->ev_fork2, 0);
-        AgentArrays Aq = h->A;
-        Aq.dense_q = h->A.dense_q + h->cap;
-        Aq.dense_n = h->A.dense_n + 4;
-        const SlabDev SLq = h->SL;
-        if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
-        else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+    cudaEventRecord(h->ev_fork2, h->stream);
+    cudaStreamWaitEvent(h->stream4, h->ev_fork2, 0);
+    AgentArrays Aq = h->A;
+    Aq.dense_q = h->A.dense_q + h->cap;
+    Aq.dense_n = h->A.dense_n + 4;
+    const SlabDev SLq = h->SL;
+    const dim3 grid(2 * SLq.edge_blocks);
+    if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+    else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+    h->launches += 1;
+    if (USE_DENSE_KERNEL) {
+        const dim3 dgrid(148 * 2);
+        cudaStream_t st = h->stream4;
+        if (h->keep_vel) LAUNCH_DENSE(true, true);
+        else LAUNCH_DENSE(false, true);
         h->launches += 1;
-        if (USE_DENSE_KERNEL) {
-            const dim3 dgrid(148 * 2);
-            cudaStream_t st = h->stream4;
-            if (dv == 1) LAUNCH_DENSE(false, true);
-            else LAUNCH_DENSE(true, true);
-            h->launches += 1;
-        }
     }
-    // k_step_dense goes to a third stream and consumes the queue of crowded agents while k_step is still producing it
-    // (see the kernel); with per-kernel timing on it runs after k_step on the main stream instead
-    const bool side = USE_DENSE_KERNEL && nb && h->overlap_dense && !h->profiling;
-    if (side) {
-        cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->stream3, h->ev_fork, 0);
-    }
+}
+
+// the frame kernel over everything (or, after launch_step_edges split the frame, over the interior) + k_step_dense
+void launch_step_interior(RtsContext* h) {
+    const uint32_t nb = h->multi ? h->cap_main : h->n;
+    const dim3 grid(blocks_for(nb, STEP_BLOCK));
+    const bool split = h->frame_is_split;
+    const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
     SlabDev SLq = h->SL;
     SLq.interior_launch = split ? 1 : 0;
     const AgentArrays& Aq = h->A;
@@ -389,46 +392,46 @@ void launch_step_kernel(RtsContext* h) {
 #undef LAUNCH_STEP
     }
     timer_end(h, KT_STEP);
-    if (nb && USE_DENSE_KERNEL) {   // the crowded agents k_step queues, one warp each
+    if (nb && USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
         timer_begin(h, KT_DENSE);
-        for (int pass = side ? 0 : 1; pass < 2; ++pass) {
-            // pass 0, next to k_step: it must never be able to fill the machine (its warps wait for k_step), 2 CTAs per SM;
-            // pass 1, after k_step on the main stream: the full grid for what is left of the queue
-            const dim3 dgrid(148 * (pass == 0 ? h->dense_side_ctas : RTS_DENSE_GRID_PER_SM));
-            cudaStream_t st = pass == 0 ? h->stream3 : h->stream;
-            if (dv == 0) LAUNCH_DENSE(false, false);
-            else if (dv == 1) LAUNCH_DENSE(false, true);
-            else if (dv == 2) LAUNCH_DENSE(true, false);
-            else LAUNCH_DENSE(true, true);
-            h->launches += 1;
-        }
+        const dim3 dgrid(148 * RTS_DENSE_GRID_PER_SM);
+        cudaStream_t st = h->stream;
+        if (dv == 0) LAUNCH_DENSE(false, false);
+        else if (dv == 1) LAUNCH_DENSE(false, true);
+        else if (dv == 2) LAUNCH_DENSE(true, false);
+        else LAUNCH_DENSE(true, true);
         timer_end(h, KT_DENSE);
-        if (side) {
-            cudaEventRecord(h->ev_dense, h->stream3);
-            cudaStreamWaitEvent(h->stream, h->ev_dense, 0);
-        }
+        h->launches += 1;
     }
-#undef LAUNCH_DENSE
     h->launches += 1;
 }
+#undef LAUNCH_DENSE
 
 // slabs: first half of a frame — run the frame kernel (which packs migrants + halo)
 int32_t frame_begin(RtsContext* h) {
-    launch_step_kernel(h);   // slabs: the send headers were zeroed by the previous k_scatter (or rts_slab_configure)
+    launch_step_edges(h);      // slabs: the send headers were zeroed by the previous k_scatter (or rts_slab_configure)
+    launch_step_interior(h);
     return RTS_OK;
 }
 
 // the stream the exchange and the ingest of this frame go to
 cudaStream_t comm_stream(const RtsContext* h) { return h->frame_is_split ? h->stream4 : h->stream; }
 
-// slabs: second half — append what arrived, then scan + reorder
+// slabs: what arrived is appended behind the frame kernel's slots (on the comm stream when the frame is split)
+void launch_ingest(RtsContext* h) {
+    const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
+    timer_begin(h, KT_INGEST);
+    k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, comm_stream(h)>>>(h->cap_main, h->SL, h->F, h->A);
+    timer_end(h, KT_INGEST);
+    h->launches += 1;
+    h->ingest_done = true;
+}
+
+// slabs: second half — ingest (unless launch_frame already did it), then scan + reorder
 int32_t frame_end(RtsContext* h) {
     if (h->multi) {
-        const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
-        timer_begin(h, KT_INGEST);
-        k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, comm_stream(h)>>>(h->cap_main, h->SL, h->F, h->A);
-        timer_end(h, KT_INGEST);
-        h->launches += 1;
+        if (!h->ingest_done) launch_ingest(h);
+        h->ingest_done = false;
         if (h->frame_is_split) {   // the interior (main stream) and the edge rows + exchange + ingest (comm stream) meet here
             cudaEventRecord(h->ev_comm, h->stream4);
             cudaStreamWaitEvent(h->stream, h->ev_comm, 0);
@@ -458,9 +461,16 @@ int32_t exchange_nccl(RtsContext* h) {
 }
 
 int32_t launch_frame(RtsContext* h) {
-    int32_t rc = frame_begin(h);
-    if (rc != RTS_OK) return rc;
-    if (h->multi && h->nranks > 1 && (rc = exchange_nccl(h)) != RTS_OK) return rc;
+    // a split slab frame enqueues edge rows -> exchange -> ingest on the (high-priority) comm stream BEFORE the interior
+    // kernel is launched, so that they do not queue up behind its CTAs
+    launch_step_edges(h);
+    int32_t rc = RTS_OK;
+    if (h->multi && h->nranks > 1 && h->frame_is_split) {
+        if ((rc = exchange_nccl(h)) != RTS_OK) return rc;
+        launch_ingest(h);
+    }
+    launch_step_interior(h);
+    if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange_nccl(h)) != RTS_OK) return rc;
     return frame_end(h);
 }
 
@@ -560,18 +570,16 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->use_graph = params->reserved[2] == 0;
     h->staged = params->reserved[3] != 0;
     h->overlap_walk = params->reserved[4] == 0;
-    h->overlap_dense = (params->reserved[5] & 7u) != 1;
-    if ((params->reserved[5] & 7u) >= 2 && (params->reserved[5] & 7u) <= 6) h->dense_side_ctas = (int)(params->reserved[5] & 7u);
-    h->overlap_exchange = (params->reserved[5] & 8u) == 0;
+    h->overlap_exchange = (params->reserved[5] & 8u) != 0;
     *out = h;
+    int prio_lo = 0, prio_hi = 0;   // the comm stream (edge rows, exchange, ingest of a slab) outranks the bulk kernels
+    cudaSetDevice(device_id);
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_dense, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_scatter, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_walk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
@@ -609,7 +617,6 @@ int32_t rts_destroy(RtsHandle h) {
     if (!h) return RTS_E_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream2);
-    cudaStreamSynchronize(h->stream3);
     cudaStreamSynchronize(h->stream4);
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
@@ -625,11 +632,9 @@ int32_t rts_destroy(RtsHandle h) {
     }
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev_scatter); cudaEventDestroy(h->ev_walk);
-    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_dense);
     cudaEventDestroy(h->ev_fork2); cudaEventDestroy(h->ev_comm);
     cudaStreamDestroy(h->stream4);
     cudaStreamDestroy(h->stream2);
-    cudaStreamDestroy(h->stream3);
     cudaStreamDestroy(h->stream);
     delete h;
     return RTS_OK;
@@ -1106,17 +1111,12 @@ int32_t rts_sync(RtsHandle h) {
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     timer_collect(h);
-    if (USE_DENSE_KERNEL && h->A.dense_n) {
-        uint32_t timed_out = 0;
-        CU(cudaMemcpy(&timed_out, h->A.dense_n + 3, 4, cudaMemcpyDeviceToHost));
-        if (timed_out) return h->fail(RTS_E_STATE, "k_step_dense", "gave up waiting for the frame kernel (agents were left unprocessed)");
-    }
     if (h->multi) {
         uint32_t n_live = 0, overflow = 0;
         CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&overflow, h->SL.overflow, 4, cudaMemcpyDeviceToHost));
         h->n = n_live;
-        if (overflow == 2u) return h->fail(RTS_E_STATE, "slab exchange", "an agent outside the edge rows crossed into the halo band (moved farther in one frame than its unit type allows)");
+        if (overflow == 2u) return h->fail(RTS_E_STATE, "slab exchange", "an agent outside the edge launch packed for a neighbour (more agents in the edge rows than the halo capacity allows for, or a move longer than its unit type allows)");
         if (overflow) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
         if (n_live > h->cap_main) return h->fail(RTS_E_CAPACITY, "slab", "population outgrew the slot capacity of this handle");
     }

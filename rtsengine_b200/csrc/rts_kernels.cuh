@@ -112,6 +112,10 @@ struct SlabDev {
     // the exchange can start while k_step<PHASE 2> is still working on the interior.
     int32_t edge_row_lo, edge_row_hi;
     int32_t interior_launch;  // set in the copy handed to PHASE 2 launches: an agent that packs there was missed by PHASE 1
+    // The PHASE 1 launch has 2*edge_blocks CTAs: the first edge_blocks cover the slots from 0 upward (the low edge rows),
+    // the others the slots from the first high edge row upward. Edge slots beyond that coverage are left to PHASE 2 and
+    // reported there if they pack.
+    uint32_t edge_blocks;
 };
 
 struct AgentArrays {
@@ -135,8 +139,7 @@ struct AgentArrays {
     uint2* cellrank;  // {next fine cell, rank inside it}
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
     uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
-    uint32_t* dense_n;   // [0] their number, [1] k_step CTAs that have finished, [2] next queue position to consume (all reset by
-                         // k_scatter), [3] a consumer timed out; [4..7] the same for the queue of a slab's edge-row launch
+    uint32_t* dense_n;   // [0] their number (reset by k_scatter); [4] the same for the queue of a slab's edge-row launch
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
@@ -319,10 +322,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) {   // the dense queues of this frame (whole / interior, and the edge rows' own) have been consumed
-        A.dense_n[0] = 0u; A.dense_n[1] = 0u; A.dense_n[2] = 0u;
-        A.dense_n[4] = 0u; A.dense_n[5] = 0u; A.dense_n[6] = 0u;
-    }
+    if (p == 0) { A.dense_n[0] = 0u; A.dense_n[4] = 0u; }   // the dense queues of this frame (whole / interior, edge rows) have been consumed
     if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
         SL.send[p >> 2].hdr[p & 3u] = 0u;
     }
@@ -664,7 +664,8 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     const float4 nav_new = make_float4(r_next.x, r_next.y, __int_as_float(pid), __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
     if (MULTI) {
         // ownership follows the physics-grid row of the new position (integer, identical on every rank)
-        const int dir = ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
+        // (an agent whose position has just become NaN — coincident agents, 0/0 in the reference too — stays where it is)
+        const int dir = !(fabsf(r_new.y) <= 3.0e38f) ? -1 : ((int)cy_new < SL.row_lo) ? 0 : (((int)cy_new >= SL.row_hi) ? 1 : -1);
         if (SL.interior_launch && ((dir >= 0 && SL.has[dir]) || (SL.has[0] && r_new.y < SL.y_lo + SL.halo) ||
                                    (SL.has[1] && r_new.y >= SL.y_hi - SL.halo)))
             *SL.overflow = 2u;   // the exchange of this frame is already under way: report (rts_sync), never drop silently
@@ -721,9 +722,20 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     __shared__ int s_first[2], s_last[2], s_mode, s_total;
 
     const int tid = threadIdx.x;
-    const uint32_t block0 = blockIdx.x * STEP_BLOCK;
-    const uint32_t p = block0 + tid;
     const uint32_t n = MULTI ? *A.n_dev : n_bound;   // slabs: the population changes every frame, the count lives on the device
+    // edge slots of a slab: [0, edge_a) and [edge_b, n)
+    // (the first and the last fine row are always edge rows: positions outside the slab's grid are clamped into them,
+    //  among them agents that left the map, whose wrapped physics row (Grid.cpp:18-24) can make them migrate)
+    uint32_t edge_a = 0u, edge_b = 0xFFFFFFFFu;
+    if (PHASE != 0) {
+        edge_a = __ldg(F.start + (uint32_t)(SL.has[0] ? SL.edge_row_lo : 1) * (uint32_t)F.nx);
+        edge_b = __ldg(F.start + (uint32_t)(SL.has[1] ? SL.edge_row_hi : F.ny - 1) * (uint32_t)F.nx);
+        edge_b = max(edge_b, edge_a);
+    }
+    const uint32_t cover = SL.edge_blocks * STEP_BLOCK;   // slots the PHASE 1 grid reaches on either side
+    uint32_t block0 = blockIdx.x * STEP_BLOCK;
+    if (PHASE == 1 && blockIdx.x >= SL.edge_blocks) block0 = edge_b + (blockIdx.x - SL.edge_blocks) * STEP_BLOCK;
+    const uint32_t p = block0 + tid;
     const bool in_range = p < n;
     const unsigned valid = __ballot_sync(0xffffffffu, in_range);
 
@@ -737,9 +749,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     const bool ghost = (mykey.y >> 2) & 1u;
     bool mine = true;   // does this launch step this slot?
     if (PHASE != 0) {
-        const uint32_t a = SL.has[0] ? __ldg(F.start + (uint32_t)SL.edge_row_lo * (uint32_t)F.nx) : 0u;
-        const uint32_t b = SL.has[1] ? __ldg(F.start + (uint32_t)SL.edge_row_hi * (uint32_t)F.nx) : 0xFFFFFFFFu;
-        mine = (PHASE == 1) == (p < a || p >= b);
+        const bool covered = (p < edge_a && p < cover) || (p >= edge_b && p - edge_b < cover);
+        mine = (PHASE == 1) ? (covered && (blockIdx.x < SL.edge_blocks ? p < edge_a : true)) : !covered;
     }
     const unsigned active = __ballot_sync(valid, !ghost && mine);  // lanes that reach the re-bin at the end
     int fx, fy;
@@ -891,8 +902,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     const bool to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
     uint32_t cell = INVALID_CELL;
     if (to_dense) {
-        *((volatile uint32_t*)A.dense_q + atomicAdd(A.dense_n, 1u)) = p;
-        __threadfence();
+        A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
     } else {
     {   // keys + insertion sort of the shared-memory part, every lane in step
         const int m = min(cnt, NBR_CAP);
@@ -970,28 +980,13 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
     if (!to_dense) A.cellrank[p] = make_uint2(cell, rank);
     }
-    if (USE_DENSE_KERNEL) {   // k_step_dense may already be running (second stream): tell it when every queue entry is out
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(A.dense_n + 1, 1u);
-        }
-    }
 }
 
 // One warp per crowded agent (see k_step): the 32 lanes scan the candidates together, sort the accepted neighbours by
 // (visit rank, gid) with a bitonic sort in shared memory, compute the force terms of 32 neighbours at a time, and add
 // them up in order (every lane redundantly, through shuffles); lane 0 then finishes the frame for the agent.
-// The kernel is launched twice per frame. A small grid goes to another stream next to k_step and consumes the queue while
-// k_step is still filling it (its CTAs are dispatched when k_step has no CTA left to dispatch, i.e. into k_step's tail); a
-// full grid follows k_step on the main stream and helps with whatever is left. A warp claims the next queue position and
-// waits for the entry to appear, or for the count of finished k_step CTAs to reach `n_producers`, after which a missing
-// entry means the queue has ended. Entries are reset to DENSE_EMPTY by the consumer. The wait is bounded (DENSE_SPIN_LIMIT).
-constexpr uint32_t DENSE_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t DENSE_SPIN_LIMIT = 1u << 21;   // x ~0.25 us
 template <bool KEEP_VEL, bool MULTI>
-__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL, uint32_t n_producers,
-                                                    uint32_t q_cap) {
+__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
     __shared__ uint2 s_list[4][DENSE_MAX];
     __shared__ float s_terms[4][7][32];
     __shared__ uint32_t s_mask[4][32];
@@ -999,32 +994,10 @@ __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineG
     const int w = threadIdx.x >> 5;
     uint2* list = s_list[w];
     const float rscatter2 = P.rscatter * P.rscatter;
-    for (;;) {
-        uint32_t p = DENSE_EMPTY;
-        if (lane == 0u) {
-            volatile uint32_t* q = A.dense_q;
-            volatile uint32_t* ctr = A.dense_n;
-            // (once k_step has finished, a queue that has been claimed to its end needs no further claim)
-            const bool drained = ctr[1] >= n_producers && ctr[2] >= ctr[0];
-            const uint32_t qi = drained ? q_cap : atomicAdd(A.dense_n + 2, 1u);   // next unclaimed queue position
-            for (uint32_t spins = 0; qi < q_cap; ++spins) {
-                p = q[qi];
-                if (p != DENSE_EMPTY) break;
-                if (ctr[1] >= n_producers) {   // every producer has finished and published: the entry is there, or never will be
-                    __threadfence();
-                    p = q[qi];
-                    break;
-                }
-                if (spins > DENSE_SPIN_LIMIT) {   // never hang the device: flag it (reported by rts_sync) and give up
-                    ctr[3] = 1u;
-                    break;
-                }
-                __nanosleep(200);
-            }
-            if (p != DENSE_EMPTY) q[qi] = DENSE_EMPTY;
-        }
-        p = __shfl_sync(0xffffffffu, p, 0);
-        if (p == DENSE_EMPTY) break;
+    const uint32_t n_warps = gridDim.x * 4u;
+    const uint32_t qn = *A.dense_n;
+    for (uint32_t qi = blockIdx.x * 4u + (uint32_t)w; qi < qn; qi += n_warps) {
+        const uint32_t p = A.dense_q[qi];
         const float4 me = A.pos4[p];
         const uint2 mykey = A.key2[p];
         const uint32_t sp = A.src[p];

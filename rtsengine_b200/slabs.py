@@ -219,6 +219,18 @@ def make_unique_id(engine_lib) -> bytes:
 
 
 def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
+    try:
+        return _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes)
+    except BaseException:
+        # a rank that fails must take the job down: its peers are waiting for it inside NCCL and would sit there until
+        # the launcher's timeout
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+
+
+def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     """N>1 leg of bench.py: weak scaling, per-GPU population fixed (args.agents per GPU, default 1.25M = 10M / 8)."""
     import torch
     import torch.distributed as dist
@@ -239,6 +251,8 @@ def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     paths = scenario.paths_of(fx)
     nx, ny = (int(v) for v in fx["n_cells"])
     base = engine.default_params(nx, ny)
+    if os.environ.get("RTS_RESERVED5"):   # diagnostic A/B of the stream-overlap switches (RtsParams.reserved[5])
+        base.reserved[5] = int(os.environ["RTS_RESERVED5"])
     agents = scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
     agents["gid"] = np.arange(n_total, dtype=np.uint32)
     bounds = partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)

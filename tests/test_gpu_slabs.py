@@ -11,8 +11,10 @@ pytestmark = pytest.mark.gpu
 
 
 # (the third case is a crowd of 1.4 agents per unit² cut by the slab boundary: the edge rows' own queue of crowded agents)
+# split: the opt-in frame layout that steps the edge rows first on a comm stream (RtsParams.reserved[5] bit 3)
+@pytest.mark.parametrize("split", [0, 8])
 @pytest.mark.parametrize("n,lo,hi,frames", [(40000, 100.0, 1100.0, 12), (6000, 380.0, 620.0, 8), (20000, 440.0, 560.0, 6)])
-def test_two_slabs_equal_one_domain(n, lo, hi, frames):
+def test_two_slabs_equal_one_domain(n, lo, hi, frames, split):
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
     a, paths = random_world(21, n, tables, lo, hi)
@@ -27,7 +29,9 @@ def test_two_slabs_equal_one_domain(n, lo, hi, frames):
         a2 = dict(a)
         a2["gid"] = np.arange(n, dtype=np.uint32)
         parts = slabs.split_agents(a2, bounds, base.ns_cell_size, base.ns_ny)
-        ranks = [slabs.SlabRank(base, bounds, r, 0, cap_migrants=4096, cap_halo=16384) for r in range(2)]
+        slab_base = engine.default_params(512, 512)
+        slab_base.reserved[5] = split
+        ranks = [slabs.SlabRank(slab_base, bounds, r, 0, cap_migrants=4096, cap_halo=16384) for r in range(2)]
         L = ranks[0].g.L
         try:
             for r, sr in enumerate(ranks):
@@ -107,3 +111,46 @@ def test_slab_handle_requires_global_ids():
         assert e.value.code == abi.RTS_E_ARG
     finally:
         sr.close()
+
+
+def test_agents_outside_the_map_do_not_break_the_edge_row_split():
+    """Positions beyond the map are clamped into the first / last fine row of a slab's grid and their physics row wraps
+    (Grid.cpp:18-24), so they can pack from rows far from the slab boundary: those rows always belong to the edge launch.
+    The frame must neither lose an agent nor report RTS_E_STATE; NaN agents stay with their owner."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    n = 6000
+    a, paths = random_world(23, n, tables, 200.0, 2300.0)
+    a["r"][:40, 1] = np.linspace(-30.0, -1.0, 40, dtype=np.float32)          # below the map (slab 0, no lower neighbour)
+    a["r"][40:80, 1] = np.linspace(2561.0, 2600.0, 40, dtype=np.float32)     # above it (slab 1, no upper neighbour)
+    a["r"][80:84] = a["r"][84:88]                                            # coincident pairs: NaN after one frame
+    base = engine.default_params(512, 512)
+    base.reserved[5] = 8                                                     # the split frame layout
+    bounds = slabs.partition_rows(a["r"][:, 1], base.ns_ny, base.ns_cell_size, 2)
+    a2 = dict(a)
+    a2["gid"] = np.arange(n, dtype=np.uint32)
+    parts = slabs.split_agents(a2, bounds, base.ns_cell_size, base.ns_ny)
+    ranks = [slabs.SlabRank(base, bounds, r, 0, cap_migrants=4096, cap_halo=16384) for r in range(2)]
+    L = ranks[0].g.L
+    try:
+        for r, sr in enumerate(ranks):
+            sr.g.upload_map(tables)
+            sr.g.upload_paths(paths)
+            sr.g.set_agents(parts[r])
+        for sr in ranks:
+            sr.g._chk(L.rts_halo_begin(sr.g.h))
+        ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+        for sr in ranks:
+            sr.g._chk(L.rts_step_end(sr.g.h))
+        for f in range(10):
+            for sr in ranks:
+                sr.g._chk(L.rts_step_begin(sr.g.h))
+            ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+            for sr in ranks:
+                sr.g._chk(L.rts_step_end(sr.g.h))
+            got = [sr.owned(("r",)) for sr in ranks]           # synchronises: raises on RTS_E_STATE / RTS_E_CAPACITY
+            gid = np.concatenate([g["gid"] for g in got])
+            assert len(gid) == n and len(np.unique(gid)) == n, f"frame {f}: agents are conserved"
+    finally:
+        for sr in ranks:
+            sr.close()

@@ -7,8 +7,7 @@ fx = scenario.load_map("map_c3.npz")
 agents, paths = scenario.config3_agents(fx, n=n)
 tables = scenario.tables_of(fx)
 only_default = len(sys.argv) > 2
-for name, idx, val in ((("default", None, 0), ("default again", None, 0)) if only_default else (("default", None, 0), ("dense on main stream", 5, 1), ("dense side grid 3/SM", 5, 3), ("dense side grid 4/SM", 5, 4),
-                       ("dense side grid 6/SM", 5, 6), ("walk on main stream", 4, 1), ("default again", None, 0))):
+for name, idx, val in ((("default", None, 0), ("default again", None, 0)) if only_default else (("default", None, 0), ("walk on main stream", 4, 1), ("no CUDA graph", 2, 1), ("default again", None, 0))):
     p = engine.default_params(1024, 1024)
     if idx is not None:
         p.reserved[idx] = val
