@@ -37,7 +37,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (the timed
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~5 ms from a thread (the timed
     region is tens of milliseconds, an `nvidia-smi -lms` child would not deliver its first row in time); nvidia-smi once
     as the fallback when NVML cannot be loaded."""
     REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
@@ -50,6 +50,11 @@ class ClockSampler:
         self.nv = None
         self.stop = threading.Event()
         self.t = None
+        self.period_s = float(os.environ.get("RTS_CLOCK_POLL_MS", "5")) * 1e-3
+        try:
+            self._open()
+        except Exception:
+            self.nv = None
 
     def _open(self):
         import pynvml as nv
@@ -78,11 +83,14 @@ class ClockSampler:
                 self._sample()
             except Exception:
                 return
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def __enter__(self):
+        # NVML is opened in the constructor: nvmlInit takes tens of milliseconds and, with 8 ranks on one host, a different
+        # time in every rank; inside the timed region that start-up skew shows up as time spent waiting for the neighbour
         try:
-            self._open()
+            if self.nv is None:
+                self._open()
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:

@@ -276,9 +276,10 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
         dist.barrier()
         torch.cuda.synchronize()
 
-    barrier()
-    sr.g.reset_timings()
-    with ClockSampler(local) as clocks:
+    sampler = ClockSampler(local)   # opens NVML here, outside the timed region (its start-up time differs from rank to rank)
+    with sampler as clocks:
+        barrier()                   # every rank enters the timed region together
+        sr.g.reset_timings()
         t0 = time.perf_counter()
         sr.g.update(K)
         sr.g.sync()
