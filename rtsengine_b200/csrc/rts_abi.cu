@@ -66,8 +66,8 @@ struct RtsContext {
     float max_type_speed = 100.f;     // max over unit types of the velocity clamp + seek speed, see set_edge_rows
     bool ingest_done = false;         // k_ingest_remote of this frame has been launched
     bool frame_is_split = false;      // this frame's edge rows, exchange and ingest are on stream4 (see split_frame)
-    bool overlap_exchange = false;    // reserved[5] bit 3 (value 8) turns the split on: it measured 2 % slower at 2 GPUs (0.262 vs
-                                      // 0.257 ms per frame) than exchanging between the frame kernel and the scan, so it is opt-in
+    bool overlap_exchange = false;    // reserved[5] bit 3 (value 8) turns the split on: at 2 GPUs it measured the same as exchanging
+                                      // between the frame kernel and the scan (0.2503 vs 0.2511 ms per frame), so it is opt-in
     bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
