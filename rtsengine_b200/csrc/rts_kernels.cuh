@@ -43,7 +43,8 @@ constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in 
 #define RTS_DENSE_GRID_PER_SM 8
 #endif
 constexpr int DENSE_MIN = RTS_DENSE_MIN;   // agents with more neighbours than this are handed to k_step_dense (one warp each)
-constexpr int DENSE_MAX = 512;             // ... up to this many (the reference itself gives up at 500, Strategy.cpp:62-65)
+constexpr int DENSE_MAX = 256;             // ... up to this many; beyond, k_step itself re-scans (the reference gives up at 500,
+                                           // Strategy.cpp:62-65). Two agents per warp share k_step_dense's 16 KB of list space.
 constexpr int SPILL_CAP = 104;    // further neighbours parked unsorted in local memory before re-scanning is needed
 // (with k_step_dense taking every agent beyond the shared-memory list, the spill list has no user and is compiled out)
 #ifdef RTS_FORCE_SPILL
@@ -992,22 +993,61 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     }
 }
 
-// One warp per crowded agent (see k_step): the 32 lanes scan the candidates together, sort the accepted neighbours by
-// (visit rank, gid) with a bitonic sort in shared memory, compute the force terms of 32 neighbours at a time, and add
-// them up in order (every lane redundantly, through shuffles); lane 0 then finishes the frame for the agent.
+// One lane GROUP per crowded agent (see k_step), DENSE_LANES = 16 lanes: two agents per warp. The kernel's duration is the
+// number of crowded agents divided by the agents in flight (registers allow ~28 warps per SM) times one agent's chain of
+// dependent memory round trips, so halving the group doubles the throughput; most crowded agents have 19..40 neighbours
+// and fill a 16-lane group well. The lanes of a group scan the candidates together, sort the accepted neighbours by
+// (visit rank, gid) with a bitonic sort in shared memory, compute the force terms of DENSE_LANES neighbours at a time, and
+// add them up in order (lanes 0..6 of the group carry the seven sums); lane 0 of the group then finishes the frame for
+// the agent. Loop bounds are made warp-uniform (maximum over the two groups) so that every __syncwarp is reached by all.
+#ifndef RTS_DENSE_LANES
+#define RTS_DENSE_LANES 32
+#endif
+constexpr uint32_t DENSE_LANES = RTS_DENSE_LANES;
+constexpr uint32_t DENSE_GROUPS = 32u / DENSE_LANES;   // agents per warp
+#ifndef RTS_DENSE_MIN_BLOCKS
+#define RTS_DENSE_MIN_BLOCKS 8
+#endif
 template <bool KEEP_VEL, bool MULTI>
-__global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
-    __shared__ uint2 s_list[4][DENSE_MAX];
-    __shared__ float s_terms[4][7][32];
-    __shared__ uint32_t s_mask[4][32];
+__global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+    __shared__ uint2 s_list[4 * DENSE_GROUPS][DENSE_MAX];
+    __shared__ uint2 s_sorted[4 * DENSE_GROUPS][DENSE_MAX];
+    __shared__ float s_terms[4 * DENSE_GROUPS][7][DENSE_LANES];
+    __shared__ uint32_t s_mask[4 * DENSE_GROUPS][DENSE_LANES];
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned grp = lane / DENSE_LANES;        // which agent of the warp
+    const unsigned gl = lane % DENSE_LANES;         // lane inside the group
+    const unsigned gshift = grp * DENSE_LANES;
+    const unsigned gmask = (DENSE_LANES == 32u) ? 0xFFFFFFFFu : ((1u << DENSE_LANES) - 1u);
     const int w = threadIdx.x >> 5;
-    uint2* list = s_list[w];
+    const unsigned slot = (unsigned)w * DENSE_GROUPS + grp;
+    uint2* list = s_list[slot];
+    uint2* sorted = s_sorted[slot];
+    float* tw = &s_terms[slot][0][0];
+    uint32_t* mw = s_mask[slot];
     const float rscatter2 = P.rscatter * P.rscatter;
-    const uint32_t n_warps = gridDim.x * 4u;
+    const uint32_t stride = gridDim.x * 4u * DENSE_GROUPS;
     const uint32_t qn = *A.dense_n;
-    for (uint32_t qi = blockIdx.x * 4u + (uint32_t)w; qi < qn; qi += n_warps) {
-        const uint32_t p = A.dense_q[qi];
+    // The tail of the frame (finish_agent: walls, seek, integration, ~2/3 of an agent's instructions) is not done by one
+    // lane per agent as the sums come out: the agents a warp works through are parked one per lane (slot index, state
+    // and sums in registers) and finished together, every lane its own agent, when 32 are parked or the queue ends.
+    uint32_t parked = 0;                       // agents parked in this warp (lane k holds the k-th)
+    uint32_t my_p = 0, my_sp = 0;
+    float4 my_me = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 my_key = make_uint2(0u, 0u);
+    ForceSums my_acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+    auto finish_parked = [&]() {
+        if (lane < parked) {
+            const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(my_p, my_sp, my_me, my_key, A.vel4[my_sp], A.nav4[my_sp], my_acc, P, M, F, A, SL);
+            A.cellrank[my_p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
+        }
+        parked = 0;
+        __syncwarp();
+    };
+    for (uint32_t q_first = (blockIdx.x * 4u + (uint32_t)w) * DENSE_GROUPS; q_first < qn; q_first += stride) {
+        const uint32_t qi = q_first + grp;
+        const bool has = qi < qn;                   // the last warp of the queue may have an idle group
+        const uint32_t p = has ? A.dense_q[qi] : A.dense_q[q_first];   // (an idle group shadows the first agent, writes nothing)
         const float4 me = A.pos4[p];
         const uint2 mykey = A.key2[p];
         const uint32_t sp = A.src[p];
@@ -1017,15 +1057,21 @@ __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineG
         int fx, fy;
         fine_coords(F, r.x, r.y, fx, fy);
         const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
-        // ---- scan: lanes stride over the three row ranges; accepted neighbours are appended with their keys
+        // ---- scan: the group's lanes stride over the three row ranges; accepted neighbours are appended with their keys
         uint32_t cnt = 0;
         for (int k = 0; k < 3; ++k) {
             const int yy = fy - 1 + k;
-            if (yy < 0 || yy >= F.ny) continue;
-            const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
-            const uint32_t qb = __ldg(F.start + rowbase + xlo), qe = __ldg(F.start + rowbase + xhi + 1);
-            for (uint32_t q0 = qb; q0 < qe; q0 += 32u) {
-                const uint32_t q = q0 + lane;
+            uint32_t qb = 0u, qe = 0u;
+            if (yy >= 0 && yy < F.ny) {
+                const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
+                qb = __ldg(F.start + rowbase + xlo);
+                qe = __ldg(F.start + rowbase + xhi + 1);
+            }
+            // warp-uniform trip count: the longer of the two groups' ranges
+            uint32_t len = qe - qb;
+            if (DENSE_GROUPS > 1u) len = max(len, __shfl_xor_sync(0xffffffffu, len, 16));
+            for (uint32_t off = 0; off < len; off += DENSE_LANES) {
+                const uint32_t q = qb + off + gl;
                 bool accept = false;
                 uint32_t key = 0;
                 if (q < qe) {
@@ -1039,69 +1085,86 @@ __global__ void __launch_bounds__(128) k_step_dense(RtsParams P, MapDev M, FineG
                         key = (rank << 28) | ok.x;
                     }
                 }
-                const unsigned hits = __ballot_sync(0xffffffffu, accept);
-                const uint32_t pos = cnt + (uint32_t)__popc(hits & ((1u << lane) - 1u));
+                const unsigned hits = (__ballot_sync(0xffffffffu, accept) >> gshift) & gmask;
+                const uint32_t pos = cnt + (uint32_t)__popc(hits & ((1u << gl) - 1u));
                 if (accept && pos < (uint32_t)DENSE_MAX) list[pos] = make_uint2(key, q);
                 cnt += (uint32_t)__popc(hits);
             }
         }
         cnt = min(cnt, (uint32_t)DENSE_MAX);   // k_step queued this agent with the same count, <= DENSE_MAX
-        // ---- bitonic sort of the list, padded to a power of two with maximal keys
-        uint32_t n2 = 32u;
-        while (n2 < cnt) n2 <<= 1;
-        for (uint32_t i = cnt + lane; i < n2; i += 32u) list[i] = make_uint2(0xFFFFFFFFu, 0u);
+        uint32_t cnt_w = cnt;                  // warp-uniform bound for the loops below
+        if (DENSE_GROUPS > 1u) cnt_w = max(cnt_w, __shfl_xor_sync(0xffffffffu, cnt_w, 16));
+        // ---- rank sort into a second list: the keys are unique (gid), so an element's position is the number of smaller
+        //      keys. Each lane takes two elements at a time and compares them with every key (one broadcast read each);
+        //      no padding, no power-of-two rounding, no barrier per step — about half the instructions of the bitonic
+        //      network for the 19..64 neighbours most crowded agents have.
         __syncwarp();
-        for (uint32_t kk = 2u; kk <= n2; kk <<= 1) {
-            for (uint32_t j = kk >> 1; j > 0u; j >>= 1) {
-                for (uint32_t i = lane; i < n2; i += 32u) {
-                    const uint32_t ixj = i ^ j;
-                    if (ixj > i) {
-                        const uint2 a = list[i], b = list[ixj];
-                        const bool up = (i & kk) == 0u;
-                        if ((a.x > b.x) == up) { list[i] = b; list[ixj] = a; }
-                    }
-                }
-                __syncwarp();
+        for (uint32_t i0 = gl; i0 < cnt_w; i0 += 2u * DENSE_LANES) {
+            const uint32_t i1 = i0 + DENSE_LANES;
+            const uint2 e0 = (i0 < cnt) ? list[i0] : make_uint2(0xFFFFFFFFu, 0u);
+            const uint2 e1 = (i1 < cnt) ? list[i1] : make_uint2(0xFFFFFFFFu, 0u);
+            uint32_t r0 = 0u, r1 = 0u;
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t kj = list[j].x;
+                r0 += (kj < e0.x) ? 1u : 0u;
+                r1 += (kj < e1.x) ? 1u : 0u;
             }
+            if (i0 < cnt) sorted[r0] = e0;
+            if (i1 < cnt) sorted[r1] = e1;
         }
-        // ---- force terms 32 neighbours at a time (one per lane), then added in key order. Only the additions have to be
-        //      sequential; the seven running sums (repulsion.xy, push.xy, dr_nn.xy, neighbour count) are independent of
-        //      one another, so lanes 0..6 each carry one of them through the chunk.
+        __syncwarp();
+        // ---- force terms DENSE_LANES neighbours at a time (one per lane), then added in key order. Only the additions have
+        //      to be sequential; the seven running sums (repulsion.xy, push.xy, dr_nn.xy, neighbour count) are independent
+        //      of one another, so lanes 0..6 of the group each carry one of them through the chunk.
         float run = 0.f;                                                 // this lane's running sum
-        const uint32_t my_bit = (lane < 2u) ? 1u : (lane < 4u) ? 2u : 4u;   // term mask bit that gates it
-        for (uint32_t base = 0; base < cnt; base += 32u) {
-            const uint32_t k = base + lane;
+        const uint32_t my_bit = (gl < 2u) ? 1u : (gl < 4u) ? 2u : 4u;   // term mask bit that gates it
+        for (uint32_t base = 0; base < cnt_w; base += DENSE_LANES) {
+            const uint32_t k = base + gl;
             ForceTerms t;
             t.mask = 0u; t.rep = V(0.f, 0.f); t.push = V(0.f, 0.f); t.dr = V(0.f, 0.f);
             if (k < cnt) {
-                const uint32_t q = list[k].y;
+                const uint32_t q = sorted[k].y;
                 t = neighbour_terms(r, me.z, me.w, state_i, __ldg(A.pos4 + q), (int)(__ldg(A.key2 + q).y & 3u), rscatter2);
             }
-            float* tw = &s_terms[w][0][0];
-            tw[0 * 32 + lane] = t.rep.x; tw[1 * 32 + lane] = t.rep.y;
-            tw[2 * 32 + lane] = t.push.x; tw[3 * 32 + lane] = t.push.y;
-            tw[4 * 32 + lane] = t.dr.x; tw[5 * 32 + lane] = t.dr.y;
-            tw[6 * 32 + lane] = 1.f;
-            s_mask[w][lane] = t.mask;
+            tw[0 * DENSE_LANES + gl] = t.rep.x; tw[1 * DENSE_LANES + gl] = t.rep.y;
+            tw[2 * DENSE_LANES + gl] = t.push.x; tw[3 * DENSE_LANES + gl] = t.push.y;
+            tw[4 * DENSE_LANES + gl] = t.dr.x; tw[5 * DENSE_LANES + gl] = t.dr.y;
+            tw[6 * DENSE_LANES + gl] = 1.f;
+            mw[gl] = t.mask;
             __syncwarp();
-            if (lane < 7u) {
-                const uint32_t m = min(32u, cnt - base);
+            if (gl < 7u && base < cnt) {
+                const uint32_t m = min(DENSE_LANES, cnt - base);
                 for (uint32_t j = 0; j < m; ++j)
-                    if (s_mask[w][j] & my_bit) run += tw[lane * 32u + j];
+                    if (mw[j] & my_bit) run += tw[gl * DENSE_LANES + j];
             }
             __syncwarp();
         }
         ForceSums acc;
-        acc.repulsion = V(__shfl_sync(0xffffffffu, run, 0), __shfl_sync(0xffffffffu, run, 1));
-        acc.push = V(__shfl_sync(0xffffffffu, run, 2), __shfl_sync(0xffffffffu, run, 3));
-        acc.dr_nn = V(__shfl_sync(0xffffffffu, run, 4), __shfl_sync(0xffffffffu, run, 5));
-        acc.n_neighbours = __shfl_sync(0xffffffffu, run, 6);
-        if (lane == 0u) {
-            const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
-            A.cellrank[p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
+        acc.repulsion = V(__shfl_sync(0xffffffffu, run, gshift + 0), __shfl_sync(0xffffffffu, run, gshift + 1));
+        acc.push = V(__shfl_sync(0xffffffffu, run, gshift + 2), __shfl_sync(0xffffffffu, run, gshift + 3));
+        acc.dr_nn = V(__shfl_sync(0xffffffffu, run, gshift + 4), __shfl_sync(0xffffffffu, run, gshift + 5));
+        acc.n_neighbours = __shfl_sync(0xffffffffu, run, gshift + 6);
+        // park the agent(s) of this round: group g's agent goes to lane parked + g (every lane of a group holds its sums)
+        for (uint32_t g = 0; g < DENSE_GROUPS; ++g) {
+            const unsigned src_lane = g * DENSE_LANES;
+            const bool g_has = __shfl_sync(0xffffffffu, has ? 1 : 0, src_lane) != 0;
+            const uint32_t g_p = __shfl_sync(0xffffffffu, p, src_lane), g_sp = __shfl_sync(0xffffffffu, sp, src_lane);
+            const float4 g_me = make_float4(__shfl_sync(0xffffffffu, me.x, src_lane), __shfl_sync(0xffffffffu, me.y, src_lane),
+                                            __shfl_sync(0xffffffffu, me.z, src_lane), __shfl_sync(0xffffffffu, me.w, src_lane));
+            const uint2 g_key = make_uint2(__shfl_sync(0xffffffffu, mykey.x, src_lane), __shfl_sync(0xffffffffu, mykey.y, src_lane));
+            ForceSums g_acc;
+            g_acc.repulsion = V(__shfl_sync(0xffffffffu, acc.repulsion.x, src_lane), __shfl_sync(0xffffffffu, acc.repulsion.y, src_lane));
+            g_acc.push = V(__shfl_sync(0xffffffffu, acc.push.x, src_lane), __shfl_sync(0xffffffffu, acc.push.y, src_lane));
+            g_acc.dr_nn = V(__shfl_sync(0xffffffffu, acc.dr_nn.x, src_lane), __shfl_sync(0xffffffffu, acc.dr_nn.y, src_lane));
+            g_acc.n_neighbours = __shfl_sync(0xffffffffu, acc.n_neighbours, src_lane);
+            if (g_has) {
+                if (lane == parked) { my_p = g_p; my_sp = g_sp; my_me = g_me; my_key = g_key; my_acc = g_acc; }
+                ++parked;
+            }
         }
-        __syncwarp();
+        if (parked + DENSE_GROUPS > 32u) finish_parked();
     }
+    if (parked) finish_parked();
 }
 
 // ------------------------------------------------------------------------------------------------
