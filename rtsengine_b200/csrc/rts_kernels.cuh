@@ -1013,7 +1013,6 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     __shared__ uint2 s_list[4 * DENSE_GROUPS][DENSE_MAX];
     __shared__ uint2 s_sorted[4 * DENSE_GROUPS][DENSE_MAX];
     __shared__ float s_terms[4 * DENSE_GROUPS][7][DENSE_LANES];
-    __shared__ uint32_t s_mask[4 * DENSE_GROUPS][DENSE_LANES];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned grp = lane / DENSE_LANES;        // which agent of the warp
     const unsigned gl = lane % DENSE_LANES;         // lane inside the group
@@ -1024,7 +1023,6 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     uint2* list = s_list[slot];
     uint2* sorted = s_sorted[slot];
     float* tw = &s_terms[slot][0][0];
-    uint32_t* mw = s_mask[slot];
     const float rscatter2 = P.rscatter * P.rscatter;
     const uint32_t stride = gridDim.x * 4u * DENSE_GROUPS;
     const uint32_t qn = *A.dense_n;
@@ -1117,7 +1115,6 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
         //      to be sequential; the seven running sums (repulsion.xy, push.xy, dr_nn.xy, neighbour count) are independent
         //      of one another, so lanes 0..6 of the group each carry one of them through the chunk.
         float run = 0.f;                                                 // this lane's running sum
-        const uint32_t my_bit = (gl < 2u) ? 1u : (gl < 4u) ? 2u : 4u;   // term mask bit that gates it
         for (uint32_t base = 0; base < cnt_w; base += DENSE_LANES) {
             const uint32_t k = base + gl;
             ForceTerms t;
@@ -1126,16 +1123,17 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
                 const uint32_t q = sorted[k].y;
                 t = neighbour_terms(r, me.z, me.w, state_i, __ldg(A.pos4 + q), (int)(__ldg(A.key2 + q).y & 3u), rscatter2);
             }
-            tw[0 * DENSE_LANES + gl] = t.rep.x; tw[1 * DENSE_LANES + gl] = t.rep.y;
-            tw[2 * DENSE_LANES + gl] = t.push.x; tw[3 * DENSE_LANES + gl] = t.push.y;
-            tw[4 * DENSE_LANES + gl] = t.dr.x; tw[5 * DENSE_LANES + gl] = t.dr.y;
-            tw[6 * DENSE_LANES + gl] = 1.f;
-            mw[gl] = t.mask;
+            // A term the reference does not add is stored as +0: the running sums start at +0 and can never become -0
+            // (x + (-x) and (+0) + (-0) round to +0), so adding +0 leaves every bit alone and the loop needs no test.
+            const bool sc = (t.mask & 4u) != 0u;
+            tw[0 * DENSE_LANES + gl] = t.rep.x; tw[1 * DENSE_LANES + gl] = t.rep.y;      // zero unless mask bit 0 (neighbour_terms)
+            tw[2 * DENSE_LANES + gl] = t.push.x; tw[3 * DENSE_LANES + gl] = t.push.y;    // zero unless mask bit 1
+            tw[4 * DENSE_LANES + gl] = sc ? t.dr.x : 0.f; tw[5 * DENSE_LANES + gl] = sc ? t.dr.y : 0.f;
+            tw[6 * DENSE_LANES + gl] = sc ? 1.f : 0.f;
             __syncwarp();
             if (gl < 7u && base < cnt) {
                 const uint32_t m = min(DENSE_LANES, cnt - base);
-                for (uint32_t j = 0; j < m; ++j)
-                    if (mw[j] & my_bit) run += tw[gl * DENSE_LANES + j];
+                for (uint32_t j = 0; j < m; ++j) run += tw[gl * DENSE_LANES + j];
             }
             __syncwarp();
         }
