@@ -22,14 +22,14 @@ constexpr bool USE_DENSE_KERNEL = RTS_USE_DENSE_KERNEL != 0;
 #ifndef RTS_STEP_BLOCK
 #define RTS_STEP_BLOCK 64
 #endif
-constexpr int STEP_BLOCK = RTS_STEP_BLOCK;   // threads per CTA of k_step. 64 x 18 CTAs per SM (55 registers, 7 KB of shared memory each) measured
+constexpr int STEP_BLOCK = RTS_STEP_BLOCK;   // threads per CTA of k_step. 64 x 18 CTAs per SM (55 registers, 8 KB of shared memory each) measured
                                             // 9 % faster over frames 20-220 of config 3 than 128 x 8 with a 16-entry list and a spill list
 #ifndef RTS_STEP_MIN_BLOCKS
 #define RTS_STEP_MIN_BLOCKS 18
 #endif
 constexpr int STEP_MIN_BLOCKS = RTS_STEP_MIN_BLOCKS;
 #ifndef RTS_NBR_CAP
-#define RTS_NBR_CAP 18
+#define RTS_NBR_CAP 16
 #endif
 constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memory per agent
 #ifndef RTS_STAGE_CAP
@@ -37,7 +37,7 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 #endif
 constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in shared memory (typically ~400)
 #ifndef RTS_DENSE_MIN
-#define RTS_DENSE_MIN 18
+#define RTS_DENSE_MIN 16
 #endif
 #ifndef RTS_DENSE_GRID_PER_SM
 #define RTS_DENSE_GRID_PER_SM 8
