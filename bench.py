@@ -290,10 +290,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every host thread, and the
+    # OpenMP runtime reads the variable when the library is loaded
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import refh
     K, Wm = args.steps, max(args.warmup, 3)
     n_world = int(os.environ.get("WORLD_SIZE", "1"))
     if refh.available(fast=True):
+        L = refh.load(True)
+        L.refh_set_omp_threads.argtypes = [__import__("ctypes").c_int]
+        L.refh_set_omp_threads(os.cpu_count() or 1)   # (in case an OpenMP runtime was initialised before the variable was set)
         rng = np.random.default_rng(1236)
         w = refh.RefWorld(512, 512, fast=True)
         placed = 0

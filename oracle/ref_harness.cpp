@@ -502,5 +502,6 @@ int refh_plan_path(void* h, float sx, float sy, float ex, float ey, float radius
 }
 
 int refh_omp_threads() { return omp_get_max_threads(); }
+void refh_set_omp_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 }  // extern "C"

@@ -587,6 +587,7 @@ void rts_oracle_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
 }
 
 int rts_oracle_threads(void) { return omp_get_max_threads(); }
+void rts_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 void rts_oracle_walk_hops(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
                           const float* xy, uint32_t n, uint32_t* hops_out) {
