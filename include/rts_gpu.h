@@ -78,9 +78,11 @@ typedef struct RtsParams {
     int32_t slab_row_lo, slab_row_hi;
     /* tuning words, 0 = default: [0] 1 = do not keep the per-step merged velocity (RtsAgentView.vel reads 0)
        [1] fine gather-cell size as float bits (default 6.0, clamped to >= 1.05*sqrt(r_max2))
-       [2] 1 = launch kernels one by one instead of replaying a CUDA graph of two frames
+       [2] 1 = launch kernels one by one instead of replaying a CUDA graph of eight frames
        [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower)
-       [4] 1 = run the triangle walk on the main stream instead of overlapping it with the next frame on a second stream */
+       [4] 1 = run the triangle walk on the main stream instead of overlapping it with the next frame on a second stream
+       [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
+           while the interior is stepped on the main stream (measured equal to the plain layout) */
     uint32_t reserved[6];
 } RtsParams;
 

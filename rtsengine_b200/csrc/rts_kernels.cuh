@@ -6,9 +6,14 @@
 //   k_scatter  : counting-sort scatter of the neighbour record {pos4,key2} into cell order, builds src[]
 //   k_walk     : triangle walk of the new positions (second stream, overlaps the next frame kernel)
 //   k_step     : the fused frame — neighbour gather, boids forces, clamp/decay, wall pass, seek, merge,
-//                wall pass, integrate, triangle walk, re-bin of the new position
+//                wall pass, integrate, slab packing, re-bin of the new position
+//   k_step_dense : the same for the crowded agents k_step queues (one warp per agent)
+//   k_arrive / k_area_sync : arrival rule (finalizeSeek) with frame-start snapshot semantics
+//   k_ingest_remote / k_halo_seed : slab exchange (arrivals appended, halo bands packed without a frame)
+//   k_cellgrid_classify / k_cellgrid_resolve : Triangulation::updateCellGrid (cell -> triangle cache)
 //   k_gather   : slot order -> caller order for rts_download
 //   k_apply    : caller order -> slot order for rts_update_agents
+//   k_coord_to_cell / k_find_triangles / k_contact_edges : stand-alone point queries
 #pragma once
 
 #include "rts_device.cuh"
