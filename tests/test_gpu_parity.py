@@ -429,3 +429,34 @@ def test_cell_grid_wide_arithmetic_on_a_tiled_map():
         g.upload_map({k: v for k, v in tables.items() if k != "cell2tri"})
         for lf in (0, 17):
             assert np.array_equal(g.build_cell_grid(lf), ow.build_cell_grid(lf))
+
+
+# ---- the diagnostic switches of RtsParams.reserved[] select other code paths, never other results -------------------
+def _bits(x):
+    return int(np.array([x], np.float32).view(np.uint32)[0])
+
+
+@pytest.mark.parametrize("idx,val,what", [(0, 1, "no per-step velocity output"), (1, _bits(7.5), "7.5-unit gather cells"),
+                                          (2, 1, "no CUDA graph"), (3, 1, "neighbour window staged in shared memory"),
+                                          (4, 1, "triangle walk on the main stream")])
+def test_diagnostic_switches_do_not_change_results(idx, val, what):
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(31, 30000, tables, 250.0, 750.0)          # 0.12 agents per unit², crowds of 10+ neighbours
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "waypoint", "r_next", "tri_idx", "ns_cell", "map_cell", "flags")
+    out = []
+    for switch in (None, (idx, val)):
+        p = engine.default_params(512, 512)
+        if switch:
+            p.reserved[switch[0]] = switch[1]
+        with engine.GpuAgentSystem(p) as g:
+            g.upload_map(tables)
+            g.upload_paths(paths)
+            g.set_agents(a)
+            g.update(19, sync=True)                                  # two graph replays + three single frames
+            out.append(g.communicate(names))
+    for k in names:
+        if k == "vel" and idx == 0:
+            assert not out[1][k].any()                               # the output is simply not kept
+            continue
+        H.assert_same_bits(out[1][k], out[0][k], f"{what}: {k}")
