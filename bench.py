@@ -194,7 +194,7 @@ def run_gpu(args):
     K, Wm = args.steps, max(args.warmup, 3)
     g.update(Wm, sync=True)
 
-    # ---- device-resident throughput: K frames (CUDA graph of 2 frames replayed), CUDA events on the launching stream ----
+    # ---- device-resident throughput: K frames (CUDA graph of 8 frames replayed), CUDA events on the launching stream ----
     g.reset_timings()
     with ClockSampler(local) as clocks:
         g.sync()
