@@ -335,6 +335,7 @@ def run_reference(args):
         value = n * K / dt
     else:
         from oracle import port
+        port.load(True).rts_oracle_set_threads(os.cpu_count() or 1)
         fx, tables, agents, paths = build_world(200_000)
         cpu = cpu_port_baseline(tables, agents, paths, budget_s=20.0)
         value, threads, kind, sample = cpu["value"], cpu["cores"], "port", cpu["sample"]

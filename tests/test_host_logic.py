@@ -66,3 +66,26 @@ def test_tiled_map_is_the_tile_map_shifted():
         cb, eb = ow_big.contact_edges(near + off, rad)
         H.assert_same_bits(cb, c1, f"tile {t} wall contact counts")
         H.assert_same_bits(eb[..., 2:], e1[..., 2:], f"tile {t} wall tangents / lengths")
+
+
+def test_reference_arm_of_the_bench_emits_the_contract_line():
+    """`bench.py --impl reference` (CPU only): one JSON line with the keys the driver reads; the verbatim reference when
+    oracle/_ref exists, the oracle port otherwise."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1")          # what torchrun exports to its workers
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "agent-updates/sec" and j["unit"] == "agent-updates/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 2
+    assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] == j["value"]
+    assert j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)       # every host thread, whatever OMP_NUM_THREADS said
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "config3" in j["config"]["workload"]
