@@ -369,9 +369,32 @@ __global__ void __launch_bounds__(256) k_walk(uint32_t n_bound, RtsParams P, Map
     uint32_t t;
     // the int32 walk needs |q| <= 16383 as well as the table bound checked at upload
     const bool small = fabsf(pos.x) <= 16383.f && fabsf(pos.y) <= 16383.f;
-    if (!WIDE && __all_sync(mask, small || !want)) t = find_triangle_warp<false>(M, P, want, pos.x, pos.y, flags, mask);
-    else t = find_triangle_warp<true>(M, P, want, pos.x, pos.y, flags, mask);
-    if (want) A.tri[A.src[d]] = t;
+    // Fast path: the triangle of the previous frame (copied forward by k_step) as a hint. A position STRICTLY inside a
+    // triangle is contained in no other one, so findTriangle — whatever cache cell it starts from, however it walks,
+    // or through its linear scan — can only end there. Agents move < 2 units per frame, so nearly all of them keep their
+    // triangle and skip the cell lookup and the walk; everything else (hint missing, on an edge, moved on) takes the
+    // reference's own path.
+    const uint32_t sp = A.src[d];
+    bool fast = false;
+    uint32_t hint = TRI_NONE;
+    if (want) {
+        hint = A.tri[sp];
+        if (hint < M.n_tris && (WIDE || small)) {
+            const iv2 q{(int32_t)pos.x, (int32_t)pos.y};   // static_cast<Vertex>(Vector2f): truncation
+            iv2 a, b, c;
+            int4 w1;
+            load_tri_verts(M, hint, a, b, c, w1);
+            const float d1 = tri_sign<WIDE>(q, a, b), d2 = tri_sign<WIDE>(q, b, c), d3 = tri_sign<WIDE>(q, c, a);
+            fast = (d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0);
+        }
+    }
+    const bool slow = want && !fast;
+    if (__any_sync(mask, slow)) {
+        if (!WIDE && __all_sync(mask, small || !slow)) t = find_triangle_warp<false>(M, P, slow, pos.x, pos.y, flags, mask);
+        else t = find_triangle_warp<true>(M, P, slow, pos.x, pos.y, flags, mask);
+    } else t = TRI_NONE;
+    if (fast) t = hint;
+    if (want) *((volatile uint32_t*)A.tri + sp) = t;
 }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
@@ -670,7 +693,10 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     angle = angle + angle_vel;
 
     // ---- K7 (triangle walk on the new position) runs in k_walk; agents that are not walked keep their index
-    if (!(P.walk_all || state_out == RTS_MOVING)) A.trin[p] = A.tri[sp];
+    // Carried forward for every agent: k_walk uses it as its hint and overwrites it with the new index. The walk of the
+    // previous frame may still be running on the second stream, so this read sees either its result or the entry it is
+    // about to replace — the same agent's triangle one frame earlier, an equally valid hint (hints are verified).
+    A.trin[p] = *((const volatile uint32_t*)A.tri + sp);
 
     // ---- write the new record at this slot; bin it for the next order
     const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
