@@ -69,6 +69,8 @@ struct RtsContext {
     bool overlap_exchange = false;    // reserved[5] bit 3 (value 8) turns the split on: at 2 GPUs it measured the same as exchanging
                                       // between the frame kernel and the scan (0.2503 vs 0.2511 ms per frame), so it is opt-in
     bool walk_pending = false;        // ev_walk has been recorded and not yet waited for by the main stream
+    bool walkq_pending = false;       // the walk queue of the last frame has not been searched yet (the next frame kernel will,
+    int walkq_parity = 0;             // ... or join_walk before anything reads the triangle indices)
     KernelTimer kt[KT_COUNT];
     double last_step_ms = 0;
     uint64_t launches = 0, steps = 0;
@@ -170,6 +172,7 @@ void timer_collect(RtsContext* h) {  // after a stream sync
 }
 
 inline uint32_t blocks_for(uint32_t n, uint32_t b) { return (n + b - 1) / b; }
+constexpr uint32_t WALK_CTAS = 148 * 4;   // CTAs at the head of k_step's grid that search the previous frame's walk queue
 
 int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     free_all(h->agent_allocs);
@@ -184,6 +187,13 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     if (h->keep_vel) { AL(vel_out, float2) AL(vel_outn, float2) }
     AL(stop_req, uint32_t)
 #undef AL
+    {   // work list of the triangle walk + its two alternating counters
+        if ((rc = dev_alloc<uint32_t>(h, &A.walk_q, (size_t)cap, h->agent_allocs)) != RTS_OK) return rc;
+        uint32_t* wn = nullptr;
+        if ((rc = dev_alloc<uint32_t>(h, &wn, 4, h->agent_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(wn, 0, 16, h->stream));
+        A.walk_n = wn;
+    }
     {   // two queues of crowded agents (whole population / interior, and the edge rows of a slab) + their counters
         if ((rc = dev_alloc<uint32_t>(h, &A.dense_q, 2 * (size_t)cap, h->agent_allocs)) != RTS_OK) return rc;
         uint32_t* dn = nullptr;
@@ -257,10 +267,19 @@ void swap_prev_order(RtsContext* h) {
 
 // scan of the counts + scatter into the new order; the "n" buffers become the previous-order arrays
 // main stream waits for the walk still running on the side stream (before anything overwrites pos4/key2/src/tri)
+void launch_walk_kernel(RtsContext* h, cudaStream_t st, int parity) {
+    if (h->M.coords_fit_i32) k_walk<false><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
+    else k_walk<true><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
+    h->launches += 1;
+}
 int32_t join_walk(RtsContext* h) {
     if (h->walk_pending) {
         CU(cudaStreamWaitEvent(h->stream, h->ev_walk, 0));
         h->walk_pending = false;
+    }
+    if (h->walkq_pending) {   // nobody has searched for the agents the last k_scatter queued: do it now
+        launch_walk_kernel(h, h->stream, h->walkq_parity);
+        h->walkq_pending = false;
     }
     return RTS_OK;
 }
@@ -274,29 +293,27 @@ int32_t launch_scan_reorder(RtsContext* h) {
     if (rc != RTS_OK) return rc;
     timer_begin(h, KT_REORDER);
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
-    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0);
+    const int wpar = h->parity;
+    const int do_walk = h->map_ready ? 1 : 0;
+    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0, h->P, h->M, wpar, do_walk);
     timer_end(h, KT_REORDER);
     h->launches += 2;
     swap_prev_order(h);
-    // triangle walk of the new order. With walk_all the next frame kernel never touches `tri`, so the walk goes to the
-    // side stream and overlaps it; otherwise (agents that are not walked copy their index) it stays on the main stream.
-    const uint32_t n_walk = h->multi ? h->cap_main : h->n;
-    if (n_walk && h->map_ready) {
-        const bool side = h->P.walk_all != 0 && h->overlap_walk && !h->profiling;
-        cudaStream_t st = side ? h->stream2 : h->stream;
-        if (side) {
-            CU(cudaEventRecord(h->ev_scatter, h->stream));
-            CU(cudaStreamWaitEvent(h->stream2, h->ev_scatter, 0));
+    // Triangle walk of the new order: k_scatter has confirmed most agents' triangle from last frame's and queued the rest.
+    // By default the queue is left to the leading CTAs of the NEXT frame kernel (launch_step_interior), so the walk
+    // overlaps the frame inside one stream; join_walk searches it earlier if something needs the indices before that.
+    // reserved[4] / profiling: a k_walk launch right here instead.
+    if (n_slots && h->map_ready) {
+        // (only with walk_all: every agent's carried index is re-verified by the next k_scatter, so it does not matter that
+        //  the frame kernel may copy an entry forward before the search has replaced it)
+        if (h->P.walk_all != 0 && h->overlap_walk && !h->profiling) {
+            h->walkq_pending = true;
+            h->walkq_parity = wpar;
+        } else {
+            timer_begin(h, KT_WALK);
+            launch_walk_kernel(h, h->stream, wpar);
+            timer_end(h, KT_WALK);
         }
-        timer_begin(h, KT_WALK);
-        if (h->M.coords_fit_i32) k_walk<false><<<blocks_for(n_walk, 256), 256, 0, st>>>(n_walk, h->P, h->M, h->A, h->multi ? 1 : 0);
-        else k_walk<true><<<blocks_for(n_walk, 256), 256, 0, st>>>(n_walk, h->P, h->M, h->A, h->multi ? 1 : 0);
-        timer_end(h, KT_WALK);
-        if (side) {
-            CU(cudaEventRecord(h->ev_walk, h->stream2));
-            h->walk_pending = true;
-        }
-        h->launches += 1;
     }
     return RTS_OK;
 }
@@ -351,8 +368,8 @@ void launch_step_edges(RtsContext* h) {
     Aq.dense_n = h->A.dense_n + 4;
     const SlabDev SLq = h->SL;
     const dim3 grid(2 * SLq.edge_blocks);
-    if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
-    else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq);
+    if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0);
+    else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0);
     h->launches += 1;
     if (USE_DENSE_KERNEL) {
         const dim3 dgrid(148 * 2);
@@ -372,12 +389,17 @@ void launch_step_interior(RtsContext* h) {
     SlabDev SLq = h->SL;
     SLq.interior_launch = split ? 1 : 0;
     const AgentArrays& Aq = h->A;
+    // leading CTAs that search the walk queue of the previous frame (see launch_scan_reorder)
+    const uint32_t wc = (h->walkq_pending && nb) ? WALK_CTAS : 0u;
+    const int wp = h->walkq_parity;
+    if (wc) h->walkq_pending = false;
+    const dim3 grid_w(grid.x + wc);
     timer_begin(h, KT_STEP);
     if (split) {
-        if (h->keep_vel) k_step<true, true, false, 2><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq);
-        else k_step<false, true, false, 2><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq);
+        if (h->keep_vel) k_step<true, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
+        else k_step<false, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
     } else if (nb) {
-#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq)
+#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp)
         const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->staged ? 1 : 0);
         switch (variant) {
             case 0: LAUNCH_STEP(false, false, false); break;
@@ -1057,9 +1079,14 @@ static int32_t build_graph(RtsContext* h) {
     if (rc != RTS_OK) return rc;
     cudaGraph_t g = nullptr;
     const uint64_t launches0 = h->launches;
+    // The first frame kernel of the graph searches the walk queue left by the frame before the graph (on a replay: by the
+    // last frame of the previous replay); that queue always has the parity opposite to the graph's first frame. Searching
+    // a queue that join_walk has already emptied is harmless (same positions, same answers).
+    const bool deferred_walk = h->P.walk_all != 0 && h->overlap_walk && !h->profiling;
+    if (deferred_walk) { h->walkq_pending = true; h->walkq_parity = par ^ 1; }
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     for (uint32_t f = 0; f < GRAPH_FRAMES && rc == RTS_OK; ++f) rc = launch_frame(h);
-    if (rc == RTS_OK) rc = join_walk(h);   // the side stream must rejoin before the capture ends
+    h->walkq_pending = false;   // (nothing has run; rts_step marks the queue pending after every replay)
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
     h->graph_launches = h->launches - launches0;
     h->launches = launches0;
@@ -1084,11 +1111,15 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
             int32_t rc = build_graph(h);
             if (rc != RTS_OK) return rc;
         }
-        int32_t rc = join_walk(h);
-        if (rc != RTS_OK) return rc;
+        const bool deferred_walk = h->P.walk_all != 0 && h->overlap_walk;
+        if (!deferred_walk) {
+            const int32_t rc = join_walk(h);
+            if (rc != RTS_OK) return rc;
+        }
         for (; done + GRAPH_FRAMES <= n_steps; done += GRAPH_FRAMES) {
             CU(cudaGraphLaunch(h->graph2[par], h->stream));
             h->launches += h->graph_launches;
+            if (deferred_walk) { h->walkq_pending = true; h->walkq_parity = par ^ 1; }   // the last frame's queue
         }
     }
     for (; done < n_steps; ++done) {

@@ -154,6 +154,8 @@ struct AgentArrays {
     float2* vel_outn;
     uint2* cellrank;  // {next fine cell, rank inside it}
     uint32_t* stop_req;  // arrival: 1 = this slot's agent stops this frame (set by k_arrive, consumed by k_step)
+    uint32_t* walk_q;    // new slots of the agents whose triangle k_scatter could not confirm from the hint (k_walk's work list)
+    uint32_t* walk_n;    // [parity] their number; k_scatter of the next frame resets it
     uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
     uint32_t* dense_n;   // [0] their number (reset by k_scatter); [4] the same for the queue of a slab's edge-row launch
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
@@ -336,65 +338,90 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 }
 
 // Counting-sort scatter of the neighbour record into the new cell order; builds src[].
-__global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi) {
+// ... and the first half of the triangle walk: the triangle of the previous frame (carried forward by k_step into
+// trin[p]) is a hint. A position STRICTLY inside a triangle is contained in no other one, so findTriangle — whatever cache
+// cell it starts from, however it walks, or through its linear scan — can only end there: the entry is already right.
+// Agents move < 2 units per frame, so nearly all of them pass; the others (hint missing, on an edge, moved on) are queued
+// for k_walk, which runs the reference's own search for them.
+__global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi, RtsParams P, MapDev M,
+                                                 int parity, int do_walk) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0) { A.dense_n[0] = 0u; A.dense_n[4] = 0u; }   // the dense queues of this frame (whole / interior, edge rows) have been consumed
+    if (p == 0) {
+        A.dense_n[0] = 0u; A.dense_n[4] = 0u;   // the dense queues of this frame (whole / interior, edge rows) have been consumed
+        A.walk_n[parity ^ 1] = 0u;              // ... and the walk queue of the previous frame (its k_walk was joined before this launch)
+    }
     if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
         SL.send[p >> 2].hdr[p & 3u] = 0u;
     }
-    if (p >= n) return;
-    const uint2 cr = A.cellrank[p];
-    if (cr.x == INVALID_CELL) return;   // ghosts / migrated agents / unused slots are dropped
-    const uint32_t d = F.start[cr.x] + cr.y;
-    A.pos4[d] = A.pos4n[p];
-    A.key2[d] = A.key2n[p];
-    A.src[d] = p;
+    bool slow = false;
+    uint32_t d = 0u;
+    if (p < n) {
+        const uint2 cr = A.cellrank[p];
+        if (cr.x != INVALID_CELL) {   // ghosts / migrated agents / unused slots are dropped
+            d = F.start[cr.x] + cr.y;
+            const float4 pos = A.pos4n[p];
+            const uint2 key = A.key2n[p];
+            A.pos4[d] = pos;
+            A.key2[d] = key;
+            A.src[d] = p;
+            const bool ghost = (key.y >> 2) & 1u;
+            if (do_walk && !ghost && (P.walk_all || (key.y & 3u) == RTS_MOVING)) {
+                slow = true;
+                const uint32_t hint = A.trin[p];
+                if (hint < M.n_tris && fabsf(pos.x) <= 1.0e9f && fabsf(pos.y) <= 1.0e9f) {
+                    const iv2 q{(int32_t)pos.x, (int32_t)pos.y};   // static_cast<Vertex>(Vector2f): truncation
+                    iv2 a, b, c;
+                    int4 w1;
+                    load_tri_verts(M, hint, a, b, c, w1);
+                    // 64-bit products: identical to the reference's int32 wherever that does not overflow
+                    const float d1 = tri_sign<true>(q, a, b), d2 = tri_sign<true>(q, b, c), d3 = tri_sign<true>(q, c, a);
+                    slow = !((d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0));
+                }
+            }
+        }
+    }
+    // warp-aggregated append to the walk queue
+    const unsigned need = __ballot_sync(0xffffffffu, slow);
+    if (need) {
+        const unsigned lane = threadIdx.x & 31u;
+        uint32_t base = 0u;
+        if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(A.walk_n + parity, (uint32_t)__popc(need));
+        base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+        if (slow) A.walk_q[base + (uint32_t)__popc(need & ((1u << lane) - 1u))] = d;
+    }
 }
 
 // The triangle walk (Triangulation::findTriangle) of the new positions, one thread per slot of the NEW order, writing
 // the previous-order `tri` array the next frame carries along. It only reads what the next frame kernel also only
 // reads (pos4, key2, src), so it runs on a second stream concurrently with the next frame kernel; its low register
 // count lets its warps fill the issue slots the divergent frame kernel leaves idle. A failed walk stores 0xFFFFFFFF.
+// The reference's findTriangle for the agents k_scatter queued: CTA `cta` of `n_ctas` (threads_per_cta threads each)
+// strides over the queue. Called by the leading CTAs of the NEXT frame kernel (the walk then overlaps the frame without a
+// second stream: a few agents outside the map need 100+ dependent hops, ~40 us for one thread) and by k_walk.
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_walk(uint32_t n_bound, RtsParams P, MapDev M, AgentArrays A, int multi) {
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = multi ? *A.n_dev : n_bound;
-    const unsigned mask = __ballot_sync(0xffffffffu, d < n);
-    if (d >= n) return;
-    const float4 pos = A.pos4[d];
-    const uint2 key = A.key2[d];
-    const bool ghost = (key.y >> 2) & 1u;
-    const bool want = !ghost && M.n_tris != 0 && (P.walk_all || (key.y & 3u) == RTS_MOVING);   // no map uploaded yet: no walk
-    uint32_t flags = 0;
-    uint32_t t;
-    // the int32 walk needs |q| <= 16383 as well as the table bound checked at upload
-    const bool small = fabsf(pos.x) <= 16383.f && fabsf(pos.y) <= 16383.f;
-    // Fast path: the triangle of the previous frame (copied forward by k_step) as a hint. A position STRICTLY inside a
-    // triangle is contained in no other one, so findTriangle — whatever cache cell it starts from, however it walks,
-    // or through its linear scan — can only end there. Agents move < 2 units per frame, so nearly all of them keep their
-    // triangle and skip the cell lookup and the walk; everything else (hint missing, on an edge, moved on) takes the
-    // reference's own path.
-    const uint32_t sp = A.src[d];
-    bool fast = false;
-    uint32_t hint = TRI_NONE;
-    if (want) {
-        hint = A.tri[sp];
-        if (hint < M.n_tris && (WIDE || small)) {
-            const iv2 q{(int32_t)pos.x, (int32_t)pos.y};   // static_cast<Vertex>(Vector2f): truncation
-            iv2 a, b, c;
-            int4 w1;
-            load_tri_verts(M, hint, a, b, c, w1);
-            const float d1 = tri_sign<WIDE>(q, a, b), d2 = tri_sign<WIDE>(q, b, c), d3 = tri_sign<WIDE>(q, c, a);
-            fast = (d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0);
+__device__ __forceinline__ void drain_walk_queue(const RtsParams& P, const MapDev& M, const AgentArrays& A, int parity, uint32_t cta,
+                                                 uint32_t n_ctas, uint32_t threads_per_cta) {
+    const uint32_t qn = A.walk_n[parity];
+    for (uint32_t base = cta * threads_per_cta; base < qn; base += n_ctas * threads_per_cta) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned mask = __ballot_sync(0xffffffffu, i < qn);
+        if (i < qn) {
+            const uint32_t d = A.walk_q[i];
+            const float4 pos = A.pos4[d];
+            const uint32_t sp = A.src[d];
+            uint32_t flags = 0;
+            uint32_t t;
+            // the int32 walk needs |q| <= 16383 as well as the table bound checked at upload
+            const bool small = fabsf(pos.x) <= 16383.f && fabsf(pos.y) <= 16383.f;
+            if (!WIDE && __all_sync(mask, small)) t = find_triangle_warp<false>(M, P, true, pos.x, pos.y, flags, mask);
+            else t = find_triangle_warp<true>(M, P, true, pos.x, pos.y, flags, mask);
+            *((volatile uint32_t*)A.tri + sp) = t;   // (the frame kernel may be reading it: see finish_agent)
         }
     }
-    const bool slow = want && !fast;
-    if (__any_sync(mask, slow)) {
-        if (!WIDE && __all_sync(mask, small || !slow)) t = find_triangle_warp<false>(M, P, slow, pos.x, pos.y, flags, mask);
-        else t = find_triangle_warp<true>(M, P, slow, pos.x, pos.y, flags, mask);
-    } else t = TRI_NONE;
-    if (fast) t = hint;
-    if (want) *((volatile uint32_t*)A.tri + sp) = t;
+}
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_walk(RtsParams P, MapDev M, AgentArrays A, int parity) {
+    drain_walk_queue<WIDE>(P, M, A, parity, blockIdx.x, gridDim.x, blockDim.x);
 }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
@@ -753,7 +780,15 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
 // neighbouring cells and the neighbour records come out of L1).
 // PHASE 0: every slot; PHASE 1: the edge rows of a slab only (see SlabDev), PHASE 2: everything else.
 template <bool KEEP_VEL, bool MULTI, bool STAGED, int PHASE = 0>
-__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL,
+                                                                      uint32_t walk_ctas, int walk_parity) {
+    // the first walk_ctas CTAs finish the triangle walk of the previous frame (the agents its k_scatter queued)
+    if (blockIdx.x < walk_ctas) {
+        if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, blockIdx.x, walk_ctas, STEP_BLOCK);
+        else drain_walk_queue<true>(P, M, A, walk_parity, blockIdx.x, walk_ctas, STEP_BLOCK);
+        return;
+    }
+    const uint32_t bid = blockIdx.x - walk_ctas;
     __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
     // neighbour records of every fine cell this CTA's agents can see, staged once (coalesced) instead of being fetched
     // ~9 times each by individual lanes. The CTA's 128 slots lie in one fine row (3 row segments) or straddle two
@@ -775,8 +810,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         edge_b = max(edge_b, edge_a);
     }
     const uint32_t cover = SL.edge_blocks * STEP_BLOCK;   // slots the PHASE 1 grid reaches on either side
-    uint32_t block0 = blockIdx.x * STEP_BLOCK;
-    if (PHASE == 1 && blockIdx.x >= SL.edge_blocks) block0 = edge_b + (blockIdx.x - SL.edge_blocks) * STEP_BLOCK;
+    uint32_t block0 = bid * STEP_BLOCK;
+    if (PHASE == 1 && bid >= SL.edge_blocks) block0 = edge_b + (bid - SL.edge_blocks) * STEP_BLOCK;
     const uint32_t p = block0 + tid;
     const bool in_range = p < n;
     const unsigned valid = __ballot_sync(0xffffffffu, in_range);
@@ -792,7 +827,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     bool mine = true;   // does this launch step this slot?
     if (PHASE != 0) {
         const bool covered = (p < edge_a && p < cover) || (p >= edge_b && p - edge_b < cover);
-        mine = (PHASE == 1) ? (covered && (blockIdx.x < SL.edge_blocks ? p < edge_a : true)) : !covered;
+        mine = (PHASE == 1) ? (covered && (bid < SL.edge_blocks ? p < edge_a : true)) : !covered;
     }
     const unsigned active = __ballot_sync(valid, !ghost && mine);  // lanes that reach the re-bin at the end
     int fx, fy;
