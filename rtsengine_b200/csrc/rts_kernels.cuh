@@ -4,7 +4,7 @@
 //   k_bin      : fine-cell id + slot rank of freshly uploaded agents (warp-aggregated atomics)
 //   k_scan_*   : exclusive scan of the per-cell counts -> cell_start
 //   k_scatter  : counting-sort scatter of the neighbour record {pos4,key2} into cell order, builds src[]
-//   k_walk     : triangle walk of the new positions (second stream, overlaps the next frame kernel)
+//   k_walk     : findTriangle for the agents k_scatter queued (normally done by the leading CTAs of the next k_step)
 //   k_step     : the fused frame — neighbour gather, boids forces, clamp/decay, wall pass, seek, merge,
 //                wall pass, integrate, slab packing, re-bin of the new position
 //   k_step_dense : the same for the crowded agents k_step queues (one warp per agent)
