@@ -82,7 +82,8 @@ typedef struct RtsParams {
        [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower)
        [4] 1 = run the triangle walk on the main stream instead of overlapping it with the next frame on a second stream
        [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
-           while the interior is stepped on the main stream (measured equal to the plain layout) */
+           while the interior is stepped on the main stream (measured equal to the plain layout);
+           16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them */
     uint32_t reserved[6];
 } RtsParams;
 

@@ -65,6 +65,7 @@ struct RtsContext {
     std::vector<RtsUnitType> types_host;
     float max_type_speed = 100.f;     // max over unit types of the velocity clamp + seek speed, see set_edge_rows
     bool ingest_done = false;         // k_ingest_remote of this frame has been launched
+    bool graph_slabs = false;         // reserved[5] bit 4 (value 16): slab frames, NCCL calls included, replayed from a CUDA graph too
     bool frame_is_split = false;      // this frame's edge rows, exchange and ingest are on stream4 (see split_frame)
     bool overlap_exchange = false;    // reserved[5] bit 3 (value 8) turns the split on: at 2 GPUs it measured the same as exchanging
                                       // between the frame kernel and the scan (0.2503 vs 0.2511 ms per frame), so it is opt-in
@@ -593,6 +594,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->staged = params->reserved[3] != 0;
     h->overlap_walk = params->reserved[4] == 0;
     h->overlap_exchange = (params->reserved[5] & 8u) != 0;
+    h->graph_slabs = (params->reserved[5] & 16u) != 0;
     *out = h;
     int prio_lo = 0, prio_hi = 0;   // the comm stream (edge rows, exchange, ingest of a slab) outranks the bulk kernels
     cudaSetDevice(device_id);
@@ -1105,7 +1107,7 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
     // (not for slab handles: capturing ncclSend/ncclRecv into the graph measured slower than launching frame by frame)
-    if (h->use_graph && !h->profiling && !h->multi && n_steps >= GRAPH_FRAMES) {
+    if (h->use_graph && !h->profiling && (!h->multi || h->graph_slabs) && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
         if (!h->graph2[par] || h->graph_n[par] != h->n) {
             int32_t rc = build_graph(h);
