@@ -80,7 +80,8 @@ typedef struct RtsParams {
        [1] fine gather-cell size as float bits (default 6.0, clamped to >= 1.05*sqrt(r_max2))
        [2] 1 = launch kernels one by one instead of replaying a CUDA graph of eight frames
        [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower)
-       [4] 1 = run the triangle walk on the main stream instead of overlapping it with the next frame on a second stream
+       [4] 1 = search the walk queue with a k_walk launch right after k_scatter instead of leaving it to the leading CTAs of
+           the next frame kernel
        [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
            while the interior is stepped on the main stream (measured equal to the plain layout);
            16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them */
