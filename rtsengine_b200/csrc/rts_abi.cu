@@ -59,8 +59,7 @@ struct RtsContext {
     size_t scratch_bytes = 0;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // the triangle walk runs on a second stream, overlapping the next frame kernel
-    cudaStream_t stream2 = nullptr, stream4 = nullptr;   // walk / slab edge rows + exchange
+    cudaStream_t stream2 = nullptr, stream4 = nullptr;   // (unused since the walk moved into the frame kernel) / slab edge rows + exchange
     cudaEvent_t ev_scatter = nullptr, ev_walk = nullptr, ev_fork2 = nullptr, ev_comm = nullptr;
     std::vector<RtsUnitType> types_host;
     float max_type_speed = 100.f;     // max over unit types of the velocity clamp + seek speed, see set_edge_rows
@@ -83,7 +82,7 @@ struct RtsContext {
     bool use_graph = true;
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
-    bool overlap_walk = true;         // triangle walk on the side stream (reserved[4] = 1 turns it off)
+    bool overlap_walk = true;         // walk queue searched by the next frame kernel's leading CTAs (reserved[4] = 1: k_walk after k_scatter)
     bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
@@ -266,15 +265,14 @@ void swap_prev_order(RtsContext* h) {
     h->parity ^= 1;
 }
 
-// scan of the counts + scatter into the new order; the "n" buffers become the previous-order arrays
-// main stream waits for the walk still running on the side stream (before anything overwrites pos4/key2/src/tri)
 void launch_walk_kernel(RtsContext* h, cudaStream_t st, int parity) {
     if (h->M.coords_fit_i32) k_walk<false><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
     else k_walk<true><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
     h->launches += 1;
 }
+// called before anything reads the triangle indices or overwrites pos4/src: searches a walk queue that is still pending
 int32_t join_walk(RtsContext* h) {
-    if (h->walk_pending) {
+    if (h->walk_pending) {   // (legacy: a walk kernel on stream2)
         CU(cudaStreamWaitEvent(h->stream, h->ev_walk, 0));
         h->walk_pending = false;
     }
@@ -285,12 +283,13 @@ int32_t join_walk(RtsContext* h) {
     return RTS_OK;
 }
 
+// scan of the counts + scatter into the new order; the "n" buffers become the previous-order arrays
 int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t nb = blocks_for(((h->F.n_cells + 1u + 7u) & ~7u), SCAN_TILE);
     timer_begin(h, KT_SCAN);
     k_scan_onepass<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
     timer_end(h, KT_SCAN);
-    int32_t rc = join_walk(h);   // the previous walk reads what the scatter is about to overwrite
+    int32_t rc = join_walk(h);   // a pending walk queue refers to what the scatter is about to overwrite (normally none is pending)
     if (rc != RTS_OK) return rc;
     timer_begin(h, KT_REORDER);
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;

@@ -391,10 +391,9 @@ __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentAr
     }
 }
 
-// The triangle walk (Triangulation::findTriangle) of the new positions, one thread per slot of the NEW order, writing
-// the previous-order `tri` array the next frame carries along. It only reads what the next frame kernel also only
-// reads (pos4, key2, src), so it runs on a second stream concurrently with the next frame kernel; its low register
-// count lets its warps fill the issue slots the divergent frame kernel leaves idle. A failed walk stores 0xFFFFFFFF.
+// The second half of the triangle walk (Triangulation::findTriangle): the search for the agents k_scatter queued. It
+// writes the previous-order `tri` array the next frame carries along and only reads what the next frame kernel also
+// only reads (pos4, src). A failed walk stores 0xFFFFFFFF.
 // The reference's findTriangle for the agents k_scatter queued: CTA `cta` of `n_ctas` (threads_per_cta threads each)
 // strides over the queue. Called by the leading CTAs of the NEXT frame kernel (the walk then overlaps the frame without a
 // second stream: a few agents outside the map need 100+ dependent hops, ~40 us for one thread) and by k_walk.
@@ -719,10 +718,11 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     const v2 r_new = r + v * P.dt;
     angle = angle + angle_vel;
 
-    // ---- K7 (triangle walk on the new position) runs in k_walk; agents that are not walked keep their index
-    // Carried forward for every agent: k_walk uses it as its hint and overwrites it with the new index. The walk of the
-    // previous frame may still be running on the second stream, so this read sees either its result or the entry it is
-    // about to replace — the same agent's triangle one frame earlier, an equally valid hint (hints are verified).
+    // ---- K7 (triangle walk on the new position) runs in k_scatter (hint test) + drain_walk_queue (search); agents that
+    // are not walked keep their index. The index is carried forward for every agent: k_scatter uses it as its hint. The
+    // search for the previous frame's queued agents may be running in this kernel's leading CTAs right now, so this read
+    // sees either its result or the entry it is about to replace — the same agent's triangle one frame earlier, an
+    // equally valid hint (hints are verified).
     A.trin[p] = *((const volatile uint32_t*)A.tri + sp);
 
     // ---- write the new record at this slot; bin it for the next order
