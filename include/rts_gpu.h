@@ -79,14 +79,26 @@ typedef struct RtsParams {
     /* tuning words, 0 = default: [0] 1 = do not keep the per-step merged velocity (RtsAgentView.vel reads 0)
        [1] fine gather-cell size as float bits (default 6.0, clamped to >= 1.05*sqrt(r_max2))
        [2] 1 = launch kernels one by one instead of replaying a CUDA graph of eight frames
-       [3] 1 = frame-kernel variant that stages each CTA's neighbour window in shared memory (measured slower)
+       [3] unused (round 1: a frame-kernel variant that staged each CTA's neighbour window in shared memory; it measured
+           20-35 % slower than the L1-served path and was removed)
        [4] 1 = search the walk queue with a k_walk launch right after k_scatter instead of leaving it to the leading CTAs of
            the next frame kernel
        [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
            while the interior is stepped on the main stream (measured equal to the plain layout);
            16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them */
     uint32_t reserved[6];
+    /* arithmetic of the frame kernel:
+       RTS_PRECISION_EXACT (0, the default): IEEE division / square root, no FMA contraction, neighbour sums added in the
+         reference's visit order — every output is bit-identical to an IEEE build of the reference (the parity configuration);
+       RTS_PRECISION_FAST (1): tolerance mode — same neighbour sets, same wall contacts, same waypoint / state / angle
+         decisions and cell / triangle indices that are exact functions of the positions it produces, but the force terms
+         use rsqrt.approx / rcp.approx, fused multiply-adds and are added in memory order: after one frame from the same
+         state positions agree to ~1e-7 relative and velocities to 1e-5 of max(|v|, 1) except where an agent's force terms
+         cancel each other (error bounded by 2e-6 of the sum of the term magnitudes). Results are not
+         reproducible bit for bit from run to run (the memory order within a fine cell comes from atomics). */
+    uint32_t precision;
 } RtsParams;
+enum { RTS_PRECISION_EXACT = 0, RTS_PRECISION_FAST = 1 };
 
 /* CDT triangle, counter-clockwise; neighbours[k] is across edge (verts[k], verts[k+1]).
    Mirrors `Triangle` of src/PathFinding/Triangulation.h:35-48 (44 B there, 48 B here). */
@@ -148,8 +160,8 @@ typedef struct RtsAgentView {
     float* inertia;      /* 2n  PhysicsComponent::inertia_vel                     [0]  */
     float* angle;        /* n   degrees                                           [0]  */
     float* angle_vel;    /* n                                                     [0]  */
-    float* radius;       /* n                                                     [3]  */
-    float* mass;         /* n                                                     [1]  */
+    float* radius;       /* n   >= 0 (the sign bit is ignored)                     [3]  */
+    float* mass;         /* n   >= 0 (the sign bit is ignored)                     [1]  */
     uint8_t* state;      /* n   MoveState                                  [STANDING]  */
     uint8_t* player;     /* n                                                     [0]  */
     uint8_t* unit_type;  /* n   index into the unit-type table                    [0]  */

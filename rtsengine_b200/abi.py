@@ -13,6 +13,7 @@ RTS_OK = 0
 RTS_E_CUDA, RTS_E_NCCL, RTS_E_ARG, RTS_E_CAPACITY, RTS_E_STATE = -1, -2, -3, -4, -5
 MOVING, STANDING, HOLDING = 0, 1, 2
 FLAG_REPLAN, FLAG_WALK_FAILED = 1, 2
+PRECISION_EXACT, PRECISION_FAST = 0, 1
 NO_TRI = 0xFFFFFFFF
 
 STATUS_NAMES = {0: "RTS_OK", -1: "RTS_E_CUDA", -2: "RTS_E_NCCL", -3: "RTS_E_ARG", -4: "RTS_E_CAPACITY",
@@ -32,6 +33,7 @@ class RtsParams(C.Structure):
         ("enable_arrival", C.c_uint32), ("walk_all", C.c_uint32),
         ("slab_row_lo", C.c_int32), ("slab_row_hi", C.c_int32),
         ("reserved", C.c_uint32 * 6),
+        ("precision", C.c_uint32),
     ]
 
 

@@ -83,7 +83,9 @@ struct RtsContext {
     // ---- slab decomposition (multi-GPU) ----
     bool multi = false;
     bool overlap_walk = true;         // walk queue searched by the next frame kernel's leading CTAs (reserved[4] = 1: k_walk after k_scatter)
-    bool staged = false;              // k_step variant that stages the CTA's candidate window in shared memory
+    bool fast = false;                // RtsParams.precision == RTS_PRECISION_FAST: tolerance-mode kernels
+    int walk_ctas_per_sm = 4;         // (RTS_WALK_CTAS_PER_SM overrides: tuning runs)
+    int n_sm = 148;                   // cudaDevAttrMultiProcessorCount of the handle's device (grids of the persistent-style kernels)
     SlabDev SL{};
     uint32_t cap_main = 0;            // slots the frame kernel may use; arrivals are appended behind them
     std::vector<void*> slab_allocs;
@@ -172,7 +174,7 @@ void timer_collect(RtsContext* h) {  // after a stream sync
 }
 
 inline uint32_t blocks_for(uint32_t n, uint32_t b) { return (n + b - 1) / b; }
-constexpr uint32_t WALK_CTAS = 148 * 4;   // CTAs at the head of k_step's grid that search the previous frame's walk queue
+inline uint32_t walk_ctas_of(const RtsContext* h) { return (uint32_t)h->n_sm * (uint32_t)h->walk_ctas_per_sm; }   // CTAs at the head of k_step's grid that search the previous frame's walk queue
 
 int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     free_all(h->agent_allocs);
@@ -266,8 +268,8 @@ void swap_prev_order(RtsContext* h) {
 }
 
 void launch_walk_kernel(RtsContext* h, cudaStream_t st, int parity) {
-    if (h->M.coords_fit_i32) k_walk<false><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
-    else k_walk<true><<<148 * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
+    if (h->M.coords_fit_i32) k_walk<false><<<h->n_sm * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
+    else k_walk<true><<<h->n_sm * 4, 256, 0, st>>>(h->P, h->M, h->A, parity);
     h->launches += 1;
 }
 // called before anything reads the triangle indices or overwrites pos4/src: searches a walk queue that is still pending
@@ -338,10 +340,14 @@ void set_edge_rows(RtsContext* h) {
 // Does this frame split the frame kernel into the edge rows (comm stream, followed there by the exchange and the ingest)
 // and the interior (main stream)? Only slab handles with a neighbour; not while per-kernel timers are on.
 bool split_frame(const RtsContext* h) {
-    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->staged && h->F.ny >= 4;
+    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->fast && h->F.ny >= 4;
 }
 
-#define LAUNCH_DENSE(KV, MU) k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq)
+#define LAUNCH_DENSE(KV, MU)                                                                         \
+    do {                                                                                             \
+        if (h->fast) k_step_dense_fast<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq);   \
+        else k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq);                \
+    } while (0)
 
 // arrival kernels, then — slab handles with a neighbour — the edge rows on the comm stream (their own queue of crowded
 // agents is drained right behind them)
@@ -372,7 +378,7 @@ void launch_step_edges(RtsContext* h) {
     else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0);
     h->launches += 1;
     if (USE_DENSE_KERNEL) {
-        const dim3 dgrid(148 * 2);
+        const dim3 dgrid(h->n_sm * 2);
         cudaStream_t st = h->stream4;
         if (h->keep_vel) LAUNCH_DENSE(true, true);
         else LAUNCH_DENSE(false, true);
@@ -383,24 +389,25 @@ void launch_step_edges(RtsContext* h) {
 // the frame kernel over everything (or, after launch_step_edges split the frame, over the interior) + k_step_dense
 void launch_step_interior(RtsContext* h) {
     const uint32_t nb = h->multi ? h->cap_main : h->n;
-    const dim3 grid(blocks_for(nb, STEP_BLOCK));
+    const uint32_t block = h->fast ? FAST_BLOCK : STEP_BLOCK;
+    const dim3 grid(blocks_for(nb, block));
     const bool split = h->frame_is_split;
     const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
     SlabDev SLq = h->SL;
     SLq.interior_launch = split ? 1 : 0;
     const AgentArrays& Aq = h->A;
     // leading CTAs that search the walk queue of the previous frame (see launch_scan_reorder)
-    const uint32_t wc = (h->walkq_pending && nb) ? WALK_CTAS : 0u;
+    const uint32_t wc = (h->walkq_pending && nb) ? walk_ctas_of(h) : 0u;
     const int wp = h->walkq_parity;
     if (wc) h->walkq_pending = false;
     const dim3 grid_w(grid.x + wc);
     timer_begin(h, KT_STEP);
-    if (split) {
+    if (split) {   // (exact mode only, see split_frame)
         if (h->keep_vel) k_step<true, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
         else k_step<false, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
     } else if (nb) {
-#define LAUNCH_STEP(KV, MU, ST) k_step<KV, MU, ST><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp)
-        const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->staged ? 1 : 0);
+#define LAUNCH_STEP(KV, MU, FA) k_step<KV, MU, FA><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp)
+        const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->fast ? 1 : 0);
         switch (variant) {
             case 0: LAUNCH_STEP(false, false, false); break;
             case 1: LAUNCH_STEP(false, false, true); break;
@@ -416,7 +423,7 @@ void launch_step_interior(RtsContext* h) {
     timer_end(h, KT_STEP);
     if (nb && USE_DENSE_KERNEL) {   // the crowded agents k_step queued, one warp each
         timer_begin(h, KT_DENSE);
-        const dim3 dgrid(148 * RTS_DENSE_GRID_PER_SM);
+        const dim3 dgrid(h->n_sm * RTS_DENSE_GRID_PER_SM);
         cudaStream_t st = h->stream;
         if (dv == 0) LAUNCH_DENSE(false, false);
         else if (dv == 1) LAUNCH_DENSE(false, true);
@@ -568,6 +575,12 @@ static int32_t check_params(RtsContext* h, const RtsParams* p) {
         return h->fail(RTS_E_ARG, "params", "cell sizes and r_max2 must be positive");
     if ((uint64_t)p->ns_nx * (uint64_t)p->ns_ny >= (1ull << 29))
         return h->fail(RTS_E_ARG, "params", "physics grid has more than 2^29 cells");
+    if (p->ns_nx > 8192 || p->ns_ny > 65536)   // key2.y packs the cell as 13 + 16 bits (pack_cs)
+        return h->fail(RTS_E_ARG, "params", "physics grid is wider than 8192 or taller than 65536 cells");
+    if (p->precision > RTS_PRECISION_FAST) return h->fail(RTS_E_ARG, "params", "unknown precision mode");
+    if (p->enable_arrival && h->multi)
+        return h->fail(RTS_E_STATE, "params", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's finished "
+                                              "area and the stop requests of ghost agents across slabs (run arrival on a single-domain handle)");
     if (p->ns_cell_size * p->ns_cell_size < p->r_max2)
         return h->fail(RTS_E_ARG, "params", "ns_cell_size is smaller than the interaction range");
     return RTS_OK;
@@ -590,13 +603,16 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->keep_vel = params->reserved[0] == 0;   // reserved[0] = 1 drops the per-step velocity output
     if (params->reserved[1]) std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float));
     h->use_graph = params->reserved[2] == 0;
-    h->staged = params->reserved[3] != 0;
+    h->fast = params->precision == RTS_PRECISION_FAST;
+    h->M.inv_ns_cs = 1.0f / params->ns_cell_size;
+    h->M.inv_map_cs = 1.0f / params->map_cell_size;
     h->overlap_walk = params->reserved[4] == 0;
     h->overlap_exchange = (params->reserved[5] & 8u) != 0;
     h->graph_slabs = (params->reserved[5] & 16u) != 0;
     *out = h;
     int prio_lo = 0, prio_hi = 0;   // the comm stream (edge rows, exchange, ingest of a slab) outranks the bulk kernels
     cudaSetDevice(device_id);
+    if (cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device_id) != cudaSuccess || h->n_sm <= 0) h->n_sm = 148;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaSetDevice(device_id) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -676,6 +692,9 @@ int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
                         params->slab_row_hi != h->P.slab_row_hi || params->ns_cell_size != h->P.ns_cell_size;
     const bool rens = params->ns_nx != h->P.ns_nx || params->ns_ny != h->P.ns_ny || params->ns_cell_size != h->P.ns_cell_size;
     h->P = *params;
+    h->fast = params->precision == RTS_PRECISION_FAST;
+    h->M.inv_ns_cs = 1.0f / params->ns_cell_size;
+    h->M.inv_map_cs = 1.0f / params->map_cell_size;
     h->drop_graphs();
     if (regrid || rens) {
         CU(cudaStreamSynchronize(h->stream));
@@ -779,18 +798,20 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
         CU(cudaMemcpyAsync(d_ft, ft.data(), ft.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(d_el, el.data(), el.size() * 4, cudaMemcpyHostToDevice, h->stream));
     }
-    // conservative wall pre-filter bitmap (see may_touch_wall)
+    // conservative wall pre-filter bitmap (see may_touch_wall): one bit per MapGrid cell, set if a wall can lie within
+    // filter_r (+1) of any point of the cell — the bounding box of every wall, grown by that reach
     const float filter_r = 8.0f;
-    const int32_t bx = (int32_t)std::ceil(P.map_nx * P.map_cell_size / WALL_BLOCK) + 1;
-    const int32_t by = (int32_t)std::ceil(P.map_ny * P.map_cell_size / WALL_BLOCK) + 1;
+    const float wall_block = P.map_cell_size;
+    const int32_t bx = (int32_t)std::ceil(P.map_nx * P.map_cell_size / wall_block) + 1;
+    const int32_t by = (int32_t)std::ceil(P.map_ny * P.map_cell_size / wall_block) + 1;
     std::vector<uint32_t> bits(((size_t)bx * by + 31) / 32, 0u);
     for (size_t e = 0; e < ft.size(); ++e) {
         const float x0 = ft[e].x, y0 = ft[e].y, x1 = x0 + ft[e].z * el[e], y1 = y0 + ft[e].w * el[e];
         const float reach = filter_r + 1.0f;
-        const int ix0 = std::max(0, (int)std::floor((std::min(x0, x1) - reach) / WALL_BLOCK));
-        const int ix1 = std::min(bx - 1, (int)std::floor((std::max(x0, x1) + reach) / WALL_BLOCK));
-        const int iy0 = std::max(0, (int)std::floor((std::min(y0, y1) - reach) / WALL_BLOCK));
-        const int iy1 = std::min(by - 1, (int)std::floor((std::max(y0, y1) + reach) / WALL_BLOCK));
+        const int ix0 = std::max(0, (int)std::floor((std::min(x0, x1) - reach) / wall_block));
+        const int ix1 = std::min(bx - 1, (int)std::floor((std::max(x0, x1) + reach) / wall_block));
+        const int iy0 = std::max(0, (int)std::floor((std::min(y0, y1) - reach) / wall_block));
+        const int iy1 = std::min(by - 1, (int)std::floor((std::max(y0, y1) + reach) / wall_block));
         for (int iy = iy0; iy <= iy1; ++iy)
             for (int ix = ix0; ix <= ix1; ++ix) {
                 const size_t b = (size_t)iy * bx + ix;
@@ -852,7 +873,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     CU(cudaStreamSynchronize(h->stream));
     M.tris = d_tris; M.n_tris = n_tris; M.cell2tri = d_c2t;
     M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
-    M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r;
+    M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r; M.inv_wall_block = 1.0f / wall_block;
     M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
     h->A.n_tris_dev_hint = n_tris;
     M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
@@ -925,7 +946,19 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
         wp[2 * k + 1] = make_float4(e.t_x, e.t_y, e.l, 0.f);
     }
     uint32_t* d_off; float4* d_wp; float2* d_end; int32_t* d_grp; float *d_ar, *d_aa;
+    float4* d_hdr;
     int32_t rc;
+    std::vector<float4> hdr(std::max<uint32_t>(np, 1));   // {offset, end offset (as bits), path_end}: one load per agent in the frame kernel
+    for (uint32_t p = 0; p < np; ++p) {
+        float4 w;
+        std::memcpy(&w.x, &paths->offsets[p], 4);
+        std::memcpy(&w.y, &paths->offsets[p + 1], 4);
+        w.z = paths->path_end[2 * p];
+        w.w = paths->path_end[2 * p + 1];
+        hdr[p] = w;
+    }
+    if ((rc = dev_alloc(h, &d_hdr, hdr.size(), h->path_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_hdr, hdr.data(), hdr.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     if ((rc = dev_alloc(h, &d_grp, np, h->path_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_ar, ng, h->path_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_aa, ng, h->path_allocs)) != RTS_OK) return rc;
@@ -943,7 +976,7 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
     if (nw) CU(cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     if (np) CU(cudaMemcpyAsync(d_end, paths->path_end, 8 * (size_t)np, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np;
+    h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np; h->M.path_hdr = d_hdr;
     h->M.path_group = d_grp; h->M.n_groups = ng; h->M.area_read = d_ar; h->M.area_acc = d_aa;
     h->drop_graphs();
     return RTS_OK;
@@ -978,6 +1011,9 @@ int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
         const uint32_t cap = std::max<uint32_t>(n + n / 8 + 1024, 1024);
         if ((rc = alloc_agents(h, cap)) != RTS_OK) return rc;
     }
+    if (agents && agents->gid)
+        for (uint32_t i = 0; i < n; ++i)
+            if (agents->gid[i] >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_set_agents", "gid >= 2^28 (the ordering key keeps 28 bits of it)");
     h->n = n;
     h->gid_is_index = !(agents && agents->gid);
     if ((rc = ingest(h, 0, n, agents)) != RTS_OK) return rc;
@@ -1003,6 +1039,9 @@ int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents) {
     if ((uint64_t)h->n + m >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_append_agents", "more than 2^28 agents");
     if (h->gid_is_index && agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses component indices as gid");
     if (!h->gid_is_index && !agents->gid) return h->fail(RTS_E_ARG, "rts_append_agents", "population uses explicit gids");
+    if (agents->gid)
+        for (uint32_t i = 0; i < m; ++i)
+            if (agents->gid[i] >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_append_agents", "gid >= 2^28 (the ordering key keeps 28 bits of it)");
     CU(cudaSetDevice(h->device));
     { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     int32_t rc;
@@ -1354,6 +1393,9 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     if (!h) return RTS_E_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad rank");
     if (h->n) return h->fail(RTS_E_STATE, "rts_slab_configure", "configure the slab before uploading agents");
+    if (h->P.enable_arrival)
+        return h->fail(RTS_E_STATE, "rts_slab_configure", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's "
+                                                          "finished area and the stop requests of ghost agents across slabs");
     const RtsParams& P = h->P;
     if (P.slab_row_lo < 0 || P.slab_row_hi > P.ns_ny || P.slab_row_lo >= P.slab_row_hi) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad slab rows in the params");
     CU(cudaSetDevice(h->device));
@@ -1367,7 +1409,6 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     SL.halo = std::sqrt(P.r_max2) * 1.05f + 0.25f;
     SL.has[0] = P.slab_row_lo > 0; SL.has[1] = P.slab_row_hi < P.ns_ny;
     SL.cap_mig = cap_migrants; SL.cap_halo = cap_halo;
-    set_edge_rows(h);
     // one buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
     const size_t bytes = 16 + (size_t)cap_migrants * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8);
     auto carve = [&](void* base, ExBuf& B) {

@@ -41,6 +41,7 @@ struct MapDev {
     const uint32_t* __restrict__ wall_bits;
     int32_t wall_bx, wall_by;
     float wall_filter_radius;
+    float inv_wall_block;     // 1 / block size of the bitmap (one MapGrid cell: 5 units)
     int32_t coords_fit_i32;   // 1: every triangle-walk product fits int32 (the reference's own arithmetic)
     // acceleration of findTriangle's linear-scan fallback (lowest triangle index containing q): per cache cell the
     // ascending list of "small" triangles whose bounding box touches the cell, plus one ascending list of the few
@@ -51,9 +52,12 @@ struct MapDev {
     uint32_t n_scan_large;
     const uint32_t* __restrict__ scan_outer;   // triangles reaching beyond the cache grid (the super-triangle fan)
     uint32_t n_scan_outer;
+    // per path {offset, end offset, path_end.x, path_end.y} in one 16-byte word (same numbers as path_off / path_end)
+    const float4* __restrict__ path_hdr;
+    // RN(1 / ns_cell_size), RN(1 / map_cell_size): used by floor_div() to skip the IEEE division on its common path
+    float inv_ns_cs, inv_map_cs;
 };
 constexpr uint32_t SCAN_LARGE_CELLS = 1024;
-constexpr float WALL_BLOCK = 20.f;
 
 struct v2 {
     float x, y;
@@ -74,16 +78,49 @@ __device__ __forceinline__ bool vequal(v2 a, v2 b) { return dist2(a, b) < 0.001f
 __device__ __forceinline__ bool veq(v2 a, v2 b) { return a.x == b.x && a.y == b.y; }
 
 // ---- Grid::coordToCell, src/Utils/Grid.cpp:18-24 ------------------------------------------------
+// floorf(x / cs), bit for bit, without the IEEE division on the common path. q~ = RN(x * RN(1/cs)) and the reference's
+// RN(x / cs) both lie within 1.8e-7 |q| of the real quotient, so whenever q~ is further than 2.5e-7 |q~| from the nearest
+// integers no integer separates the two and their floors agree; otherwise (and for NaN / |q| >= 2^23, where the
+// fractional part is 0) the division is done. inv_cs must be RN(1/cs).
+__device__ __forceinline__ float floor_div(float x, float cs, float inv_cs) {
+    const float q = x * inv_cs;
+    float f = floorf(q);
+    const float d = q - f;
+    const float m = fabsf(q) * 2.5e-7f;
+    if (!(d > m && d < 1.f - m)) f = floorf(x / cs);
+    return f;
+}
 // size_t(floor(x/cs)) % n.  The common case (0 <= floor < 2^31) stays in 32 bits; anything else takes
 // the 64-bit path that reproduces x86-64's float -> size_t conversion (signed convert, wrap mod 2^64).
-__device__ __forceinline__ uint32_t axis_cell(float x, float cs, int32_t n) {
-    const float f = floorf(x / cs);
-    if (f >= 0.f && f < 2147483648.f) return (uint32_t)f % (uint32_t)n;
+__device__ __forceinline__ uint32_t cell_of_floor(float f, int32_t n) {
+    if (f >= 0.f && f < 2147483648.f) {
+        const uint32_t u = (uint32_t)f;
+        return u < (uint32_t)n ? u : u % (uint32_t)n;   // (inside the map nothing wraps: no division)
+    }
     const uint64_t u = (uint64_t)(int64_t)f;   // cvttss2si semantics
     return (uint32_t)(u % (uint64_t)n);
 }
+__device__ __forceinline__ uint32_t axis_cell(float x, float cs, int32_t n) { return cell_of_floor(floorf(x / cs), n); }
+__device__ __forceinline__ uint32_t axis_cell(float x, float cs, float inv_cs, int32_t n) { return cell_of_floor(floor_div(x, cs, inv_cs), n); }
 __device__ __forceinline__ uint32_t coord_to_cell(float x, float y, int32_t nx, int32_t ny, float cs) {
     return axis_cell(x, cs, nx) + axis_cell(y, cs, ny) * (uint32_t)nx;
+}
+
+// ---- approximations of the tolerance mode (RtsParams.precision = RTS_PRECISION_FAST) only ---------------------------
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// ... with one Newton step (relative error ~1e-7): the once-per-agent normalisations, whose result is scaled by a speed
+__device__ __forceinline__ float rsqrt_nr(float x) {
+    const float y = rsqrt_fast(x);
+    return y * __fmaf_rn(-0.5f * x * y, y, 1.5f);
 }
 
 // ---- AcosTable<1000>::angle, src/core.h:139-150 ---------------------------------------------------
@@ -351,7 +388,7 @@ __device__ __forceinline__ int contact_walls(const MapDev& M, const RtsParams& P
 // (a contact needs dist(r, segment) <= radius; the bitmap marks every block within wall_filter_radius+1 of a wall).
 __device__ __forceinline__ bool may_touch_wall(const MapDev& M, v2 r, float radius) {
     if (!M.wall_bits || !(radius <= M.wall_filter_radius)) return true;
-    const float fx = r.x * (1.f / WALL_BLOCK), fy = r.y * (1.f / WALL_BLOCK);
+    const float fx = r.x * M.inv_wall_block, fy = r.y * M.inv_wall_block;
     if (!(fx >= 0.f && fy >= 0.f && fx < (float)M.wall_bx && fy < (float)M.wall_by)) return true;   // outside the map (or NaN)
     const uint32_t b = (uint32_t)(int)fy * (uint32_t)M.wall_bx + (uint32_t)(int)fx;
     return (__ldg(M.wall_bits + (b >> 5)) >> (b & 31u)) & 1u;

@@ -37,10 +37,24 @@ constexpr int STEP_MIN_BLOCKS = RTS_STEP_MIN_BLOCKS;
 #define RTS_NBR_CAP 16
 #endif
 constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memory per agent
-#ifndef RTS_STAGE_CAP
-#define RTS_STAGE_CAP 640
+#ifndef RTS_FAST_BLOCK
+#define RTS_FAST_BLOCK 128
 #endif
-constexpr int STAGE_CAP = RTS_STAGE_CAP;   // neighbour records a CTA stages in shared memory (typically ~400)
+#ifndef RTS_FAST_MIN_BLOCKS
+#define RTS_FAST_MIN_BLOCKS 10
+#endif
+constexpr int FAST_BLOCK = RTS_FAST_BLOCK;             // threads per CTA of the tolerance-mode k_step (no shared memory: registers set the occupancy)
+constexpr int FAST_MIN_BLOCKS = RTS_FAST_MIN_BLOCKS;
+#ifndef RTS_FAST_DENSE_CAND
+#define RTS_FAST_DENSE_CAND 64
+#endif
+constexpr uint32_t FAST_DENSE_CAND = RTS_FAST_DENSE_CAND;   // tolerance mode: agents with more CANDIDATES than this (slots in their 3x3 fine
+                                                            // cells; ~12 at config-3 density) are handed to k_step_dense, where
+                                                            // FAST_DENSE_LANES lanes share one agent's candidates
+#ifndef RTS_FAST_DENSE_LANES
+#define RTS_FAST_DENSE_LANES 8
+#endif
+constexpr uint32_t FAST_DENSE_LANES = RTS_FAST_DENSE_LANES;
 #ifndef RTS_DENSE_MIN
 #define RTS_DENSE_MIN 16
 #endif
@@ -69,6 +83,21 @@ __device__ __forceinline__ int cs_cy(uint32_t y) { return (int)(y >> 16); }
 __device__ __forceinline__ uint32_t ns_pack(const RtsParams& P, float x, float y, uint32_t ghost, uint32_t state) {
     return pack_cs(axis_cell(x, P.ns_cell_size, P.ns_nx), axis_cell(y, P.ns_cell_size, P.ns_ny), ghost, state);
 }
+// is the physics-grid cell in key word `ky` one of the (up to) nine cells calcNearestCells gives an agent in cell
+// (cxi, cyi)?  (Grid.cpp:103-118: offsets -1..1 on the cell coordinates, cells outside the grid dropped — no wrapping.)
+// Always true for two agents inside the map that are within the interaction range; an agent that was pushed over the map
+// edge has a cell index wrapped modulo the grid (Grid.cpp:18-24) and is then NOT a neighbour of the agents next to it.
+__device__ __forceinline__ bool cell_is_adjacent(uint32_t ky, int cxi, int cyi) {
+    const int dxc = cs_cx(ky) - cxi, dyc = cs_cy(ky) - cyi;
+    return dxc >= -1 && dxc <= 1 && dyc >= -1 && dyc <= 1;
+}
+// pos4 = {x, y, radius, mass}; the MoveState is mirrored in the sign bits of radius (bit 0) and mass (bit 1) — both are
+// non-negative quantities — so that the neighbour loop gets the neighbour's state with its position, without a second load
+__device__ __forceinline__ float4 pack_pos(float x, float y, float radius, float mass, uint32_t state) {
+    return make_float4(x, y, __uint_as_float((__float_as_uint(radius) & 0x7FFFFFFFu) | ((state & 1u) << 31)),
+                       __uint_as_float((__float_as_uint(mass) & 0x7FFFFFFFu) | ((state & 2u) << 30)));
+}
+__device__ __forceinline__ int pos_state(float4 o) { return (int)((__float_as_uint(o.z) >> 31) | ((__float_as_uint(o.w) >> 31) << 1)); }
 // nav4.w bits: waypoint 0..15 | unit_type 16..23 | player 24..27 | flags 28..31
 __device__ __forceinline__ uint32_t pack_misc(uint32_t wp, uint32_t type, uint32_t player, uint32_t flags) {
     return (wp & 0xFFFFu) | ((type & 0xFFu) << 16) | ((player & 0xFu) << 24) | ((flags & 0xFu) << 28);
@@ -521,7 +550,7 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
     if ((key.y & 3u) != RTS_MOVING || ((key.y >> 2) & 1u)) return;
     const float4 nav4 = A.nav4[A.src[p]];
     const int32_t pid = __float_as_int(nav4.z);
-    if (pid < 0) return;
+    if (pid < 0 || (uint32_t)pid >= M.n_paths) return;   // (a stale id beyond the uploaded table counts as "no path")
     const uint32_t p0 = __ldg(M.path_off + pid), last = __ldg(M.path_off + pid + 1) - 1;
     const uint32_t w0 = min(p0 + (__float_as_uint(nav4.w) & 0xFFFFu), last);
     v2 r_next = V(nav4.x, nav4.y);
@@ -530,7 +559,8 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
     const v2 path_end = V(pe.x, pe.y);
     if (!vequal(path_end, r_next)) return;
     const int32_t g_i = __ldg(M.path_group + pid);
-    const float4 me = A.pos4[p];
+    float4 me = A.pos4[p];
+    me.z = fabsf(me.z);   // (sign bits of radius / mass carry the state, see pack_pos)
     const v2 r = V(me.x, me.y);
     const float finish_radius = sqrtf(M.area_read[g_i] / 3.14159265358979323846f);
     const float dist_to_end = sqrtf(dist2(path_end, r));
@@ -549,13 +579,13 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
             if (q == p) continue;
             const float4 o = A.pos4[q];
             const v2 dr = V(o.x, o.y) - r;
-            const float rr = me.z + o.z;
+            const float rr = me.z + fabsf(o.z);
             if (!(norm2(dr) < 10.f * rr * rr)) continue;
             if (!(sqrtf(norm2(r - V(o.x, o.y))) < P.finish_radius)) continue;
             const uint2 ok = A.key2[q];
             if ((ok.y & 3u) != RTS_MOVING || ((ok.y >> 2) & 1u)) continue;
             const int32_t pj = __float_as_int(A.nav4[A.src[q]].z);
-            if (pj < 0 || __ldg(M.path_group + pj) != g_i) continue;
+            if (pj < 0 || (uint32_t)pj >= M.n_paths || __ldg(M.path_group + pj) != g_i) continue;
             if (atomicExch(A.stop_req + q, 1u) == 0u) atomicAdd(M.area_acc + g_i, area_unit);
         }
     }
@@ -572,15 +602,16 @@ struct ForceTerms {
     v2 rep, push, dr;
     uint32_t mask;   // bit 0: repulsion term present, bit 1: push term, bit 2: scatter contribution
 };
-__device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float mass_i, int state_i, float4 o, int state_j, float rscatter2) {
+__device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float mass_i, int state_i, float4 o, float rscatter2) {
     ForceTerms t;
     t.mask = 0u;
     t.rep = V(0.f, 0.f);
     t.push = V(0.f, 0.f);
     const v2 dr = V(o.x, o.y) - r;
     t.dr = dr;
-    const float r_collision = o.z + radius;
-    const float mass_j = o.w;
+    const int state_j = pos_state(o);
+    const float r_collision = fabsf(o.z) + radius;
+    const float mass_j = fabsf(o.w);
     const float r_collision_sq = r_collision * r_collision;
     const float d_surfs = norm2(dr);
     const float x = r_collision_sq / d_surfs;
@@ -609,11 +640,16 @@ __device__ __forceinline__ void add_terms(ForceSums& S, v2 rep, v2 push, v2 dr, 
 // Everything of the frame after the neighbour sums: scatter term, clamp, decay, wall pass, seek, merge, wall pass,
 // integration, migration / halo packing, and the write of the new record at slot p. Returns the fine cell of the new
 // position (the caller ranks it).
-template <bool KEEP_VEL, bool MULTI>
+// FAST (tolerance mode): the normalisations use rsqrt.approx instead of IEEE sqrt + division. Everything that DECIDES
+// something — the wall contact set, the acos-table bin of turnTowards, the waypoint predicates of needsUpdating, the cell
+// indices of the new position — is still evaluated with the reference's own arithmetic (or a shortcut that provably
+// gives the same answer), so after one frame from the same state the discrete outputs (state, waypoint, r_next, flags,
+// angle, angle_vel) are bit-identical to the exact mode and only vel / inertia / r carry rounding-level differences.
+template <bool KEEP_VEL, bool MULTI, bool FAST>
 __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4 me, uint2 mykey, float4 vel4, float4 nav4, const ForceSums& sums,
                                                  const RtsParams& P, const MapDev& M, const FineGrid& F, const AgentArrays& A, const SlabDev& SL) {
     const v2 r = V(me.x, me.y);
-    const float radius = me.z, mass_i = me.w;
+    const float radius = fabsf(me.z), mass_i = fabsf(me.w);
     const uint32_t gid = mykey.x;
     const int state_i = (int)(mykey.y & 3u);
     const uint32_t misc = __float_as_uint(nav4.w);
@@ -622,19 +658,31 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     const float n_neighbours = sums.n_neighbours;
 
     // ---- P2 tail: applyForces, PhysicsSystem.cpp:104-116
-    dr_nn = dr_nn / n_neighbours;
-    if (n_neighbours > 1.f) scatter = (dr_nn / norm(dr_nn)) * ut.max_speed;
+    if (FAST) {
+        // mean / |mean| = sum / |sum|
+        if (n_neighbours > 1.f) scatter = dr_nn * (rsqrt_nr(norm2(dr_nn)) * ut.max_speed);
+    } else {
+        dr_nn = dr_nn / n_neighbours;
+        if (n_neighbours > 1.f) scatter = (dr_nn / norm(dr_nn)) * ut.max_speed;
+    }
     v2 inertia = V(vel4.x, vel4.y);
     inertia = inertia + ((repulsion * P.mul_repulse + push * P.mul_push) + scatter * P.mul_scatter);
 
-    // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry)
-    v2 vp = V(0.f, 0.f);
-    float speed = norm(vp);
-    if (speed > P.sys_max_speed) vp = vp / (speed * P.sys_max_speed);
-    vp = vp + inertia;
+    // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry, so the
+    //      `vel /= speed*max_speed` clamp at :27-30 never fires)
+    v2 vp = inertia;
     const float max_vel = ut.max_speed * P.mul_velocity;
-    speed = norm(vp);
-    if (speed > max_vel) vp = vp * (max_vel / speed);
+    if (FAST) {
+        const float s2 = norm2(vp);
+        if (s2 > max_vel * max_vel) vp = vp * (max_vel * rsqrt_nr(s2));
+    } else {
+        vp = V(0.f, 0.f);
+        float speed = norm(vp);
+        if (speed > P.sys_max_speed) vp = vp / (speed * P.sys_max_speed);
+        vp = vp + inertia;
+        speed = norm(vp);
+        if (speed > max_vel) vp = vp * (max_vel / speed);
+    }
     const float lm = ut.lambda * P.mul_decay;
     const float decay = (lm < 1.f) ? lm : 1.f;
     inertia = inertia - inertia * decay;
@@ -658,8 +706,9 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
         angle_vel = 0.f;
         pid = -1;
     }
-    if (state_out == RTS_MOVING && pid >= 0) {
-        const uint32_t p0 = __ldg(M.path_off + pid), p1 = __ldg(M.path_off + pid + 1);
+    if (state_out == RTS_MOVING && pid >= 0 && (uint32_t)pid < M.n_paths) {   // (a stale id beyond the uploaded table counts as "no path")
+        const float4 hdr = __ldg(M.path_hdr + pid);
+        const uint32_t p0 = __float_as_uint(hdr.x), p1 = __float_as_uint(hdr.y);
         const uint32_t last = p1 - 1;
         const uint32_t w0 = min(p0 + wp, last);
         const uint32_t w1 = min(w0 + 1, last);
@@ -667,16 +716,37 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
         const float4 wn = __ldg(M.waypoints + 2 * (size_t)w1);
         if (r_next.x != r_next.x) r_next = V(wa.x, wa.y);
         const v2 r_nn = V(wn.x, wn.y);
-        const v2 path_end = V(__ldg(M.path_end + pid).x, __ldg(M.path_end + pid).y);
+        const v2 path_end = V(hdr.z, hdr.w);
 
         const v2 dr_to_target = r_next - r;
+        const float n2_target = norm2(dr_to_target);
+        // |dr_to_target| feeds three comparisons (against radius and RHARD) that decide discrete things. FAST: the
+        // rsqrt-based norm (relative error < 3e-7) is replaced by the IEEE one whenever it is close to a threshold.
+        float norm_dr, inv_norm_dr = 0.f;
+        if (FAST) {
+            inv_norm_dr = rsqrt_nr(n2_target);
+            norm_dr = n2_target * inv_norm_dr;
+            if (!(fabsf(norm_dr - radius) > 1e-5f * radius && fabsf(norm_dr - P.rhard) > 1e-5f * P.rhard)) norm_dr = sqrtf(n2_target);   // also 0 and NaN
+        } else norm_dr = sqrtf(n2_target);
         {   // turnTowards, SeekSystem.cpp:344-385 (the component-local angle edit is never communicated, :322-342)
             float ang = angle;
             if (ang > 180) ang -= 360;
             if (ang < -180) ang += 360;
             float desired;
-            if (norm2(dr_to_target) == 0) desired = ut.desired_angle;
-            else desired = table_angle(M.acos_table, dr_to_target);
+            if (n2_target == 0) desired = ut.desired_angle;
+            else if (FAST) {
+                // AcosTable<1000>::angle (core.h:139-150): bin = floor((x/|v| + 1) / 2 * 1000). The approximate bin
+                // coordinate is within 1e-3 of the reference's; unless it is that close to an integer both floor alike
+                const float bq = (dr_to_target.x * inv_norm_dr + 1.0f) * 500.f;
+                const float bf = floorf(bq);
+                const float bd = bq - bf;
+                if (bd > 2e-3f && bd < 1.f - 2e-3f) {
+                    int bin = (int)bf;
+                    if (bin >= 1000) bin = 999;
+                    if (bin < 0) bin = 0;
+                    desired = __ldg(M.acos_table + bin) * (2.f * (dr_to_target.y > 0) - 1.f);
+                } else desired = table_angle(M.acos_table, dr_to_target);
+            } else desired = table_angle(M.acos_table, dr_to_target);
             float d_angle = desired - ang;
             if (d_angle > 180) d_angle = -360 + d_angle;
             if (d_angle < -180) d_angle = 360 + d_angle;
@@ -684,8 +754,7 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
             if (d_angle < 0) angle_vel = (d_angle > -ut.turn_rate) ? d_angle : -ut.turn_rate;
             if (fabsf(d_angle) < ut.turn_rate) angle_vel = 0;
         }
-        const float norm_dr = norm(dr_to_target);
-        if (norm_dr > radius) vs = (dr_to_target / norm_dr) * ut.seek_max_speed;
+        if (norm_dr > radius) vs = FAST ? dr_to_target * (inv_norm_dr * ut.seek_max_speed) : (dr_to_target / norm_dr) * ut.seek_max_speed;
 
         bool upd;  // needsUpdating, SeekSystem.cpp:181-233
         if (vequal(r_next, path_end)) upd = false;
@@ -704,10 +773,15 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
         }
         if (upd) {  // updateTarget, SeekSystem.cpp:277-304
             const v2 dn = r_nn - r;
-            const float ndn = norm(dn);
             r_next = r_nn;
             if (p0 + wp < last) wp++;
-            if (ndn > 0) vs = (dn / ndn) * ut.seek_max_speed;
+            if (FAST) {
+                const float n2 = norm2(dn);
+                if (n2 > 0) vs = dn * (rsqrt_nr(n2) * ut.seek_max_speed);
+            } else {
+                const float ndn = norm(dn);
+                if (ndn > 0) vs = (dn / ndn) * ut.seek_max_speed;
+            }
             if (!veq(r_nn, path_end)) flags |= RTS_FLAG_REPLAN;
         }
     }
@@ -726,8 +800,8 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     A.trin[p] = *((const volatile uint32_t*)A.tri + sp);
 
     // ---- write the new record at this slot; bin it for the next order
-    const float4 pos_new = make_float4(r_new.x, r_new.y, radius, mass_i);
-    const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, P.ns_ny);
+    const float4 pos_new = pack_pos(r_new.x, r_new.y, radius, mass_i, (uint32_t)state_out);
+    const uint32_t cx_new = axis_cell(r_new.x, P.ns_cell_size, M.inv_ns_cs, P.ns_nx), cy_new = axis_cell(r_new.y, P.ns_cell_size, M.inv_ns_cs, P.ns_ny);
     uint32_t cs_new = pack_cs(cx_new, cy_new, 0u, (uint32_t)state_out);
     const float4 vel_new = make_float4(inertia.x, inertia.y, angle, angle_vel);
     const float4 nav_new = make_float4(r_next.x, r_next.y, __int_as_float(pid), __uint_as_float(pack_misc(wp, (misc >> 16) & 0xFFu, (misc >> 24) & 0xFu, flags)));
@@ -776,27 +850,102 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tolerance mode: the candidates of the three fine rows are visited as ONE virtual range (no per-row loops: the trip
+// count of a warp is the longest total, not the sum of the longest rows) and the force terms of applyForces
+// (PhysicsSystem.cpp:69-102) are evaluated branch-free for every candidate and added where they apply — no neighbour
+// list, no ordering, one rsqrt.approx per candidate. The ACCEPTANCE test is the reference's own arithmetic
+// (dx*dx + dy*dy < r_max2, separately rounded products), so the neighbour set is the reference's set.
+struct FastScan {
+    v2 r;
+    float radius, mass_i;
+    bool standing;        // state_i == STANDING: the push term applies
+    float r_max2, rscatter2;
+    uint32_t self;        // own slot
+    bool near_edge;       // the 3x3 window touches a clamp cell of the fine grid: candidates may lie outside the map
+    int cxi, cyi;         // own physics-grid cell
+    uint32_t qb0, len0, qb1, len1, qb2, len2;   // slot ranges of the three fine rows
+};
+// PUSH: some lane of the warp is STANDING (the push term exists). CHECKS: some lane's window touches the edge of the
+// fine grid (physics-cell adjacency must be checked, see cell_is_adjacent) or RSCATTER^2 < r_max2 (the scatter condition
+// is not implied by the acceptance). Both are decided per warp, so that the common case carries neither.
+template <bool PUSH, bool CHECKS>
+__device__ __forceinline__ void fast_candidate(ForceSums& S, const FastScan& c, const float4 o, const uint32_t q, bool valid, const uint2* __restrict__ key2) {
+    const float dx = o.x - c.r.x, dy = o.y - c.r.y;
+    const float d2 = dx * dx + dy * dy;                 // norm2(dr), as the reference rounds it
+    bool acc = valid && d2 < c.r_max2 && q != c.self;
+    if (CHECKS) {
+        if (c.near_edge && acc) acc = cell_is_adjacent(key2[q].y, c.cxi, c.cyi);
+    }
+    const float mass_j = fabsf(o.w);
+    const float rc = fabsf(o.z) + c.radius;
+    const float rc2 = rc * rc;
+    const float inv_d = rsqrt_fast(d2);
+    const float x = rc2 * (inv_d * inv_d);
+    const float w = mass_j * rcp_fast(c.mass_i + mass_j);
+    const float m3 = (3.f * x) * (x * x);
+    const float mag = fminf(m3, 50000.0f);
+    const float s_rep = (acc && x > 0.8f) ? (mag * w) * inv_d : 0.f;
+    S.repulsion.x = __fmaf_rn(-dx, s_rep, S.repulsion.x);
+    S.repulsion.y = __fmaf_rn(-dy, s_rep, S.repulsion.y);
+    // state_j == MOVING (= 0): both sign bits of {radius, mass} clear
+    const bool moving_j = acc && (__float_as_int(o.z) | __float_as_int(o.w)) >= 0;
+    if (PUSH) {
+        const float s_push = (c.standing && moving_j && x > 0.75f) ? x * w : 0.f;
+        S.push.x = __fmaf_rn(-dx, s_push, S.push.x);
+        S.push.y = __fmaf_rn(-dy, s_push, S.push.y);
+    }
+    // x > rc2 / RSCATTER^2  <=>  d2 < RSCATTER^2, implied by d2 < r_max2 unless RSCATTER^2 < r_max2
+    const bool sc = CHECKS ? (moving_j && d2 < c.rscatter2) : moving_j;
+    S.dr_nn.x += sc ? dx : 0.f;
+    S.dr_nn.y += sc ? dy : 0.f;
+    S.n_neighbours += sc ? 1.f : 0.f;
+}
+// candidates v0, v0 + vstep, ... of the virtual range (vstep = 1: one thread does them all; vstep = lanes of a group)
+template <bool PUSH, bool CHECKS>
+__device__ __forceinline__ void fast_loop(ForceSums& S, const FastScan& c, const float4* __restrict__ pos4, const uint2* __restrict__ key2,
+                                          uint32_t v0, uint32_t vstep) {
+    const uint32_t l01 = c.len0 + c.len1, total = l01 + c.len2;
+    const uint32_t o1 = c.qb1 - c.len0, o2 = c.qb2 - l01;
+    auto slot = [&](uint32_t v) { return v + (v < c.len0 ? c.qb0 : (v < l01 ? o1 : o2)); };
+#pragma unroll 1
+    for (uint32_t v = v0; v < total; v += 2u * vstep) {
+        const uint32_t vb = v + vstep;
+        const bool hb = vb < total;
+        const uint32_t qa = slot(v), qb = slot(hb ? vb : v);
+        const float4 oa = pos4[qa], ob = pos4[qb];       // both loads in flight
+        fast_candidate<PUSH, CHECKS>(S, c, oa, qa, true, key2);
+        fast_candidate<PUSH, CHECKS>(S, c, ob, qb, hb, key2);
+    }
+}
+// `lanes`: the lanes of the warp that call this together (the variant is chosen per warp)
+__device__ __forceinline__ void fast_accumulate(ForceSums& S, const FastScan& c, const float4* __restrict__ pos4, const uint2* __restrict__ key2,
+                                                uint32_t v0, uint32_t vstep, unsigned lanes) {
+    const bool push = __any_sync(lanes, c.standing);
+    const bool checks = __any_sync(lanes, c.near_edge) || !(c.rscatter2 >= c.r_max2);
+    if (!push && !checks) fast_loop<false, false>(S, c, pos4, key2, v0, vstep);
+    else if (push && !checks) fast_loop<true, false>(S, c, pos4, key2, v0, vstep);
+    else if (!push) fast_loop<false, true>(S, c, pos4, key2, v0, vstep);
+    else fast_loop<true, true>(S, c, pos4, key2, v0, vstep);
+}
+
+// ------------------------------------------------------------------------------------------------
 // The fused frame. One thread per slot (agents of one fine cell are adjacent, so a warp reads a few
 // neighbouring cells and the neighbour records come out of L1).
+// FAST = false: bit-exact mode — accepted neighbours are collected, sorted into the reference's visit order and added
+// up in that order with IEEE arithmetic. FAST = true: tolerance mode (see fast_accumulate).
 // PHASE 0: every slot; PHASE 1: the edge rows of a slab only (see SlabDev), PHASE 2: everything else.
-template <bool KEEP_VEL, bool MULTI, bool STAGED, int PHASE = 0>
-__global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL,
-                                                                      uint32_t walk_ctas, int walk_parity) {
+template <bool KEEP_VEL, bool MULTI, bool FAST, int PHASE = 0>
+__global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MIN_BLOCKS : STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL,
+                                                                                 uint32_t walk_ctas, int walk_parity) {
     // the first walk_ctas CTAs finish the triangle walk of the previous frame (the agents its k_scatter queued)
     if (blockIdx.x < walk_ctas) {
-        if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, blockIdx.x, walk_ctas, STEP_BLOCK);
-        else drain_walk_queue<true>(P, M, A, walk_parity, blockIdx.x, walk_ctas, STEP_BLOCK);
+        if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, blockIdx.x, walk_ctas, FAST ? FAST_BLOCK : STEP_BLOCK);
+        else drain_walk_queue<true>(P, M, A, walk_parity, blockIdx.x, walk_ctas, FAST ? FAST_BLOCK : STEP_BLOCK);
         return;
     }
     const uint32_t bid = blockIdx.x - walk_ctas;
-    __shared__ uint2 s_kq[NBR_CAP][STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
-    // neighbour records of every fine cell this CTA's agents can see, staged once (coalesced) instead of being fetched
-    // ~9 times each by individual lanes. The CTA's 128 slots lie in one fine row (3 row segments) or straddle two
-    // (6 segments); anything else, or more than STAGE_CAP records, falls back to reading global memory.
-    __shared__ float4 s_pos[STAGED ? STAGE_CAP : 1];
-    __shared__ uint2 s_key[STAGED ? STAGE_CAP : 1];
-    __shared__ uint32_t s_seg_gb[6], s_seg_off[6];
-    __shared__ int s_first[2], s_last[2], s_mode, s_total;
+    constexpr uint32_t BLOCK = FAST ? FAST_BLOCK : STEP_BLOCK;
+    __shared__ uint2 s_kq[FAST ? 1 : NBR_CAP][FAST ? 1 : STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
 
     const int tid = threadIdx.x;
     const uint32_t n = MULTI ? *A.n_dev : n_bound;   // slabs: the population changes every frame, the count lives on the device
@@ -809,12 +958,11 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         edge_b = __ldg(F.start + (uint32_t)(SL.has[1] ? SL.edge_row_hi : F.ny - 1) * (uint32_t)F.nx);
         edge_b = max(edge_b, edge_a);
     }
-    const uint32_t cover = SL.edge_blocks * STEP_BLOCK;   // slots the PHASE 1 grid reaches on either side
-    uint32_t block0 = bid * STEP_BLOCK;
-    if (PHASE == 1 && bid >= SL.edge_blocks) block0 = edge_b + (bid - SL.edge_blocks) * STEP_BLOCK;
+    const uint32_t cover = SL.edge_blocks * BLOCK;   // slots the PHASE 1 grid reaches on either side
+    uint32_t block0 = bid * BLOCK;
+    if (PHASE == 1 && bid >= SL.edge_blocks) block0 = edge_b + (bid - SL.edge_blocks) * BLOCK;
     const uint32_t p = block0 + tid;
     const bool in_range = p < n;
-    const unsigned valid = __ballot_sync(0xffffffffu, in_range);
 
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
     uint2 mykey = make_uint2(0u, 4u);
@@ -829,62 +977,9 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         const bool covered = (p < edge_a && p < cover) || (p >= edge_b && p - edge_b < cover);
         mine = (PHASE == 1) ? (covered && (bid < SL.edge_blocks ? p < edge_a : true)) : !covered;
     }
-    const unsigned active = __ballot_sync(valid, !ghost && mine);  // lanes that reach the re-bin at the end
+    const unsigned active = __ballot_sync(0xffffffffu, in_range && !ghost && mine);  // lanes that reach the re-bin at the end
     int fx, fy;
     fine_coords(F, r.x, r.y, fx, fy);
-
-    // ---- stage the candidate window of the CTA
-    if (STAGED && block0 < n) {
-        const uint32_t last_valid = min(n, block0 + STEP_BLOCK) - 1u;
-        if (p == block0) { s_first[0] = fx; s_first[1] = fy; }
-        if (p == last_valid) { s_last[0] = fx; s_last[1] = fy; }
-    }
-    if (STAGED) __syncthreads();
-    if (STAGED && tid < 32) {
-        uint32_t gb = 0, len = 0;
-        int mode = 0;
-        if (block0 < n) {
-            const int fx0 = s_first[0], fy0 = s_first[1], fx1 = s_last[0], fy1 = s_last[1];
-            mode = (fy1 == fy0) ? 1 : ((fy1 == fy0 + 1) ? 2 : 0);
-            if (tid < 6 && mode) {
-                int row, x0, x1;
-                if (mode == 1) { row = (tid < 3) ? fy0 - 1 + tid : -1; x0 = fx0 - 1; x1 = fx1 + 1; }
-                else if (tid < 3) { row = fy0 - 1 + tid; x0 = fx0 - 1; x1 = F.nx - 1; }
-                else { row = fy1 - 1 + (tid - 3); x0 = 0; x1 = fx1 + 1; }
-                x0 = max(x0, 0);
-                x1 = min(x1, F.nx - 1);
-                if (row >= 0 && row < F.ny) {
-                    const uint32_t rowbase = (uint32_t)row * (uint32_t)F.nx;
-                    gb = __ldg(F.start + rowbase + x0);
-                    len = __ldg(F.start + rowbase + x1 + 1) - gb;
-                }
-            }
-        }
-        uint32_t incl = len;   // prefix over the 6 segment lengths
-        for (int o = 1; o < 8; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 5);
-        if (tid < 6) { s_seg_gb[tid] = gb; s_seg_off[tid] = incl - len; }
-        if (tid == 0) { s_mode = (total <= (uint32_t)STAGE_CAP) ? mode : 0; s_total = (int)total; }
-    }
-    if (STAGED) __syncthreads();
-    const int mode = STAGED ? s_mode : 0;
-    if (STAGED && mode) {
-        const int total = s_total;
-        for (int i = tid; i < total; i += STEP_BLOCK) {
-            int sg = 0;
-#pragma unroll
-            for (int k = 1; k < 6; ++k) sg += ((uint32_t)i >= s_seg_off[k]) ? 1 : 0;   // offsets are non-decreasing
-            // empty trailing segments share the last offset; the last segment whose offset is <= i and that is non-empty
-            // is found because an empty segment k has off[k] == off[k+1] and i >= off[k+1] moves past it
-            const uint32_t q = s_seg_gb[sg] + ((uint32_t)i - s_seg_off[sg]);
-            s_pos[i] = A.pos4[q];
-            s_key[i] = A.key2[q];
-        }
-    }
-    if (STAGED) __syncthreads();
 
     if (!in_range) {
         if (MULTI && PHASE != 1 && p < n_bound) A.cellrank[p] = make_uint2(INVALID_CELL, 0u);   // unused slot
@@ -893,41 +988,61 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         A.cellrank[p] = make_uint2(INVALID_CELL, 0u);
     } else {
     const uint32_t sp = A.src[p];
-    const float radius = me.z, mass_i = me.w;
-    const uint32_t gid = mykey.x;
+    const float radius = fabsf(me.z), mass_i = fabsf(me.w);
     const int state_i = (int)(mykey.y & 3u);
     const int cxi = cs_cx(mykey.y), cyi = cs_cy(mykey.y);
 
-    const float4 vel4 = A.vel4[sp];
-    const float4 nav4 = A.nav4[sp];
-    const uint32_t misc = __float_as_uint(nav4.w);
-    const RtsUnitType ut = M.unit_types[(misc >> 16) & 0xFFu];
-
-    // ---- P1: neighbour pass (Strategy.cpp:10-68) over the 3x3 fine cells; accepted neighbours are kept
-    //      sorted by (reference visit rank of their 60-unit cell, gid) = the reference's visit order
+    // ---- P1: neighbour pass (Strategy.cpp:10-68) over the 3x3 fine cells
     const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
     const int ylo = max(fy - 1, 0), yhi = min(fy + 1, F.ny - 1);
+    // a candidate outside the map sits in a clamp cell of the fine grid; only then can its physics-grid cell fail to be
+    // one of the nine calcNearestCells visits (see cell_is_adjacent)
+    const bool near_edge = fx <= 1 || fx >= F.nx - 2 || fy <= 1 || fy >= F.ny - 2;
 
-    // candidate index ranges of the three fine rows (each row's 3 cells are contiguous in slot order). Candidates are
-    // addressed through generic pointers: the staged copy in shared memory, or the global arrays (fallback)
-    const float4* cand_pos = mode ? s_pos : A.pos4;
-    const uint2* cand_key = mode ? s_key : A.key2;
-    const int seg0 = (mode == 2 && fy != s_first[1]) ? 3 : 0;
+    // candidate index ranges of the three fine rows (each row's 3 cells are contiguous in slot order)
     uint32_t row_qb[3], row_qe[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int yy = fy - 1 + k;
         if (yy >= ylo && yy <= yhi) {
             const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
-            const uint32_t shift = mode ? s_seg_off[seg0 + k] - s_seg_gb[seg0 + k] : 0u;   // global slot -> staged index
-            row_qb[k] = __ldg(F.start + rowbase + xlo) + shift;
-            row_qe[k] = __ldg(F.start + rowbase + xhi + 1) + shift;
+            row_qb[k] = __ldg(F.start + rowbase + xlo);
+            row_qe[k] = __ldg(F.start + rowbase + xhi + 1);
         } else {
             row_qb[k] = 0u;
             row_qe[k] = 0u;
         }
     }
-    const uint32_t self_idx = p + (mode ? s_seg_off[seg0 + 1] - s_seg_gb[seg0 + 1] : 0u);
+    ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+    const float rscatter2 = P.rscatter * P.rscatter;
+    bool to_dense = false;
+    uint32_t cell = INVALID_CELL;
+    if (FAST) {
+        FastScan c;
+        c.r = r; c.radius = radius; c.mass_i = mass_i; c.standing = state_i == RTS_STANDING;
+        c.r_max2 = P.r_max2; c.rscatter2 = rscatter2; c.self = p; c.near_edge = near_edge; c.cxi = cxi; c.cyi = cyi;
+        c.qb0 = row_qb[0]; c.len0 = row_qe[0] - row_qb[0];
+        c.qb1 = row_qb[1]; c.len1 = row_qe[1] - row_qb[1];
+        c.qb2 = row_qb[2]; c.len2 = row_qe[2] - row_qb[2];
+        // An agent in a crowd would keep this thread busy long after the rest of its warp is done; it is queued for
+        // k_step_dense, where a group of lanes shares its candidates.
+        to_dense = USE_DENSE_KERNEL && c.len0 + c.len1 + c.len2 > FAST_DENSE_CAND;
+        const unsigned lanes = __ballot_sync(active, !to_dense);
+        if (to_dense) A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
+        else {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vel4 + sp));   // the frame tail's loads: on their way while the candidates are scanned
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.nav4 + sp));
+            fast_accumulate(acc, c, A.pos4, A.key2, 0u, 1u, lanes);
+            // (the rest of the agent's record is fetched only now: nothing of it is needed while the candidates are scanned)
+            cell = finish_agent<KEEP_VEL, MULTI, true>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
+        }
+    } else {
+    const float4 vel4 = A.vel4[sp];
+    const float4 nav4 = A.nav4[sp];
+    //      accepted neighbours are kept sorted by (reference visit rank of their 60-unit cell, gid) = the reference's visit order
+    const float4* cand_pos = A.pos4;
+    const uint2* cand_key = A.key2;
+    const uint32_t self_idx = p;
     auto for_each_accepted = [&](auto&& fn) {   // candidates within the interaction range, in slot order
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
@@ -941,7 +1056,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
                 for (int u = 0; u < 4; ++u) {
                     const uint32_t q = q0 + u;
                     const v2 dr = V(o[u].x, o[u].y) - r;
-                    if (q < qe && norm2(dr) < P.r_max2 && q != self_idx) fn(q);
+                    if (q < qe && norm2(dr) < P.r_max2 && q != self_idx && (!near_edge || cell_is_adjacent(cand_key[q].y, cxi, cyi))) fn(q);
                 }
             }
         }
@@ -957,11 +1072,9 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         return (rank << 28) | ok.x;
     };
 
-    ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
-    const float rscatter2 = P.rscatter * P.rscatter;
     // applyForces loop body, PhysicsSystem.cpp:69-102
     auto accumulate = [&](uint32_t q) {
-        const ForceTerms t = neighbour_terms(r, radius, mass_i, state_i, cand_pos[q], (int)(cand_key[q].y & 3u), rscatter2);
+        const ForceTerms t = neighbour_terms(r, radius, mass_i, state_i, cand_pos[q], rscatter2);
         add_terms(acc, t.rep, t.push, t.dr, t.mask);
     };
 
@@ -976,8 +1089,7 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
     // A crowded agent (DENSE_MIN < neighbours <= DENSE_MAX) would keep this thread busy for tens of thousands of
     // instructions while the rest of its warp idles, and the slowest such thread sets the duration of the whole kernel.
     // It is queued for k_step_dense instead, where a warp shares the scan, the sort and the force terms of ONE agent.
-    const bool to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
-    uint32_t cell = INVALID_CELL;
+    to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
     if (to_dense) {
         A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
     } else {
@@ -1052,7 +1164,8 @@ __global__ void __launch_bounds__(STEP_BLOCK, STEP_MIN_BLOCKS) k_step(uint32_t n
         }
     }
 
-    cell = finish_agent<KEEP_VEL, MULTI>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
+    cell = finish_agent<KEEP_VEL, MULTI, false>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
+    }
     }
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
     if (!to_dense) A.cellrank[p] = make_uint2(cell, rank);
@@ -1102,7 +1215,7 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     ForceSums my_acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
     auto finish_parked = [&]() {
         if (lane < parked) {
-            const uint32_t cell = finish_agent<KEEP_VEL, MULTI>(my_p, my_sp, my_me, my_key, A.vel4[my_sp], A.nav4[my_sp], my_acc, P, M, F, A, SL);
+            const uint32_t cell = finish_agent<KEEP_VEL, MULTI, false>(my_p, my_sp, my_me, my_key, A.vel4[my_sp], A.nav4[my_sp], my_acc, P, M, F, A, SL);
             A.cellrank[my_p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
         }
         parked = 0;
@@ -1142,8 +1255,8 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
                     const float4 o = __ldg(A.pos4 + q);
                     const v2 dr = V(o.x, o.y) - r;
                     if (norm2(dr) < P.r_max2 && q != p) {
-                        accept = true;
                         const uint2 ok = __ldg(A.key2 + q);
+                        accept = cell_is_adjacent(ok.y, cxi, cyi);   // (only an agent outside the map can fail this, see k_step)
                         const int idx = (cs_cx(ok.y) - cxi + 1) * 3 + (cs_cy(ok.y) - cyi + 1);
                         const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
                         key = (rank << 28) | ok.x;
@@ -1187,7 +1300,7 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
             t.mask = 0u; t.rep = V(0.f, 0.f); t.push = V(0.f, 0.f); t.dr = V(0.f, 0.f);
             if (k < cnt) {
                 const uint32_t q = sorted[k].y;
-                t = neighbour_terms(r, me.z, me.w, state_i, __ldg(A.pos4 + q), (int)(__ldg(A.key2 + q).y & 3u), rscatter2);
+                t = neighbour_terms(r, fabsf(me.z), fabsf(me.w), state_i, __ldg(A.pos4 + q), rscatter2);
             }
             // A term the reference does not add is stored as +0: the running sums start at +0 and can never become -0
             // (x + (-x) and (+0) + (-0) round to +0), so adding +0 leaves every bit alone and the loop needs no test.
@@ -1231,6 +1344,93 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     if (parked) finish_parked();
 }
 
+// Tolerance-mode counterpart of k_step_dense: FAST_DENSE_LANES lanes share the candidates of one crowded agent (every lane
+// takes every FAST_DENSE_LANES-th candidate, branch-free terms as in k_step), the seven sums are reduced with shuffles —
+// no lists, no ordering, no shared memory. The frame tail is run for 32 parked agents at a time, one per lane.
+template <bool KEEP_VEL, bool MULTI>
+__global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
+    constexpr uint32_t GL = FAST_DENSE_LANES, GROUPS = 32u / GL;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned grp = lane / GL, gl = lane % GL;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t stride = gridDim.x * (blockDim.x >> 5) * GROUPS;
+    const uint32_t qn = *A.dense_n;
+    const float rscatter2 = P.rscatter * P.rscatter;
+    uint32_t parked = 0;                       // agents parked in this warp (lane k holds the k-th)
+    uint32_t my_p = 0, my_sp = 0;
+    float4 my_me = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 my_key = make_uint2(0u, 0u);
+    ForceSums my_acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+    auto finish_parked = [&]() {
+        if (lane < parked) {
+            const uint32_t cell = finish_agent<KEEP_VEL, MULTI, true>(my_p, my_sp, my_me, my_key, A.vel4[my_sp], A.nav4[my_sp], my_acc, P, M, F, A, SL);
+            A.cellrank[my_p] = make_uint2(cell, atomicAdd(F.count + cell, 1u));
+        }
+        parked = 0;
+        __syncwarp();
+    };
+    for (uint32_t q_first = warp * GROUPS; q_first < qn; q_first += stride) {
+        const uint32_t qi = q_first + grp;
+        const bool has = qi < qn;                   // the last warp of the queue may have idle groups
+        const uint32_t p = A.dense_q[has ? qi : q_first];
+        const float4 me = A.pos4[p];
+        const uint2 mykey = A.key2[p];
+        const uint32_t sp = A.src[p];
+        int fx, fy;
+        fine_coords(F, me.x, me.y, fx, fy);
+        const int xlo = max(fx - 1, 0), xhi = min(fx + 1, F.nx - 1);
+        FastScan c;
+        c.r = V(me.x, me.y); c.radius = fabsf(me.z); c.mass_i = fabsf(me.w); c.standing = (mykey.y & 3u) == RTS_STANDING;
+        c.r_max2 = P.r_max2; c.rscatter2 = rscatter2; c.self = p;
+        c.near_edge = fx <= 1 || fx >= F.nx - 2 || fy <= 1 || fy >= F.ny - 2;
+        c.cxi = cs_cx(mykey.y); c.cyi = cs_cy(mykey.y);
+        uint32_t qb[3], ql[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int yy = fy - 1 + k;
+            qb[k] = 0u; ql[k] = 0u;
+            if (yy >= 0 && yy < F.ny) {
+                const uint32_t rowbase = (uint32_t)yy * (uint32_t)F.nx;
+                qb[k] = __ldg(F.start + rowbase + xlo);
+                ql[k] = __ldg(F.start + rowbase + xhi + 1) - qb[k];
+            }
+        }
+        c.qb0 = qb[0]; c.len0 = ql[0]; c.qb1 = qb[1]; c.len1 = ql[1]; c.qb2 = qb[2]; c.len2 = ql[2];
+        ForceSums S{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+        const unsigned lanes = __ballot_sync(0xffffffffu, has);
+        if (has) fast_accumulate(S, c, A.pos4, A.key2, gl, GL, lanes);
+        __syncwarp();
+#pragma unroll
+        for (uint32_t off = GL >> 1; off > 0; off >>= 1) {   // sum over the lanes of the group
+            S.repulsion.x += __shfl_xor_sync(0xffffffffu, S.repulsion.x, off); S.repulsion.y += __shfl_xor_sync(0xffffffffu, S.repulsion.y, off);
+            S.push.x += __shfl_xor_sync(0xffffffffu, S.push.x, off); S.push.y += __shfl_xor_sync(0xffffffffu, S.push.y, off);
+            S.dr_nn.x += __shfl_xor_sync(0xffffffffu, S.dr_nn.x, off); S.dr_nn.y += __shfl_xor_sync(0xffffffffu, S.dr_nn.y, off);
+            S.n_neighbours += __shfl_xor_sync(0xffffffffu, S.n_neighbours, off);
+        }
+        // park the agents of this round: group g's agent goes to lane parked + g (every lane of a group holds its sums)
+#pragma unroll
+        for (uint32_t g = 0; g < GROUPS; ++g) {
+            const unsigned src_lane = g * GL;
+            const bool g_has = __shfl_sync(0xffffffffu, has ? 1 : 0, src_lane) != 0;
+            const uint32_t g_p = __shfl_sync(0xffffffffu, p, src_lane), g_sp = __shfl_sync(0xffffffffu, sp, src_lane);
+            const float4 g_me = make_float4(__shfl_sync(0xffffffffu, me.x, src_lane), __shfl_sync(0xffffffffu, me.y, src_lane),
+                                            __shfl_sync(0xffffffffu, me.z, src_lane), __shfl_sync(0xffffffffu, me.w, src_lane));
+            const uint2 g_key = make_uint2(__shfl_sync(0xffffffffu, mykey.x, src_lane), __shfl_sync(0xffffffffu, mykey.y, src_lane));
+            ForceSums g_acc;
+            g_acc.repulsion = V(__shfl_sync(0xffffffffu, S.repulsion.x, src_lane), __shfl_sync(0xffffffffu, S.repulsion.y, src_lane));
+            g_acc.push = V(__shfl_sync(0xffffffffu, S.push.x, src_lane), __shfl_sync(0xffffffffu, S.push.y, src_lane));
+            g_acc.dr_nn = V(__shfl_sync(0xffffffffu, S.dr_nn.x, src_lane), __shfl_sync(0xffffffffu, S.dr_nn.y, src_lane));
+            g_acc.n_neighbours = __shfl_sync(0xffffffffu, S.n_neighbours, src_lane);
+            if (g_has) {
+                if (lane == parked) { my_p = g_p; my_sp = g_sp; my_me = g_me; my_key = g_key; my_acc = g_acc; }
+                ++parked;
+            }
+        }
+        if (parked + GROUPS > 32u) finish_parked();
+    }
+    if (parked) finish_parked();
+}
+
 // ------------------------------------------------------------------------------------------------
 // rts_download: slot order -> caller order (dest = gid when gids are component indices, else slot)
 struct Staging {
@@ -1258,8 +1458,8 @@ __global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int 
     if (S.inertia) S.inertia[o] = make_float2(vel4.x, vel4.y);
     if (S.angle) S.angle[o] = vel4.z;
     if (S.angle_vel) S.angle_vel[o] = vel4.w;
-    if (S.radius) S.radius[o] = pos.z;
-    if (S.mass) S.mass[o] = pos.w;
+    if (S.radius) S.radius[o] = fabsf(pos.z);   // (the sign bits mirror the state, see pack_pos)
+    if (S.mass) S.mass[o] = fabsf(pos.w);
     if (S.state) S.state[o] = (uint8_t)(key.y & 3u);
     if (S.player) S.player[o] = (uint8_t)((misc >> 24) & 0xFu);
     if (S.unit_type) S.unit_type[o] = (uint8_t)((misc >> 16) & 0xFFu);
@@ -1283,8 +1483,8 @@ __global__ void k_ingest(uint32_t n, uint32_t first, Staging S, AgentArrays A) {
     if (i >= n) return;
     const uint32_t d = first + i;
     const float2 r = S.r[i];
-    A.pos4n[d] = make_float4(r.x, r.y, S.radius ? S.radius[i] : 3.f, S.mass ? S.mass[i] : 1.f);
     const uint32_t state = S.state ? S.state[i] : (uint32_t)RTS_STANDING;
+    A.pos4n[d] = pack_pos(r.x, r.y, S.radius ? S.radius[i] : 3.f, S.mass ? S.mass[i] : 1.f, state);
     A.key2n[d] = make_uint2(S.gid ? S.gid[i] : d, pack_cs(0u, 0u, 0u, state));
     const float2 in = S.inertia ? S.inertia[i] : make_float2(0.f, 0.f);
     A.vel4n[d] = make_float4(in.x, in.y, S.angle ? S.angle[i] : 0.f, S.angle_vel ? S.angle_vel[i] : 0.f);
@@ -1314,6 +1514,7 @@ __global__ void k_apply(uint32_t n, Staging S, AgentArrays A) {
     if (S.radius) pos.z = S.radius[g];
     if (S.mass) pos.w = S.mass[g];
     if (S.state) key.y = (key.y & ~3u) | (S.state[g] & 3u);
+    pos = pack_pos(pos.x, pos.y, pos.z, pos.w, key.y & 3u);
     if (S.inertia) { const float2 v = S.inertia[g]; vel4.x = v.x; vel4.y = v.y; }
     if (S.angle) vel4.z = S.angle[g];
     if (S.angle_vel) vel4.w = S.angle_vel[g];

@@ -83,3 +83,44 @@ def rel_err(got, want):
     """vector-norm relative error per agent: |got-want|_2 / max(|want|_2, 1)   """
     d = np.linalg.norm(np.asarray(got, np.float64) - np.asarray(want, np.float64), axis=-1)
     return d / np.maximum(np.linalg.norm(np.asarray(want, np.float64), axis=-1), 1.0)
+
+
+def force_term_magnitudes(a, r_max2=30.0, mul_repulse=1.0, mul_push=0.1, mul_scatter=0.1, max_speed=25.0):
+    """Per agent: T = sum over its physics neighbours of the MAGNITUDES of the force terms applyForces adds
+    (PhysicsSystem.cpp:69-116), times their multipliers. |computed sum - reference sum| of ANY implementation that
+    evaluates the same terms with relative error eps is bounded by eps*T, whatever the cancellation between the terms;
+    the tolerance-mode gate uses it where the plain 1e-5 gate (relative to the RESULT) is ill-posed.
+    Float64 arithmetic, neighbour pairs from a KD-tree."""
+    from scipy.spatial import cKDTree
+    r = np.asarray(a["r"], np.float64)
+    ok = np.isfinite(r).all(1)
+    idx = np.nonzero(ok)[0]
+    tree = cKDTree(r[idx])
+    pairs = tree.query_pairs(np.sqrt(r_max2) * (1 + 1e-9), output_type="ndarray")
+    i = np.concatenate([idx[pairs[:, 0]], idx[pairs[:, 1]]])
+    j = np.concatenate([idx[pairs[:, 1]], idx[pairs[:, 0]]])
+    dr = r[j] - r[i]
+    d2 = (dr * dr).sum(1)
+    keep = d2 > 0
+    i, j, dr, d2 = i[keep], j[keep], dr[keep], d2[keep]
+    rad = np.asarray(a["radius"], np.float64)
+    mass = np.asarray(a["mass"], np.float64)
+    state = np.asarray(a["state"])
+    rc2 = (rad[i] + rad[j]) ** 2
+    x = rc2 / d2
+    w = mass[j] / (mass[i] + mass[j])
+    rep = np.where(x > 0.8, np.minimum(3 * x ** 3, 50000.0) * w, 0.0) * mul_repulse
+    push = np.where((state[j] == 0) & (state[i] == 1) & (x > 0.75), np.sqrt(d2) * x * w, 0.0) * mul_push
+    n = len(r)
+    T = np.bincount(i, rep + push, minlength=n)
+    # scatter = mean_dr / |mean_dr| * max_speed: the direction of a sum of offsets; its error is the terms' error over |sum|
+    mv = state[j] == 0
+    sx = np.bincount(i[mv], dr[mv, 0], minlength=n)
+    sy = np.bincount(i[mv], dr[mv, 1], minlength=n)
+    sabs = np.bincount(i[mv], np.sqrt(d2[mv]), minlength=n)
+    cnt = np.bincount(i[mv], minlength=n)
+    snorm = np.hypot(sx, sy)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        amp = np.where(cnt > 1, sabs / np.maximum(snorm, 1e-30), 0.0)
+    T = T + mul_scatter * max_speed * np.minimum(amp, 1e12)
+    return T

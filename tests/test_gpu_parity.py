@@ -204,6 +204,36 @@ def test_agents_outside_the_map_and_coincident_agents():
                 H.assert_same_bits(out[k][sane], ref[k][sane], f"step {s} {k}")
 
 
+def test_crowds_straddling_the_map_edges():
+    """An agent pushed over the map edge gets a physics cell wrapped modulo the grid (size_t arithmetic, Grid.cpp:18-24);
+    calcNearestCells (Grid.cpp:103-118) does not wrap, so the reference never pairs it with the in-map agents 2-3 units
+    away, although they are well within the interaction range. Dense bands across x = 0, y = 0 and x = W, 3 frames."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(31, 6000, tables, -40.0, 300.0)
+    rng = np.random.default_rng(7)
+    a["r"][:400] = rng.uniform(-8, 8, (400, 2))                                                   # straddling x = 0 and y = 0
+    a["r"][1500:3000] = np.stack([rng.uniform(2552, 2568, 1500), rng.uniform(100, 400, 1500)], 1)   # straddling x = W = 2560
+    a["r"][3000:3600] = np.stack([rng.uniform(100, 400, 600), rng.uniform(2554, 2566, 600)], 1)     # straddling y = H
+    ref = {k: v.copy() for k, v in a.items()}
+    ow = port.OracleWorld(port.default_params(512, 512), tables, paths)
+    # the case really has in-map / off-map pairs within the interaction range
+    from scipy.spatial import cKDTree
+    pairs = cKDTree(a["r"].astype(np.float64)).query_pairs(5.0, output_type="ndarray")
+    off = ((a["r"] < 0) | (a["r"] >= 2560)).any(1)
+    assert (off[pairs[:, 0]] != off[pairs[:, 1]]).sum() > 200
+    names = ("r", "vel", "inertia", "state", "ns_cell", "map_cell", "waypoint", "tri_idx")
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        for s in range(3):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            sane = np.isfinite(ref["r"]).all(1)
+            for k in names:
+                H.assert_same_bits(out[k][sane], ref[k][sane], f"step {s} {k}")
+
+
 def test_single_agent():
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
