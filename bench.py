@@ -171,13 +171,138 @@ def cpu_port_baseline(tables, agents, paths, budget_s=20.0):
             "kind": "port", "sample": f"{n} agents x {steps} frames of the same workload (oracle/rts_oracle.c, -Ofast, OpenMP)"}
 
 
+PRECISION_NAMES = {0: "exact", 1: "fast"}
+
+
+def time_mode(g, agents, n, K, Wm, repeats, precision_name):
+    """K frames from the SAME state (initial population + Wm warm-up frames), `repeats` times; median device time.
+    Then the per-kernel durations over the same frames (profiling mode: kernels launched one by one, a CUDA-event pair
+    around each — crowd density, hence kernel time, depends on the frame index)."""
+    ms, launches = [], 0
+    for _ in range(repeats):
+        g.set_agents(agents)
+        g.update(Wm, sync=True)
+        g.reset_timings()
+        g.update(K)
+        g.sync()
+        t = g.timings()
+        ms.append(t.last_step_ms)
+        launches = int(t.kernel_launches)
+    g.set_agents(agents)
+    g.update(Wm, sync=True)
+    g.set_profiling(True)
+    g.reset_timings()
+    g.update(K, sync=True)
+    kt = {k: g.kernel_time_ms(k)[0] for k in ("step", "dense", "scan", "reorder", "walk")}
+    g.set_profiling(False)
+    med = float(np.median(ms))
+    return {"precision": precision_name, "value": n * K / (med * 1e-3), "ms_per_step": med / K, "repeat_ms_per_step": [m / K for m in ms],
+            "launches": launches, "kernel_ms": kt}
+
+
+def roofline_of(m, n, peak, peak_src, traffic):
+    step_ms = m["kernel_ms"]["step"]
+    achieved = ALGO_BYTES_PER_UPDATE * n / (step_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "k_step", "precision": m["precision"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * n, "kernel_ms": m["kernel_ms"],
+            "whole_frame_frac": ALGO_BYTES_PER_UPDATE * n / (m["ms_per_step"] * 1e-3) / 1e9 / peak}
+
+
+def k_step_traffic(n, precision_name):
+    """DRAM bytes per k_step launch from the committed ncu capture of the same build (profiles/k_step_traffic.json)"""
+    tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+    try:
+        tj = json.load(open(tp)).get(precision_name)
+        if tj and int(tj.get("agents", 0)) == n:
+            return tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
+def e2e_leg(g, n, agents, K, Wm):
+    """The same metric through the System2-shaped calls with HOST buffers (pinned), per frame:
+         updateSharedData : the entities the host touched since the last frame (here: a move command for 1 000 agents per
+                            frame)                                           -> rts_update_agents_indexed   (H2D)
+         update           : rts_step(1)
+         communicate      : what the two systems write into SharedData — vel, angle_vel, state, target (21 B per agent,
+                            PhysicsSystem.cpp:118-127, SeekSystem.cpp:322-342)  -> rts_download              (D2H, synchronises)
+       The loop's own integration r += vel*dt (ECS.cpp:98-113) reproduces the device's position bit for bit, so positions
+       never travel (tests/test_gpu_adapter.py runs exactly this protocol inside the reference's frame loop)."""
+    g.set_agents(agents)
+    g.update(Wm, sync=True)
+    board = {"vel": pinned((n, 2), np.float32), "angle_vel": pinned((n,), np.float32), "state": pinned((n,), np.uint8),
+             "r_next": pinned((n, 2), np.float32)}
+    m = min(1000, n)
+    cmd = {"state": pinned((m,), np.uint8), "path_id": pinned((m,), np.int32), "waypoint": pinned((m,), np.int32),
+           "r_next": pinned((m, 2), np.float32)}
+    idx_t, idx = pinned((m,), np.int32)
+    idx_u = idx.view(np.uint32)
+    cmd["state"][1][:] = agents["state"][:m]
+    cmd["waypoint"][1][:] = 1
+    cmd["r_next"][1][:] = np.nan
+    down_ptrs = {k: v[1].ctypes.data for k, v in board.items()}
+    cmd_ptrs = {k: v[1].ctypes.data for k, v in cmd.items()}
+    h2d = idx.nbytes + sum(v[1].nbytes for v in cmd.values())
+    d2h = sum(v[1].nbytes for v in board.values())
+    rng = np.random.default_rng(7)
+
+    def frame(f):
+        # the command of this frame: m distinct agents are sent (again) onto the path of their start region
+        first = int(rng.integers(0, n - m + 1))
+        idx_u[:] = np.arange(first, first + m, dtype=np.uint32)
+        cmd["path_id"][1][:] = agents["path_id"][first:first + m]
+        cmd["state"][1][:] = agents["state"][first:first + m]
+        g.update_shared_data_indexed_ptrs(idx.ctypes.data, m, cmd_ptrs)   # System2::updateSharedData   (H2D)
+        g.update(1)                                                      # System2::update
+        g.communicate_ptrs(down_ptrs)                                    # System2::communicate        (D2H, synchronises)
+
+    for f in range(3):
+        frame(f)
+    Ke = min(K, 100)
+    t0 = time.perf_counter()
+    for f in range(Ke):
+        frame(f)
+    e2e_s = time.perf_counter() - t0
+    return {"value": n * Ke / e2e_s, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+            "api": "GpuAgentSystem.update_shared_data_indexed -> update -> communicate (rts_update_agents_indexed / rts_step / "
+                   "rts_download), pinned host buffers; 1000 commanded agents up, {vel, angle_vel, state, target} of every agent down"}
+
+
+def config4_single_gpu(args, local, K, Wm):
+    """BASELINE config 4 on ONE GPU (the denominator of the 8-GPU scaling figure): 10M agents on the 8192x8192-cell map"""
+    from rtsengine_b200 import abi, engine, scenario
+    tile = scenario.load_map("map_c3.npz")
+    fx = scenario.tile_map(tile, 8, 8)
+    n4 = args.agents4
+    agents = scenario.tiled_agents(tile, 8, 8, n4 // 64, seed=1237)
+    n4 = len(agents["r"])
+    p = engine.default_params(8192, 8192)
+    p.precision = abi.PRECISION_FAST
+    with engine.GpuAgentSystem(p, device=local) as g:
+        g.upload_map(scenario.tables_of(fx))
+        g.upload_paths(scenario.paths_of(fx))
+        ms = []
+        for _ in range(3):
+            g.set_agents(agents)
+            g.update(Wm, sync=True)
+            g.reset_timings()
+            g.update(K)
+            g.sync()
+            ms.append(g.timings().last_step_ms)
+        med = float(np.median(ms))
+    return {"workload": "config4: 10M agents, 8192x8192-cell map (8x8 config-3 tiles, 12 800 buildings, 4096 groups), one GPU, "
+                        "tolerance mode", "agents": n4, "value": n4 * K / (med * 1e-3), "unit": "agent-updates/s", "ms_per_step": med / K,
+            "repeat_ms_per_step": [m / K for m in ms], "precision": "fast"}
+
+
 def run_gpu(args):
     import torch
-    import torch.distributed as dist
     from rtsengine_b200 import abi, engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from rtsengine_b200 import slabs
@@ -185,84 +310,32 @@ def run_gpu(args):
 
     n = args.agents
     fx, tables, agents, paths = build_world(n)
-    params = engine.default_params(1024, 1024)
-    g = engine.GpuAgentSystem(params, device=local)
-    g.upload_map(tables)
-    g.upload_paths(paths)
-    g.set_agents(agents)
-
     K, Wm = args.steps, max(args.warmup, 3)
-    g.update(Wm, sync=True)
-
-    # ---- device-resident throughput: K frames (CUDA graph of 8 frames replayed), CUDA events on the launching stream ----
-    g.reset_timings()
-    with ClockSampler(local) as clocks:
-        g.sync()
-        g.update(K)
-        g.sync()
-    t = g.timings()
-    total_ms = t.last_step_ms
-    launches = int(t.kernel_launches)
-    value = n * K / (total_ms * 1e-3)
-
-    # ---- per-kernel durations over THE SAME frames: same initial state, same warm-up, then K frames launched one by
-    #      one with a CUDA-event pair around every kernel (crowd density, hence kernel time, depends on the frame index) ----
-    g.set_agents(agents)
-    g.update(Wm, sync=True)
-    g.set_profiling(True)
-    g.reset_timings()
-    g.update(K, sync=True)
-    kt = {k: g.kernel_time_ms(k) for k in ("step", "dense", "scan", "reorder", "walk")}
-    g.set_profiling(False)
-    step_ms = kt["step"][0]
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_UPDATE * n / (step_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
-    if os.path.exists(tp):
+    modes = {}
+    e2e = None
+    with ClockSampler(local) as clocks:
+        for prec in (abi.PRECISION_FAST, abi.PRECISION_EXACT):
+            params = engine.default_params(1024, 1024)
+            params.precision = prec
+            with engine.GpuAgentSystem(params, device=local) as g:
+                g.upload_map(tables)
+                g.upload_paths(paths)
+                modes[prec] = time_mode(g, agents, n, K, Wm, args.repeats, PRECISION_NAMES[prec])
+                if prec == args.precision:
+                    e2e = e2e_leg(g, n, agents, K, Wm)
+    head = modes[args.precision]
+    other = modes[1 - args.precision]
+    roofline = roofline_of(head, n, peak, peak_src, k_step_traffic(n, head["precision"]))
+    roofline["other_mode"] = roofline_of(other, n, peak, peak_src, k_step_traffic(n, other["precision"]))
+    roofline["other_mode"].update(value=other["value"], ms_per_step=other["ms_per_step"])
+
+    c4 = None
+    if not args.no_config4:
         try:
-            tj = json.load(open(tp))
-            if int(tj.get("agents", 0)) == n:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
-    roofline = {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * n,
-                "kernel_ms": {k: v[0] for k, v in kt.items()},
-                "whole_frame_frac": ALGO_BYTES_PER_UPDATE * n / (total_ms / K * 1e-3) / 1e9 / peak}
-
-    # ---- end to end through the System2-shaped API with HOST buffers (pinned): per frame
-    #      updateSharedData (H2D blackboard) -> update -> communicate (D2H blackboard) ----
-    #      The blackboard (SharedData, ECS.h:136-145) lives in pinned host memory; the same buffers are uploaded and
-    #      written back, as the reference's systems read and write entity2shared_data in place.
-    g.set_agents(agents)
-    g.update(Wm, sync=True)
-    board = {"r": pinned((n, 2), np.float32), "vel": pinned((n, 2), np.float32), "angle": pinned((n,), np.float32),
-             "angle_vel": pinned((n,), np.float32), "state": pinned((n,), np.uint8), "r_next": pinned((n, 2), np.float32)}
-    cur = g.communicate(("r", "angle", "angle_vel", "state"))
-    for k in cur:
-        board[k][1][:] = cur[k]
-    up_ptrs = {k: board[k][1].ctypes.data for k in ("r", "angle", "angle_vel", "state")}
-    down_ptrs = {k: v[1].ctypes.data for k, v in board.items()}
-    h2d = sum(board[k][1].nbytes for k in up_ptrs)
-    d2h = sum(v[1].nbytes for v in board.values())
-
-    def e2e_frame():
-        g.update_shared_data_ptrs(up_ptrs)     # System2::updateSharedData   (H2D)
-        g.update(1)                            # System2::update
-        g.communicate_ptrs(down_ptrs)          # System2::communicate        (D2H, synchronises)
-
-    for _ in range(3):
-        e2e_frame()
-    Ke = min(K, 100)
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_frame()
-    e2e_s = time.perf_counter() - t0
-    e2e = {"value": n * Ke / e2e_s, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
-           "api": "GpuAgentSystem.update_shared_data -> update -> communicate (rts_update_agents/rts_step/rts_download), pinned host buffers"}
-    g.close()
+            c4 = config4_single_gpu(args, local, K, Wm)
+        except Exception as e:
+            c4 = {"value": None, "error": str(e)}
 
     cpu = None
     if not args.no_cpu:
@@ -272,14 +345,20 @@ def run_gpu(args):
             cpu = {"value": None, "unit": "agent-updates/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
 
     line = {
-        "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": 1, "steps": K, "warmup": Wm,
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "metric": "agent-updates/sec", "value": head["value"], "unit": "agent-updates/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "config3: 1M agents, 64 groups on precomputed funnel paths, 1024x1024-cell CDT map with 200 buildings",
                    "agents": n, "map_cells": [1024, 1024], "buildings": 200, "groups": 64,
+                   "precision": head["precision"] + (" (RtsParams.precision = RTS_PRECISION_FAST: reference neighbour sets, wall contacts, waypoint "
+                                                     "decisions and index functions; force terms to 1e-5, gated by tests/test_gpu_fast.py)"
+                                                     if head["precision"] == "fast" else " (bit-identical to the IEEE build of the reference)"),
+                   "timing": f"median of {args.repeats} repetitions of the same {K} frames (initial population + {Wm} warm-up frames each time)",
                    "l2_policy": f"inputs larger than L2: {n} agents x ~190 B touched per frame across ping-pong buffers "
                                 f"({n * 190 / 1e6:.0f} MB vs 126 MB L2); no explicit flush"},
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "repeat_ms_per_step": head["repeat_ms_per_step"],
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline, "config4_1gpu": c4,
+        "cpu_baseline": cpu,
     }
     print(json.dumps(line))
 
@@ -333,6 +412,9 @@ def run_reference(args):
         kind, sample = "reference", (f"{n} agents (reference cap N_MAX_NAVIGABLE_BOIDS) at config-3 density in a {side:.0f}² window, 50 buildings, "
                                      f"verbatim reference TUs -Ofast, {K} frames")
         value = n * K / dt
+        ref_agents = n
+        ref_workload = (f"config-3 DENSITY on the reference's own scale: {n} agents (its cap) in a {side:.0f}x{side:.0f}-unit window of a "
+                        f"512x512-cell map with 50 buildings, one command group on funnel paths planned by the reference's PathFinder2")
     else:
         from oracle import port
         port.load(True).rts_oracle_set_threads(os.cpu_count() or 1)
@@ -340,10 +422,14 @@ def run_reference(args):
         cpu = cpu_port_baseline(tables, agents, paths, budget_s=20.0)
         value, threads, kind, sample = cpu["value"], cpu["cores"], "port", cpu["sample"]
         dt = None
+        ref_agents = 200_000
+        ref_workload = "config 3 at 200 000 agents (oracle port; the verbatim reference build is not present on this box)"
     line = {"impl": "reference", "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": n_world,
             "steps": K, "warmup": Wm, "ms_per_step": (1e3 * dt / K) if dt else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config3: 1M agents, 64 groups on precomputed funnel paths, 1024x1024-cell CDT map with 200 buildings"},
+            "config": {"workload": ref_workload, "agents": ref_agents, "same_config_as_gpu_arm": False,
+                       "why": "the reference caps at 5 000 navigable agents (src/core.h:46) and 10 000 entities (src/ECS.h:19): config 3 itself "
+                              "(1M agents) cannot run on it; the same-config CPU comparator is the GPU arm's cpu_baseline (oracle port, 1M agents)"},
             "cpu_baseline": {"value": value, "unit": "agent-updates/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -356,6 +442,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--agents", type=int, default=1_000_000)
+    ap.add_argument("--agents4", type=int, default=10_000_000, help="population of the config-4 legs")
+    ap.add_argument("--precision", type=int, default=1, choices=[0, 1], help="headline arithmetic: 1 = tolerance mode, 0 = bit-exact mode")
+    ap.add_argument("--repeats", type=int, default=5, help="repetitions of the timed window (median reported)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

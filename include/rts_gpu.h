@@ -10,7 +10,7 @@
  *   boids forces, clamp, inertia decay               src/Systems/PhysicsSystem.cpp:16-117
  *   wall constraint, applied twice                   src/Systems/PhysicsSystem.cpp:130-162, src/Edges.cpp:245-296
  *   seek toward the funnel waypoint, turn, advance   src/Systems/SeekSystem.cpp:76-111,181-233,277-304,344-385
- *   merge velocities, integrate                      src/Systems/*System.cpp communicate(), src/ECS.cpp:92-113
+ *   merge velocities, integrate                      src/Systems/{Physics,Seek}System.cpp communicate(), src/ECS.cpp:92-113
  *   point-in-triangle walk on the CDT                src/PathFinding/Triangulation.cpp:1497-1567
  *
  * The structs are plain data; every pointer is a HOST pointer unless its name ends in _dev.
@@ -85,7 +85,8 @@ typedef struct RtsParams {
            the next frame kernel
        [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
            while the interior is stepped on the main stream (measured equal to the plain layout);
-           16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them */
+           16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them
+           32 = keep the ncclSend/ncclRecv exchange instead of the peer-memory exchange (rts_slab_exchange_mode) */
     uint32_t reserved[6];
     /* arithmetic of the frame kernel:
        RTS_PRECISION_EXACT (0, the default): IEEE division / square root, no FMA contraction, neighbour sums added in the
@@ -220,6 +221,12 @@ int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int
 /* replaces: System2::updateSharedData (PhysicsSystem.cpp:165-173, SeekSystem.cpp:307-316): overwrite the non-NULL
    fields of every agent from caller-order arrays (the ECS blackboard), then re-bin */
 int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields);
+/* the same for the m agents the host actually touched since the last frame (a move command, an edit): `indices` are
+   distinct component indices, every non-NULL array of `fields` holds m entries in the order of `indices`. Only those
+   m records cross the bus; the population is re-binned only if positions are among the fields. This is what a drop-in
+   System2::updateSharedData sends when it tracks which entities the game changed instead of copying the whole blackboard
+   (PhysicsSystem.cpp:165-173 copies all of it every frame because on the CPU that is free). */
+int32_t rts_update_agents_indexed(RtsHandle h, const uint32_t* indices, uint32_t m, const RtsAgentView* fields);
 uint32_t rts_agent_count(RtsHandle h);
 /* CommandGroupManager2::group2finished_surface_area_ (CommandGroupManager.h:133): read / overwrite, n = number of groups */
 int32_t rts_get_finished_area(RtsHandle h, float* out, uint32_t n);
@@ -268,6 +275,13 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
    every rank calls rts_comm_init.  libnccl.so.2 is resolved with dlopen at this point, not at load time. */
 int32_t rts_comm_unique_id(void* out128);
 int32_t rts_comm_init(RtsHandle h, const void* id128);
+/* how this handle exchanges with its neighbours: 0 = not a slab handle, 1 = ncclSend/ncclRecv of the exchange buffers every
+   frame, 2 = peer exchange — rts_comm_init also maps the neighbours' receive buffers into this process (CUDA IPC handles
+   gathered with ncclAllGather) and a small kernel then writes this rank's halo / migrant records straight into them over
+   NVLink, exactly as many as were packed, with an epoch flag per direction; the frame has no NCCL call left in it and is
+   replayed from a CUDA graph like the single-GPU frame. Falls back to 1 if any rank cannot map its neighbour (or with
+   RtsParams.reserved[5] bit 5 (value 32) set). Collective: every rank must call rts_comm_init. */
+int32_t rts_slab_exchange_mode(RtsHandle h);
 /* after rts_set_agents on every rank: exchange the halo bands once so the first frame sees its ghosts */
 int32_t rts_halo_refresh(RtsHandle h);
 /* split-phase variants for a host that moves the buffers itself (and for emulating two ranks on one device):

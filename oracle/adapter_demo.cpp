@@ -231,11 +231,26 @@ int main(int argc, char** argv) {
         B.pf->issuePaths2(comps, groups[g], seek->entity2compvec_ind_, targets[g]);
     }
 
-    long mismatches = 0, compared = 0;
+    long mismatches = 0, compared = 0, uploaded = 0;
     int first_bad_frame = -1;
     int replans = 0;
     double t_cpu = 0, t_gpu = 0;
+    // a later command (frame 25): half of the units that are still STANDING get a destination of their own. In world B this
+    // is the only thing the blackboard shadow of the slot does not already know — exactly those entities are re-sent.
+    std::vector<int> late;
+    for (int i = 0; i < n_agents; ++i)
+        if (A.shared->at(i).state == MoveState::STANDING && i % 2 == 0) late.push_back(i);
+    const sf::Vector2f late_target = {1600.f, 900.f};   // (far from every unit: the arrival rule, an opt-in of the GPU path, must not fire)
     for (int f = 0; f < frames; ++f) {
+        if (f == 25 && !late.empty()) {
+            for (int e : late) { A.shared->at(e).state = MoveState::MOVING; B.shared->at(e).state = MoveState::MOVING; }
+            A.ss->issuePaths2(late, late_target);
+            if (gpu) {
+                auto& comps = seek->getComponents();
+                for (int e : late) comps.at(seek->entity2compvec_ind_.at(e)).path_end = late_target;
+                B.pf->issuePaths2(comps, late, seek->entity2compvec_ind_, late_target);
+            }
+        }
         // ---------------- world A: ECSystem::update with the reference systems (as oracle/ref_harness.cpp)
         double t0 = omp_get_wtime();
         A.ps->updateSharedData(*A.shared, A.active);
@@ -264,6 +279,7 @@ int main(int argc, char** argv) {
         t0 = omp_get_wtime();
         phys->updateSharedData(*B.shared, B.active);
         seek->updateSharedData(*B.shared, B.active);
+        if (f > 0) uploaded += seek->uploaded_last_frame;   // (frame 0 sends the whole population once)
         {   // the planner part of SeekSystem::update (SeekSystem.cpp:65) stays on the host
             auto& comps = seek->getComponents();
             const size_t pending = B.pf->to_update_groups_.size();
@@ -301,6 +317,11 @@ int main(int argc, char** argv) {
                             same_bits(velA[i].x, velB[i].x) && same_bits(velA[i].y, velB[i].y) &&
                             same_bits(a.transform.angle, b.transform.angle) && same_bits(a.transform.angle_vel, b.transform.angle_vel) &&
                             a.state == b.state && same_bits(a.target.x, b.target.x) && same_bits(a.target.y, b.target.y);
+            if (!ok && getenv("RTS_DEMO_TRACE") && mismatches + bad < 12)
+                fprintf(stderr, "frame %d agent %d late %d: r %.9g %.9g | %.9g %.9g  vel %.9g %.9g | %.9g %.9g  angle %.9g | %.9g  angle_vel %.9g | %.9g  state %d | %d  target %.9g %.9g | %.9g %.9g\n",
+                        f, i, (int)(std::find(late.begin(), late.end(), i) != late.end()), a.transform.r.x, a.transform.r.y, b.transform.r.x, b.transform.r.y,
+                        velA[i].x, velA[i].y, velB[i].x, velB[i].y, a.transform.angle, b.transform.angle, a.transform.angle_vel, b.transform.angle_vel,
+                        (int)a.state, (int)b.state, a.target.x, a.target.y, b.target.x, b.target.y);
             bad += !ok;
             ++compared;
         }
@@ -310,7 +331,8 @@ int main(int argc, char** argv) {
     int moving = 0;
     for (int i = 0; i < n_agents; ++i) moving += A.shared->at(i).state == MoveState::MOVING;
     printf("{\"agents\": %d, \"buildings\": %d, \"frames\": %d, \"cell_grid_mismatches\": %ld, \"compared\": %ld, \"mismatches\": %ld, \"first_bad_frame\": %d, "
-           "\"replans\": %d, \"moving_at_end\": %d, \"cpu_ms_per_frame\": %.3f, \"gpu_adapter_ms_per_frame\": %.3f}\n",
-           n_agents, n_buildings, frames, cell_grid_mismatches, compared, mismatches, first_bad_frame, replans, moving, 1e3 * t_cpu / frames, 1e3 * t_gpu / frames);
+           "\"replans\": %d, \"moving_at_end\": %d, \"late_command\": %d, \"entities_resent_after_frame0\": %ld, \"cpu_ms_per_frame\": %.3f, \"gpu_adapter_ms_per_frame\": %.3f}\n",
+           n_agents, n_buildings, frames, cell_grid_mismatches, compared, mismatches, first_bad_frame, replans, moving, (int)late.size(), uploaded,
+           1e3 * t_cpu / frames, 1e3 * t_gpu / frames);
     return (mismatches || cell_grid_mismatches) ? 3 : 0;
 }

@@ -10,11 +10,14 @@
 //                                                  the whole fused frame on the GPU in update()
 //
 // Frame protocol (ECSystem::update, src/ECS.cpp:65-113):
-//   updateSharedData : blackboard r / angle / angle_vel / state  -> rts_update_agents          (H2D)
+//   updateSharedData : the entities whose blackboard entry differs from what the device already holds (a command changed
+//                      the state, the game moved a unit) -> rts_update_agents_indexed                     (H2D, few records)
 //   update           : windows the planner rewrote -> rts_upload_paths ; rts_step(1)
 //   communicate      : rts_download -> SharedData.transform.vel = merged, wall-projected velocity of the frame,
-//                      .angle_vel, .state, .target.  The loop's own integration (ECS.cpp:98-113) then computes
-//                      r += vel*dt, which is bit-identical to the position the GPU integrated.
+//                      .angle_vel, .state, .target (21 B per agent + 8 B of re-plan flags / waypoint index).  The loop's own
+//                      integration (ECS.cpp:98-113) then computes r += vel*dt, which is bit-identical to the position the
+//                      GPU integrated — so the device state IS the blackboard and nothing has to travel back up. The slot
+//                      keeps a shadow of what the blackboard will hold after that integration; updateSharedData compares.
 // The second wall pass that ECSystem::update runs on the PhysicsSystem (ECS.cpp:92-95) is already part of the
 // fused frame, so those three lines are removed when the adapter is installed.
 //
@@ -48,6 +51,8 @@ struct GpuSeekSlot : System2 {
     // command group of each component (CommandGroupManager2::entity2command_group, CommandGroupManager.h:130); the host
     // copies it here after addGroup / removeFromGroup. Empty: every agent is its own group (no arrival cascade).
     std::vector<int32_t> command_group;
+    bool mirror_inertia = true;          // also copy PhysicsComponent::inertia_vel back every frame (8 B per agent; nothing on the GPU path reads it)
+    uint32_t uploaded_last_frame = 0;    // entities the last updateSharedData had to send (diagnostic)
 
     GpuSeekSlot(ComponentID id, const RtsParams& params, int device = 0) : System2(id) {
         check(rts_create(&params, device, &h), "rts_create");
@@ -65,21 +70,40 @@ struct GpuSeekSlot : System2 {
     void updateSharedData(const std::array<SharedData, N_MAX_ENTITIES>& data, const std::vector<Entity>& active) override {
         auto& seek = getComponents();
         const uint32_t n = (uint32_t)seek.size();
+        const bool population_was_dirty = population_dirty;
+        const bool full = population_dirty || shadow_r_.size() != 2 * (size_t)n;
         if (population_dirty) uploadPopulation(data);
-        r_.resize(2 * n); angle_.resize(n); angle_vel_.resize(n); state_.resize(n);
+        if (full) {
+            shadow_r_.assign(2 * (size_t)n, 0.f); shadow_angle_.assign(n, 0.f); shadow_angle_vel_.assign(n, 0.f); shadow_state_.assign(n, 0);
+        }
+        dirty_.clear(); d_r_.clear(); d_angle_.clear(); d_angle_vel_.clear(); d_state_.clear();
         for (const auto ent : active) {
             const int i = entity2compvec_ind_.at(ent.ind);
             if (i < 0) continue;
             const auto& sd = data.at(ent.ind);
-            r_[2 * i] = sd.transform.r.x; r_[2 * i + 1] = sd.transform.r.y;
-            angle_[i] = sd.transform.angle; angle_vel_[i] = sd.transform.angle_vel;
-            state_[i] = (uint8_t)sd.state;
+            const uint8_t st = (uint8_t)sd.state;
+            // bitwise comparison with the shadow (a NaN position never equals itself: it is simply re-sent)
+            const bool same = !full && sd.transform.r.x == shadow_r_[2 * i] && sd.transform.r.y == shadow_r_[2 * i + 1] &&
+                              sd.transform.angle == shadow_angle_[i] && sd.transform.angle_vel == shadow_angle_vel_[i] && st == shadow_state_[i];
+            if (!same) {
+                if (!population_was_dirty) {   // (a full upload has just sent everything)
+                    dirty_.push_back((uint32_t)i);
+                    d_r_.push_back(sd.transform.r.x); d_r_.push_back(sd.transform.r.y);
+                    d_angle_.push_back(sd.transform.angle); d_angle_vel_.push_back(sd.transform.angle_vel); d_state_.push_back(st);
+                }
+                shadow_r_[2 * i] = sd.transform.r.x; shadow_r_[2 * i + 1] = sd.transform.r.y;
+                shadow_angle_[i] = sd.transform.angle; shadow_angle_vel_[i] = sd.transform.angle_vel; shadow_state_[i] = st;
+            }
             seek[i].transform = sd.transform;   // the host-side planner reads positions from the components
             seek[i].state = sd.state;
         }
-        RtsAgentView v{};
-        v.r = r_.data(); v.angle = angle_.data(); v.angle_vel = angle_vel_.data(); v.state = state_.data();
-        check(rts_update_agents(h, &v), "rts_update_agents");
+        uploaded_last_frame = (uint32_t)dirty_.size();
+        if (!dirty_.empty()) {
+            RtsAgentView v{};
+            v.r = d_r_.data(); v.angle = d_angle_.data(); v.angle_vel = d_angle_vel_.data(); v.state = d_state_.data();
+            check(rts_update_agents_indexed(h, dirty_.data(), (uint32_t)dirty_.size(), &v), "rts_update_agents_indexed");
+            check(rts_sync(h), "rts_sync");   // (the staging copies read the vectors above)
+        }
     }
 
     void update() override {
@@ -91,24 +115,35 @@ struct GpuSeekSlot : System2 {
         auto* self = const_cast<GpuSeekSlot*>(this);
         auto& seek = self->getComponents();
         const uint32_t n = (uint32_t)seek.size();
-        self->vel_.resize(2 * n); self->r_next_.resize(2 * n); self->flags_.resize(n); self->inertia_.resize(2 * n);
+        self->vel_.resize(2 * n); self->r_next_.resize(2 * n); self->flags_.resize(n); self->angle_vel_.resize(n); self->state_.resize(n);
         self->waypoint_.resize(n);
         RtsAgentView v{};
         v.vel = self->vel_.data(); v.angle_vel = self->angle_vel_.data(); v.state = self->state_.data();
-        v.r_next = self->r_next_.data(); v.flags = self->flags_.data(); v.inertia = self->inertia_.data();
+        v.r_next = self->r_next_.data(); v.flags = self->flags_.data();
         v.waypoint = self->waypoint_.data();
+        if (physics && mirror_inertia) { self->inertia_.resize(2 * n); v.inertia = self->inertia_.data(); }
         self->check(rts_download(h, &v), "rts_download");
+        const float dt_frame = dt;   // ECS.h:18, the step the loop integrates with
         for (uint32_t i = 0; i < n; ++i) {
             auto& sd = data.at(compvec_ind2entity_ind_.at(i));
             sd.target = {r_next_[2 * i], r_next_[2 * i + 1]};                 // SeekSystem.cpp:330
             sd.state = static_cast<MoveState>(state_[i]);                     // :331
             sd.transform.vel = {vel_[2 * i], vel_[2 * i + 1]};                // PhysicsSystem.cpp:118-127 + SeekSystem.cpp:337
             sd.transform.angle_vel = angle_vel_[i];                           // :339
+            // what the blackboard will hold once the loop has integrated (ECS.cpp:110-111) = what the device holds now
+            if (self->shadow_r_.size() == 2 * (size_t)n) {
+                sf::Vector2f r = sd.transform.r;
+                r += sd.transform.vel * dt_frame;
+                float angle = sd.transform.angle;
+                angle += sd.transform.angle_vel;
+                self->shadow_r_[2 * i] = r.x; self->shadow_r_[2 * i + 1] = r.y;
+                self->shadow_angle_[i] = angle; self->shadow_angle_vel_[i] = angle_vel_[i]; self->shadow_state_[i] = state_[i];
+            }
             auto& c = seek[i];
             c.r_next = sd.target;
             if (waypoint_[i] > 0) { c.portal_next = c.portal_next_next; }     // updateTarget shifted the window (:290-291)
             if (flags_[i] & RTS_FLAG_REPLAN) { c.needs_update = true; self->replan_.push_back((int)i); }   // :294-303
-            if (physics) physics->getComponents()[i].inertia_vel = {inertia_[2 * i], inertia_[2 * i + 1]};
+            if (physics && mirror_inertia) physics->getComponents()[i].inertia_vel = {inertia_[2 * i], inertia_[2 * i + 1]};
         }
     }
 
@@ -119,8 +154,12 @@ struct GpuSeekSlot : System2 {
     void markPathsDirty() { paths_dirty = true; }
 
 private:
-    std::vector<float> r_, angle_, angle_vel_, vel_, r_next_, inertia_;
+    std::vector<float> angle_vel_, vel_, r_next_, inertia_;
     std::vector<uint8_t> state_;
+    // shadow of the blackboard as the device holds it, and the per-frame dirty list
+    std::vector<float> shadow_r_, shadow_angle_, shadow_angle_vel_, d_r_, d_angle_, d_angle_vel_;
+    std::vector<uint8_t> shadow_state_, d_state_;
+    std::vector<uint32_t> dirty_;
     std::vector<uint32_t> flags_;
     std::vector<int32_t> waypoint_;
     std::vector<int> replan_;

@@ -93,6 +93,11 @@ struct RtsContext {
     void* ex_send[2] = {nullptr, nullptr};
     void* ex_recv[2] = {nullptr, nullptr};
     uint32_t* n_dev = nullptr;
+    // peer exchange over NVLink (CUDA IPC): see SlabDev / k_push
+    void* arena = nullptr;            // this rank's receive buffers (2 directions x 2 parities) + flags + epoch words, exported to the neighbours
+    void* peer_arena[2] = {nullptr, nullptr};   // the neighbours' arenas as mapped into this process
+    bool want_peer = true;            // reserved[5] bit 5 (value 32): keep the per-frame ncclSend/ncclRecv exchange instead
+    bool exchange_pending = false;    // a peer exchange has been launched since the last k_scatter (which ticks the epoch)
     // NCCL, resolved at run time
     void* nccl_lib = nullptr;
     ncclComm_t comm = nullptr;
@@ -104,6 +109,8 @@ struct RtsContext {
     decltype(&ncclGroupStart) p_ncclGroupStart = nullptr;
     decltype(&ncclGroupEnd) p_ncclGroupEnd = nullptr;
     decltype(&ncclGetErrorString) p_ncclGetErrorString = nullptr;
+    decltype(&ncclAllGather) p_ncclAllGather = nullptr;
+    decltype(&ncclAllReduce) p_ncclAllReduce = nullptr;
 
     void drop_graphs() {
         for (auto& g : graph2)
@@ -297,7 +304,9 @@ int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t n_slots = h->multi ? h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo) : h->n;
     const int wpar = h->parity;
     const int do_walk = h->map_ready ? 1 : 0;
-    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0, h->P, h->M, wpar, do_walk);
+    const int tick = (h->multi && h->SL.peer_mode && h->exchange_pending) ? 1 : 0;
+    h->exchange_pending = false;
+    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0, h->P, h->M, wpar, do_walk, tick);
     timer_end(h, KT_REORDER);
     h->launches += 2;
     swap_prev_order(h);
@@ -489,17 +498,30 @@ int32_t exchange_nccl(RtsContext* h) {
     return RTS_OK;
 }
 
+// neighbour exchange over peer memory: one small kernel writes this rank's records into the neighbours' receive buffers
+int32_t exchange_peer(RtsContext* h) {
+    cudaStream_t st = comm_stream(h);
+    timer_begin(h, KT_EXCHANGE);
+    const uint32_t most = std::max(h->SL.cap_mig, h->SL.cap_halo);
+    k_push<<<dim3(std::min<uint32_t>(std::max<uint32_t>(blocks_for(most, 256 * 4), 1u), 32u), 2), 256, 0, st>>>(h->SL);
+    timer_end(h, KT_EXCHANGE);
+    h->launches += 1;
+    h->exchange_pending = true;
+    return RTS_OK;
+}
+int32_t exchange(RtsContext* h) { return h->SL.peer_mode ? exchange_peer(h) : exchange_nccl(h); }
+
 int32_t launch_frame(RtsContext* h) {
     // a split slab frame enqueues edge rows -> exchange -> ingest on the (high-priority) comm stream BEFORE the interior
     // kernel is launched, so that they do not queue up behind its CTAs
     launch_step_edges(h);
     int32_t rc = RTS_OK;
     if (h->multi && h->nranks > 1 && h->frame_is_split) {
-        if ((rc = exchange_nccl(h)) != RTS_OK) return rc;
+        if ((rc = exchange(h)) != RTS_OK) return rc;
         launch_ingest(h);
     }
     launch_step_interior(h);
-    if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange_nccl(h)) != RTS_OK) return rc;
+    if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange(h)) != RTS_OK) return rc;
     return frame_end(h);
 }
 
@@ -609,6 +631,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->overlap_walk = params->reserved[4] == 0;
     h->overlap_exchange = (params->reserved[5] & 8u) != 0;
     h->graph_slabs = (params->reserved[5] & 16u) != 0;
+    h->want_peer = (params->reserved[5] & 32u) == 0;
     *out = h;
     int prio_lo = 0, prio_hi = 0;   // the comm stream (edge rows, exchange, ingest of a slab) outranks the bulk kernels
     cudaSetDevice(device_id);
@@ -661,6 +684,9 @@ int32_t rts_destroy(RtsHandle h) {
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
     free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
+    for (auto& pa : h->peer_arena)
+        if (pa) { cudaIpcCloseMemHandle(pa); pa = nullptr; }
+    if (h->arena) cudaFree(h->arena);
     if (h->comm && h->p_ncclCommDestroy) h->p_ncclCommDestroy(h->comm);
     if (h->n_dev) cudaFree(h->n_dev);
     if (h->F.count) { cudaFree(h->F.count); cudaFree(h->F.start); cudaFree(h->F.partial); cudaFree(h->F.status); cudaFree(h->F.ticket); }
@@ -761,7 +787,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     const size_t n_tri_cells = (size_t)P.tri_nx * P.tri_ny;
     for (size_t c = 0; cell2tri && c < n_tri_cells; ++c)
         if (cell2tri[c] != 0xFFFFFFFFu && cell2tri[c] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "cell2tri entry out of range");
-    int4* d_tris; uint32_t* d_c2t;
+    int4* d_tris = nullptr; uint32_t* d_c2t = nullptr;
     int32_t rc;
     if ((rc = dev_alloc(h, &d_tris, t4.size(), h->table_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_c2t, n_tri_cells, h->table_allocs)) != RTS_OK) return rc;
@@ -897,7 +923,7 @@ int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_
     CU(cudaSetDevice(h->device));
     { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     CU(cudaStreamSynchronize(h->stream));
-    RtsUnitType* d;
+    RtsUnitType* d = nullptr;
     void* old = const_cast<RtsUnitType*>(h->M.unit_types);
     int32_t rc = dev_alloc(h, &d, 256, h->type_allocs);
     if (rc != RTS_OK) return rc;
@@ -1087,6 +1113,41 @@ int32_t rts_update_agents(RtsHandle h, const RtsAgentView* fields) {
     return rebin(h);
 }
 
+int32_t rts_update_agents_indexed(RtsHandle h, const uint32_t* indices, uint32_t m, const RtsAgentView* fields) {
+    if (!h || !fields) return RTS_E_ARG;
+    if (m == 0) return RTS_OK;
+    if (!indices) return h->fail(RTS_E_ARG, "rts_update_agents_indexed", "null indices");
+    if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_update_agents_indexed", "needs component-index gids");
+    if (m > h->n) return h->fail(RTS_E_ARG, "rts_update_agents_indexed", "more indices than agents");
+    for (uint32_t k = 0; k < m; ++k)
+        if (indices[k] >= h->n) return h->fail(RTS_E_ARG, "rts_update_agents_indexed", "index out of range");
+    if (fields->path_id)
+        for (uint32_t k = 0; k < m; ++k)
+            if (fields->path_id[k] >= (int32_t)h->M.n_paths) return h->fail(RTS_E_ARG, "rts_update_agents_indexed", "path_id out of range");
+    CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    Staging S;
+    int32_t rc = stage_in(h, fields, m, &S);   // m entries per field, compact
+    if (rc != RTS_OK) return rc;
+    // index list and the slot-of-gid map live in the generic scratch buffer: [inv: cap][idx: m]
+    if ((rc = ensure_scratch(h, sizeof(uint32_t) * ((size_t)h->cap + m))) != RTS_OK) return rc;
+    uint32_t* inv = static_cast<uint32_t*>(h->scratch);
+    uint32_t* idx = inv + h->cap;
+    CU(cudaMemcpyAsync(idx, indices, sizeof(uint32_t) * (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    k_slot_of_gid<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, h->A.key2, inv);
+    if (fields->r) {   // positions change: current state -> "n" buffers (slot order), edit there, re-bin
+        Staging none{};
+        k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, none, h->A);
+        k_apply_indexed<true><<<blocks_for(m, 128), 128, 0, h->stream>>>(m, idx, inv, S, h->A);
+        h->launches += 3;
+        return rebin(h);
+    }
+    k_apply_indexed<false><<<blocks_for(m, 128), 128, 0, h->stream>>>(m, idx, inv, S, h->A);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
 uint32_t rts_agent_count(RtsHandle h) { return h ? h->n : 0; }
 
 int32_t rts_get_finished_area(RtsHandle h, float* out, uint32_t n) {
@@ -1145,7 +1206,9 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
     // (not for slab handles: capturing ncclSend/ncclRecv into the graph measured slower than launching frame by frame)
-    if (h->use_graph && !h->profiling && (!h->multi || h->graph_slabs) && n_steps >= GRAPH_FRAMES) {
+    // (slab handles: only with the peer exchange — every node is a kernel; capturing ncclSend/ncclRecv measured slower than
+    //  launching frame by frame)
+    if (h->use_graph && !h->profiling && (!h->multi || h->graph_slabs || h->SL.peer_mode) && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
         if (!h->graph2[par] || h->graph_n[par] != h->n) {
             int32_t rc = build_graph(h);
@@ -1187,6 +1250,7 @@ int32_t rts_sync(RtsHandle h) {
         CU(cudaMemcpy(&n_live, h->n_dev, 4, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&overflow, h->SL.overflow, 4, cudaMemcpyDeviceToHost));
         h->n = n_live;
+        if (overflow == 3u) return h->fail(RTS_E_NCCL, "slab exchange", "the neighbour's records never arrived (peer exchange timed out after 20 s: a rank died or fell out of step)");
         if (overflow == 2u) return h->fail(RTS_E_STATE, "slab exchange", "an agent outside the edge launch packed for a neighbour (more agents in the edge rows than the halo capacity allows for, or a move longer than its unit type allows)");
         if (overflow) return h->fail(RTS_E_CAPACITY, "slab exchange", "migrant / halo buffer overflow (raise the capacities of rts_slab_configure)");
         if (n_live > h->cap_main) return h->fail(RTS_E_CAPACITY, "slab", "population outgrew the slot capacity of this handle");
@@ -1259,21 +1323,16 @@ int32_t rts_command_agents(RtsHandle h, const uint32_t* indices, uint32_t m, int
     if (!indices) return h->fail(RTS_E_ARG, "rts_command_agents", "null indices");
     if (!h->gid_is_index) return h->fail(RTS_E_STATE, "rts_command_agents", "needs component-index gids");
     if (path_id >= (int32_t)h->M.n_paths) return h->fail(RTS_E_ARG, "rts_command_agents", "path_id out of range");
-    const uint32_t n = h->n;
-    std::vector<uint8_t> st(n);
-    std::vector<int32_t> pid(n), wp(n);
-    std::vector<float> rn(2 * (size_t)n);
+    // only the commanded agents travel (rts_update_agents_indexed): state, path, waypoint 0, r_next = "take it from the path"
+    std::vector<uint8_t> st(m, state);
+    std::vector<int32_t> pid(m, path_id), wp(m, 0);
+    std::vector<float> rn(2 * (size_t)m, std::nanf(""));
     RtsAgentView v{};
     v.state = st.data(); v.path_id = pid.data(); v.waypoint = wp.data(); v.r_next = rn.data();
-    int32_t rc = rts_download(h, &v);
+    const int32_t rc = rts_update_agents_indexed(h, indices, m, &v);
     if (rc != RTS_OK) return rc;
-    const float qnan = std::nanf("");
-    for (uint32_t k = 0; k < m; ++k) {
-        const uint32_t i = indices[k];
-        if (i >= n) return h->fail(RTS_E_ARG, "rts_command_agents", "index out of range");
-        st[i] = state; pid[i] = path_id; wp[i] = 0; rn[2 * i] = qnan; rn[2 * i + 1] = qnan;
-    }
-    return rts_update_agents(h, &v);
+    CU(cudaStreamSynchronize(h->stream));   // the staging copies read these host vectors
+    return RTS_OK;
 }
 
 int32_t rts_get_timings(RtsHandle h, RtsTimings* out) {
@@ -1409,22 +1468,10 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     SL.halo = std::sqrt(P.r_max2) * 1.05f + 0.25f;
     SL.has[0] = P.slab_row_lo > 0; SL.has[1] = P.slab_row_hi < P.ns_ny;
     SL.cap_mig = cap_migrants; SL.cap_halo = cap_halo;
-    // one buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
-    const size_t bytes = 16 + (size_t)cap_migrants * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8);
-    auto carve = [&](void* base, ExBuf& B) {
-        char* p = static_cast<char*>(base);
-        B.hdr = reinterpret_cast<uint32_t*>(p); p += 16;
-        B.m_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
-        B.m_vel4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
-        B.m_nav4 = reinterpret_cast<float4*>(p); p += (size_t)cap_migrants * 16;
-        B.h_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_halo * 16;
-        B.m_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_migrants * 8;
-        B.h_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_halo * 8;
-        B.m_velout = reinterpret_cast<float2*>(p); p += (size_t)cap_migrants * 8;
-        B.m_tri = reinterpret_cast<uint32_t*>(p);
-    };
+    const size_t bytes = exbuf_bytes(cap_migrants, cap_halo);   // layout: carve_exbuf
+    auto carve = [&](void* base, ExBuf& B) { B = carve_exbuf(base, cap_migrants, cap_halo); };
     for (int d = 0; d < 2; ++d) {
-        char* a; char* b;
+        char* a = nullptr; char* b = nullptr;
         int32_t rc;
         if ((rc = dev_alloc<char>(h, &a, bytes, h->slab_allocs)) != RTS_OK) return rc;
         if ((rc = dev_alloc<char>(h, &b, bytes, h->slab_allocs)) != RTS_OK) return rc;
@@ -1450,6 +1497,68 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     return setup_fine_grid(h);
 }
 
+// Peer exchange set-up (all ranks, collective): every rank allocates its receive arena, the CUDA IPC handles travel through
+// ncclAllGather, each rank maps its neighbours' arenas. All or nothing: unless EVERY rank succeeded (ncclAllReduce of a
+// flag) the handle stays on the ncclSend/ncclRecv exchange.
+static int32_t setup_peer_exchange(RtsContext* h) {
+    SlabDev& SL = h->SL;
+    SL.peer_mode = 0;
+    if (h->nranks < 2) return RTS_OK;
+    const size_t buf = exbuf_bytes(SL.cap_mig, SL.cap_halo);
+    const size_t flags_off = 4 * buf, epoch_off = flags_off + 64, arena_bytes = epoch_off + 64;
+    int ok = h->want_peer ? 1 : 0;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok && (cudaMalloc(&h->arena, arena_bytes) != cudaSuccess || cudaMemset(h->arena, 0, arena_bytes) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine, h->arena) != cudaSuccess)) ok = 0;
+    cudaGetLastError();
+    // handles of all ranks
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    char *d_mine = nullptr, *d_all = nullptr;
+    int* d_ok = nullptr;
+    CU(cudaMalloc(&d_mine, 64));
+    CU(cudaMalloc(&d_all, 64 * (size_t)h->nranks));
+    CU(cudaMalloc(&d_ok, sizeof(int)));
+    CU(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+    ncclResult_t r = h->p_ncclAllGather(d_mine, d_all, 64, ncclUint8, h->comm, h->stream);
+    if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclAllGather", h->p_ncclGetErrorString(r));
+    std::vector<cudaIpcMemHandle_t> all((size_t)h->nranks);
+    CU(cudaMemcpyAsync(all.data(), d_all, 64 * (size_t)h->nranks, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int d = 0; d < 2 && ok; ++d) {
+        if (!SL.has[d]) continue;
+        const int peer = h->rank + (d == 0 ? -1 : 1);
+        if (cudaIpcOpenMemHandle(&h->peer_arena[d], all[(size_t)peer], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    r = h->p_ncclAllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, h->comm, h->stream);
+    if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclAllReduce", h->p_ncclGetErrorString(r));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d_mine); cudaFree(d_all); cudaFree(d_ok);
+    if (!ok) {   // somebody could not: everybody keeps NCCL
+        for (auto& pa : h->peer_arena)
+            if (pa) { cudaIpcCloseMemHandle(pa); pa = nullptr; }
+        if (h->arena) { cudaFree(h->arena); h->arena = nullptr; }
+        return RTS_OK;
+    }
+    char* base = static_cast<char*>(h->arena);
+    for (int d = 0; d < 2; ++d) {
+        for (int par = 0; par < 2; ++par) {
+            SL.recv_base[d][par] = base + (size_t)(2 * d + par) * buf;
+            SL.peer_base[d][par] = h->peer_arena[d] ? static_cast<char*>(h->peer_arena[d]) + (size_t)(2 * (1 - d) + par) * buf : nullptr;
+        }
+        SL.flag_local[d] = reinterpret_cast<uint32_t*>(base + flags_off) + d;
+        SL.flag_peer[d] = h->peer_arena[d] ? reinterpret_cast<uint32_t*>(static_cast<char*>(h->peer_arena[d]) + flags_off) + (1 - d) : nullptr;
+    }
+    SL.epoch = reinterpret_cast<uint32_t*>(base + epoch_off);
+    SL.peer_mode = 1;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+int32_t rts_slab_exchange_mode(RtsHandle h) { return h ? (h->multi ? (h->SL.peer_mode ? 2 : 1) : 0) : -1; }
+
 int32_t rts_comm_unique_id(void* out128) {
     if (!out128) return RTS_E_ARG;
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -1472,12 +1581,13 @@ int32_t rts_comm_init(RtsHandle h, const void* id128) {
     h->p_##name = reinterpret_cast<decltype(&name)>(dlsym(h->nccl_lib, #name));                 \
     if (!h->p_##name) return h->fail(RTS_E_NCCL, "dlsym", #name);
     SYM(ncclCommInitRank) SYM(ncclCommDestroy) SYM(ncclSend) SYM(ncclRecv) SYM(ncclGroupStart) SYM(ncclGroupEnd) SYM(ncclGetErrorString)
+    SYM(ncclAllGather) SYM(ncclAllReduce)
 #undef SYM
     ncclUniqueId id;
     std::memcpy(&id, id128, sizeof(id));
     const ncclResult_t r = h->p_ncclCommInitRank(&h->comm, h->nranks, id, h->rank);
     if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclCommInitRank", h->p_ncclGetErrorString(r));
-    return RTS_OK;
+    return setup_peer_exchange(h);
 }
 
 // first half of a frame (frame kernel + packing of migrants / halo) — the caller moves the buffers, then rts_step_end
@@ -1511,7 +1621,7 @@ int32_t rts_halo_begin(RtsHandle h) {
 int32_t rts_halo_refresh(RtsHandle h) {
     int32_t rc = rts_halo_begin(h);
     if (rc != RTS_OK) return rc;
-    if (h->nranks > 1 && (rc = exchange_nccl(h)) != RTS_OK) return rc;
+    if (h->nranks > 1 && (rc = exchange(h)) != RTS_OK) return rc;
     return frame_end(h);
 }
 // single-device emulation of two neighbouring ranks (tests): lower.send[up] -> upper.recv[down] and back

@@ -144,6 +144,24 @@ struct ExBuf {
     float4* h_pos4;     // halo: the neighbour record only
     uint2* h_key2;
 };
+// one exchange buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
+__host__ __device__ inline ExBuf carve_exbuf(void* base, uint32_t cap_mig, uint32_t cap_halo) {
+    ExBuf B;
+    char* p = static_cast<char*>(base);
+    B.hdr = reinterpret_cast<uint32_t*>(p); p += 16;
+    B.m_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_mig * 16;
+    B.m_vel4 = reinterpret_cast<float4*>(p); p += (size_t)cap_mig * 16;
+    B.m_nav4 = reinterpret_cast<float4*>(p); p += (size_t)cap_mig * 16;
+    B.h_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_halo * 16;
+    B.m_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_mig * 8;
+    B.h_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_halo * 8;
+    B.m_velout = reinterpret_cast<float2*>(p); p += (size_t)cap_mig * 8;
+    B.m_tri = reinterpret_cast<uint32_t*>(p);
+    return B;
+}
+__host__ __device__ inline size_t exbuf_bytes(uint32_t cap_mig, uint32_t cap_halo) {
+    return (16 + (size_t)cap_mig * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8) + 15) & ~(size_t)15;
+}
 struct SlabDev {
     int32_t row_lo, row_hi;   // physics-grid rows owned: [row_lo, row_hi)
     float y_lo, y_hi;         // = row * ns_cell_size
@@ -151,7 +169,18 @@ struct SlabDev {
     int32_t has[2];           // neighbour present in direction 0 / 1
     uint32_t cap_mig, cap_halo;
     ExBuf send[2], recv[2];
-    uint32_t* overflow;       // sticky: 1 = a migrant / halo record did not fit its buffer, 2 = an agent outside the edge rows packed
+    uint32_t* overflow;       // sticky: 1 = a migrant / halo record did not fit its buffer, 2 = an agent outside the edge rows packed,
+                              // 3 = the neighbour's records of this frame never arrived (peer exchange timed out)
+    // ---- peer exchange (NVLink, CUDA IPC): the neighbour's receive buffers are mapped into this process and k_push writes
+    // this rank's records straight into them; a flag per direction carries the epoch (frame counter) of the last complete
+    // delivery. Receive buffers are double-buffered by epoch parity: the neighbour may already deliver frame e+1 while
+    // frame e is being ingested (it cannot be two frames ahead: its frame e+2 needs this rank's frame e+1 delivery).
+    int32_t peer_mode;
+    char* recv_base[2][2];    // [direction][parity] this rank's receive buffers (same layout as send / recv: carve_exbuf)
+    char* peer_base[2][2];    // [direction][parity] where records sent in `direction` land: the neighbour's recv_base[1 - direction]
+    uint32_t* flag_local[2];  // [direction] epoch + 1 of the last delivery that arrived from that direction
+    uint32_t* flag_peer[2];   // [direction] the neighbour's flag_local[1 - direction]
+    uint32_t* epoch;          // [0] exchanges completed (k_scatter ticks it), [1..2] CTA counters of k_push per direction
     // Edge rows (fine-grid rows relative to FineGrid::row0): slots of rows < edge_row_lo or >= edge_row_hi can send
     // something to a neighbour this frame (halo band + one frame of travel). k_step<PHASE 1> steps exactly those, so that
     // the exchange can start while k_step<PHASE 2> is still working on the interior.
@@ -373,8 +402,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // Agents move < 2 units per frame, so nearly all of them pass; the others (hint missing, on an edge, moved on) are queued
 // for k_walk, which runs the reference's own search for them.
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi, RtsParams P, MapDev M,
-                                                 int parity, int do_walk) {
+                                                 int parity, int do_walk, int tick_epoch) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0 && tick_epoch) SL.epoch[0] += 1u;   // one peer exchange has been delivered and ingested (see k_push)
     if (p == 0) {
         A.dense_n[0] = 0u; A.dense_n[4] = 0u;   // the dense queues of this frame (whole / interior, edge rows) have been consumed
         A.walk_n[parity ^ 1] = 0u;              // ... and the walk queue of the previous frame (its k_walk was joined before this launch)
@@ -454,16 +484,70 @@ __global__ void __launch_bounds__(256) k_walk(RtsParams P, MapDev M, AgentArrays
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
+// Peer exchange, sending side: the records k_step (or k_halo_seed) packed into the local send buffers are copied — exactly
+// as many as the headers count — into the neighbour's receive buffer of this epoch's parity over NVLink; the last CTA of a
+// direction then publishes epoch + 1 in the neighbour's flag. grid = (CTAs, 2 directions).
+__global__ void __launch_bounds__(256) k_push(SlabDev SL) {
+    const int dir = (int)blockIdx.y;
+    if (!SL.has[dir]) return;
+    const uint32_t e = *((volatile uint32_t*)SL.epoch);
+    const ExBuf src = SL.send[dir];
+    const ExBuf dst = carve_exbuf(SL.peer_base[dir][e & 1u], SL.cap_mig, SL.cap_halo);
+    const uint32_t nm = min(src.hdr[0], SL.cap_mig), nh = min(src.hdr[1], SL.cap_halo);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < max(nm, nh); i += stride) {
+        if (i < nm) {
+            dst.m_pos4[i] = src.m_pos4[i]; dst.m_vel4[i] = src.m_vel4[i]; dst.m_nav4[i] = src.m_nav4[i];
+            dst.m_key2[i] = src.m_key2[i]; dst.m_velout[i] = src.m_velout[i]; dst.m_tri[i] = src.m_tri[i];
+        }
+        if (i < nh) { dst.h_pos4[i] = src.h_pos4[i]; dst.h_key2[i] = src.h_key2[i]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { dst.hdr[0] = nm; dst.hdr[1] = nh; dst.hdr[2] = src.hdr[2]; dst.hdr[3] = e; }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(SL.epoch + 1 + dir, 1u);
+        if (done == gridDim.x - 1) {          // every CTA of this direction has written and fenced its share
+            SL.epoch[1 + dir] = 0u;
+            __threadfence_system();
+            *((volatile uint32_t*)SL.flag_peer[dir]) = e + 1u;
+        }
+    }
+}
+
+// Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
+// frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
+// Peer mode: waits for the neighbour's flag of this epoch first (bounded: a neighbour that never delivers is reported
+// through SL.overflow = 3 after ~20 s instead of hanging the device).
 __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArrays A) {
     const uint32_t cap_mig = SL.cap_mig, cap_halo = SL.cap_halo;
+    const int dir = (int)blockIdx.y;                       // both directions in one launch
+    ExBuf B = SL.recv[dir];
+    if (SL.peer_mode) {
+        const uint32_t e = *((volatile uint32_t*)SL.epoch);
+        if (SL.has[dir]) {
+            if (threadIdx.x == 0) {
+                const volatile uint32_t* flag = SL.flag_local[dir];
+                unsigned long long t0 = 0, now = 0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                while ((int32_t)(*flag - (e + 1u)) < 0) {
+                    __nanosleep(100);
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (now - t0 > 20000000000ull) { *SL.overflow = 3u; break; }
+                }
+                __threadfence_system();
+            }
+            __syncthreads();
+        }
+        B = carve_exbuf(SL.recv_base[dir][e & 1u], cap_mig, cap_halo);
+    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cap_mig + cap_halo) return;
-    const int dir = (int)blockIdx.y;                       // both directions in one launch
-    const ExBuf& B = SL.recv[dir];
     const uint32_t slot = base0 + (uint32_t)dir * (cap_mig + cap_halo) + i;
     const bool is_mig = i < cap_mig;
     const uint32_t k = is_mig ? i : i - cap_mig;
-    const uint32_t cnt = is_mig ? min(B.hdr[0], cap_mig) : min(B.hdr[1], cap_halo);
+    const bool present = !SL.peer_mode || SL.has[dir];     // (peer mode: a missing neighbour's buffer is never written)
+    const uint32_t cnt = !present ? 0u : (is_mig ? min(((volatile uint32_t*)B.hdr)[0], cap_mig) : min(((volatile uint32_t*)B.hdr)[1], cap_halo));
     if (k >= cnt) {
         A.cellrank[slot] = make_uint2(INVALID_CELL, 0u);
         return;
@@ -1531,6 +1615,49 @@ __global__ void k_apply(uint32_t n, Staging S, AgentArrays A) {
     A.nav4n[d] = nav4;
     A.trin[d] = A.tri[sp];
     if (A.vel_outn) A.vel_outn[d] = A.vel_out[sp];
+}
+
+// rts_update_agents_indexed: the host touched m agents (commands, edits) — only their fields travel.
+// k_slot_of_gid inverts slot -> gid (component-index gids), k_apply_indexed overwrites the non-null fields of the m listed
+// agents IN PLACE (current order); with positions among the fields the caller re-bins afterwards (TO_N: the write goes to
+// the "n" buffers that a preceding k_apply has filled in slot order).
+__global__ void k_slot_of_gid(uint32_t n, const uint2* __restrict__ key2, uint32_t* __restrict__ inv) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) inv[key2[d].x] = d;
+}
+template <bool TO_N>
+__global__ void k_apply_indexed(uint32_t m, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ inv, Staging S, AgentArrays A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const uint32_t d = inv[idx[k]];
+    const uint32_t sp = TO_N ? d : A.src[d];
+    float4* pos4 = TO_N ? A.pos4n : A.pos4;
+    uint2* key2 = TO_N ? A.key2n : A.key2;
+    float4* vel4p = TO_N ? A.vel4n : A.vel4;
+    float4* nav4p = TO_N ? A.nav4n : A.nav4;
+    float4 pos = pos4[d];
+    uint2 key = key2[d];
+    float4 vel4 = vel4p[sp];
+    float4 nav4 = nav4p[sp];
+    uint32_t misc = __float_as_uint(nav4.w);
+    pos.z = fabsf(pos.z); pos.w = fabsf(pos.w);
+    if (S.r) { const float2 r = S.r[k]; pos.x = r.x; pos.y = r.y; }
+    if (S.radius) pos.z = S.radius[k];
+    if (S.mass) pos.w = S.mass[k];
+    if (S.state) key.y = (key.y & ~3u) | (S.state[k] & 3u);
+    if (S.inertia) { const float2 v = S.inertia[k]; vel4.x = v.x; vel4.y = v.y; }
+    if (S.angle) vel4.z = S.angle[k];
+    if (S.angle_vel) vel4.w = S.angle_vel[k];
+    if (S.r_next) { const float2 v = S.r_next[k]; nav4.x = v.x; nav4.y = v.y; }
+    if (S.path_id) nav4.z = __int_as_float(S.path_id[k]);
+    if (S.waypoint) misc = (misc & ~0xFFFFu) | ((uint32_t)S.waypoint[k] & 0xFFFFu);
+    if (S.unit_type) misc = (misc & ~(0xFFu << 16)) | ((uint32_t)S.unit_type[k] << 16);
+    if (S.player) misc = (misc & ~(0xFu << 24)) | (((uint32_t)S.player[k] & 0xFu) << 24);
+    nav4.w = __uint_as_float(misc);
+    pos4[d] = pack_pos(pos.x, pos.y, pos.z, pos.w, key.y & 3u);
+    key2[d] = key;
+    vel4p[sp] = vel4;
+    nav4p[sp] = nav4;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ def load_library():
         "rts_remove_agents": (i32, [H, vp, u32]),
         "rts_command_agents": (i32, [H, vp, u32, i32, C.c_uint8]),
         "rts_update_agents": (i32, [H, AV]),
+        "rts_update_agents_indexed": (i32, [H, vp, u32, AV]),
         "rts_agent_count": (u32, [H]),
         "rts_get_finished_area": (i32, [H, vp, u32]),
         "rts_set_finished_area": (i32, [H, vp, u32]),
@@ -73,6 +74,7 @@ def load_library():
         "rts_slab_configure": (i32, [H, i32, i32, u32, u32]),
         "rts_comm_unique_id": (i32, [vp]),
         "rts_comm_init": (i32, [H, vp]),
+        "rts_slab_exchange_mode": (i32, [H]),
         "rts_halo_refresh": (i32, [H]),
         "rts_step_begin": (i32, [H]),
         "rts_halo_begin": (i32, [H]),
@@ -214,6 +216,19 @@ class GpuAgentSystem:
         keep: list = []
         v = abi.agent_view({k: a for k, a in fields.items() if k not in abi.DOWNLOAD_ONLY}, self.n, keep)
         self._chk(self.L.rts_update_agents(self.h, C.byref(v)))
+
+    def update_shared_data_indexed(self, indices, fields: dict):
+        """System2::updateSharedData for the entities the host touched: `fields` arrays hold len(indices) entries"""
+        idx = np.ascontiguousarray(indices, np.uint32)
+        keep: list = []
+        v = abi.agent_view({k: a for k, a in fields.items() if k not in abi.DOWNLOAD_ONLY}, len(idx), keep)
+        self._chk(self.L.rts_update_agents_indexed(self.h, idx.ctypes.data, len(idx), C.byref(v)))
+
+    def update_shared_data_indexed_ptrs(self, idx_ptr: int, m: int, ptrs: dict):
+        v = abi.RtsAgentView()
+        for k, p in ptrs.items():
+            setattr(v, k, p)
+        self._chk(self.L.rts_update_agents_indexed(self.h, idx_ptr, m, C.byref(v)))
 
     def update(self, n_steps: int = 1, sync: bool = False):
         self._chk(self.L.rts_step(self.h, n_steps))

@@ -230,8 +230,111 @@ def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
         os._exit(1)
 
 
+def _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, precision, K, Wm, repeats, reserved5=0, clock_sampler=None):
+    """One multi-GPU workload: the population cut into `world` y-slabs at agent-count quantiles of physics-grid rows, `repeats`
+    repetitions of the same K frames (re-uploaded + Wm warm-up frames each time), device time = max over ranks, median over
+    repetitions. Returns (result dict, the SlabRank left open for the caller — close it)."""
+    from . import scenario
+    tables = scenario.tables_of(fx)
+    paths = scenario.paths_of(fx)
+    nx, ny = (int(v) for v in fx["n_cells"])
+    base = engine.default_params(nx, ny)
+    base.precision = precision
+    base.reserved[5] = reserved5
+    bounds = partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
+    parts = split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
+    # exchange capacities from the density: agents in a halo band / crossing a boundary per frame, with a wide margin
+    per_unit_height = n_total / (ny * 5.0)
+    cap_halo = int(max(4096, 6 * per_unit_height * halo_width(base.r_max2)))
+    cap_mig = int(max(1024, 6 * per_unit_height * 2.0))
+    sr = SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
+    uid = [make_unique_id(sr.g.L) if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sr.init_comm(uid[0])
+    sr.g.upload_map(tables)
+    sr.g.upload_paths(paths)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    ms, launches, wall = [], 0, 0.0
+    for rep in range(repeats):
+        sr.g.set_agents(parts[rank])
+        sr.halo_refresh()
+        sr.g.update(Wm, sync=True)
+        barrier()                   # every rank enters the timed region together
+        sr.g.reset_timings()
+        t0 = time.perf_counter()
+        sr.g.update(K)
+        sr.g.sync()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([sr.g.timings().last_step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms.append(float(t.item()))
+        launches = int(sr.g.timings().kernel_launches)
+    own = sr.owned(("r",))
+    cnt = torch.tensor([len(own["gid"])], device="cuda", dtype=torch.int64)
+    dist.all_reduce(cnt)
+    med = float(np.median(ms))
+    res = {"value": n_total * K / (med * 1e-3), "unit": "agent-updates/s", "ms_per_step": med / K, "repeat_ms_per_step": [m / K for m in ms],
+           "agents": n_total, "slab_rows": bounds, "gpu_launches": launches,
+           "conservation": {"agents_after": int(cnt.item()), "agents_before": n_total},
+           "exchange": {0: "none", 1: "ncclSend/ncclRecv per frame", 2: "peer memory over NVLink (CUDA IPC, k_push + epoch flags), frames replayed from a CUDA graph"}[
+               int(sr.g.L.rts_slab_exchange_mode(sr.g.h))],
+           "wall_s_last_repeat": wall}
+    return res, sr
+
+
+def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_gpu, frames=24):
+    """T10 over the REAL inter-GPU path: the slabs (bit-exact mode) against a single-domain handle stepping the same
+    population on rank 0; every agent, every float compared as bits. Returns the number of differing agents."""
+    from . import scenario
+    fx = scenario.tile_map(tile, 1, world)
+    n_total = per_gpu * world
+    agents = scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
+    agents["gid"] = np.arange(n_total, dtype=np.uint32)
+    res, sr = _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, abi.PRECISION_EXACT, frames, 3, 1)
+    names = ("r", "inertia", "angle", "angle_vel", "state", "tri_idx", "waypoint", "r_next")
+    own = sr.owned(names)
+    sr.close()
+    dtypes = {name: dt for name, dt, _ in abi.AGENT_FIELDS}
+    comps = {name: k for name, _, k in abi.AGENT_FIELDS}
+    ref = {}
+    if rank == 0:
+        base = engine.default_params(*(int(v) for v in fx["n_cells"]))
+        with engine.GpuAgentSystem(base, device=local) as one:
+            one.upload_map(scenario.tables_of(fx))
+            one.upload_paths(scenario.paths_of(fx))
+            one.set_agents({k: v for k, v in agents.items() if k != "gid"})
+            one.update(3 + frames, sync=True)
+            ref = one.communicate(names)
+    bad = np.zeros(len(own["gid"]), bool)
+    for k in names:
+        shape = (n_total, comps[k]) if comps[k] > 1 else (n_total,)
+        width = np.dtype(dtypes[k]).itemsize
+        t = torch.empty(shape, dtype={4: torch.int32, 1: torch.uint8}[width], device="cuda")
+        if rank == 0:
+            t.copy_(torch.from_numpy(ref[k].view({4: np.int32, 1: np.uint8}[width]).reshape(shape)))
+        dist.broadcast(t, src=0)
+        want = t.cpu().numpy()[own["gid"].astype(np.int64)]
+        got = own[k].view({4: np.int32, 1: np.uint8}[width]).reshape(want.shape)
+        if len(got):
+            bad |= (got != want).reshape(len(got), -1).any(1)
+    n_bad = torch.tensor([int(bad.sum()), len(own["gid"])], device="cuda", dtype=torch.int64)
+    dist.all_reduce(n_bad)
+    return {"mismatching_agents": int(n_bad[0].item()), "agents_compared": int(n_bad[1].item()), "frames": 3 + frames,
+            "fields": list(names), "precision": "exact", "exchange": res["exchange"],
+            "what": f"{world} slabs over the real inter-GPU exchange vs ONE single-domain handle on rank 0, same {n_total} agents "
+                    f"({world} config-3 tiles), every agent, bitwise"}
+
+
 def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
-    """N>1 leg of bench.py: weak scaling, per-GPU population fixed (args.agents per GPU, default 1.25M = 10M / 8)."""
+    """N>1 leg of bench.py.
+    Headline line (continuity with round 1): WEAK scaling of the N=1 workload — `world` config-3 tiles stacked in y,
+    args.agents per GPU. Added: `config4` = BASELINE config 4 itself, STRONG scaling (10M agents on the 8192x8192-cell map
+    cut into `world` slabs; bench.py --gpus 1 reports the same population on one GPU as `config4_1gpu`), and
+    `parity_vs_single_domain` = the slabs against one domain, bitwise, over the real exchange."""
     import torch
     import torch.distributed as dist
     from . import engine, scenario
@@ -243,86 +346,74 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     per_gpu = args.agents
     n_total = per_gpu * world
-    # weak scaling of the N=1 workload: `world` config-3 tiles stacked in y (1024 x 1024*world cells), per_gpu agents per
-    # tile at config-3 density, 64 command groups per tile; slabs are cut at agent-count quantiles of physics-grid rows
+    K, Wm = args.steps, max(args.warmup, 3)
+    precision = args.precision
+    reserved5 = int(os.environ.get("RTS_RESERVED5", "0"))   # diagnostic A/B of the exchange switches (RtsParams.reserved[5])
     tile = scenario.load_map("map_c3.npz")
+
+    # ---- weak scaling of config 3
     fx = scenario.tile_map(tile, 1, world)
-    tables = scenario.tables_of(fx)
-    paths = scenario.paths_of(fx)
     nx, ny = (int(v) for v in fx["n_cells"])
-    base = engine.default_params(nx, ny)
-    if os.environ.get("RTS_RESERVED5"):   # diagnostic A/B of the stream-overlap switches (RtsParams.reserved[5])
-        base.reserved[5] = int(os.environ["RTS_RESERVED5"])
     agents = scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
     agents["gid"] = np.arange(n_total, dtype=np.uint32)
-    bounds = partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
-    parts = split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
-    # exchange capacities from the density: agents in a halo band / crossing a boundary per frame, with a wide margin
-    per_unit_height = per_gpu / (fx["tile_cells"][1] * 5.0)
-    cap_halo = int(max(4096, 6 * per_unit_height * halo_width(base.r_max2)))
-    cap_mig = int(max(1024, 6 * per_unit_height * 2.0))
-    sr = SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
-    uid = [make_unique_id(sr.g.L) if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    sr.init_comm(uid[0])
-    sr.g.upload_map(tables)
-    sr.g.upload_paths(paths)
-    sr.g.set_agents(parts[rank])
-    sr.halo_refresh()
-    K, Wm = args.steps, max(args.warmup, 3)
-    sr.g.update(Wm, sync=True)
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local)   # opens NVML here, outside the timed region (its start-up time differs from rank to rank)
     with sampler as clocks:
-        barrier()                   # every rank enters the timed region together
-        sr.g.reset_timings()
-        t0 = time.perf_counter()
-        sr.g.update(K)
-        sr.g.sync()
-        wall = time.perf_counter() - t0
-    dev_ms = sr.g.timings().last_step_ms
-    launches = int(sr.g.timings().kernel_launches)
-    t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
-    own = sr.owned(("r",))
-    cnt = torch.tensor([len(own["gid"])], device="cuda", dtype=torch.int64)
-    dist.all_reduce(cnt)
-    barrier()
+        main, sr = _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, precision, K, Wm, args.repeats, reserved5)
     if os.environ.get("RTS_BENCH_RANK_TRACE"):   # diagnostic: per-rank kernel times of a further (serialised) 40 frames
         sr.g.set_profiling(True)
         sr.g.reset_timings()
         sr.g.update(40, sync=True)
         ms = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in engine.KERNELS}
-        print(json.dumps({"rank": rank, "dev_ms_per_frame": dev_ms / K, "owned": len(own["gid"]), "kernel_ms": ms}),
-              file=sys.stderr, flush=True)
+        print(json.dumps({"rank": rank, "kernel_ms": ms}), file=sys.stderr, flush=True)
         sr.g.set_profiling(False)
-        barrier()
+        dist.barrier()
+    sr.close()
+    del agents
+
+    # ---- BASELINE config 4, strong scaling
+    c4 = None
+    if not args.no_config4:
+        fx4 = scenario.tile_map(tile, 8, 8)
+        a4 = scenario.tiled_agents(tile, 8, 8, args.agents4 // 64, seed=1237)
+        n4 = len(a4["r"])
+        a4["gid"] = np.arange(n4, dtype=np.uint32)
+        c4, sr4 = _slab_case(dist, torch, engine, rank, world, local, fx4, a4, n4, precision, K, Wm, 3, reserved5)
+        sr4.close()
+        del a4
+        c4["workload"] = (f"config4: {n4} agents on the 8192x8192-cell map (8x8 config-3 tiles, 12 800 buildings, 4096 groups) cut into "
+                          f"{world} y-slabs; strong scaling — bench.py --gpus 1 reports the same population on one GPU as config4_1gpu")
+        c4["precision"] = PRECISION_LABEL[precision]
+
+    # ---- the slabs against a single domain, bitwise, over the real exchange
+    parity = None
+    if not os.environ.get("RTS_BENCH_NO_PARITY"):
+        parity = _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, min(per_gpu, 250_000))
+
     if rank == 0:
         peak, peak_src = measured_peak()
-        value = n_total * K / (max_ms * 1e-3)
         line = {
-            "metric": "agent-updates/sec", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": "agent-updates/sec", "value": main["value"], "unit": "agent-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"config3 x {world}: {per_gpu} agents per GPU, {world} config-3 tiles stacked in y ({nx}x{ny} cells, "
-                                   f"{200 * world} buildings, {64 * world} groups), y-slabs aligned to physics-grid rows, NCCL halo + migration "
-                                   f"exchange every frame",
-                       "agents": n_total, "agents_per_gpu": per_gpu, "slab_rows": bounds,
+                                   f"{200 * world} buildings, {64 * world} groups), y-slabs aligned to physics-grid rows, halo + migration "
+                                   f"exchange every frame ({main['exchange']})",
+                       "agents": n_total, "agents_per_gpu": per_gpu, "slab_rows": main["slab_rows"], "precision": PRECISION_LABEL[precision],
+                       "timing": f"median of {args.repeats} repetitions of the same {K} frames, max over ranks of the device time",
                        "l2_policy": "inputs larger than L2 (per-GPU state > 126 MB); no explicit flush"},
-            "clocks": clocks.summary(), "gpu_launches": launches,
-            "conservation": {"agents_after": int(cnt.item()), "agents_before": n_total},
-            "e2e": {"value": n_total * K / wall, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "multi-GPU leg keeps state device-resident; host wall-clock around rts_step on rank 0"},
-            "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": algo_bytes * per_gpu / (max_ms / K * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": algo_bytes * per_gpu / (max_ms / K * 1e-3) / 1e9 / peak,
+            "repeat_ms_per_step": main["repeat_ms_per_step"],
+            "clocks": clocks.summary(), "gpu_launches": main["gpu_launches"],
+            "conservation": main["conservation"],
+            "e2e": {"value": n_total * K / main["wall_s_last_repeat"], "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "multi-GPU leg keeps state device-resident; host wall-clock around rts_step on rank 0 (no end-to-end claim at N>1)"},
+            "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "traffic": None, "peak_source": peak_src},
+            "config4": c4, "parity_vs_single_domain": parity,
             "cpu_baseline": None,
         }
         print(json.dumps(line))
-    sr.close()
     dist.destroy_process_group()
+
+
+PRECISION_LABEL = {0: "exact", 1: "fast"}

@@ -88,4 +88,6 @@ def test_reference_arm_of_the_bench_emits_the_contract_line():
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] == j["value"]
     assert j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)       # every host thread, whatever OMP_NUM_THREADS said
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "config3" in j["config"]["workload"]
+    # the record says what really ran: the reference cannot hold config 3 (5 000-agent cap), so the arm runs its density
+    assert j["config"]["same_config_as_gpu_arm"] is False and j["config"]["agents"] in (5000, 200000)
+    assert "config-3" in j["config"]["workload"] or "config 3" in j["config"]["workload"]
