@@ -349,7 +349,7 @@ void set_edge_rows(RtsContext* h) {
 // Does this frame split the frame kernel into the edge rows (comm stream, followed there by the exchange and the ingest)
 // and the interior (main stream)? Only slab handles with a neighbour; not while per-kernel timers are on.
 bool split_frame(const RtsContext* h) {
-    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->fast && h->F.ny >= 4;
+    return h->multi && h->overlap_exchange && !h->profiling && (h->SL.has[0] || h->SL.has[1]) && !h->fast && !h->SL.peer_mode && h->F.ny >= 4;
 }
 
 #define LAUNCH_DENSE(KV, MU)                                                                         \
@@ -404,6 +404,7 @@ void launch_step_interior(RtsContext* h) {
     const int dv = (h->keep_vel ? 2 : 0) | (h->multi ? 1 : 0);
     SlabDev SLq = h->SL;
     SLq.interior_launch = split ? 1 : 0;
+    SLq.publish_here = 1;   // (read by k_step_dense* only: the last packing kernel of the frame)
     const AgentArrays& Aq = h->A;
     // leading CTAs that search the walk queue of the previous frame (see launch_scan_reorder)
     const uint32_t wc = (h->walkq_pending && nb) ? walk_ctas_of(h) : 0u;
@@ -498,18 +499,17 @@ int32_t exchange_nccl(RtsContext* h) {
     return RTS_OK;
 }
 
-// neighbour exchange over peer memory: one small kernel writes this rank's records into the neighbours' receive buffers
-int32_t exchange_peer(RtsContext* h) {
-    cudaStream_t st = comm_stream(h);
-    timer_begin(h, KT_EXCHANGE);
-    const uint32_t most = std::max(h->SL.cap_mig, h->SL.cap_halo);
-    k_push<<<dim3(std::min<uint32_t>(std::max<uint32_t>(blocks_for(most, 256 * 4), 1u), 32u), 2), 256, 0, st>>>(h->SL);
-    timer_end(h, KT_EXCHANGE);
-    h->launches += 1;
+// neighbour exchange over peer memory: the frame's kernels have written their records into the neighbours' buffers and the
+// last CTA of k_step_dense* has published them (publish_to_peers); only a halo refresh without a frame needs a launch
+int32_t exchange_peer(RtsContext* h, bool published_by_frame) {
+    if (!published_by_frame) {
+        k_publish<<<1, 32, 0, comm_stream(h)>>>(h->SL);
+        h->launches += 1;
+    }
     h->exchange_pending = true;
     return RTS_OK;
 }
-int32_t exchange(RtsContext* h) { return h->SL.peer_mode ? exchange_peer(h) : exchange_nccl(h); }
+int32_t exchange(RtsContext* h, bool published_by_frame) { return h->SL.peer_mode ? exchange_peer(h, published_by_frame) : exchange_nccl(h); }
 
 int32_t launch_frame(RtsContext* h) {
     // a split slab frame enqueues edge rows -> exchange -> ingest on the (high-priority) comm stream BEFORE the interior
@@ -517,11 +517,11 @@ int32_t launch_frame(RtsContext* h) {
     launch_step_edges(h);
     int32_t rc = RTS_OK;
     if (h->multi && h->nranks > 1 && h->frame_is_split) {
-        if ((rc = exchange(h)) != RTS_OK) return rc;
+        if ((rc = exchange(h, false)) != RTS_OK) return rc;
         launch_ingest(h);
     }
     launch_step_interior(h);
-    if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange(h)) != RTS_OK) return rc;
+    if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange(h, USE_DENSE_KERNEL)) != RTS_OK) return rc;
     return frame_end(h);
 }
 
@@ -1462,6 +1462,7 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     free_all(h->slab_allocs);
     cap_migrants = (cap_migrants + 3u) & ~3u;
     cap_halo = (cap_halo + 3u) & ~3u;
+    if (cap_migrants >= (1u << 20) || cap_halo >= (1u << 20)) return h->fail(RTS_E_ARG, "rts_slab_configure", "exchange capacities must stay below 2^20 records");
     SlabDev SL{};
     SL.row_lo = P.slab_row_lo; SL.row_hi = P.slab_row_hi;
     SL.y_lo = P.slab_row_lo * P.ns_cell_size; SL.y_hi = P.slab_row_hi * P.ns_cell_size;
@@ -1548,8 +1549,8 @@ static int32_t setup_peer_exchange(RtsContext* h) {
             SL.recv_base[d][par] = base + (size_t)(2 * d + par) * buf;
             SL.peer_base[d][par] = h->peer_arena[d] ? static_cast<char*>(h->peer_arena[d]) + (size_t)(2 * (1 - d) + par) * buf : nullptr;
         }
-        SL.flag_local[d] = reinterpret_cast<uint32_t*>(base + flags_off) + d;
-        SL.flag_peer[d] = h->peer_arena[d] ? reinterpret_cast<uint32_t*>(static_cast<char*>(h->peer_arena[d]) + flags_off) + (1 - d) : nullptr;
+        SL.flag_local[d] = reinterpret_cast<unsigned long long*>(base + flags_off) + d;
+        SL.flag_peer[d] = h->peer_arena[d] ? reinterpret_cast<unsigned long long*>(static_cast<char*>(h->peer_arena[d]) + flags_off) + (1 - d) : nullptr;
     }
     SL.epoch = reinterpret_cast<uint32_t*>(base + epoch_off);
     SL.peer_mode = 1;
@@ -1621,7 +1622,7 @@ int32_t rts_halo_begin(RtsHandle h) {
 int32_t rts_halo_refresh(RtsHandle h) {
     int32_t rc = rts_halo_begin(h);
     if (rc != RTS_OK) return rc;
-    if (h->nranks > 1 && (rc = exchange(h)) != RTS_OK) return rc;
+    if (h->nranks > 1 && (rc = exchange(h, false)) != RTS_OK) return rc;
     return frame_end(h);
 }
 // single-device emulation of two neighbouring ranks (tests): lower.send[up] -> upper.recv[down] and back

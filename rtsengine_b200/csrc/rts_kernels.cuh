@@ -171,16 +171,19 @@ struct SlabDev {
     ExBuf send[2], recv[2];
     uint32_t* overflow;       // sticky: 1 = a migrant / halo record did not fit its buffer, 2 = an agent outside the edge rows packed,
                               // 3 = the neighbour's records of this frame never arrived (peer exchange timed out)
-    // ---- peer exchange (NVLink, CUDA IPC): the neighbour's receive buffers are mapped into this process and k_push writes
-    // this rank's records straight into them; a flag per direction carries the epoch (frame counter) of the last complete
+    // ---- peer exchange (NVLink, CUDA IPC): the neighbour's receive buffers are mapped into this process and the kernels write
+    // records straight into them; a flag per direction carries the epoch (frame counter) of the last complete
     // delivery. Receive buffers are double-buffered by epoch parity: the neighbour may already deliver frame e+1 while
     // frame e is being ingested (it cannot be two frames ahead: its frame e+2 needs this rank's frame e+1 delivery).
+    // k_step / k_step_dense* / k_halo_seed write their records directly into the neighbour's buffer (pack_target); the slot
+    // counters stay local, and the last CTA of the frame's last packing kernel copies them across and raises the flag.
     int32_t peer_mode;
     char* recv_base[2][2];    // [direction][parity] this rank's receive buffers (same layout as send / recv: carve_exbuf)
     char* peer_base[2][2];    // [direction][parity] where records sent in `direction` land: the neighbour's recv_base[1 - direction]
-    uint32_t* flag_local[2];  // [direction] epoch + 1 of the last delivery that arrived from that direction
-    uint32_t* flag_peer[2];   // [direction] the neighbour's flag_local[1 - direction]
-    uint32_t* epoch;          // [0] exchanges completed (k_scatter ticks it), [1..2] CTA counters of k_push per direction
+    unsigned long long* flag_local[2];  // [direction] peer_word of the last delivery that arrived from that direction
+    unsigned long long* flag_peer[2];   // [direction] the neighbour's flag_local[1 - direction]
+    uint32_t* epoch;          // [0] exchanges completed (k_scatter ticks it), [1] CTA counter of publish_to_peers
+    int32_t publish_here;     // set in the copy handed to the last packing kernel of a frame: it publishes (publish_to_peers)
     // Edge rows (fine-grid rows relative to FineGrid::row0): slots of rows < edge_row_lo or >= edge_row_hi can send
     // something to a neighbour this frame (halo band + one frame of travel). k_step<PHASE 1> steps exactly those, so that
     // the exchange can start while k_step<PHASE 2> is still working on the interior.
@@ -191,6 +194,39 @@ struct SlabDev {
     // reported there if they pack.
     uint32_t edge_blocks;
 };
+
+// where the records packed for direction `dir` are written: the local send buffer, or — peer exchange — straight into the
+// neighbour's receive buffer of this epoch's parity (the slot COUNTERS stay local: send[dir].hdr; publish_to_peers copies them)
+__device__ __forceinline__ ExBuf pack_target(const SlabDev& SL, int dir) {
+    if (!SL.peer_mode) return SL.send[dir];
+    const uint32_t e = *((volatile uint32_t*)SL.epoch);
+    return carve_exbuf(SL.peer_base[dir][e & 1u], SL.cap_mig, SL.cap_halo);
+}
+// Peer exchange, end of the packing: called by every CTA of the LAST kernel of a frame that packs (k_step_dense*, or
+// k_publish after k_halo_seed). Every thread that wrote a record into a neighbour's buffer has already executed a
+// system-scope fence behind it (finish_agent, k_halo_seed), and the frame kernel ended before this one started, so when the
+// last CTA arrives here every record of the frame has landed. It then publishes ONE 64-bit word per neighbour:
+// {epoch + 1 : 24 | migrants : 20 | halo records : 20} — flag and header in a single store, no second round trip.
+__device__ __forceinline__ unsigned long long peer_word(uint32_t epoch1, uint32_t nm, uint32_t nh) {
+    return ((unsigned long long)(epoch1 & 0xFFFFFFu) << 40) | ((unsigned long long)(nm & 0xFFFFFu) << 20) | (unsigned long long)(nh & 0xFFFFFu);
+}
+__device__ __forceinline__ void publish_to_peers(const SlabDev& SL) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(SL.epoch + 1, 1u);
+        if (done == gridDim.x * gridDim.y - 1) {
+            SL.epoch[1] = 0u;
+            __threadfence();
+            const uint32_t e = *((volatile uint32_t*)SL.epoch);
+            for (int dir = 0; dir < 2; ++dir) {
+                if (!SL.has[dir]) continue;
+                volatile uint32_t* lh = SL.send[dir].hdr;
+                *((volatile unsigned long long*)SL.flag_peer[dir]) = peer_word(e + 1u, min(lh[0], SL.cap_mig), min(lh[1], SL.cap_halo));
+            }
+        }
+    }
+}
 
 struct AgentArrays {
     uint32_t* n_dev;  // live slots of the CURRENT order (owned agents + ghosts); written by the scan
@@ -484,6 +520,11 @@ __global__ void __launch_bounds__(256) k_walk(RtsParams P, MapDev M, AgentArrays
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
+// Peer exchange after k_halo_seed (no frame, hence no k_step_dense to do it): publish what was packed
+__global__ void k_publish(SlabDev SL) { publish_to_peers(SL); }
+
+// Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
+// frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
 // Peer exchange, sending side: the records k_step (or k_halo_seed) packed into the local send buffers are copied — exactly
 // as many as the headers count — into the neighbour's receive buffer of this epoch's parity over NVLink; the last CTA of a
 // direction then publishes epoch + 1 in the neighbour's flag. grid = (CTAs, 2 directions).
@@ -523,21 +564,27 @@ __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArr
     const uint32_t cap_mig = SL.cap_mig, cap_halo = SL.cap_halo;
     const int dir = (int)blockIdx.y;                       // both directions in one launch
     ExBuf B = SL.recv[dir];
+    __shared__ unsigned long long s_word;
+    uint32_t peer_nm = 0u, peer_nh = 0u;
     if (SL.peer_mode) {
         const uint32_t e = *((volatile uint32_t*)SL.epoch);
         if (SL.has[dir]) {
             if (threadIdx.x == 0) {
-                const volatile uint32_t* flag = SL.flag_local[dir];
-                unsigned long long t0 = 0, now = 0;
+                const volatile unsigned long long* flag = SL.flag_local[dir];
+                unsigned long long t0 = 0, now = 0, w;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-                while ((int32_t)(*flag - (e + 1u)) < 0) {
+                // (24-bit epochs: "arrived" = not behind this frame's epoch + 1, modulo 2^24)
+                while ((((uint32_t)((w = *flag) >> 40) - (e + 1u)) & 0xFFFFFFu) >= 0x800000u) {
                     __nanosleep(100);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (now - t0 > 20000000000ull) { *SL.overflow = 3u; break; }
+                    if (now - t0 > 20000000000ull) { *SL.overflow = 3u; w = 0ull; break; }
                 }
+                s_word = w;
                 __threadfence_system();
             }
             __syncthreads();
+            peer_nm = (uint32_t)(s_word >> 20) & 0xFFFFFu;
+            peer_nh = (uint32_t)s_word & 0xFFFFFu;
         }
         B = carve_exbuf(SL.recv_base[dir][e & 1u], cap_mig, cap_halo);
     }
@@ -546,8 +593,8 @@ __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArr
     const uint32_t slot = base0 + (uint32_t)dir * (cap_mig + cap_halo) + i;
     const bool is_mig = i < cap_mig;
     const uint32_t k = is_mig ? i : i - cap_mig;
-    const bool present = !SL.peer_mode || SL.has[dir];     // (peer mode: a missing neighbour's buffer is never written)
-    const uint32_t cnt = !present ? 0u : (is_mig ? min(((volatile uint32_t*)B.hdr)[0], cap_mig) : min(((volatile uint32_t*)B.hdr)[1], cap_halo));
+    const uint32_t cnt = SL.peer_mode ? (is_mig ? min(peer_nm, cap_mig) : min(peer_nh, cap_halo))   // (0 without a neighbour)
+                                      : (is_mig ? min(B.hdr[0], cap_mig) : min(B.hdr[1], cap_halo));
     if (k >= cnt) {
         A.cellrank[slot] = make_uint2(INVALID_CELL, 0u);
         return;
@@ -602,14 +649,17 @@ __global__ void k_halo_seed(uint32_t n_bound, RtsParams P, FineGrid F, AgentArra
     if (A.vel_outn) A.vel_outn[p] = A.vel_out[sp];
     if (SL.has[0] && pos.y < SL.y_lo + SL.halo) {
         const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
-        if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos; SL.send[0].h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        const ExBuf B = pack_target(SL, 0);
+        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); }
         else *SL.overflow = 1u;
     }
     if (SL.has[1] && pos.y >= SL.y_hi - SL.halo) {
         const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
-        if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos; SL.send[1].h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        const ExBuf B = pack_target(SL, 1);
+        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); }
         else *SL.overflow = 1u;
     }
+    if (SL.peer_mode && ((SL.has[0] && pos.y < SL.y_lo + SL.halo) || (SL.has[1] && pos.y >= SL.y_hi - SL.halo))) __threadfence_system();
     int fx, fy;
     fine_coords(F, pos.x, pos.y, fx, fy);
     const uint32_t cell = (uint32_t)fy * (uint32_t)F.nx + (uint32_t)fx;
@@ -899,8 +949,8 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
         if (dir >= 0 && SL.has[dir]) {
             // migrate: full record to the neighbour; the local copy stays one more frame as a ghost (it is within
             // one frame's travel of the boundary, i.e. inside the halo band of this slab)
-            const ExBuf& B = SL.send[dir];
-            const uint32_t k = atomicAdd(B.hdr + 0, 1u);
+            const ExBuf B = pack_target(SL, dir);
+            const uint32_t k = atomicAdd(SL.send[dir].hdr + 0, 1u);
             if (k < SL.cap_mig) {
                 B.m_pos4[k] = pos_new;
                 B.m_key2[k] = make_uint2(gid, cs_new);
@@ -913,15 +963,21 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
         } else {
             if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
-                if (k < SL.cap_halo) { SL.send[0].h_pos4[k] = pos_new; SL.send[0].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                const ExBuf B = pack_target(SL, 0);
+                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); }
                 else *SL.overflow = 1u;
             }
             if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
-                if (k < SL.cap_halo) { SL.send[1].h_pos4[k] = pos_new; SL.send[1].h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                const ExBuf B = pack_target(SL, 1);
+                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); }
                 else *SL.overflow = 1u;
             }
         }
+        // peer exchange: this thread's records must have ARRIVED in the neighbour's memory before the kernel may end (the
+        // flag that announces them is raised by a later kernel, which orders nothing about another kernel's posted writes)
+        if (SL.peer_mode && (dir >= 0 || (SL.has[0] && r_new.y < SL.y_lo + SL.halo) || (SL.has[1] && r_new.y >= SL.y_hi - SL.halo)))
+            __threadfence_system();
     }
     A.pos4n[p] = pos_new;
     A.key2n[p] = make_uint2(gid, cs_new);
@@ -1426,6 +1482,7 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
         if (parked + DENSE_GROUPS > 32u) finish_parked();
     }
     if (parked) finish_parked();
+    if (MULTI && SL.peer_mode && SL.publish_here) publish_to_peers(SL);
 }
 
 // Tolerance-mode counterpart of k_step_dense: FAST_DENSE_LANES lanes share the candidates of one crowded agent (every lane
@@ -1513,6 +1570,7 @@ __global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, 
         if (parked + GROUPS > 32u) finish_parked();
     }
     if (parked) finish_parked();
+    if (MULTI && SL.peer_mode && SL.publish_here) publish_to_peers(SL);
 }
 
 // ------------------------------------------------------------------------------------------------

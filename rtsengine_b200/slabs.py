@@ -387,7 +387,8 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     # ---- the slabs against a single domain, bitwise, over the real exchange
     parity = None
     if not os.environ.get("RTS_BENCH_NO_PARITY"):
-        parity = _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, min(per_gpu, 250_000))
+        parity = _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, min(per_gpu, 250_000),
+                                          frames=int(os.environ.get("RTS_PARITY_FRAMES", "24")))
 
     if rank == 0:
         peak, peak_src = measured_peak()
