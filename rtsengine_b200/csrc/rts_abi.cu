@@ -47,6 +47,7 @@ struct RtsContext {
     uint32_t* c2t_dev = nullptr;   // writable alias of M.cell2tri
     bool map_ready = false, gid_is_index = true, keep_vel = true, profiling = false;
     float fine_cs = 6.0f;
+    bool fine_cs_auto = true;         // no explicit RtsParams.reserved[1]: the gather-cell size follows the population density (rts_set_agents)
     std::string err;
     // owned device allocations of the tables
     std::vector<void*> table_allocs, path_allocs, type_allocs;
@@ -623,7 +624,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->device = device_id;
     h->P = *params;
     h->keep_vel = params->reserved[0] == 0;   // reserved[0] = 1 drops the per-step velocity output
-    if (params->reserved[1]) std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float));
+    if (params->reserved[1]) { std::memcpy(&h->fine_cs, &params->reserved[1], sizeof(float)); h->fine_cs_auto = false; }
     h->use_graph = params->reserved[2] == 0;
     h->fast = params->precision == RTS_PRECISION_FAST;
     h->M.inv_ns_cs = 1.0f / params->ns_cell_size;
@@ -1040,6 +1041,29 @@ int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
     if (agents && agents->gid)
         for (uint32_t i = 0; i < n; ++i)
             if (agents->gid[i] >= (1u << 28)) return h->fail(RTS_E_ARG, "rts_set_agents", "gid >= 2^28 (the ordering key keeps 28 bits of it)");
+    if (h->fine_cs_auto && n) {
+        // Gather cells sized for ~0.8 agents each (never below the interaction range: setup_fine_grid clamps): on a sparse map
+        // (config 4: 0.006 agents per unit²) 6-unit cells would be 80 % empty and the per-frame scan over them — 46 M cells on
+        // 8192² — would cost more than the neighbour search saves.
+        // Density = agents over their bounding box (clipped to the map / the slab).
+        const RtsParams& P = h->P;
+        const float W = P.map_nx * P.map_cell_size, y0 = P.slab_row_lo * P.ns_cell_size, y1 = std::min(P.map_ny * P.map_cell_size, P.slab_row_hi * P.ns_cell_size);
+        float bx0 = W, bx1 = 0.f, by0 = y1, by1 = y0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float x = agents->r[2 * i], y = agents->r[2 * i + 1];
+            if (x < bx0) bx0 = x;
+            if (x > bx1) bx1 = x;
+            if (y < by0) by0 = y;
+            if (y > by1) by1 = y;
+        }
+        bx0 = std::max(bx0, 0.f); bx1 = std::min(bx1, W); by0 = std::max(by0, y0); by1 = std::min(by1, y1);
+        const double area = std::max(1.0, (double)std::max(bx1 - bx0, 6.f) * (double)std::max(by1 - by0, 6.f));
+        const float want = std::min(16.0f, std::max(6.0f, (float)std::sqrt(0.8 * area / (double)n)));
+        if (std::fabs(want - h->fine_cs) > 0.15f * h->fine_cs) {
+            h->fine_cs = want;
+            if ((rc = setup_fine_grid(h)) != RTS_OK) return rc;
+        }
+    }
     h->n = n;
     h->gid_is_index = !(agents && agents->gid);
     if ((rc = ingest(h, 0, n, agents)) != RTS_OK) return rc;

@@ -293,8 +293,11 @@ __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* smem)
 }
 
 // One-pass exclusive scan of the cell counts (decoupled look-back): tiles are handed out by an atomic ticket, so a tile
-// only ever waits for tiles that already started; flags carry an epoch, so nothing is reset between launches (the
-// kernel is replayed from a CUDA graph with frozen arguments).
+// only ever waits for tiles that already started. Every tile publishes its AGGREGATE as soon as it is known and its
+// INCLUSIVE PREFIX once its own look-back is done; the look-back (warp 0, 32 predecessors per round) stops at the nearest
+// predecessor that already has a prefix, so its length does not grow with the number of tiles (46 M cells on the
+// config-4 map: 22 000 tiles). Flags carry an epoch, so nothing is reset between launches (the kernel is replayed from a
+// CUDA graph with frozen arguments): status word = {flag : 32 | value : 32}, flag = 2*epoch + 1 (aggregate) / + 2 (prefix).
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint32_t* n_out) {
     static_assert(SCAN_ITEMS == 8, "two uint4 per thread");
     __shared__ uint32_t smem[32];
@@ -323,20 +326,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint3
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
     const uint32_t aggregate = block_reduce_sum(s, smem);
-    // publish this tile's sum, then add up the sums of all earlier tiles (they all hold a ticket, so they will publish);
-    // every thread polls a strided share of them, so the wait is one round trip, not a chain
-    const uint32_t flag_now = epoch + 1u;   // epoch starts at 0 and status words at 0: flag 0 never matches
-    if (threadIdx.x == 0) atomicExch(F.status + tile, ((unsigned long long)flag_now << 32) | aggregate);
-    uint32_t before = 0;
-    for (uint32_t j = threadIdx.x; j < tile; j += SCAN_THREADS) {
-        unsigned long long wv;
-        do { wv = *((volatile unsigned long long*)(F.status + j)); } while ((uint32_t)(wv >> 32) != flag_now);   // plain L2 reads
-        before += (uint32_t)wv;
-    }
-    before = block_reduce_sum(before, smem);
-    if (threadIdx.x == 0) s_prefix = before;
-    // exclusive scan of the per-thread sums
+    const uint32_t flag_a = 2u * epoch + 1u, flag_p = 2u * epoch + 2u;   // (epoch starts at 0 and status words at 0: flag 0 never matches)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) atomicExch(F.status + tile, ((unsigned long long)(tile == 0u ? flag_p : flag_a) << 32) | aggregate);
+    if (w == 0) {
+        uint32_t before = 0;
+        for (int64_t j0 = (int64_t)tile - 1; j0 >= 0; j0 -= 32) {
+            const int64_t j = j0 - lane;          // lane 0 looks at the nearest predecessor
+            uint32_t fl = flag_p, val = 0u;       // (beyond tile 0: an empty prefix)
+            if (j >= 0) {
+                unsigned long long wv;
+                do { wv = *((volatile unsigned long long*)(F.status + j)); fl = (uint32_t)(wv >> 32); } while (fl != flag_a && fl != flag_p);   // plain L2 reads
+                val = (uint32_t)wv;
+            }
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, fl == flag_p);
+            const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;   // nearest predecessor whose inclusive prefix is known
+            uint32_t c = (lane <= stop) ? val : 0u;
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+            before += __shfl_sync(0xffffffffu, c, 0);
+            if (has_prefix) break;
+        }
+        if (lane == 0) {
+            s_prefix = before;
+            if (tile != 0u) atomicExch(F.status + tile, ((unsigned long long)flag_p << 32) | (before + aggregate));
+        }
+    }
+    // exclusive scan of the per-thread sums
     uint32_t incl = s;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
