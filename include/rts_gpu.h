@@ -291,6 +291,16 @@ int32_t rts_halo_begin(RtsHandle h);
 int32_t rts_step_end(RtsHandle h);
 int32_t rts_slab_exchange_local(RtsHandle lower, RtsHandle upper);
 
+/* Slab rebalancing (boundaries follow agent-count quantiles, re-evaluated every K frames — crowds that drain
+   through corridors pile up in a few slabs otherwise). rts_slab_row_counts: owned agents per physics-grid row (ns_ny
+   entries); the host sums them over the ranks and picks new boundaries. rts_slab_set_rows: this handle now owns rows
+   [row_lo, row_hi) — call it on both sides of a moved boundary between the same two frames. The agents of the rows that
+   changed hands migrate during the next frame through the ordinary migrant buffers (so at most cap_migrants of them per
+   direction; the host moves a boundary by fewer rows if they would not fit). Results stay bit-identical to the
+   single-domain run: ownership never enters the arithmetic. */
+int32_t rts_slab_row_counts(RtsHandle h, uint32_t* counts);
+int32_t rts_slab_set_rows(RtsHandle h, int32_t row_lo, int32_t row_hi);
+
 /* raw CUDA stream of the handle (cudaStream_t as void*), so a host that owns device buffers can order work after it */
 void* rts_stream(RtsHandle h);
 

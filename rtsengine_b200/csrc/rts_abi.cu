@@ -1584,6 +1584,54 @@ static int32_t setup_peer_exchange(RtsContext* h) {
 
 int32_t rts_slab_exchange_mode(RtsHandle h) { return h ? (h->multi ? (h->SL.peer_mode ? 2 : 1) : 0) : -1; }
 
+// ---- slab rebalancing ---------------------------------------------------------------------------------------------
+int32_t rts_slab_row_counts(RtsHandle h, uint32_t* counts) {
+    if (!h || !counts) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_slab_row_counts", "not a slab handle");
+    CU(cudaSetDevice(h->device));
+    const uint32_t rows = (uint32_t)h->P.ns_ny;
+    int32_t rc = ensure_scratch(h, sizeof(uint32_t) * (size_t)rows);
+    if (rc != RTS_OK) return rc;
+    uint32_t* hist = static_cast<uint32_t*>(h->scratch);
+    CU(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)rows, h->stream));
+    const uint32_t n_slots = h->cap_main + 2 * (h->SL.cap_mig + h->SL.cap_halo);
+    if (n_slots) k_row_hist<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(h->n_dev, h->A.key2, hist, rows);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(counts, hist, sizeof(uint32_t) * (size_t)rows, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
+int32_t rts_slab_set_rows(RtsHandle h, int32_t row_lo, int32_t row_hi) {
+    if (!h) return RTS_E_ARG;
+    if (!h->multi) return h->fail(RTS_E_STATE, "rts_slab_set_rows", "not a slab handle");
+    if (row_lo < 0 || row_hi > h->P.ns_ny || row_lo >= row_hi) return h->fail(RTS_E_ARG, "rts_slab_set_rows", "bad rows");
+    if ((row_lo > 0) != (h->SL.has[0] != 0) || (row_hi < h->P.ns_ny) != (h->SL.has[1] != 0))
+        return h->fail(RTS_E_ARG, "rts_slab_set_rows", "the outermost slabs keep the map edge: only boundaries shared with a neighbour move");
+    if (row_lo == h->P.slab_row_lo && row_hi == h->P.slab_row_hi) return RTS_OK;
+    CU(cudaSetDevice(h->device));
+    int32_t rc = rts_sync(h);   // also refreshes h->n (owned + ghost slots)
+    if (rc != RTS_OK) return rc;
+    h->P.slab_row_lo = row_lo; h->P.slab_row_hi = row_hi;
+    SlabDev& SL = h->SL;
+    SL.row_lo = row_lo; SL.row_hi = row_hi;
+    SL.y_lo = row_lo * h->P.ns_cell_size; SL.y_hi = row_hi * h->P.ns_cell_size;
+    // the gather grid follows the slab (one physics row of margin on either side): current state -> "n" buffers -> new grid.
+    // Ownership is decided by the frame kernel from the physics row of each agent's position, so the agents of the rows
+    // that changed hands simply migrate in the next frame (their count must fit the migrant capacity).
+    if ((rc = setup_fine_grid(h)) != RTS_OK) return rc;
+    if (h->n) {
+        Staging none{};
+        k_apply<<<blocks_for(h->n, 256), 256, 0, h->stream>>>(h->n, none, h->A);
+        h->launches += 1;
+        if ((rc = rebin(h)) != RTS_OK) return rc;
+    }
+    h->drop_graphs();
+    CU(cudaStreamSynchronize(h->stream));
+    return RTS_OK;
+}
+
 int32_t rts_comm_unique_id(void* out128) {
     if (!out128) return RTS_E_ARG;
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);

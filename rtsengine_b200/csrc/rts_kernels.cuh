@@ -535,6 +535,16 @@ __global__ void __launch_bounds__(256) k_walk(RtsParams P, MapDev M, AgentArrays
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
+// rts_slab_row_counts: owned agents per physics-grid row (the load figure slab rebalancing works with)
+__global__ void k_row_hist(const uint32_t* __restrict__ n_dev, const uint2* __restrict__ key2, uint32_t* __restrict__ hist, uint32_t ns_ny) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= *n_dev) return;
+    const uint32_t ky = key2[d].y;
+    if ((ky >> 2) & 1u) return;   // ghost
+    const uint32_t row = (uint32_t)cs_cy(ky);
+    if (row < ns_ny) atomicAdd(hist + row, 1u);
+}
+
 // Peer exchange after k_halo_seed (no frame, hence no k_step_dense to do it): publish what was packed
 __global__ void k_publish(SlabDev SL) { publish_to_peers(SL); }
 

@@ -75,6 +75,8 @@ def load_library():
         "rts_comm_unique_id": (i32, [vp]),
         "rts_comm_init": (i32, [H, vp]),
         "rts_slab_exchange_mode": (i32, [H]),
+        "rts_slab_row_counts": (i32, [H, vp]),
+        "rts_slab_set_rows": (i32, [H, i32, i32]),
         "rts_halo_refresh": (i32, [H]),
         "rts_step_begin": (i32, [H]),
         "rts_halo_begin": (i32, [H]),

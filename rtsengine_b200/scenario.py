@@ -261,3 +261,29 @@ def tiled_agents(fx_tile: dict, tx: int, ty: int, n_per_tile: int, seed: int = 1
             a["r"][:] = r + np.array([i * W_t, j * W_t], np.float32)
             parts.append(a)
     return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 5: dense crowd funnelled through narrow corridors (tests/golden/map_c5.npz, built through the
+# reference's CDT / Edges code by tests/golden/make_golden.py::make_map_c5)
+# ---------------------------------------------------------------------------------------------------------
+def config5_agents(fx: dict, n: int = 4_000_000, seed: int = 1238, lo=None, hi=None):
+    """n agents uniform over the free space of the window [lo, hi] (default: the whole map — 4M agents are 0.16 per
+    unit², four times config 3), radius 3 / mass 1, all MOVING: the left half heads right through the corridor nearest
+    to it, the right half heads left (counter-flow in every corridor). Paths: mouth -> far mouth -> plaza."""
+    rng = np.random.default_rng(seed)
+    n_corr, pitch, width, x0, n_seg, seg, gap = (int(v) for v in fx["corridors"])
+    W = int(fx["n_cells"][0]) * 5.0
+    xa, xb = x0 * 5.0, (x0 + n_seg * (seg + gap) - gap) * 5.0
+    a = _blank(n)
+    a["r"][:] = free_positions(fx, n, rng, lo=lo, hi=hi)
+    a["angle"][:] = rng.uniform(-180, 180, n)
+    x, y = a["r"][:, 0], a["r"][:, 1]
+    k = np.clip(np.rint((y / 5.0 - width / 2.0) / pitch), 0, n_corr - 1).astype(np.int64)
+    d = (x >= W / 2).astype(np.int64)
+    a["path_id"][:] = 2 * k + d
+    before = np.where(d == 0, x < xa, x > xb)
+    inside = (x >= xa) & (x <= xb)
+    a["waypoint"][:] = np.where(before, 1, np.where(inside, 2, 3))
+    a["state"][:] = abi.MOVING
+    return a, paths_of(fx)

@@ -50,6 +50,38 @@ def partition_rows(y: np.ndarray, ns_ny: int, ns_cell: float, nranks: int) -> li
     return bounds
 
 
+def rebalanced_bounds(hist: np.ndarray, bounds: list, cap_migrants: int, max_shift: int = 4, tolerance: float = 0.10) -> list:
+    """New slab boundaries from the GLOBAL per-row agent counts: quantile boundaries (as partition_rows), but every
+    boundary moves only if its two slabs differ by more than `tolerance`, by at most `max_shift` rows, and by no more rows
+    than whose agents fit 80 % of the migrant capacity (they travel through the ordinary migrant buffers in one frame).
+    Deterministic: every rank computes the same list from the same all-reduced histogram."""
+    hist = np.asarray(hist, np.int64)
+    nranks = len(bounds) - 1
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    total = int(cum[-1])
+    new = list(bounds)
+    for g in range(1, nranks):
+        below = int(cum[bounds[g]] - cum[bounds[g - 1]])
+        above = int(cum[bounds[g + 1]] - cum[bounds[g]])
+        if abs(below - above) <= tolerance * max(below, above, 1):
+            continue
+        target = int(np.searchsorted(cum, total * g / nranks, side="left"))
+        step = int(np.clip(target - bounds[g], -max_shift, max_shift))
+        b = bounds[g]
+        moved = 0
+        while step != 0:
+            row = b if step > 0 else b - 1            # the row that changes hands next
+            if moved + int(hist[row]) > 0.8 * cap_migrants:
+                break
+            moved += int(hist[row])
+            b += 1 if step > 0 else -1
+            step -= 1 if step > 0 else -1
+        new[g] = b
+    for g in range(1, nranks):                        # keep every slab at least one row tall and the list increasing
+        new[g] = min(max(new[g], new[g - 1] + 1), len(hist) - (nranks - g))
+    return new
+
+
 def row_of(y: np.ndarray, ns_cell: float, ns_ny: int) -> np.ndarray:
     """Grid::coordToCell row (floor(y/cs) % ny) for in-map positions"""
     return (np.floor(np.asarray(y, np.float32) / np.float32(ns_cell)).astype(np.int64)) % ns_ny
@@ -197,6 +229,16 @@ class SlabRank:
 
     def halo_refresh(self):
         self.g._chk(self.g.L.rts_halo_refresh(self.g.h))
+
+    def row_counts(self) -> np.ndarray:
+        """owned agents per physics-grid row (whole map: ns_ny entries)"""
+        out = np.zeros(int(self.params.ns_ny), np.uint32)
+        self.g._chk(self.g.L.rts_slab_row_counts(self.g.h, out.ctypes.data))
+        return out
+
+    def set_rows(self, lo: int, hi: int):
+        self.g._chk(self.g.L.rts_slab_set_rows(self.g.h, int(lo), int(hi)))
+        self.params.slab_row_lo, self.params.slab_row_hi = int(lo), int(hi)
 
     def owned(self, names=("r",)):
         """download, drop ghosts, sort by gid"""

@@ -163,10 +163,62 @@ def make_map_c3(cells=1024, n_buildings=200, n_groups=64, sub=8, seed=7, name="m
     w.close()
 
 
+def make_map_c5(cells=2048, n_corridors=64, width=6, seg=60, gap=4, x0=64, name="map_c5.npz"):
+    """BASELINE config 5: 2048² cells, 64 parallel corridors `width` cells wide running in x, bounded by walls that are
+    chains of seg x thick-cell octagonal blocks (corner 1) inserted through the reference's own CDT / Edges code
+    (refh_add_building = MapGrid.cpp:1095-1312), `gap` cells apart (alleys between neighbouring corridors). Open plazas at
+    both ends. Paths are straight legs (mouth -> far mouth -> plaza), one per corridor and direction."""
+    w = refh.RefWorld(cells, cells)
+    pitch = cells // n_corridors                 # 32 cells: a corridor and the wall above it
+    thick = pitch - width                        # wall blocks fill the space between two corridors
+    n_seg = (cells - 2 * x0) // (seg + gap)
+    blds = []
+    # wall row k lies below corridor k (rows k*pitch + width .. (k+1)*pitch); one more wall row closes the first corridor from above
+    for k in range(-1, n_corridors):
+        y_lo = k * pitch + width + (pitch - width) // 2 - thick // 2 if k >= 0 else None
+        if k < 0:
+            continue                             # corridor 0 is bounded above by the map edge region (margin rows)
+        cy = k * pitch + width + thick // 2
+        if cy + thick // 2 + 2 >= cells:
+            continue
+        for s_ in range(n_seg):
+            cx = x0 + s_ * (seg + gap) + seg // 2
+            if w.add_building(cx, cy, seg, thick, 1) != 0:
+                raise RuntimeError(w.L.refh_last_error(w.h).decode())
+            blds.append((cx, cy, seg, thick))
+    w.finalize_map()
+    assert w.consistent()
+    tables = w.tables()
+    W = cells * 5.0
+    xa, xb = x0 * 5.0, (x0 + n_seg * (seg + gap) - gap) * 5.0        # corridor mouths
+    off, wps, ends, group_of = [0], [], [], []
+    for k in range(n_corridors):
+        yc = (k * pitch + width / 2.0) * 5.0
+        for direction in (0, 1):                 # 0: left -> right, 1: right -> left
+            a, b = (xa, xb) if direction == 0 else (xb, xa)
+            far = (W - 100.0) if direction == 0 else 100.0
+            path = np.array([[a - (40.0 if direction == 0 else -40.0), yc], [a, yc], [b, yc], [far, yc]], np.float32)
+            wps.append(path)
+            ends.append(path[-1])
+            group_of.append(2 * k + direction)
+            off.append(off[-1] + len(path))
+    nw = off[-1]
+    np.savez_compressed(os.path.join(OUT, name), **tables, buildings=np.array(blds, np.int32),
+                        path_offsets=np.array(off, np.uint32), path_waypoints=np.concatenate(wps).astype(np.float32),
+                        path_portals=np.zeros((nw, 5), np.float32), path_end=np.array(ends, np.float32),
+                        path_group=np.array(group_of, np.int32),
+                        corridors=np.array([n_corridors, pitch, width, x0, n_seg, seg, gap], np.int32))
+    print(name, "triangles", len(tables["tri_verts"]), "wall blocks", len(blds), "paths", len(ends))
+    w.close()
+
+
 def main():
     import resource
     resource.setrlimit(resource.RLIMIT_AS, (12 << 30, 12 << 30))   # a runaway reference planner must not take the box down
     assert refh.available(), "build oracle/_ref first: make -C oracle ref"
+    if len(sys.argv) > 1 and sys.argv[1] == "c5":                  # only the corridor map (the other fixtures are unchanged)
+        make_map_c5()
+        return
     L = refh.load()
 
     # ---- known answers of the reference's own tests ------------------------------------------------

@@ -155,3 +155,26 @@ def test_fast_mode_config3_1m():
             out = gf.communicate(NAMES)
             st = check_one_frame(out, ref, a, P, ow, (1024, 1024), f"config 3, frame {start}")
             print("config3 frame", start, st)
+
+
+def test_fast_mode_config5_corridors():
+    """the corridor crowd of BASELINE config 5 (120k agents at the full case's density, one in seven touching a wall):
+    three frames, each entered from the oracle's state"""
+    from rtsengine_b200 import scenario
+    fx = H.load("map_c5.npz")
+    tables = H.tables_of(fx)
+    a0, paths = scenario.config5_agents(fx, n=120_000, lo=(200, 2400), hi=(3000, 3700))
+    ref = abi.alloc_agent_arrays(len(a0["r"]), set(H.ALL_FIELDS))
+    for k, v in a0.items():
+        ref[k][:] = v
+    P = engine.default_params(2048, 2048)
+    ow = port.OracleWorld(port.default_params(2048, 2048), tables, paths)
+    with make_system(tables, paths, map_cells=(2048, 2048), precision=abi.PRECISION_FAST) as g:
+        for s in range(3):
+            a_in = {k: v.copy() for k, v in ref.items()}
+            g.set_agents({k: v for k, v in a_in.items() if k not in abi.DOWNLOAD_ONLY})
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(NAMES)
+            st = check_one_frame(out, ref, a_in, P, ow, (2048, 2048), f"config 5 step {s}", min_plain=0.99)
+    print("config5", st)

@@ -306,6 +306,67 @@ def test_full_size_properties_1m():
             H.assert_same_bits(out[k][idx][core], sub[k][core], f"1M sample {k}")
 
 
+def test_full_population_1m_five_frames_from_a_crowded_state():
+    """BASELINE config 3, EVERY agent, EVERY float, five consecutive frames entered from the state after 100 frames (crowds
+    have formed around the 64 destinations: the crowded-agent kernel, wall contacts and waypoint advances are all in
+    play) — against the oracle stepping the same 1M agents on the host."""
+    from rtsengine_b200 import scenario
+    fx = H.load("map_c3.npz")
+    tables = H.tables_of(fx)
+    a0, paths = scenario.config3_agents(fx, n=1_000_000, seed=1236)
+    a = abi.alloc_agent_arrays(len(a0["r"]), set(H.ALL_FIELDS))
+    for k, v in a0.items():
+        a[k][:] = v
+    upload = [k for k in a if k not in abi.DOWNLOAD_ONLY]
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "tri_idx", "ns_cell", "map_cell", "r_next", "waypoint", "flags")
+    ow = port.OracleWorld(port.default_params(1024, 1024), tables, paths)
+    with make_system(tables, paths, map_cells=(1024, 1024)) as g:
+        g.set_agents({k: a[k] for k in upload})
+        g.update(100)
+        cur = g.communicate(tuple(upload))
+        ref = {k: v.copy() for k, v in a.items()}
+        for k in upload:
+            ref[k][:] = cur[k]
+        # density check: this really is a crowded state
+        cell = (ref["r"][:, 0] // 6).astype(np.int64) * 4096 + (ref["r"][:, 1] // 6).astype(np.int64)
+        assert np.bincount(cell[cell >= 0]).max() >= 12
+        g.set_agents({k: ref[k] for k in upload})      # (flags restart at 0 on both sides)
+        for s in range(5):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(out[k], ref[k], f"frame {100 + s + 1} {k}")
+            assert H.rel_err(out["r"], ref["r"]).max() <= TOL
+
+
+def test_baseline_config5_corridors_120k():
+    """BASELINE configs[4] geometry: the 2048x2048-cell corridor map (64 corridors 6 cells wide between chains of wall
+    blocks, built through the reference's own CDT / Edges code), 120k agents at the full case's density (0.13 per unit²,
+    ~11 neighbours each, counter-flow) in a window over eight corridors and a plaza — 12 frames, every agent, bit-exact
+    against the oracle. One agent in seven is in contact with a wall."""
+    from rtsengine_b200 import scenario
+    fx = H.load("map_c5.npz")
+    tables = H.tables_of(fx)
+    a0, paths = scenario.config5_agents(fx, n=120_000, lo=(200, 2400), hi=(3000, 3700))
+    a = abi.alloc_agent_arrays(len(a0["r"]), set(H.ALL_FIELDS))
+    for k, v in a0.items():
+        a[k][:] = v
+    ref = {k: v.copy() for k, v in a.items()}
+    ow = port.OracleWorld(port.default_params(2048, 2048), tables, paths)
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "tri_idx", "ns_cell", "map_cell", "r_next", "waypoint", "flags")
+    with make_system(tables, paths, map_cells=(2048, 2048)) as g:
+        g.set_agents(a)
+        for s in range(12):
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(out[k], ref[k], f"frame {s} {k}")
+    walls = ow.contact_edges(ref["r"], ref["radius"])[0]
+    assert (walls > 0).mean() > 0.08 and np.isfinite(ref["r"]).all()
+
+
 def test_arrival_rule_matches_oracle_and_tracks_the_reference_cascade():
     """SeekSystem::finalizeSeek (SeekSystem.cpp:235-275) with frame-start snapshot semantics: GPU == oracle bit for bit
     over the whole arrival of a 1 500-agent group (BASELINE config 1 geometry, shortened). The oracle's rule itself is

@@ -154,3 +154,70 @@ def test_agents_outside_the_map_do_not_break_the_edge_row_split():
     finally:
         for sr in ranks:
             sr.close()
+
+
+def test_moving_the_slab_boundary_keeps_the_result_bit_identical():
+    """Rebalancing (rts_slab_row_counts / rts_slab_set_rows): the boundary between two slabs is moved twice during the run;
+    the agents of the rows that change hands migrate through the ordinary buffers, and every frame still equals the
+    single-domain run bit for bit. The row histogram of the two handles adds up to the population."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    n = 30000
+    a, paths = random_world(23, n, tables, 100.0, 1100.0)
+    base = engine.default_params(512, 512)
+    names = ("r", "inertia", "angle", "angle_vel", "state", "tri_idx", "waypoint", "r_next", "flags")
+    with engine.GpuAgentSystem(base) as one:
+        one.upload_map(tables)
+        one.upload_paths(paths)
+        one.set_agents(a)
+        bounds = slabs.partition_rows(a["r"][:, 1], base.ns_ny, base.ns_cell_size, 2)
+        a2 = dict(a)
+        a2["gid"] = np.arange(n, dtype=np.uint32)
+        parts = slabs.split_agents(a2, bounds, base.ns_cell_size, base.ns_ny)
+        ranks = [slabs.SlabRank(engine.default_params(512, 512), bounds, r, 0, cap_migrants=8192, cap_halo=16384) for r in range(2)]
+        L = ranks[0].g.L
+        try:
+            for r, sr in enumerate(ranks):
+                sr.g.upload_map(tables)
+                sr.g.upload_paths(paths)
+                sr.g.set_agents(parts[r])
+            for sr in ranks:
+                sr.g._chk(L.rts_halo_begin(sr.g.h))
+            ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+            for sr in ranks:
+                sr.g._chk(L.rts_step_end(sr.g.h))
+            moves = {3: +2, 7: -3}                      # frame -> rows the boundary moves by
+            for f in range(12):
+                if f in moves:
+                    for sr in ranks:
+                        sr.g.sync()
+                    hist = ranks[0].row_counts().astype(np.int64) + ranks[1].row_counts().astype(np.int64)
+                    assert hist.sum() == n
+                    bounds = [bounds[0], bounds[1] + moves[f], bounds[2]]
+                    changing = hist[min(bounds[1], bounds[1] - moves[f]):max(bounds[1], bounds[1] - moves[f])].sum()
+                    assert 0 < changing < 8192
+                    ranks[0].set_rows(bounds[0], bounds[1])
+                    ranks[1].set_rows(bounds[1], bounds[2])
+                one.update(1)
+                for sr in ranks:
+                    sr.g._chk(L.rts_step_begin(sr.g.h))
+                ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+                for sr in ranks:
+                    sr.g._chk(L.rts_step_end(sr.g.h))
+                ref = one.communicate(names)
+                got = [sr.owned(names) for sr in ranks]
+                gid = np.concatenate([g["gid"] for g in got])
+                assert len(gid) == n and len(np.unique(gid)) == n, "agents are conserved, each owned exactly once"
+                order = np.argsort(gid)
+                finite = np.isfinite(ref["r"]).all(1)
+                for k in names:
+                    merged = np.concatenate([g[k] for g in got])[order]
+                    H.assert_same_bits(merged[finite], ref[k][finite], f"frame {f} {k}")
+                for r, g in enumerate(got):
+                    rows = slabs.row_of(g["r"][:, 1], base.ns_cell_size, base.ns_ny)
+                    ok = np.isfinite(g["r"][:, 1])
+                    if f - 1 not in moves and f not in moves:      # (one frame after a move the hand-over is complete)
+                        assert ((rows[ok] >= bounds[r]) & (rows[ok] < bounds[r + 1])).all()
+        finally:
+            for sr in ranks:
+                sr.close()

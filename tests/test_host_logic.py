@@ -91,3 +91,16 @@ def test_reference_arm_of_the_bench_emits_the_contract_line():
     # the record says what really ran: the reference cannot hold config 3 (5 000-agent cap), so the arm runs its density
     assert j["config"]["same_config_as_gpu_arm"] is False and j["config"]["agents"] in (5000, 200000)
     assert "config-3" in j["config"]["workload"] or "config 3" in j["config"]["workload"]
+
+
+def test_rebalanced_bounds_follow_the_histogram_within_the_migrant_capacity():
+    """slab rebalancing (host side): boundaries move toward the agent-count quantiles, at most max_shift rows, never more
+    rows than whose agents fit the migrant buffers, and not at all inside the tolerance"""
+    import numpy as np
+    from rtsengine_b200 import slabs
+    hist = np.array([100] * 10 + [400] * 10 + [100] * 10)
+    assert slabs.rebalanced_bounds(hist, [0, 10, 20, 30], cap_migrants=2000) == [0, 13, 18, 30]
+    assert slabs.rebalanced_bounds(hist, [0, 10, 20, 30], cap_migrants=500) == [0, 11, 19, 30]     # one 400-agent row fits, two do not
+    assert slabs.rebalanced_bounds(np.array([100] * 30), [0, 10, 20, 30], cap_migrants=500) == [0, 10, 20, 30]
+    b = slabs.rebalanced_bounds(np.array([0] * 29 + [1000]), [0, 10, 20, 30], cap_migrants=10 ** 6, max_shift=100)
+    assert b[0] == 0 and b[-1] == 30 and all(b[i] < b[i + 1] for i in range(3))
