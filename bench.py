@@ -298,6 +298,35 @@ def config4_single_gpu(args, local, K, Wm):
             "repeat_ms_per_step": [m / K for m in ms], "precision": "fast"}
 
 
+def config5_single_gpu(args, local):
+    """BASELINE config 5 on ONE GPU: 4M agents through the corridor map (the crowded-agent kernel and the wall pass at work)"""
+    from rtsengine_b200 import abi, engine, scenario
+    fx = scenario.load_map("map_c5.npz")
+    agents, paths = scenario.config5_agents(fx, n=args.agents5, seed=1238)
+    n5 = len(agents["r"])
+    p = engine.default_params(2048, 2048)
+    p.precision = abi.PRECISION_FAST
+    frames = 100
+    with engine.GpuAgentSystem(p, device=local) as g:
+        g.upload_map(scenario.tables_of(fx))
+        g.upload_paths(paths)
+        g.set_agents(agents)
+        g.update(8, sync=True)
+        g.reset_timings()
+        g.update(frames)
+        g.sync()
+        ms = g.timings().last_step_ms
+        g.set_agents(agents)
+        g.update(8, sync=True)
+        g.set_profiling(True)
+        g.reset_timings()
+        g.update(frames, sync=True)
+        kt = {k: g.kernel_time_ms(k)[0] for k in ("step", "dense", "scan", "reorder")}
+    return {"workload": f"config5: {n5} agents on the 2048x2048-cell corridor map (64 corridors 6 cells wide), counter-flow, one GPU, tolerance mode",
+            "agents": n5, "frames": frames, "value": n5 * frames / (ms * 1e-3), "unit": "agent-updates/s", "ms_per_step": ms / frames,
+            "kernel_ms": kt, "precision": "fast"}
+
+
 def run_gpu(args):
     import torch
     from rtsengine_b200 import abi, engine
@@ -337,6 +366,13 @@ def run_gpu(args):
         except Exception as e:
             c4 = {"value": None, "error": str(e)}
 
+    c5 = None
+    if not args.no_config5:
+        try:
+            c5 = config5_single_gpu(args, local)
+        except Exception as e:
+            c5 = {"value": None, "error": str(e)}
+
     cpu = None
     if not args.no_cpu:
         try:
@@ -357,7 +393,7 @@ def run_gpu(args):
                    "l2_policy": f"inputs larger than L2: {n} agents x ~190 B touched per frame across ping-pong buffers "
                                 f"({n * 190 / 1e6:.0f} MB vs 126 MB L2); no explicit flush"},
         "repeat_ms_per_step": head["repeat_ms_per_step"],
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline, "config4_1gpu": c4,
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": head["launches"], "roofline": roofline, "config4_1gpu": c4, "config5_1gpu": c5,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
@@ -446,6 +482,8 @@ def main():
     ap.add_argument("--precision", type=int, default=1, choices=[0, 1], help="headline arithmetic: 1 = tolerance mode, 0 = bit-exact mode")
     ap.add_argument("--repeats", type=int, default=5, help="repetitions of the timed window (median reported)")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 leg")
+    ap.add_argument("--agents5", type=int, default=4_000_000, help="population of the config-5 leg")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

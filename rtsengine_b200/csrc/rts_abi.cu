@@ -1227,14 +1227,15 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     if (!h) return RTS_E_ARG;
     if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_step", "rts_upload_map has not been called");
     CU(cudaSetDevice(h->device));
-    CU(cudaEventRecord(h->ev0, h->stream));
     uint32_t done = 0;
-    // (not for slab handles: capturing ncclSend/ncclRecv into the graph measured slower than launching frame by frame)
+    bool ev0_recorded = false;
     // (slab handles: only with the peer exchange — every node is a kernel; capturing ncclSend/ncclRecv measured slower than
     //  launching frame by frame)
     if (h->use_graph && !h->profiling && (!h->multi || h->graph_slabs || h->SL.peer_mode) && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
-        if (!h->graph2[par] || h->graph_n[par] != h->n) {
+        // (a slab handle's kernels take the live count from the device and cover fixed slot capacities: its graph does not
+        //  depend on h->n, which rts_sync refreshes with a different value after every frame)
+        if (!h->graph2[par] || (!h->multi && h->graph_n[par] != h->n)) {
             int32_t rc = build_graph(h);
             if (rc != RTS_OK) return rc;
         }
@@ -1243,12 +1244,15 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
             const int32_t rc = join_walk(h);
             if (rc != RTS_OK) return rc;
         }
+        CU(cudaEventRecord(h->ev0, h->stream));   // (after a possible graph build: capture is host work, the device idles)
+        ev0_recorded = true;
         for (; done + GRAPH_FRAMES <= n_steps; done += GRAPH_FRAMES) {
             CU(cudaGraphLaunch(h->graph2[par], h->stream));
             h->launches += h->graph_launches;
             if (deferred_walk) { h->walkq_pending = true; h->walkq_parity = par ^ 1; }   // the last frame's queue
         }
     }
+    if (!ev0_recorded) CU(cudaEventRecord(h->ev0, h->stream));
     for (; done < n_steps; ++done) {
         const int32_t rc = launch_frame(h);
         if (rc != RTS_OK) return rc;

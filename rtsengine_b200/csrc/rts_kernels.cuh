@@ -46,13 +46,18 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 constexpr int FAST_BLOCK = RTS_FAST_BLOCK;             // threads per CTA of the tolerance-mode k_step (no shared memory: registers set the occupancy)
 constexpr int FAST_MIN_BLOCKS = RTS_FAST_MIN_BLOCKS;
 #ifndef RTS_FAST_DENSE_CAND
-#define RTS_FAST_DENSE_CAND 64
+#define RTS_FAST_DENSE_CAND 256
 #endif
 constexpr uint32_t FAST_DENSE_CAND = RTS_FAST_DENSE_CAND;   // tolerance mode: agents with more CANDIDATES than this (slots in their 3x3 fine
-                                                            // cells; ~12 at config-3 density) are handed to k_step_dense, where
-                                                            // FAST_DENSE_LANES lanes share one agent's candidates
+                                                            // cells; ~12 at config-3 density, ~52 in the corridors of config 5) are
+                                                            // handed to k_step_dense_fast, where FAST_DENSE_LANES lanes share one agent's
+                                                            // candidates. One thread per agent is the efficient form — neighbouring
+                                                            // slots are equally crowded, so warps stay converged — and the hand-over
+                                                            // only has to bound the longest single thread (measured: 64 -> 256 takes
+                                                            // config 5 from 0.85 to 0.69 ms per frame and config 3's late frames from
+                                                            // 0.122 to 0.107)
 #ifndef RTS_FAST_DENSE_LANES
-#define RTS_FAST_DENSE_LANES 8
+#define RTS_FAST_DENSE_LANES 16
 #endif
 constexpr uint32_t FAST_DENSE_LANES = RTS_FAST_DENSE_LANES;
 #ifndef RTS_DENSE_MIN

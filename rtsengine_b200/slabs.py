@@ -371,6 +371,75 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
                     f"({world} config-3 tiles), every agent, bitwise"}
 
 
+def _config5_case(dist, torch, engine, rank, world, local, n5, precision, frames, chunk, reserved5=0):
+    """BASELINE config 5: 4M agents funnelled through the corridor map, `world` slabs, counter-flow; the crowd drains
+    unevenly, so every `chunk` frames the per-row agent counts are all-reduced and the slab boundaries follow the quantiles
+    (rebalanced_bounds -> rts_slab_set_rows). Device time of the chunks, max over ranks; the re-binning that a boundary move
+    costs is reported separately (host wall clock)."""
+    from . import scenario
+    fx = scenario.load_map("map_c5.npz")
+    agents, paths = scenario.config5_agents(fx, n=n5, seed=1238)
+    agents["gid"] = np.arange(n5, dtype=np.uint32)
+    nx, ny = (int(v) for v in fx["n_cells"])
+    base = engine.default_params(nx, ny)
+    base.precision = precision
+    base.reserved[5] = reserved5
+    bounds = partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
+    parts = split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
+    per_unit_height = n5 / (ny * 5.0)
+    # the crowd is far from uniform (a slab boundary can run along a jammed corridor): capacities for 25x the mean density in
+    # the halo band, and for one whole physics row of agents at 4x the mean as migrants (rebalancing moves whole rows)
+    cap_halo = int(max(65536, 25 * per_unit_height * halo_width(base.r_max2)))
+    cap_mig = int(max(65536, 4 * per_unit_height * base.ns_cell_size))
+    sr = SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
+    uid = [make_unique_id(sr.g.L) if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sr.init_comm(uid[0])
+    sr.g.upload_map(scenario.tables_of(fx))
+    sr.g.upload_paths(paths)
+    sr.g.set_agents(parts[rank])
+    sr.halo_refresh()
+    sr.g.update(8, sync=True)
+    dev_ms, moves, t_reb, imbalance = 0.0, 0, 0.0, []
+    done = 0
+    while done < frames:
+        k = min(chunk, frames - done)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sr.g.reset_timings()
+        sr.g.update(k)
+        sr.g.sync()
+        t = torch.tensor([sr.g.timings().last_step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms += float(t.item())
+        done += k
+        if world > 1 and done < frames:
+            t0 = time.perf_counter()
+            hist = torch.from_numpy(sr.row_counts().astype(np.int64)).cuda()
+            dist.all_reduce(hist)
+            hist = hist.cpu().numpy()
+            cum = np.concatenate([[0], np.cumsum(hist)])
+            owned = np.diff(cum[bounds])
+            imbalance.append(float(owned.max() / max(owned.mean(), 1)))
+            new = rebalanced_bounds(hist, bounds, cap_mig)
+            if new != bounds:
+                sr.set_rows(new[rank], new[rank + 1])
+                bounds = new
+                moves += 1
+            t_reb += time.perf_counter() - t0
+    own = sr.owned(("r",))
+    cnt = torch.tensor([len(own["gid"])], device="cuda", dtype=torch.int64)
+    dist.all_reduce(cnt)
+    res = {"workload": f"config5: {n5} agents on the 2048x2048-cell corridor map (64 corridors 6 cells wide, 1 890 wall blocks), counter-flow, "
+                       f"{world} y-slabs re-balanced every {chunk} frames", "agents": n5, "frames": frames,
+           "value": n5 * frames / (dev_ms * 1e-3), "unit": "agent-updates/s", "ms_per_step": dev_ms / frames,
+           "rebalance": {"every_frames": chunk, "boundary_moves": moves, "host_s_total": t_reb, "max_over_mean_owned": imbalance,
+                         "slab_rows_final": bounds},
+           "conservation": {"agents_after": int(cnt.item()), "agents_before": n5}, "precision": PRECISION_LABEL[precision]}
+    sr.close()
+    return res
+
+
 def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     """N>1 leg of bench.py.
     Headline line (continuity with round 1): WEAK scaling of the N=1 workload — `world` config-3 tiles stacked in y,
@@ -426,6 +495,11 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
                           f"{world} y-slabs; strong scaling — bench.py --gpus 1 reports the same population on one GPU as config4_1gpu")
         c4["precision"] = PRECISION_LABEL[precision]
 
+    # ---- BASELINE config 5: dense corridors, slabs re-balanced while the crowd drains
+    c5 = None
+    if not args.no_config5:
+        c5 = _config5_case(dist, torch, engine, rank, world, local, args.agents5, precision, max(K, 100), 25, reserved5)
+
     # ---- the slabs against a single domain, bitwise, over the real exchange
     parity = None
     if not os.environ.get("RTS_BENCH_NO_PARITY"):
@@ -452,7 +526,7 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
             "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "traffic": None, "peak_source": peak_src},
-            "config4": c4, "parity_vs_single_domain": parity,
+            "config4": c4, "config5": c5, "parity_vs_single_domain": parity,
             "cpu_baseline": None,
         }
         print(json.dumps(line))
