@@ -98,6 +98,14 @@ typedef struct RtsParams {
          cancel each other (error bounded by 2e-6 of the sum of the term magnitudes). Results are not
          reproducible bit for bit from run to run (the memory order within a fine cell comes from atomics). */
     uint32_t precision;
+    /* Alignment term (Reynolds velocity matching) — an EXTENSION, off by default and in every parity run: the reference
+       carries the ALIGN multiplier (UI.cpp:124), the radius RALLIGN (core.h:97) and the per-neighbour velocity difference
+       InteractionData::dv (ECS.h:473-483), but the code that would use them is commented out (PhysicsSystem.cpp:87-91).
+       With enable_alignment = 1, for a MOVING agent i:  inertia_vel += mul_align * mean(v_j - v_i)  over the physics
+       neighbours j that are MOVING and satisfy x > r_collision^2 / ralign^2 (the predicate of the commented code), v = the
+       merged velocity of the previous frame. Single-domain handles that keep the per-step velocity only. */
+    uint32_t enable_alignment;
+    float ralign; /* 50, src/core.h:97 */
 } RtsParams;
 enum { RTS_PRECISION_EXACT = 0, RTS_PRECISION_FAST = 1 };
 
@@ -206,6 +214,24 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
    Triangulation::last_found_tri_ind_ on entry (Triangulation.h:147; it only matters when the first cell centre lies on a
    triangle edge). cell2tri_out (host, tri_nx*tri_ny entries) may be NULL. */
 int32_t rts_build_cell_grid(RtsHandle h, uint32_t last_found_tri, uint32_t* cell2tri_out);
+/* replaces: the SAME hook after ONE building insert (Game.cpp:38-48 -> MapGrid.cpp:1095-1312): the CDT changes in a small
+   neighbourhood and eight walls join eight lines of the edge finders; only that travels instead of the whole table set.
+     n_tris_total                      size of Triangulation::triangles_ after the insert (>= before: inserts only append)
+     tri_indices / tri_records [n_changed]   every triangle whose record differs from what the handle holds, incl. all new ones
+     line_orient / line_index / line_counts [n_lines_changed], line_edges   the COMPLETE new content of every wall line that
+                                       changed (edge_array2_[line] after the re-sort, MapGrid.cpp:1277-1303), concatenated
+     last_found_tri                    Triangulation::last_found_tri_ind_ (only matters if cache cell 0 is affected)
+   The handle patches the triangle table, appends the changed lines to its wall pool, rebuilds the scan lists of the cache
+   cells the old and new records touch and re-runs Triangulation::updateCellGrid for that band of cache rows — the
+   cell -> triangle cache stays identical to the reference's full rebuild. RTS_E_CAPACITY: the slack of the device tables
+   is used up, call rts_upload_map. */
+int32_t rts_update_map_region(RtsHandle h, uint32_t n_tris_total, const uint32_t* tri_indices, const RtsTriangle* tri_records,
+                              uint32_t n_changed, const uint32_t* line_orient, const uint32_t* line_index, const uint32_t* line_counts,
+                              const RtsEdge* line_edges, uint32_t n_lines_changed, uint32_t last_found_tri);
+/* host-to-device bytes of the last rts_upload_map / rts_update_map_region call, and of the last full rts_upload_map */
+int32_t rts_map_upload_bytes(RtsHandle h, uint64_t* last_call, uint64_t* last_full_upload);
+/* the handle's current cell -> triangle cache (tri_nx * tri_ny entries), without rebuilding it */
+int32_t rts_get_cell_grid(RtsHandle h, uint32_t* cell2tri_out);
 int32_t rts_upload_unit_types(RtsHandle h, const RtsUnitType* types, uint32_t n_types);
 /* replaces: PathFinder2::setPathOfAgent writing windows into PathFinderComponents (PathFinder2.cpp:326-380) */
 int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths);

@@ -326,6 +326,12 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
     uint8_t* s0 = (uint8_t*)malloc(n ? n : 1);
     memcpy(r0, a->r, sizeof(float) * 2 * n);
     memcpy(s0, a->state, n);
+    /* alignment extension (RtsParams.enable_alignment): neighbours see the merged velocity of the previous frame */
+    float* v0 = NULL;
+    if (P->enable_alignment && a->vel) {
+        v0 = (float*)malloc(sizeof(float) * 2 * (n ? n : 1));
+        memcpy(v0, a->vel, sizeof(float) * 2 * n);
+    }
 
     /* ---- arrival (SeekSystem::finalizeSeek, SeekSystem.cpp:235-275) with frame-start snapshot semantics: see
        RtsParams.enable_arrival. stop[i] = agent i stops this frame. The cone rule (neighboursInFrontReachedEnd, :153-179)
@@ -399,8 +405,8 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
             }
         cells[ncells++] = ci;                   /* centre last, Strategy.cpp:34 */
 
-        v2 repulsion = V(0, 0), push = V(0, 0), scatter = V(0, 0), dr_nn = V(0, 0);
-        float n_neighbours = 0;
+        v2 repulsion = V(0, 0), push = V(0, 0), scatter = V(0, 0), dr_nn = V(0, 0), align = V(0, 0);
+        float n_neighbours = 0, n_align = 0;
         for (int c = 0; c < ncells; ++c) {
             for (uint32_t k = g.cell_start[cells[c]]; k < g.cell_start[cells[c] + 1]; ++k) {
                 const uint32_t j = g.cell_items[k];
@@ -423,12 +429,18 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
                     dr_nn = vadd(dr_nn, dr);
                     n_neighbours++;
                 }
+                /* extension: the predicate of the commented-out block PhysicsSystem.cpp:87-91 (without the group test) */
+                if (v0 && state_i == RTS_MOVING && state_j == RTS_MOVING && x > r_collision_sq / (P->ralign * P->ralign)) {
+                    align = vadd(align, vsub(V(v0[2 * j], v0[2 * j + 1]), V(v0[2 * i], v0[2 * i + 1])));
+                    n_align++;
+                }
             }
         }
         dr_nn = vdiv(dr_nn, n_neighbours);
         if (n_neighbours > 1) scatter = vmul(vdiv(dr_nn, vnorm(dr_nn)), ut->max_speed);
         v2 inertia = V(a->inertia[2 * i], a->inertia[2 * i + 1]);
         inertia = vadd(inertia, vadd(vadd(vmul(repulsion, P->mul_repulse), vmul(push, P->mul_push)), vmul(scatter, P->mul_scatter)));
+        if (v0 && n_align > 0) inertia = vadd(inertia, vmul(vdiv(align, n_align), P->mul_align));
 
         /* ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (vel is 0 on entry) ---- */
         v2 vp = V(0, 0);
@@ -539,7 +551,7 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
         if (a->map_cell) a->map_cell[i] = (uint32_t)coord_to_cell(r_new.x, r_new.y, P->map_nx, P->map_ny, P->map_cell_size);
         if (a->flags) a->flags[i] = flags;
     }
-    free(r0); free(s0); free(cell_of); free(g.cell_start); free(g.cell_items); free(stop);
+    free(v0); free(r0); free(s0); free(cell_of); free(g.cell_start); free(g.cell_items); free(stop);
     return rc;
 }
 
@@ -580,7 +592,7 @@ void rts_oracle_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
     p->mul_push = 0.1f; p->mul_repulse = 1.f; p->mul_scatter = 0.1f; p->mul_align = 1.f; p->mul_seek = 1.f;
     p->mul_decay = 1.f; p->mul_velocity = 2.f;
     p->dt = (float)(1. / 60.f); /* constexpr float dt = 1. / 60.f, ECS.h:18 */
-    p->rhard = 3.f; p->rscatter = 50.f; p->sys_max_speed = 25.f;
+    p->rhard = 3.f; p->rscatter = 50.f; p->sys_max_speed = 25.f; p->ralign = 50.f;
     p->finish_angle = 36; p->finish_radius = 50; p->finish_n_steps = 1; p->finish_cone_len = 10;
     p->enable_arrival = 0; p->walk_all = 1;
     p->slab_row_lo = 0; p->slab_row_hi = p->ns_ny;

@@ -34,6 +34,7 @@ class RtsParams(C.Structure):
         ("slab_row_lo", C.c_int32), ("slab_row_hi", C.c_int32),
         ("reserved", C.c_uint32 * 6),
         ("precision", C.c_uint32),
+        ("enable_alignment", C.c_uint32), ("ralign", C.c_float),
     ]
 
 

@@ -51,6 +51,15 @@ struct RtsContext {
     std::string err;
     // owned device allocations of the tables
     std::vector<void*> table_allocs, path_allocs, type_allocs;
+    // host mirrors + writable device aliases of the map tables: rts_update_map_region patches them in place
+    std::vector<RtsTriangle> tris_host;
+    std::vector<uint2> line_se_host, scan_se_host;
+    std::vector<uint32_t> wall_bits_host;
+    uint32_t tri_cap = 0, edge_pool_cap = 0, edge_pool_used = 0, scan_pool_cap = 0, scan_pool_used = 0, scan_large_cap = 0, scan_outer_cap = 0;
+    int4* tris_w = nullptr; uint2* line_se_w = nullptr; float4* edge_ft_w = nullptr; float* edge_l_w = nullptr;
+    uint2* scan_se_w = nullptr; uint32_t* scan_list_w = nullptr; uint32_t* scan_large_w = nullptr; uint32_t* scan_outer_w = nullptr;
+    uint32_t* wall_bits_w = nullptr;
+    uint64_t upload_bytes_last = 0, upload_bytes_full = 0;   // H2D bytes of the last map call / of the last full rts_upload_map
     std::vector<void*> agent_allocs;
     // staging for upload / download (caller order), sized to cap
     Staging S{};
@@ -416,6 +425,9 @@ void launch_step_interior(RtsContext* h) {
     if (split) {   // (exact mode only, see split_frame)
         if (h->keep_vel) k_step<true, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
         else k_step<false, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
+    } else if (nb && h->P.enable_alignment) {   // extension: single-domain handles that keep the velocity (checked by check_params)
+        if (h->fast) k_step<true, false, true, 0, true><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
+        else k_step<true, false, false, 0, true><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
     } else if (nb) {
 #define LAUNCH_STEP(KV, MU, FA) k_step<KV, MU, FA><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp)
         const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->fast ? 1 : 0);
@@ -570,7 +582,7 @@ void rts_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
     p->mul_push = 0.1f; p->mul_repulse = 1.f; p->mul_scatter = 0.1f; p->mul_align = 1.f; p->mul_seek = 1.f;
     p->mul_decay = 1.f; p->mul_velocity = 2.f;
     p->dt = (float)(1. / 60.f);
-    p->rhard = 3.f; p->rscatter = 50.f; p->sys_max_speed = 25.f;
+    p->rhard = 3.f; p->rscatter = 50.f; p->sys_max_speed = 25.f; p->ralign = 50.f;
     p->finish_angle = 36; p->finish_radius = 50; p->finish_n_steps = 1; p->finish_cone_len = 10;
     p->enable_arrival = 0; p->walk_all = 1;
     p->slab_row_lo = 0; p->slab_row_hi = p->ns_ny;
@@ -601,6 +613,9 @@ static int32_t check_params(RtsContext* h, const RtsParams* p) {
     if (p->ns_nx > 8192 || p->ns_ny > 65536)   // key2.y packs the cell as 13 + 16 bits (pack_cs)
         return h->fail(RTS_E_ARG, "params", "physics grid is wider than 8192 or taller than 65536 cells");
     if (p->precision > RTS_PRECISION_FAST) return h->fail(RTS_E_ARG, "params", "unknown precision mode");
+    if (p->enable_alignment && (h->multi || p->reserved[0] != 0))
+        return h->fail(RTS_E_STATE, "params", "enable_alignment needs a single-domain handle that keeps the per-step velocity (halo records carry no velocity)");
+    if (p->enable_alignment && !(p->ralign > 0)) return h->fail(RTS_E_ARG, "params", "ralign must be positive");
     if (p->enable_arrival && h->multi)
         return h->fail(RTS_E_STATE, "params", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's finished "
                                               "area and the stop requests of ghost agents across slabs (run arrival on a single-domain handle)");
@@ -737,19 +752,22 @@ int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
 
 // Triangulation::updateCellGrid on the device (see k_cellgrid_classify): fills the handle's cell -> triangle cache from
 // the uploaded triangles
-int32_t build_cell_grid(RtsContext* h, uint32_t last_found) {
+int32_t build_cell_grid(RtsContext* h, uint32_t last_found, uint32_t z_lo = 0, uint32_t z_hi = 0xFFFFFFFFu) {
     const uint32_t n_cells = (uint32_t)h->P.tri_nx * (uint32_t)h->P.tri_ny;
+    z_hi = std::min(z_hi, n_cells);
+    if (z_lo >= z_hi) return RTS_OK;
+    const uint32_t span = z_hi - z_lo;
     uint32_t* first = nullptr;
     uint8_t* amb = nullptr;
-    CU(cudaMalloc(&first, sizeof(uint32_t) * (size_t)n_cells));
-    if (cudaMalloc(&amb, n_cells) != cudaSuccess) { cudaFree(first); return h->fail(RTS_E_CUDA, "build_cell_grid", "out of device memory"); }
-    const uint32_t nb = blocks_for(n_cells, 128);
+    CU(cudaMalloc(&first, sizeof(uint32_t) * (size_t)span));
+    if (cudaMalloc(&amb, span) != cudaSuccess) { cudaFree(first); return h->fail(RTS_E_CUDA, "build_cell_grid", "out of device memory"); }
+    const uint32_t nb = blocks_for(span, 128);
     if (h->M.coords_fit_i32) {
-        k_cellgrid_classify<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb);
-        k_cellgrid_resolve<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb);
+        k_cellgrid_classify<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb, z_lo, z_hi);
+        k_cellgrid_resolve<false><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb, z_lo, z_hi);
     } else {
-        k_cellgrid_classify<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb);
-        k_cellgrid_resolve<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb);
+        k_cellgrid_classify<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, h->c2t_dev, first, amb, z_lo, z_hi);
+        k_cellgrid_resolve<true><<<nb, 128, 0, h->stream>>>(h->P, h->M, last_found, h->c2t_dev, first, amb, z_lo, z_hi);
     }
     h->launches += 2;
     const cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -760,6 +778,48 @@ int32_t build_cell_grid(RtsContext* h, uint32_t last_found) {
     return RTS_OK;
 }
 
+extern "C++" {
+namespace {
+inline int4 tri_word(const RtsTriangle& T, int k) {
+    if (k == 0) return make_int4(T.vx[0], T.vy[0], T.vx[1], T.vy[1]);
+    if (k == 1) return make_int4(T.vx[2], T.vy[2], (int)T.neighbours[0], (int)T.neighbours[1]);
+    return make_int4((int)T.neighbours[2], T.is_constrained[0] | (T.is_constrained[1] << 1) | (T.is_constrained[2] << 2) | (T.type << 8), 0, 0);
+}
+// cache cells a triangle's bounding box touches (clipped to the grid; x0 > x1 = entirely outside)
+struct CellBox { int x0, x1, y0, y1; };
+inline CellBox tri_cells(const RtsParams& P, const RtsTriangle& T) {
+    auto range = [&](int32_t lo, int32_t hi, int32_t n, int& c0, int& c1) {
+        c0 = std::max((int)std::floor((float)lo / P.tri_cell_size), 0);
+        c1 = std::min((int)std::floor((float)hi / P.tri_cell_size), n - 1);
+    };
+    CellBox b;
+    range(std::min({T.vx[0], T.vx[1], T.vx[2]}), std::max({T.vx[0], T.vx[1], T.vx[2]}), P.tri_nx, b.x0, b.x1);
+    range(std::min({T.vy[0], T.vy[1], T.vy[2]}), std::max({T.vy[0], T.vy[1], T.vy[2]}), P.tri_ny, b.y0, b.y1);
+    return b;
+}
+inline bool tri_is_outer(const RtsParams& P, const RtsTriangle& T) {
+    const float gw = P.tri_nx * P.tri_cell_size, gh = P.tri_ny * P.tri_cell_size;
+    const int32_t xmin = std::min({T.vx[0], T.vx[1], T.vx[2]}), xmax = std::max({T.vx[0], T.vx[1], T.vx[2]});
+    const int32_t ymin = std::min({T.vy[0], T.vy[1], T.vy[2]}), ymax = std::max({T.vy[0], T.vy[1], T.vy[2]});
+    return xmin < 0 || ymin < 0 || (float)xmax > gw || (float)ymax > gh;
+}
+inline bool box_is_large(const CellBox& b) { return (uint64_t)(b.x1 - b.x0 + 1) * (uint64_t)(b.y1 - b.y0 + 1) > SCAN_LARGE_CELLS; }
+// wall pre-filter bits an edge sets (see may_touch_wall): every block its bounding box, grown by the reach, touches
+template <class Fn>
+inline void wall_blocks(const RtsParams& P, int32_t bx, int32_t by, float filter_r, float4 ft, float l, Fn fn) {
+    const float wall_block = P.map_cell_size;
+    const float x0 = ft.x, y0 = ft.y, x1 = x0 + ft.z * l, y1 = y0 + ft.w * l;
+    const float reach = filter_r + 1.0f;
+    const int ix0 = std::max(0, (int)std::floor((std::min(x0, x1) - reach) / wall_block));
+    const int ix1 = std::min(bx - 1, (int)std::floor((std::max(x0, x1) + reach) / wall_block));
+    const int iy0 = std::max(0, (int)std::floor((std::min(y0, y1) - reach) / wall_block));
+    const int iy1 = std::min(by - 1, (int)std::floor((std::max(y0, y1) + reach) / wall_block));
+    for (int iy = iy0; iy <= iy1; ++iy)
+        for (int ix = ix0; ix <= ix1; ++ix) fn((size_t)iy * bx + ix);
+}
+}  // namespace
+}  // extern "C++"
+
 int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri, const RtsWallTable* walls) {
     if (!h) return RTS_E_ARG;
     if (!tris || !n_tris || !walls) return h->fail(RTS_E_ARG, "rts_upload_map", "null table");
@@ -769,44 +829,46 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     free_all(h->table_allocs);
     h->map_ready = false;
     const RtsParams& P = h->P;
+    uint64_t bytes = 0;
     const uint32_t expect[4] = {(uint32_t)P.map_ny + 1, (uint32_t)(P.map_nx + P.map_ny) + 1, (uint32_t)P.map_nx + 1,
                                 (uint32_t)(P.map_nx + P.map_ny) + 1};
     for (int o = 0; o < 4; ++o) {
         if (!walls->line_offsets[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "null line_offsets");
         if (walls->n_lines[o] != expect[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "n_lines does not match the MapGrid (Edges.cpp:6-19)");
     }
-    // triangles -> 3 x int4
+    // triangles -> 3 x int4 (device capacity with slack: rts_update_map_region appends the triangles a CDT insert creates)
     std::vector<int4> t4(3 * (size_t)n_tris);
     for (uint32_t t = 0; t < n_tris; ++t) {
         const RtsTriangle& T = tris[t];
         for (int k = 0; k < 3; ++k)
             if (T.neighbours[k] != 0xFFFFFFFFu && T.neighbours[k] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "triangle neighbour out of range");
-        t4[3 * t + 0] = make_int4(T.vx[0], T.vy[0], T.vx[1], T.vy[1]);
-        t4[3 * t + 1] = make_int4(T.vx[2], T.vy[2], (int)T.neighbours[0], (int)T.neighbours[1]);
-        t4[3 * t + 2] = make_int4((int)T.neighbours[2], T.is_constrained[0] | (T.is_constrained[1] << 1) | (T.is_constrained[2] << 2) | (T.type << 8), 0, 0);
+        for (int k = 0; k < 3; ++k) t4[3 * t + k] = tri_word(T, k);
     }
     const size_t n_tri_cells = (size_t)P.tri_nx * P.tri_ny;
     for (size_t c = 0; cell2tri && c < n_tri_cells; ++c)
         if (cell2tri[c] != 0xFFFFFFFFu && cell2tri[c] >= n_tris) return h->fail(RTS_E_ARG, "rts_upload_map", "cell2tri entry out of range");
+    h->tris_host.assign(tris, tris + n_tris);
+    h->tri_cap = n_tris + n_tris / 2 + 4096;
     int4* d_tris = nullptr; uint32_t* d_c2t = nullptr;
     int32_t rc;
-    if ((rc = dev_alloc(h, &d_tris, t4.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_tris, 3 * (size_t)h->tri_cap, h->table_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_c2t, n_tri_cells, h->table_allocs)) != RTS_OK) return rc;
     CU(cudaMemcpyAsync(d_tris, t4.data(), t4.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-    if (cell2tri) CU(cudaMemcpyAsync(d_c2t, cell2tri, n_tri_cells * 4, cudaMemcpyHostToDevice, h->stream));
-    // walls -> one CSR
-    std::vector<uint32_t> off;
+    bytes += t4.size() * sizeof(int4);
+    if (cell2tri) { CU(cudaMemcpyAsync(d_c2t, cell2tri, n_tri_cells * 4, cudaMemcpyHostToDevice, h->stream)); bytes += n_tri_cells * 4; }
+    // walls -> per line {first, end} into one edge pool
+    std::vector<uint2> se;
     std::vector<float4> ft;
     std::vector<float> el;
     MapDev& M = h->M;
     for (int o = 0; o < 4; ++o) {
-        M.line_base[o] = (uint32_t)off.size();
-        M.edge_base[o] = (uint32_t)ft.size();
+        M.line_base[o] = (uint32_t)se.size();
         M.n_lines[o] = walls->n_lines[o];
         const uint32_t* lo = walls->line_offsets[o];
-        for (uint32_t l = 0; l <= walls->n_lines[o]; ++l) {
-            if (l && lo[l] < lo[l - 1]) return h->fail(RTS_E_ARG, "rts_upload_map", "line_offsets not monotone");
-            off.push_back(lo[l]);
+        const uint32_t base = (uint32_t)ft.size();
+        for (uint32_t l = 0; l < walls->n_lines[o]; ++l) {
+            if (lo[l + 1] < lo[l]) return h->fail(RTS_E_ARG, "rts_upload_map", "line_offsets not monotone");
+            se.push_back(make_uint2(base + lo[l], base + lo[l + 1]));
         }
         const uint32_t ne = lo[walls->n_lines[o]];
         if (ne && !walls->edges[o]) return h->fail(RTS_E_ARG, "rts_upload_map", "null edges");
@@ -816,96 +878,88 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
             el.push_back(E.l);
         }
     }
-    uint32_t* d_off; float4* d_ft; float* d_el;
-    if ((rc = dev_alloc(h, &d_off, off.size(), h->table_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_ft, ft.size(), h->table_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_el, el.size(), h->table_allocs)) != RTS_OK) return rc;
-    CU(cudaMemcpyAsync(d_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    h->line_se_host = se;
+    h->edge_pool_used = (uint32_t)ft.size();
+    h->edge_pool_cap = h->edge_pool_used + h->edge_pool_used / 2 + 4096;
+    uint2* d_se = nullptr; float4* d_ft = nullptr; float* d_el = nullptr;
+    if ((rc = dev_alloc(h, &d_se, se.size(), h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_ft, h->edge_pool_cap, h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_el, h->edge_pool_cap, h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_se, se.data(), se.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+    bytes += se.size() * sizeof(uint2);
     if (!ft.empty()) {
         CU(cudaMemcpyAsync(d_ft, ft.data(), ft.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(d_el, el.data(), el.size() * 4, cudaMemcpyHostToDevice, h->stream));
+        bytes += ft.size() * 20;
     }
     // conservative wall pre-filter bitmap (see may_touch_wall): one bit per MapGrid cell, set if a wall can lie within
     // filter_r (+1) of any point of the cell — the bounding box of every wall, grown by that reach
     const float filter_r = 8.0f;
-    const float wall_block = P.map_cell_size;
-    const int32_t bx = (int32_t)std::ceil(P.map_nx * P.map_cell_size / wall_block) + 1;
-    const int32_t by = (int32_t)std::ceil(P.map_ny * P.map_cell_size / wall_block) + 1;
-    std::vector<uint32_t> bits(((size_t)bx * by + 31) / 32, 0u);
-    for (size_t e = 0; e < ft.size(); ++e) {
-        const float x0 = ft[e].x, y0 = ft[e].y, x1 = x0 + ft[e].z * el[e], y1 = y0 + ft[e].w * el[e];
-        const float reach = filter_r + 1.0f;
-        const int ix0 = std::max(0, (int)std::floor((std::min(x0, x1) - reach) / wall_block));
-        const int ix1 = std::min(bx - 1, (int)std::floor((std::max(x0, x1) + reach) / wall_block));
-        const int iy0 = std::max(0, (int)std::floor((std::min(y0, y1) - reach) / wall_block));
-        const int iy1 = std::min(by - 1, (int)std::floor((std::max(y0, y1) + reach) / wall_block));
-        for (int iy = iy0; iy <= iy1; ++iy)
-            for (int ix = ix0; ix <= ix1; ++ix) {
-                const size_t b = (size_t)iy * bx + ix;
-                bits[b >> 5] |= 1u << (b & 31);
-            }
-    }
-    uint32_t* d_bits;
+    const int32_t bx = (int32_t)std::ceil(P.map_nx * P.map_cell_size / P.map_cell_size) + 1;
+    const int32_t by = (int32_t)std::ceil(P.map_ny * P.map_cell_size / P.map_cell_size) + 1;
+    std::vector<uint32_t>& bits = h->wall_bits_host;
+    bits.assign(((size_t)bx * by + 31) / 32, 0u);
+    for (size_t e = 0; e < ft.size(); ++e) wall_blocks(P, bx, by, filter_r, ft[e], el[e], [&](size_t b) { bits[b >> 5] |= 1u << (b & 31); });
+    uint32_t* d_bits = nullptr;
     if ((rc = dev_alloc(h, &d_bits, bits.size(), h->table_allocs)) != RTS_OK) return rc;
     CU(cudaMemcpyAsync(d_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    // scan lists for findTriangle's linear-scan fallback (see MapDev)
+    bytes += bits.size() * 4;
+    // scan lists for findTriangle's linear-scan fallback (see MapDev): per cache cell the ascending list of the small triangles
+    // whose bounding box touches it
     std::vector<uint32_t> scan_off(n_tri_cells + 1, 0u), scan_list, scan_large, scan_outer;
     {
-        auto cell_range = [&](int32_t lo, int32_t hi, int32_t n, int& c0, int& c1) {
-            c0 = (int)std::floor((float)lo / P.tri_cell_size);
-            c1 = (int)std::floor((float)hi / P.tri_cell_size);
-            c0 = std::max(c0, 0);
-            c1 = std::min(c1, n - 1);
-        };
-        std::vector<int> bx0(n_tris), bx1(n_tris), by0(n_tris), by1(n_tris);
+        std::vector<CellBox> box(n_tris);
         std::vector<uint8_t> large(n_tris, 0);
         for (uint32_t t = 0; t < n_tris; ++t) {
             const RtsTriangle& T = tris[t];
-            {
-                const float gw = P.tri_nx * P.tri_cell_size, gh = P.tri_ny * P.tri_cell_size;
-                const int32_t xmin = std::min({T.vx[0], T.vx[1], T.vx[2]}), xmax = std::max({T.vx[0], T.vx[1], T.vx[2]});
-                const int32_t ymin = std::min({T.vy[0], T.vy[1], T.vy[2]}), ymax = std::max({T.vy[0], T.vy[1], T.vy[2]});
-                if (xmin < 0 || ymin < 0 || (float)xmax > gw || (float)ymax > gh) scan_outer.push_back(t);
-            }
-            cell_range(std::min({T.vx[0], T.vx[1], T.vx[2]}), std::max({T.vx[0], T.vx[1], T.vx[2]}), P.tri_nx, bx0[t], bx1[t]);
-            cell_range(std::min({T.vy[0], T.vy[1], T.vy[2]}), std::max({T.vy[0], T.vy[1], T.vy[2]}), P.tri_ny, by0[t], by1[t]);
-            if (bx0[t] > bx1[t] || by0[t] > by1[t]) continue;   // entirely outside the grid
-            const uint64_t cells = (uint64_t)(bx1[t] - bx0[t] + 1) * (uint64_t)(by1[t] - by0[t] + 1);
-            if (cells > SCAN_LARGE_CELLS) { large[t] = 1; scan_large.push_back(t); continue; }
-            for (int y = by0[t]; y <= by1[t]; ++y)
-                for (int x = bx0[t]; x <= bx1[t]; ++x) scan_off[(size_t)y * P.tri_nx + x + 1]++;
+            if (tri_is_outer(P, T)) scan_outer.push_back(t);
+            box[t] = tri_cells(P, T);
+            if (box[t].x0 > box[t].x1 || box[t].y0 > box[t].y1) continue;   // entirely outside the grid
+            if (box_is_large(box[t])) { large[t] = 1; scan_large.push_back(t); continue; }
+            for (int y = box[t].y0; y <= box[t].y1; ++y)
+                for (int x = box[t].x0; x <= box[t].x1; ++x) scan_off[(size_t)y * P.tri_nx + x + 1]++;
         }
         for (size_t c = 0; c < n_tri_cells; ++c) scan_off[c + 1] += scan_off[c];
         scan_list.resize(scan_off[n_tri_cells]);
         std::vector<uint32_t> fill(scan_off.begin(), scan_off.end() - 1);
         for (uint32_t t = 0; t < n_tris; ++t) {   // ascending t => every cell list is ascending
-            if (large[t] || bx0[t] > bx1[t] || by0[t] > by1[t]) continue;
-            for (int y = by0[t]; y <= by1[t]; ++y)
-                for (int x = bx0[t]; x <= bx1[t]; ++x) scan_list[fill[(size_t)y * P.tri_nx + x]++] = t;
+            if (large[t] || box[t].x0 > box[t].x1 || box[t].y0 > box[t].y1) continue;
+            for (int y = box[t].y0; y <= box[t].y1; ++y)
+                for (int x = box[t].x0; x <= box[t].x1; ++x) scan_list[fill[(size_t)y * P.tri_nx + x]++] = t;
         }
     }
-    uint32_t *d_soff, *d_slist, *d_slarge, *d_souter;
-    if ((rc = dev_alloc(h, &d_souter, scan_outer.size(), h->table_allocs)) != RTS_OK) return rc;
+    h->scan_se_host.resize(n_tri_cells);
+    for (size_t c = 0; c < n_tri_cells; ++c) h->scan_se_host[c] = make_uint2(scan_off[c], scan_off[c + 1]);
+    h->scan_pool_used = (uint32_t)scan_list.size();
+    h->scan_pool_cap = h->scan_pool_used + h->scan_pool_used / 2 + 65536;
+    h->scan_large_cap = (uint32_t)scan_large.size() + 1024;
+    h->scan_outer_cap = (uint32_t)scan_outer.size() + 1024;
+    uint2* d_sse = nullptr; uint32_t *d_slist = nullptr, *d_slarge = nullptr, *d_souter = nullptr;
+    if ((rc = dev_alloc(h, &d_souter, h->scan_outer_cap, h->table_allocs)) != RTS_OK) return rc;
     if (!scan_outer.empty()) CU(cudaMemcpyAsync(d_souter, scan_outer.data(), scan_outer.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    if ((rc = dev_alloc(h, &d_soff, scan_off.size(), h->table_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_slist, scan_list.size(), h->table_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_slarge, scan_large.size(), h->table_allocs)) != RTS_OK) return rc;
-    CU(cudaMemcpyAsync(d_soff, scan_off.data(), scan_off.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = dev_alloc(h, &d_sse, n_tri_cells, h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_slist, h->scan_pool_cap, h->table_allocs)) != RTS_OK) return rc;
+    if ((rc = dev_alloc(h, &d_slarge, h->scan_large_cap, h->table_allocs)) != RTS_OK) return rc;
+    CU(cudaMemcpyAsync(d_sse, h->scan_se_host.data(), n_tri_cells * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
     if (!scan_list.empty()) CU(cudaMemcpyAsync(d_slist, scan_list.data(), scan_list.size() * 4, cudaMemcpyHostToDevice, h->stream));
     if (!scan_large.empty()) CU(cudaMemcpyAsync(d_slarge, scan_large.data(), scan_large.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    bytes += n_tri_cells * sizeof(uint2) + (scan_list.size() + scan_large.size() + scan_outer.size()) * 4;
     // int32 triangle walk is exact iff no product can overflow: |coord| <= 16383 (see tri_sign)
     int32_t cmax = 0;
     for (uint32_t t = 0; t < n_tris; ++t)
         for (int k = 0; k < 3; ++k) cmax = std::max(cmax, std::max(std::abs(tris[t].vx[k]), std::abs(tris[t].vy[k])));
     CU(cudaStreamSynchronize(h->stream));
     M.tris = d_tris; M.n_tris = n_tris; M.cell2tri = d_c2t;
-    M.line_off = d_off; M.edge_ft = d_ft; M.edge_l = d_el;
-    M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r; M.inv_wall_block = 1.0f / wall_block;
+    M.line_se = d_se; M.edge_ft = d_ft; M.edge_l = d_el;
+    M.wall_bits = d_bits; M.wall_bx = bx; M.wall_by = by; M.wall_filter_radius = filter_r; M.inv_wall_block = 1.0f / P.map_cell_size;
     M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
     h->A.n_tris_dev_hint = n_tris;
-    M.scan_off = d_soff; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
+    M.scan_se = d_sse; M.scan_list = d_slist; M.scan_large = d_slarge; M.n_scan_large = (uint32_t)scan_large.size();
     M.scan_outer = d_souter; M.n_scan_outer = (uint32_t)scan_outer.size();
     h->c2t_dev = d_c2t;
+    h->tris_w = d_tris; h->line_se_w = d_se; h->edge_ft_w = d_ft; h->edge_l_w = d_el; h->scan_se_w = d_sse; h->scan_list_w = d_slist;
+    h->scan_large_w = d_slarge; h->scan_outer_w = d_souter; h->wall_bits_w = d_bits;
+    h->upload_bytes_last = h->upload_bytes_full = bytes;
     if (!cell2tri && (rc = build_cell_grid(h, 0u)) != RTS_OK) return rc;   // no host cache given: built here
     h->map_ready = true;
     h->drop_graphs();
@@ -915,6 +969,232 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
         if ((rc = rebin(h)) != RTS_OK) return rc;
         CU(cudaStreamSynchronize(h->stream));
     }
+    return RTS_OK;
+}
+
+// Game::updateTriangulation after ONE building insert (Game.cpp:38-48, MapGrid.cpp:1095-1312): the CDT changed in a small
+// neighbourhood (a few dozen triangle records rewritten or appended), eight walls joined eight lines. Only that travels.
+int32_t rts_update_map_region(RtsHandle h, uint32_t n_tris_total, const uint32_t* tri_indices, const RtsTriangle* tri_records, uint32_t n_changed,
+                              const uint32_t* line_orient, const uint32_t* line_index, const uint32_t* line_counts, const RtsEdge* line_edges,
+                              uint32_t n_lines_changed, uint32_t last_found_tri) {
+    if (!h) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_update_map_region", "rts_upload_map has not been called");
+    if ((n_changed && (!tri_indices || !tri_records)) || (n_lines_changed && (!line_orient || !line_index || !line_counts)))
+        return h->fail(RTS_E_ARG, "rts_update_map_region", "null array");
+    const RtsParams& P = h->P;
+    MapDev& M = h->M;
+    const uint32_t n_old = M.n_tris;
+    if (n_tris_total < n_old) return h->fail(RTS_E_ARG, "rts_update_map_region", "the triangle table cannot shrink (send the whole map)");
+    if (n_tris_total > h->tri_cap) return h->fail(RTS_E_CAPACITY, "rts_update_map_region", "triangle capacity exhausted: call rts_upload_map");
+    // ---- validate, then patch the host mirror of the triangles; the cache cells whose lists / entries can change are those
+    //      the bounding boxes of the old and the new records touch
+    std::vector<uint8_t> seen_new(n_tris_total - n_old, 0);
+    for (uint32_t k = 0; k < n_changed; ++k) {
+        if (tri_indices[k] >= n_tris_total) return h->fail(RTS_E_ARG, "rts_update_map_region", "triangle index out of range");
+        if (tri_indices[k] >= n_old) seen_new[tri_indices[k] - n_old] = 1;
+        for (int e = 0; e < 3; ++e)
+            if (tri_records[k].neighbours[e] != 0xFFFFFFFFu && tri_records[k].neighbours[e] >= n_tris_total)
+                return h->fail(RTS_E_ARG, "rts_update_map_region", "triangle neighbour out of range");
+    }
+    for (uint8_t v : seen_new)
+        if (!v) return h->fail(RTS_E_ARG, "rts_update_map_region", "every appended triangle must be among the changed records");
+    uint64_t edges_new = 0;
+    for (uint32_t k = 0; k < n_lines_changed; ++k) {
+        if (line_orient[k] > 3 || line_index[k] >= M.n_lines[line_orient[k]]) return h->fail(RTS_E_ARG, "rts_update_map_region", "wall line out of range");
+        edges_new += line_counts[k];
+    }
+    if (edges_new && !line_edges) return h->fail(RTS_E_ARG, "rts_update_map_region", "null edges");
+    if (h->edge_pool_used + edges_new > h->edge_pool_cap) return h->fail(RTS_E_CAPACITY, "rts_update_map_region", "wall pool exhausted: call rts_upload_map");
+    CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    CU(cudaStreamSynchronize(h->stream));
+    uint64_t bytes = 0;
+    int rx0 = P.tri_nx, rx1 = -1, ry0 = P.tri_ny, ry1 = -1;   // affected cache cells
+    bool any_large = false, any_outer = false;
+    auto grow = [&](const RtsTriangle& T) {
+        const CellBox b = tri_cells(P, T);
+        if (tri_is_outer(P, T)) any_outer = true;
+        if (b.x0 > b.x1 || b.y0 > b.y1) return;
+        if (box_is_large(b)) { any_large = true; return; }
+        rx0 = std::min(rx0, b.x0); rx1 = std::max(rx1, b.x1); ry0 = std::min(ry0, b.y0); ry1 = std::max(ry1, b.y1);
+    };
+    h->tris_host.resize(n_tris_total);
+    std::vector<int4> t4(3 * (size_t)n_changed);
+    for (uint32_t k = 0; k < n_changed; ++k) {
+        const uint32_t t = tri_indices[k];
+        if (t < n_old) grow(h->tris_host[t]);
+        h->tris_host[t] = tri_records[k];
+        grow(tri_records[k]);
+        for (int w = 0; w < 3; ++w) t4[3 * (size_t)k + w] = tri_word(tri_records[k], w);
+    }
+    // staging in the generic scratch buffer
+    auto stage = [&](const void* src, size_t nbytes, void** dev) -> int32_t {
+        *dev = nullptr;
+        if (!nbytes) return RTS_OK;
+        void* d = nullptr;
+        if (cudaMalloc(&d, nbytes) != cudaSuccess) return h->fail(RTS_E_CUDA, "rts_update_map_region", "out of device memory");
+        if (cudaMemcpyAsync(d, src, nbytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { cudaFree(d); return h->fail(RTS_E_CUDA, "rts_update_map_region", "copy failed"); }
+        bytes += nbytes;
+        *dev = d;
+        return RTS_OK;
+    };
+    std::vector<void*> temps;
+    auto staged = [&](const void* src, size_t nbytes) -> void* {
+        void* d = nullptr;
+        if (stage(src, nbytes, &d) == RTS_OK && d) temps.push_back(d);
+        return d;
+    };
+    int32_t rc = RTS_OK;
+    // ---- triangles
+    if (n_changed) {
+        uint32_t* d_idx = static_cast<uint32_t*>(staged(tri_indices, 4 * (size_t)n_changed));
+        int4* d_val = static_cast<int4*>(staged(t4.data(), t4.size() * sizeof(int4)));
+        if (!d_idx || !d_val) rc = RTS_E_CUDA;
+        else k_scatter_tris<<<blocks_for(n_changed, 128), 128, 0, h->stream>>>(n_changed, d_idx, d_val, h->tris_w);
+    }
+    // ---- walls: every changed line is appended at the end of the pool and the line redirected; new wall bits are OR-ed in
+    if (rc == RTS_OK && n_lines_changed) {
+        std::vector<uint32_t> se_idx;
+        std::vector<uint2> se_val;
+        std::vector<float4> ft;
+        std::vector<float> el;
+        std::vector<uint32_t> bit_idx, bit_val;
+        const RtsEdge* E = line_edges;
+        const uint32_t first = h->edge_pool_used;
+        for (uint32_t k = 0; k < n_lines_changed; ++k) {
+            const uint32_t line = M.line_base[line_orient[k]] + line_index[k];
+            const uint32_t beg = first + (uint32_t)ft.size();
+            for (uint32_t e = 0; e < line_counts[k]; ++e, ++E) {
+                const float4 f = make_float4(E->from_x, E->from_y, E->t_x, E->t_y);
+                ft.push_back(f);
+                el.push_back(E->l);
+                wall_blocks(P, M.wall_bx, M.wall_by, M.wall_filter_radius, f, E->l, [&](size_t b) {
+                    const uint32_t bit = 1u << (b & 31);
+                    if (!(h->wall_bits_host[b >> 5] & bit)) { h->wall_bits_host[b >> 5] |= bit; bit_idx.push_back((uint32_t)(b >> 5)); bit_val.push_back(bit); }
+                });
+            }
+            se_idx.push_back(line);
+            se_val.push_back(make_uint2(beg, beg + line_counts[k]));
+            h->line_se_host[line] = se_val.back();
+        }
+        if (!ft.empty()) {
+            CU(cudaMemcpyAsync(h->edge_ft_w + first, ft.data(), ft.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaMemcpyAsync(h->edge_l_w + first, el.data(), el.size() * 4, cudaMemcpyHostToDevice, h->stream));
+            bytes += ft.size() * 20;
+        }
+        h->edge_pool_used += (uint32_t)ft.size();
+        uint32_t* d_idx = static_cast<uint32_t*>(staged(se_idx.data(), 4 * se_idx.size()));
+        uint2* d_val = static_cast<uint2*>(staged(se_val.data(), 8 * se_val.size()));
+        if (!d_idx || !d_val) rc = RTS_E_CUDA;
+        else k_scatter_u2<<<blocks_for((uint32_t)se_idx.size(), 128), 128, 0, h->stream>>>((uint32_t)se_idx.size(), d_idx, d_val, h->line_se_w);
+        if (rc == RTS_OK && !bit_idx.empty()) {
+            {
+                // several bits of one word may be new: merged on the host, one OR per word on the device
+                std::vector<uint32_t> widx, wval;
+                for (size_t i = 0; i < bit_idx.size(); ++i) {
+                    size_t j = 0;
+                    for (; j < widx.size(); ++j) if (widx[j] == bit_idx[i]) break;
+                    if (j == widx.size()) { widx.push_back(bit_idx[i]); wval.push_back(0u); }
+                    wval[j] |= bit_val[i];
+                }
+                uint32_t* d_wi = static_cast<uint32_t*>(staged(widx.data(), 4 * widx.size()));
+                uint32_t* d_wv = static_cast<uint32_t*>(staged(wval.data(), 4 * wval.size()));
+                if (!d_wi || !d_wv) rc = RTS_E_CUDA;
+                else k_scatter_u32<<<blocks_for((uint32_t)widx.size(), 128), 128, 0, h->stream>>>((uint32_t)widx.size(), d_wi, d_wv, h->wall_bits_w, 1);
+            }
+        }
+    }
+    // ---- scan lists of the affected cells, rebuilt from the mirror and appended to the pool
+    if (rc == RTS_OK && rx0 <= rx1 && ry0 <= ry1) {
+        const int w = rx1 - rx0 + 1, hgt = ry1 - ry0 + 1;
+        std::vector<std::vector<uint32_t>> lists((size_t)w * hgt);
+        for (uint32_t t = 0; t < n_tris_total; ++t) {   // ascending t => ascending lists
+            const CellBox b = tri_cells(P, h->tris_host[t]);
+            if (b.x0 > b.x1 || b.y0 > b.y1 || box_is_large(b)) continue;
+            if (b.x1 < rx0 || b.x0 > rx1 || b.y1 < ry0 || b.y0 > ry1) continue;
+            for (int y = std::max(b.y0, ry0); y <= std::min(b.y1, ry1); ++y)
+                for (int x = std::max(b.x0, rx0); x <= std::min(b.x1, rx1); ++x) lists[(size_t)(y - ry0) * w + (x - rx0)].push_back(t);
+        }
+        std::vector<uint32_t> flat, se_idx;
+        std::vector<uint2> se_val;
+        for (int y = 0; y < hgt; ++y)
+            for (int x = 0; x < w; ++x) {
+                const auto& L = lists[(size_t)y * w + x];
+                const uint32_t cell = (uint32_t)(ry0 + y) * (uint32_t)P.tri_nx + (uint32_t)(rx0 + x);
+                const uint32_t beg = h->scan_pool_used + (uint32_t)flat.size();
+                flat.insert(flat.end(), L.begin(), L.end());
+                se_idx.push_back(cell);
+                se_val.push_back(make_uint2(beg, beg + (uint32_t)L.size()));
+            }
+        if (h->scan_pool_used + flat.size() > h->scan_pool_cap) rc = h->fail(RTS_E_CAPACITY, "rts_update_map_region", "scan-list pool exhausted: call rts_upload_map");
+        else {
+            if (!flat.empty()) {
+                CU(cudaMemcpyAsync(h->scan_list_w + h->scan_pool_used, flat.data(), 4 * flat.size(), cudaMemcpyHostToDevice, h->stream));
+                bytes += 4 * flat.size();
+            }
+            h->scan_pool_used += (uint32_t)flat.size();
+            for (size_t i = 0; i < se_idx.size(); ++i) h->scan_se_host[se_idx[i]] = se_val[i];
+            uint32_t* d_idx = static_cast<uint32_t*>(staged(se_idx.data(), 4 * se_idx.size()));
+            uint2* d_val = static_cast<uint2*>(staged(se_val.data(), 8 * se_val.size()));
+            if (!d_idx || !d_val) rc = RTS_E_CUDA;
+            else k_scatter_u2<<<blocks_for((uint32_t)se_idx.size(), 128), 128, 0, h->stream>>>((uint32_t)se_idx.size(), d_idx, d_val, h->scan_se_w);
+        }
+    }
+    // ---- the few large / outer triangles: their lists are rebuilt whole when one of them changed
+    if (rc == RTS_OK && (any_large || any_outer)) {
+        std::vector<uint32_t> large, outer;
+        for (uint32_t t = 0; t < n_tris_total; ++t) {
+            const RtsTriangle& T = h->tris_host[t];
+            if (tri_is_outer(P, T)) outer.push_back(t);
+            const CellBox b = tri_cells(P, T);
+            if (!(b.x0 > b.x1 || b.y0 > b.y1) && box_is_large(b)) large.push_back(t);
+        }
+        if (large.size() > h->scan_large_cap || outer.size() > h->scan_outer_cap) rc = h->fail(RTS_E_CAPACITY, "rts_update_map_region", "large-triangle list exhausted: call rts_upload_map");
+        else {
+            if (!large.empty()) CU(cudaMemcpyAsync(h->scan_large_w, large.data(), 4 * large.size(), cudaMemcpyHostToDevice, h->stream));
+            if (!outer.empty()) CU(cudaMemcpyAsync(h->scan_outer_w, outer.data(), 4 * outer.size(), cudaMemcpyHostToDevice, h->stream));
+            bytes += 4 * (large.size() + outer.size());
+            M.n_scan_large = (uint32_t)large.size();
+            M.n_scan_outer = (uint32_t)outer.size();
+        }
+    }
+    if (rc == RTS_OK) {
+        int32_t cmax = M.coords_fit_i32 ? 0 : 16384;
+        for (uint32_t k = 0; k < n_changed; ++k)
+            for (int e = 0; e < 3; ++e) cmax = std::max(cmax, std::max(std::abs(tri_records[k].vx[e]), std::abs(tri_records[k].vy[e])));
+        M.coords_fit_i32 = cmax <= 16383 ? 1 : 0;
+        M.n_tris = n_tris_total;
+        h->A.n_tris_dev_hint = n_tris_total;
+    }
+    const cudaError_t ce = cudaStreamSynchronize(h->stream);
+    for (void* t : temps) cudaFree(t);
+    if (rc != RTS_OK) return rc;
+    if (ce != cudaSuccess) return h->fail(RTS_E_CUDA, "rts_update_map_region", cudaGetErrorString(ce));
+    // ---- Triangulation::updateCellGrid for the band of cache rows around the change (one more row on either side: a run of
+    //      ambiguous cells is resolved from its predecessor in zig-zag order)
+    if (rx0 <= rx1 && ry0 <= ry1) {
+        const uint32_t j0 = (uint32_t)std::max(ry0 - 1, 0), j1 = (uint32_t)std::min(ry1 + 1, P.tri_ny - 1);
+        if ((rc = build_cell_grid(h, last_found_tri, j0 * (uint32_t)P.tri_nx, (j1 + 1) * (uint32_t)P.tri_nx)) != RTS_OK) return rc;
+    }
+    if (any_large && (rc = build_cell_grid(h, last_found_tri)) != RTS_OK) return rc;   // a triangle spanning > 1024 cells changed: whole grid
+    h->upload_bytes_last = bytes;
+    h->drop_graphs();
+    return RTS_OK;
+}
+
+int32_t rts_get_cell_grid(RtsHandle h, uint32_t* cell2tri_out) {
+    if (!h || !cell2tri_out) return RTS_E_ARG;
+    if (!h->map_ready) return h->fail(RTS_E_STATE, "rts_get_cell_grid", "rts_upload_map has not been called");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(cell2tri_out, h->c2t_dev, sizeof(uint32_t) * (size_t)h->P.tri_nx * h->P.tri_ny, cudaMemcpyDeviceToHost));
+    return RTS_OK;
+}
+
+int32_t rts_map_upload_bytes(RtsHandle h, uint64_t* last_call, uint64_t* last_full_upload) {
+    if (!h) return RTS_E_ARG;
+    if (last_call) *last_call = h->upload_bytes_last;
+    if (last_full_upload) *last_full_upload = h->upload_bytes_full;
     return RTS_OK;
 }
 
@@ -1480,6 +1760,7 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     if (!h) return RTS_E_ARG;
     if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad rank");
     if (h->n) return h->fail(RTS_E_STATE, "rts_slab_configure", "configure the slab before uploading agents");
+    if (h->P.enable_alignment) return h->fail(RTS_E_STATE, "rts_slab_configure", "enable_alignment is not supported on a slab handle (halo records carry no velocity)");
     if (h->P.enable_arrival)
         return h->fail(RTS_E_STATE, "rts_slab_configure", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's "
                                                           "finished area and the stop requests of ghost agents across slabs");

@@ -17,12 +17,13 @@ struct MapDev {
     const int4* __restrict__ tris;
     uint32_t n_tris;
     const uint32_t* __restrict__ cell2tri;
-    // walls: CSR over the concatenated lines of the four orientations
-    const uint32_t* __restrict__ line_off;  // sum(n_lines)+4 entries; orientation o starts at line_base[o]
+    // walls: per line {first, end} into one edge pool, the lines of the four orientations concatenated (orientation o starts
+    // at line_base[o]). Explicit ranges instead of CSR offsets: rts_update_map_region appends a changed line at the end of
+    // the pool and redirects the line, nothing else moves.
+    const uint2* __restrict__ line_se;
     const float4* __restrict__ edge_ft;     // {from.x from.y t.x t.y}
     const float* __restrict__ edge_l;
     uint32_t line_base[4];
-    uint32_t edge_base[4];
     uint32_t n_lines[4];
     // paths: 2 x float4 per waypoint {w.x w.y p.from.x p.from.y | p.t.x p.t.y p.l 0}
     const uint32_t* __restrict__ path_off;
@@ -46,7 +47,7 @@ struct MapDev {
     // acceleration of findTriangle's linear-scan fallback (lowest triangle index containing q): per cache cell the
     // ascending list of "small" triangles whose bounding box touches the cell, plus one ascending list of the few
     // "large" triangles (bounding box over SCAN_LARGE_CELLS cells)
-    const uint32_t* __restrict__ scan_off;
+    const uint2* __restrict__ scan_se;      // per cache cell {first, end} into scan_list (same pool scheme as the walls)
     const uint32_t* __restrict__ scan_list;
     const uint32_t* __restrict__ scan_large;
     uint32_t n_scan_large;
@@ -250,7 +251,7 @@ __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const Rt
     const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
     uint32_t t = TRI_NONE;
     bool done = false;
-    if (want && M.scan_off) {
+    if (want && M.scan_se) {
         // A query outside the cache grid (an agent pushed over the map edge: the reference has no outer wall) gets its
         // start triangle from a cell index wrapped modulo the grid (Grid.cpp:18-24), i.e. from the far side of the map,
         // and the walk needs 100+ hops. Out there only the few triangles of the super-triangle fan exist. If the
@@ -268,14 +269,15 @@ __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const Rt
         }
     }
     if (want && !done) t = find_triangle_walk<WIDE>(M, P, q, flags);
-    if (want && t == TRI_NEED_SCAN && M.scan_off) {
+    if (want && t == TRI_NEED_SCAN && M.scan_se) {
         // the reference scans every triangle in index order; a triangle that contains q has q inside its bounding box,
         // so only the triangles listed for q's cache cell (and the large ones) can be the answer
         const float cxf = floorf((float)q.x / P.tri_cell_size), cyf = floorf((float)q.y / P.tri_cell_size);
         if (cxf >= 0.f && cyf >= 0.f && cxf < (float)P.tri_nx && cyf < (float)P.tri_ny) {
             const uint32_t cell = (uint32_t)cxf + (uint32_t)cyf * (uint32_t)P.tri_nx;
             uint32_t best = TRI_NONE;
-            for (uint32_t k = __ldg(M.scan_off + cell), e = __ldg(M.scan_off + cell + 1); k < e; ++k) {
+            const uint2 se = __ldg(M.scan_se + cell);
+            for (uint32_t k = se.x, e = se.y; k < e; ++k) {
                 const uint32_t i = __ldg(M.scan_list + k);
                 iv2 a, b, c;
                 int4 w1;
@@ -352,14 +354,14 @@ __device__ __forceinline__ int contact_walls(const MapDev& M, const RtsParams& P
         const v2 dir = (o == 0) ? V(1.f, 0.f) : (o == 1) ? V(1.f, 1.f) : (o == 2) ? V(0.f, 1.f) : V(1.f, -1.f);
         const int lo = max(base - D, 0), hi = min(base + D, (int)M.n_lines[o] - 1);
         if (lo > hi) continue;
-        const uint32_t* off = M.line_off + M.line_base[o];
-        uint32_t beg = __ldg(off + lo);
+        const uint2* se = M.line_se + M.line_base[o];
 #pragma unroll 1
         for (int L = lo; L <= hi; ++L) {
-            const uint32_t end = __ldg(off + L + 1);
+            const uint2 range = __ldg(se + L);
+            const uint32_t beg = range.x, end = range.y;
             if (end != beg) {
-                const float4* E = M.edge_ft + M.edge_base[o] + beg;
-                const float* El = M.edge_l + M.edge_base[o] + beg;
+                const float4* E = M.edge_ft + beg;
+                const float* El = M.edge_l + beg;
                 const int size = (int)(end - beg);
                 // std::lower_bound (libstdc++ bisection) with comp(e, r) = dot(r - e.from, dir) > 0
                 int first_i = 0, len = size;
@@ -375,10 +377,9 @@ __device__ __forceinline__ int contact_walls(const MapDev& M, const RtsParams& P
                 if (first == size - 1) last = size - 1;
                 for (int k = first; k <= last; ++k) {
                     const float4 e = __ldg(E + k);
-                    if (touching(e, __ldg(El + k), r, radius)) { fn(e.z, e.w, M.edge_base[o] + beg + (uint32_t)k); ++count; }
+                    if (touching(e, __ldg(El + k), r, radius)) { fn(e.z, e.w, beg + (uint32_t)k); ++count; }
                 }
             }
-            beg = end;
         }
     }
     return count;

@@ -761,12 +761,14 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
 struct ForceSums {
     v2 repulsion, push, dr_nn;
     float n_neighbours;
+    v2 align;          // alignment extension (RtsParams.enable_alignment): sum of v_j - v_i, and how many
+    float n_align;
 };
 struct ForceTerms {
     v2 rep, push, dr;
-    uint32_t mask;   // bit 0: repulsion term present, bit 1: push term, bit 2: scatter contribution
+    uint32_t mask;   // bit 0: repulsion term present, bit 1: push term, bit 2: scatter contribution, bit 3: alignment contribution
 };
-__device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float mass_i, int state_i, float4 o, float rscatter2) {
+__device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float mass_i, int state_i, float4 o, float rscatter2, float ralign2 = 0.f) {
     ForceTerms t;
     t.mask = 0u;
     t.rep = V(0.f, 0.f);
@@ -790,6 +792,7 @@ __device__ __forceinline__ ForceTerms neighbour_terms(v2 r, float radius, float 
         t.mask |= 2u;
     }
     if (state_j == RTS_MOVING && x > r_collision_sq / rscatter2) t.mask |= 4u;
+    if (ralign2 > 0.f && state_i == RTS_MOVING && state_j == RTS_MOVING && x > r_collision_sq / ralign2) t.mask |= 8u;
     return t;
 }
 __device__ __forceinline__ void add_terms(ForceSums& S, v2 rep, v2 push, v2 dr, uint32_t mask) {
@@ -809,7 +812,7 @@ __device__ __forceinline__ void add_terms(ForceSums& S, v2 rep, v2 push, v2 dr, 
 // indices of the new position — is still evaluated with the reference's own arithmetic (or a shortcut that provably
 // gives the same answer), so after one frame from the same state the discrete outputs (state, waypoint, r_next, flags,
 // angle, angle_vel) are bit-identical to the exact mode and only vel / inertia / r carry rounding-level differences.
-template <bool KEEP_VEL, bool MULTI, bool FAST>
+template <bool KEEP_VEL, bool MULTI, bool FAST, bool ALIGN = false>
 __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4 me, uint2 mykey, float4 vel4, float4 nav4, const ForceSums& sums,
                                                  const RtsParams& P, const MapDev& M, const FineGrid& F, const AgentArrays& A, const SlabDev& SL) {
     const v2 r = V(me.x, me.y);
@@ -831,6 +834,7 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
     }
     v2 inertia = V(vel4.x, vel4.y);
     inertia = inertia + ((repulsion * P.mul_repulse + push * P.mul_push) + scatter * P.mul_scatter);
+    if (ALIGN && sums.n_align > 0.f) inertia = inertia + (sums.align / sums.n_align) * P.mul_align;   // extension, see RtsParams.enable_alignment
 
     // ---- P3: PhysicsSystem::update body, PhysicsSystem.cpp:22-44 (component velocity is 0 on entry, so the
     //      `vel /= speed*max_speed` clamp at :27-30 never fires)
@@ -1034,11 +1038,17 @@ struct FastScan {
     bool near_edge;       // the 3x3 window touches a clamp cell of the fine grid: candidates may lie outside the map
     int cxi, cyi;         // own physics-grid cell
     uint32_t qb0, len0, qb1, len1, qb2, len2;   // slot ranges of the three fine rows
+    // alignment extension
+    bool moving;          // state_i == MOVING
+    float ralign2;
+    v2 vi;                // own merged velocity of the previous frame
+    const uint32_t* src;  // slot -> previous-order index
+    const float2* vel_out;
 };
 // PUSH: some lane of the warp is STANDING (the push term exists). CHECKS: some lane's window touches the edge of the
 // fine grid (physics-cell adjacency must be checked, see cell_is_adjacent) or RSCATTER^2 < r_max2 (the scatter condition
 // is not implied by the acceptance). Both are decided per warp, so that the common case carries neither.
-template <bool PUSH, bool CHECKS>
+template <bool PUSH, bool CHECKS, bool ALIGN>
 __device__ __forceinline__ void fast_candidate(ForceSums& S, const FastScan& c, const float4 o, const uint32_t q, bool valid, const uint2* __restrict__ key2) {
     const float dx = o.x - c.r.x, dy = o.y - c.r.y;
     const float d2 = dx * dx + dy * dy;                 // norm2(dr), as the reference rounds it
@@ -1069,9 +1079,17 @@ __device__ __forceinline__ void fast_candidate(ForceSums& S, const FastScan& c, 
     S.dr_nn.x += sc ? dx : 0.f;
     S.dr_nn.y += sc ? dy : 0.f;
     S.n_neighbours += sc ? 1.f : 0.f;
+    if (ALIGN) {
+        if (c.moving && moving_j && d2 < c.ralign2) {
+            const float2 vj = c.vel_out[c.src[q]];
+            S.align.x += vj.x - c.vi.x;
+            S.align.y += vj.y - c.vi.y;
+            S.n_align += 1.f;
+        }
+    }
 }
 // candidates v0, v0 + vstep, ... of the virtual range (vstep = 1: one thread does them all; vstep = lanes of a group)
-template <bool PUSH, bool CHECKS>
+template <bool PUSH, bool CHECKS, bool ALIGN>
 __device__ __forceinline__ void fast_loop(ForceSums& S, const FastScan& c, const float4* __restrict__ pos4, const uint2* __restrict__ key2,
                                           uint32_t v0, uint32_t vstep) {
     const uint32_t l01 = c.len0 + c.len1, total = l01 + c.len2;
@@ -1083,19 +1101,21 @@ __device__ __forceinline__ void fast_loop(ForceSums& S, const FastScan& c, const
         const bool hb = vb < total;
         const uint32_t qa = slot(v), qb = slot(hb ? vb : v);
         const float4 oa = pos4[qa], ob = pos4[qb];       // both loads in flight
-        fast_candidate<PUSH, CHECKS>(S, c, oa, qa, true, key2);
-        fast_candidate<PUSH, CHECKS>(S, c, ob, qb, hb, key2);
+        fast_candidate<PUSH, CHECKS, ALIGN>(S, c, oa, qa, true, key2);
+        fast_candidate<PUSH, CHECKS, ALIGN>(S, c, ob, qb, hb, key2);
     }
 }
 // `lanes`: the lanes of the warp that call this together (the variant is chosen per warp)
+template <bool ALIGN>
 __device__ __forceinline__ void fast_accumulate(ForceSums& S, const FastScan& c, const float4* __restrict__ pos4, const uint2* __restrict__ key2,
                                                 uint32_t v0, uint32_t vstep, unsigned lanes) {
+    if (ALIGN) { fast_loop<true, true, true>(S, c, pos4, key2, v0, vstep); return; }   // (the opt-in extension takes the general loop)
     const bool push = __any_sync(lanes, c.standing);
     const bool checks = __any_sync(lanes, c.near_edge) || !(c.rscatter2 >= c.r_max2);
-    if (!push && !checks) fast_loop<false, false>(S, c, pos4, key2, v0, vstep);
-    else if (push && !checks) fast_loop<true, false>(S, c, pos4, key2, v0, vstep);
-    else if (!push) fast_loop<false, true>(S, c, pos4, key2, v0, vstep);
-    else fast_loop<true, true>(S, c, pos4, key2, v0, vstep);
+    if (!push && !checks) fast_loop<false, false, false>(S, c, pos4, key2, v0, vstep);
+    else if (push && !checks) fast_loop<true, false, false>(S, c, pos4, key2, v0, vstep);
+    else if (!push) fast_loop<false, true, false>(S, c, pos4, key2, v0, vstep);
+    else fast_loop<true, true, false>(S, c, pos4, key2, v0, vstep);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1104,7 +1124,7 @@ __device__ __forceinline__ void fast_accumulate(ForceSums& S, const FastScan& c,
 // FAST = false: bit-exact mode — accepted neighbours are collected, sorted into the reference's visit order and added
 // up in that order with IEEE arithmetic. FAST = true: tolerance mode (see fast_accumulate).
 // PHASE 0: every slot; PHASE 1: the edge rows of a slab only (see SlabDev), PHASE 2: everything else.
-template <bool KEEP_VEL, bool MULTI, bool FAST, int PHASE = 0>
+template <bool KEEP_VEL, bool MULTI, bool FAST, int PHASE = 0, bool ALIGN = false>
 __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MIN_BLOCKS : STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL,
                                                                                  uint32_t walk_ctas, int walk_parity) {
     // the first walk_ctas CTAs finish the triangle walk of the previous frame (the agents its k_scatter queued)
@@ -1183,12 +1203,17 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
             row_qe[k] = 0u;
         }
     }
-    ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
+    ForceSums acc{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f, V(0.f, 0.f), 0.f};
     const float rscatter2 = P.rscatter * P.rscatter;
+    const float ralign2 = ALIGN ? P.ralign * P.ralign : 0.f;
     bool to_dense = false;
     uint32_t cell = INVALID_CELL;
     if (FAST) {
         FastScan c;
+        if (ALIGN) {
+            const float2 vi = A.vel_out[sp];
+            c.moving = state_i == RTS_MOVING; c.ralign2 = ralign2; c.vi = V(vi.x, vi.y); c.src = A.src; c.vel_out = A.vel_out;
+        }
         c.r = r; c.radius = radius; c.mass_i = mass_i; c.standing = state_i == RTS_STANDING;
         c.r_max2 = P.r_max2; c.rscatter2 = rscatter2; c.self = p; c.near_edge = near_edge; c.cxi = cxi; c.cyi = cyi;
         c.qb0 = row_qb[0]; c.len0 = row_qe[0] - row_qb[0];
@@ -1196,15 +1221,15 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
         c.qb2 = row_qb[2]; c.len2 = row_qe[2] - row_qb[2];
         // An agent in a crowd would keep this thread busy long after the rest of its warp is done; it is queued for
         // k_step_dense, where a group of lanes shares its candidates.
-        to_dense = USE_DENSE_KERNEL && c.len0 + c.len1 + c.len2 > FAST_DENSE_CAND;
+        to_dense = USE_DENSE_KERNEL && !ALIGN && c.len0 + c.len1 + c.len2 > FAST_DENSE_CAND;   // (the alignment extension stays in this kernel)
         const unsigned lanes = __ballot_sync(active, !to_dense);
         if (to_dense) A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
         else {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vel4 + sp));   // the frame tail's loads: on their way while the candidates are scanned
             asm volatile("prefetch.global.L2 [%0];" ::"l"(A.nav4 + sp));
-            fast_accumulate(acc, c, A.pos4, A.key2, 0u, 1u, lanes);
+            fast_accumulate<ALIGN>(acc, c, A.pos4, A.key2, 0u, 1u, lanes);
             // (the rest of the agent's record is fetched only now: nothing of it is needed while the candidates are scanned)
-            cell = finish_agent<KEEP_VEL, MULTI, true>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
+            cell = finish_agent<KEEP_VEL, MULTI, true, ALIGN>(p, sp, me, mykey, A.vel4[sp], A.nav4[sp], acc, P, M, F, A, SL);
         }
     } else {
     const float4 vel4 = A.vel4[sp];
@@ -1243,9 +1268,16 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     };
 
     // applyForces loop body, PhysicsSystem.cpp:69-102
+    v2 v_own = V(0.f, 0.f);
+    if (ALIGN) { const float2 vi = A.vel_out[sp]; v_own = V(vi.x, vi.y); }
     auto accumulate = [&](uint32_t q) {
-        const ForceTerms t = neighbour_terms(r, radius, mass_i, state_i, cand_pos[q], rscatter2);
+        const ForceTerms t = neighbour_terms(r, radius, mass_i, state_i, cand_pos[q], rscatter2, ralign2);
         add_terms(acc, t.rep, t.push, t.dr, t.mask);
+        if (ALIGN && (t.mask & 8u)) {
+            const float2 vj = A.vel_out[A.src[q]];
+            acc.align = acc.align + (V(vj.x, vj.y) - v_own);
+            acc.n_align += 1.f;
+        }
     };
 
     // Accepted candidates beyond NBR_CAP are parked (index only) in a per-thread list in local memory.
@@ -1259,7 +1291,7 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     // A crowded agent (DENSE_MIN < neighbours <= DENSE_MAX) would keep this thread busy for tens of thousands of
     // instructions while the rest of its warp idles, and the slowest such thread sets the duration of the whole kernel.
     // It is queued for k_step_dense instead, where a warp shares the scan, the sort and the force terms of ONE agent.
-    to_dense = USE_DENSE_KERNEL && cnt > DENSE_MIN && cnt <= DENSE_MAX;
+    to_dense = USE_DENSE_KERNEL && !ALIGN && cnt > DENSE_MIN && cnt <= DENSE_MAX;   // (the alignment extension stays in this kernel: re-scan path)
     if (to_dense) {
         A.dense_q[atomicAdd(A.dense_n, 1u)] = p;
     } else {
@@ -1334,7 +1366,7 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
         }
     }
 
-    cell = finish_agent<KEEP_VEL, MULTI, false>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
+    cell = finish_agent<KEEP_VEL, MULTI, false, ALIGN>(p, sp, me, mykey, vel4, nav4, acc, P, M, F, A, SL);
     }
     }
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
@@ -1569,7 +1601,7 @@ __global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, 
         c.qb0 = qb[0]; c.len0 = ql[0]; c.qb1 = qb[1]; c.len1 = ql[1]; c.qb2 = qb[2]; c.len2 = ql[2];
         ForceSums S{V(0.f, 0.f), V(0.f, 0.f), V(0.f, 0.f), 0.f};
         const unsigned lanes = __ballot_sync(0xffffffffu, has);
-        if (has) fast_accumulate(S, c, A.pos4, A.key2, gl, GL, lanes);
+        if (has) fast_accumulate<false>(S, c, A.pos4, A.key2, gl, GL, lanes);
         __syncwarp();
 #pragma unroll
         for (uint32_t off = GL >> 1; off > 0; off >>= 1) {   // sum over the lanes of the group
@@ -1768,11 +1800,13 @@ __device__ __forceinline__ iv2 cell_centre(int i, int j, float cs) {
     const float cx = (float)i * cs + cs / 2.f, cy = (float)j * cs + cs / 2.f;   // Triangulation.cpp:1838
     return iv2{(int32_t)cx, (int32_t)cy};
 }
+// Both kernels work on the zig-zag positions [z_lo, z_hi): the whole grid for a full build, the band of cache rows around a
+// local change for rts_update_map_region (first_hit / ambiguous are indexed from z_lo; a run of ambiguous cells that begins
+// before z_lo starts from that predecessor's current entry).
 template <bool WIDE>
-__global__ void k_cellgrid_classify(RtsParams P, MapDev M, uint32_t* cell2tri, uint32_t* first_hit, uint8_t* ambiguous) {
-    const uint32_t z = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_cells = (uint32_t)P.tri_nx * (uint32_t)P.tri_ny;
-    if (z >= n_cells) return;
+__global__ void k_cellgrid_classify(RtsParams P, MapDev M, uint32_t* cell2tri, uint32_t* first_hit, uint8_t* ambiguous, uint32_t z_lo, uint32_t z_hi) {
+    const uint32_t z = z_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= z_hi) return;
     int i, j;
     zigzag_cell(z, P.tri_nx, P.tri_ny, i, j);
     const iv2 q = cell_centre(i, j, P.tri_cell_size);
@@ -1787,34 +1821,50 @@ __global__ void k_cellgrid_classify(RtsParams P, MapDev M, uint32_t* cell2tri, u
             ++hits;
         }
     };
-    for (uint32_t k = __ldg(M.scan_off + cell), e = __ldg(M.scan_off + cell + 1); k < e; ++k) test(__ldg(M.scan_list + k));
+    const uint2 se = __ldg(M.scan_se + cell);
+    for (uint32_t k = se.x, e = se.y; k < e; ++k) test(__ldg(M.scan_list + k));
     for (uint32_t k = 0; k < M.n_scan_large; ++k) test(__ldg(M.scan_large + k));
     cell2tri[cell] = first;
-    first_hit[z] = first;
-    ambiguous[z] = hits > 1 ? 1 : 0;
+    first_hit[z - z_lo] = first;
+    ambiguous[z - z_lo] = hits > 1 ? 1 : 0;
 }
 template <bool WIDE>
 __global__ void k_cellgrid_resolve(RtsParams P, MapDev M, uint32_t last_found, uint32_t* cell2tri, const uint32_t* first_hit,
-                                   const uint8_t* ambiguous) {
-    const uint32_t z0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_cells = (uint32_t)P.tri_nx * (uint32_t)P.tri_ny;
-    if (z0 >= n_cells || !ambiguous[z0] || (z0 > 0 && ambiguous[z0 - 1])) return;   // heads of ambiguous runs only
+                                   const uint8_t* ambiguous, uint32_t z_lo, uint32_t z_hi) {
+    const uint32_t z0 = z_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (z0 >= z_hi || !ambiguous[z0 - z_lo] || (z0 > z_lo && ambiguous[z0 - z_lo - 1])) return;   // heads of ambiguous runs only
     int i, j;
     uint32_t prev = last_found;
-    if (z0 > 0) {   // the predecessor is unambiguous, its entry is final
+    if (z0 > 0) {   // the predecessor is unambiguous (or outside the band), its entry is final
         zigzag_cell(z0 - 1, P.tri_nx, P.tri_ny, i, j);
         prev = cell2tri[(uint32_t)j * (uint32_t)P.tri_nx + (uint32_t)i];
     }
     if (prev >= M.n_tris) prev = TRI_NONE;
-    for (uint32_t z = z0; z < n_cells && ambiguous[z]; ++z) {
+    for (uint32_t z = z0; z < z_hi && ambiguous[z - z_lo]; ++z) {
         zigzag_cell(z, P.tri_nx, P.tri_ny, i, j);
         const iv2 q = cell_centre(i, j, P.tri_cell_size);
         uint32_t flags = 0;
         uint32_t t = find_triangle_from<WIDE>(M, q, prev, flags);
-        if (t == TRI_NEED_SCAN) t = first_hit[z];   // the reference's linear scan returns the lowest containing index
+        if (t == TRI_NEED_SCAN) t = first_hit[z - z_lo];   // the reference's linear scan returns the lowest containing index
         cell2tri[(uint32_t)j * (uint32_t)P.tri_nx + (uint32_t)i] = t;
         if (t != TRI_NONE) prev = t;
     }
+}
+
+// rts_update_map_region: a few records of a device table are replaced (index list + values staged by the host)
+__global__ void k_scatter_u32(uint32_t n, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ val, uint32_t* __restrict__ dst, int or_into) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = or_into ? (dst[idx[i]] | val[i]) : val[i];
+}
+__global__ void k_scatter_u2(uint32_t n, const uint32_t* __restrict__ idx, const uint2* __restrict__ val, uint2* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = val[i];
+}
+__global__ void k_scatter_tris(uint32_t n, const uint32_t* __restrict__ idx, const int4* __restrict__ val, int4* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t t = idx[i];
+    dst[3 * t] = val[3 * i]; dst[3 * t + 1] = val[3 * i + 1]; dst[3 * t + 2] = val[3 * i + 2];
 }
 
 // stand-alone queries

@@ -47,6 +47,9 @@ def load_library():
         "rts_last_error": (C.c_char_p, [H]),
         "rts_set_params": (i32, [H, PP]),
         "rts_upload_map": (i32, [H, vp, u32, vp, C.POINTER(abi.RtsWallTable)]),
+        "rts_update_map_region": (i32, [H, u32, vp, vp, u32, vp, vp, vp, vp, u32, u32]),
+        "rts_map_upload_bytes": (i32, [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+        "rts_get_cell_grid": (i32, [H, vp]),
         "rts_upload_unit_types": (i32, [H, vp, u32]),
         "rts_upload_paths": (i32, [H, C.POINTER(abi.RtsPathTable)]),
         "rts_set_agents": (i32, [H, u32, AV]),
@@ -167,6 +170,41 @@ class GpuAgentSystem:
         walls = abi.wall_table(tables, keep)
         self._chk(self.L.rts_upload_map(self.h, tris.ctypes.data, len(tris), None if c2t is None else c2t.ctypes.data,
                                         C.byref(walls)))
+
+    def update_map_region(self, before: dict, after: dict, last_found: int = 0):
+        """Game::updateTriangulation after a building insert: diff of two table sets (as Triangulation::triangles_ and the
+        edge finders hold them before / after the insert) -> rts_update_map_region. Returns (changed triangles, changed lines)."""
+        tb = abi.triangles_array(before["tri_verts"], before["tri_nbrs"], before.get("tri_constrained"))
+        ta = abi.triangles_array(after["tri_verts"], after["tri_nbrs"], after.get("tri_constrained"))
+        nb, na = len(tb), len(ta)
+        same = np.zeros(na, bool)
+        same[:nb] = (tb.view(np.uint8).reshape(nb, -1) == ta[:nb].view(np.uint8).reshape(nb, -1)).all(1)
+        idx = np.nonzero(~same)[0].astype(np.uint32)
+        recs = np.ascontiguousarray(ta[idx])
+        orient, index, counts, edges = [], [], [], []
+        for o in range(4):
+            ob, oa = before[f"line_off{o}"], after[f"line_off{o}"]
+            eb, ea = before[f"edges{o}"], after[f"edges{o}"]
+            for l in range(len(oa) - 1):
+                new = ea[oa[l]:oa[l + 1]]
+                old = eb[ob[l]:ob[l + 1]]
+                if new.shape != old.shape or not np.array_equal(new.view(np.uint32), old.view(np.uint32)):
+                    orient.append(o); index.append(l); counts.append(len(new)); edges.append(new)
+        e = np.ascontiguousarray(np.concatenate(edges).astype(np.float32)) if edges else np.zeros((0, 5), np.float32)
+        orient, index, counts = (np.array(v, np.uint32) for v in (orient, index, counts))
+        self._chk(self.L.rts_update_map_region(self.h, na, idx.ctypes.data, recs.ctypes.data, len(idx), orient.ctypes.data, index.ctypes.data,
+                                               counts.ctypes.data, e.ctypes.data, len(orient), int(last_found)))
+        return len(idx), len(orient)
+
+    def map_upload_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(self.L.rts_map_upload_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def cell_grid(self) -> np.ndarray:
+        out = np.zeros(int(self.params.tri_nx) * int(self.params.tri_ny), np.uint32)
+        self._chk(self.L.rts_get_cell_grid(self.h, out.ctypes.data))
+        return out
 
     def build_cell_grid(self, last_found=0) -> np.ndarray:
         """Triangulation::updateCellGrid on the device; returns (and installs) the cell -> triangle cache"""

@@ -212,12 +212,39 @@ def make_map_c5(cells=2048, n_corridors=64, width=6, seg=60, gap=4, x0=64, name=
     w.close()
 
 
+def make_map_insert(name="map_insert.npz", seed=11):
+    """f3: the table set before and after ONE building insert (Game::updateTriangulation, Game.cpp:38-48): 512² cells, 40
+    buildings, then a 41st inserted into the live CDT through the same reference code; the reference's own updateCellGrid
+    ran after both. tests/test_gpu_parity.py feeds the difference to rts_update_map_region."""
+    rng = np.random.default_rng(seed)
+    w = refh.RefWorld(512, 512)
+    blds, occ = place_buildings(w, 40, rng, 30, 260, (512, 512))
+    w.finalize_map()
+    before = w.tables()
+    lf_before = w.last_found()
+    while True:
+        cx, cy = (int(v) for v in rng.integers(60, 230, 2))
+        if not occ[cx - 7:cx + 7, cy - 7:cy + 7].any():
+            break
+    assert w.add_building(cx, cy, 8, 8, 1) == 0
+    w.finalize_map()
+    assert w.consistent()
+    after = w.tables()
+    np.savez_compressed(os.path.join(OUT, name), **{"a_" + k: v for k, v in before.items()}, **{"b_" + k: v for k, v in after.items()},
+                        new_building=np.array([cx, cy, 8, 8], np.int32), last_found_before=np.array(lf_before))
+    print(name, "triangles", len(before["tri_verts"]), "->", len(after["tri_verts"]), "new building at", cx, cy)
+    w.close()
+
+
 def main():
     import resource
     resource.setrlimit(resource.RLIMIT_AS, (12 << 30, 12 << 30))   # a runaway reference planner must not take the box down
     assert refh.available(), "build oracle/_ref first: make -C oracle ref"
     if len(sys.argv) > 1 and sys.argv[1] == "c5":                  # only the corridor map (the other fixtures are unchanged)
         make_map_c5()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "insert":              # only the before / after pair of a building insert
+        make_map_insert()
         return
     L = refh.load()
 

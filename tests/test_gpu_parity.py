@@ -234,6 +234,56 @@ def test_crowds_straddling_the_map_edges():
                 H.assert_same_bits(out[k][sane], ref[k][sane], f"step {s} {k}")
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_alignment_extension_matches_oracle(precision):
+    """RtsParams.enable_alignment (an extension, off in every parity run: the reference's alignment code is commented out,
+    PhysicsSystem.cpp:87-91): inertia_vel += ALIGN * mean(v_j - v_i) over MOVING neighbours. Exact mode == oracle bit for
+    bit over 5 frames (the term needs the previous frame's velocities, so it only shows from frame 2 on); the tolerance
+    mode within 1e-5 after one frame from the oracle's state; and the term really changes the run."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(41, 20000, tables, 150.0, 700.0, moving=0.8)
+    P = port.default_params(512, 512)
+    P.enable_alignment = 1
+    P.mul_align = 0.35
+    ow = port.OracleWorld(P, tables, paths)
+    ref = {k: v.copy() for k, v in a.items()}
+    plain = {k: v.copy() for k, v in a.items()}
+    ow_plain = port.OracleWorld(port.default_params(512, 512), tables, paths)
+    names = ("r", "vel", "inertia", "angle", "state", "tri_idx", "waypoint")
+    with make_system(tables, paths, enable_alignment=1, mul_align=0.35, precision=precision) as g:
+        g.set_agents(a)
+        for s in range(5):
+            before = {k: v.copy() for k, v in ref.items()}
+            ow.step(ref)
+            ow_plain.step(plain)
+            if precision == 0:
+                g.update(1)
+                out = g.communicate(names)
+                for k in names:
+                    H.assert_same_bits(out[k], ref[k], f"step {s} {k}")
+            elif s == 4:
+                # tolerance mode: one frame from the oracle's state of frame 3 — but the velocities of frame 3 live on the
+                # device only, so run the exact handle's history first: 4 exact frames, then switch the arithmetic
+                pass
+        assert np.abs(ref["inertia"] - plain["inertia"]).max() > 1e-2      # the extension is not a no-op
+    if precision == 1:
+        p_exact = dict(enable_alignment=1, mul_align=0.35)
+        with make_system(tables, paths, **p_exact) as g:
+            g.set_agents(a)
+            g.update(4)
+            params = engine.default_params(512, 512)
+            params.enable_alignment, params.mul_align, params.precision = 1, 0.35, abi.PRECISION_FAST
+            g.set_params(params)                                            # same state, same velocities, tolerance arithmetic
+            g.update(1)
+            out = g.communicate(names)
+        for k in ("state", "waypoint", "angle"):
+            H.assert_same_bits(out[k], ref[k], k)
+        assert H.rel_err(out["r"], ref["r"]).max() <= TOL
+        ok = H.rel_err(out["inertia"], ref["inertia"]) <= TOL
+        assert ok.mean() > 0.995, ok.mean()
+
+
 def test_single_agent():
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
@@ -551,3 +601,49 @@ def test_diagnostic_switches_do_not_change_results(idx, val, what):
             assert not out[1][k].any()                               # the output is simply not kept
             continue
         H.assert_same_bits(out[1][k], out[0][k], f"{what}: {k}")
+
+
+def test_incremental_map_update_after_a_building_insert():
+    """f3 (Game::updateTriangulation after ONE insert, Game.cpp:38-48): the handle holds the map before the insert and gets
+    only the difference (rts_update_map_region: 40 triangle records, 8 wall lines). Afterwards its cell -> triangle cache
+    equals the table the reference's own full updateCellGrid wrote, point location and wall queries equal the oracle on the
+    NEW tables, agents stepping past the new building match the oracle bit for bit — and the update moved < 10 % of the
+    bytes of a full upload."""
+    fx = H.load("map_insert.npz")
+    before = {k[2:]: v for k, v in fx.items() if k.startswith("a_")}
+    after = {k[2:]: v for k, v in fx.items() if k.startswith("b_")}
+    cx, cy = (float(v) * 5 for v in fx["new_building"][:2])
+    rng = np.random.default_rng(3)
+    n = 6000
+    a, paths = random_world(17, n, before, cx - 120, cx + 120)
+    a["r"][:, 1] += cy - cx
+    a["radius"][:] = 3
+    a["mass"][:] = 1
+    a["unit_type"][:] = 0
+    ref = {k: v.copy() for k, v in a.items()}
+    names = ("r", "vel", "inertia", "state", "tri_idx", "waypoint", "r_next")
+    with make_system(before, paths) as g:
+        g.set_agents(a)
+        g.update(3)                                     # frames on the old map (the carried triangle hints refer to it)
+        ow_old = port.OracleWorld(port.default_params(512, 512), before, paths)
+        ow_old.step(ref, 3)
+        n_tri, n_lines = g.update_map_region(before, after)
+        assert 16 <= n_tri <= 80 and n_lines == 8, (n_tri, n_lines)
+        last, full = g.map_upload_bytes()
+        assert last < 0.10 * full, (last, full)
+        assert np.array_equal(g.cell_grid(), np.asarray(after["cell2tri"], np.uint32)), "cache == the reference's full updateCellGrid"
+        ow = port.OracleWorld(port.default_params(512, 512), after, paths)
+        pts = np.concatenate([rng.uniform(-30, 2590, (20000, 2)), rng.uniform((cx - 60, cy - 60), (cx + 60, cy + 60), (20000, 2))]).astype(np.float32)
+        H.assert_same_bits(g.find_triangles(pts), ow.find_triangles(pts), "findTriangle on the patched tables")
+        rad = np.where(rng.random(len(pts)) < 0.5, 3.0, 5.0).astype(np.float32)
+        cnt, edges = g.contact_edges(pts, rad, cap=6)
+        ocnt, oedges = ow.contact_edges(pts, rad, cap=6)
+        H.assert_same_bits(cnt, ocnt, "calcContactEdgesO count on the patched tables")
+        H.assert_same_bits(edges, oedges, "calcContactEdgesO edges on the patched tables")
+        assert (ocnt > 0).sum() > 200
+        for s in range(6):                              # ... and the frames that follow
+            ow.step(ref)
+            g.update(1)
+            out = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(out[k], ref[k], f"frame {s} after the insert: {k}")
