@@ -241,7 +241,82 @@ int main(int argc, char** argv) {
     for (int i = 0; i < n_agents; ++i)
         if (A.shared->at(i).state == MoveState::STANDING && i % 2 == 0) late.push_back(i);
     const sf::Vector2f late_target = {1600.f, 900.f};   // (far from every unit: the arrival rule, an opt-in of the GPU path, must not fire)
+    // Game::updateTriangulation in the middle of the run (frame 40): ONE more building, in the way of the units. World A gets it
+    // through the reference's own code; world B's host-side CDT / Edges (the planner's) get it the same way, and the GPU
+    // slot receives only the DIFFERENCE (rts_update_map_region): the triangle records that changed and the eight wall lines.
+    long map_update_bytes = 0, map_full_bytes = 0;
+    int map_changed_tris = 0, map_changed_lines = 0;
     for (int f = 0; f < frames; ++f) {
+        if (f == 40) {
+            int bx = -1, by = -1;
+            for (int tries = 0; tries < 2000 && bx < 0; ++tries) {
+                const int cx = 100 + rng() % 80, cy = 100 + rng() % 80;
+                if (!blocked(cx - 7, cy - 7, cx + 7, cy + 7)) { bx = cx; by = cy; }
+            }
+            if (bx >= 0) {
+                auto snapshot_lines = [&](RefWorld& w) {
+                    std::vector<std::vector<Edgef>> lines;
+                    for (int o = 0; o < 4; ++o)
+                        for (auto& line : w.edges->edge_finders_[o]->edge_array2_) lines.emplace_back(line.begin(), line.end());
+                    return lines;
+                };
+                const auto tris_before = B.cdt->triangles_;
+                const auto lines_before = snapshot_lines(B);
+                for (int k = 0; k < 2; ++k)
+                    if (refh_add_building(W[k], bx, by, 8, 8, 1) != 0 || refh_finalize_map(W[k]) != 0) { printf("{\"error\": \"mid-run building\"}\n"); return 1; }
+                if (gpu) {
+                    auto& cdt = *B.cdt;
+                    auto same_tri = [](const Triangle& a, const Triangle& b) {
+                        for (int k = 0; k < 3; ++k)
+                            if (a.verts[k].x != b.verts[k].x || a.verts[k].y != b.verts[k].y || a.neighbours[k] != b.neighbours[k] ||
+                                a.is_constrained[k] != b.is_constrained[k]) return false;
+                        return true;
+                    };
+                    std::vector<uint32_t> idx;
+                    std::vector<RtsTriangle> rec;
+                    for (size_t t = 0; t < cdt.triangles_.size(); ++t) {
+                        if (t < tris_before.size() && same_tri(tris_before[t], cdt.triangles_[t])) continue;
+                        RtsTriangle r{};
+                        for (int k = 0; k < 3; ++k) {
+                            r.vx[k] = cdt.triangles_[t].verts[k].x; r.vy[k] = cdt.triangles_[t].verts[k].y;
+                            r.neighbours[k] = cdt.triangles_[t].neighbours[k]; r.is_constrained[k] = cdt.triangles_[t].is_constrained[k];
+                        }
+                        idx.push_back((uint32_t)t);
+                        rec.push_back(r);
+                    }
+                    const auto lines_after = snapshot_lines(B);
+                    std::vector<uint32_t> l_orient, l_index, l_count;
+                    std::vector<RtsEdge> l_edges;
+                    size_t flat = 0;
+                    for (int o = 0; o < 4; ++o) {
+                        const size_t n_lines = B.edges->edge_finders_[o]->edge_array2_.size();
+                        for (size_t l = 0; l < n_lines; ++l, ++flat) {
+                            const auto& a = lines_before[flat];
+                            const auto& b = lines_after[flat];
+                            bool same = a.size() == b.size();
+                            for (size_t e = 0; same && e < a.size(); ++e)
+                                same = a[e].from.x == b[e].from.x && a[e].from.y == b[e].from.y && a[e].t.x == b[e].t.x && a[e].t.y == b[e].t.y && a[e].l == b[e].l;
+                            if (same) continue;
+                            l_orient.push_back((uint32_t)o); l_index.push_back((uint32_t)l); l_count.push_back((uint32_t)b.size());
+                            for (auto& s : b) l_edges.push_back({s.from.x, s.from.y, s.t.x, s.t.y, s.l});
+                        }
+                    }
+                    if (rts_update_map_region(seek->h, (uint32_t)cdt.triangles_.size(), idx.data(), rec.data(), (uint32_t)idx.size(), l_orient.data(),
+                                              l_index.data(), l_count.data(), l_edges.data(), (uint32_t)l_orient.size(), 0u) != RTS_OK) {
+                        printf("{\"error\": \"rts_update_map_region: %s\"}\n", rts_last_error(seek->h));
+                        return 2;
+                    }
+                    uint64_t last = 0, full = 0;
+                    rts_map_upload_bytes(seek->h, &last, &full);
+                    map_update_bytes = (long)last; map_full_bytes = (long)full;
+                    map_changed_tris = (int)idx.size(); map_changed_lines = (int)l_orient.size();
+                    // the patched cache against the table the reference's full updateCellGrid has just written (world B's host CDT)
+                    std::vector<uint32_t> dev(cdt.cell2triangle_ind_.size());
+                    if (rts_get_cell_grid(seek->h, dev.data()) != RTS_OK) { printf("{\"error\": \"rts_get_cell_grid\"}\n"); return 2; }
+                    for (size_t c = 0; c < dev.size(); ++c) cell_grid_mismatches += dev[c] != (uint32_t)cdt.cell2triangle_ind_[c];
+                }
+            }
+        }
         if (f == 25 && !late.empty()) {
             for (int e : late) { A.shared->at(e).state = MoveState::MOVING; B.shared->at(e).state = MoveState::MOVING; }
             A.ss->issuePaths2(late, late_target);
@@ -331,8 +406,10 @@ int main(int argc, char** argv) {
     int moving = 0;
     for (int i = 0; i < n_agents; ++i) moving += A.shared->at(i).state == MoveState::MOVING;
     printf("{\"agents\": %d, \"buildings\": %d, \"frames\": %d, \"cell_grid_mismatches\": %ld, \"compared\": %ld, \"mismatches\": %ld, \"first_bad_frame\": %d, "
-           "\"replans\": %d, \"moving_at_end\": %d, \"late_command\": %d, \"entities_resent_after_frame0\": %ld, \"cpu_ms_per_frame\": %.3f, \"gpu_adapter_ms_per_frame\": %.3f}\n",
+           "\"replans\": %d, \"moving_at_end\": %d, \"late_command\": %d, \"entities_resent_after_frame0\": %ld, \"map_update\": {\"changed_triangles\": %d, \"changed_wall_lines\": %d, \"bytes\": %ld, \"full_upload_bytes\": %ld}, "
+           "\"cpu_ms_per_frame\": %.3f, \"gpu_adapter_ms_per_frame\": %.3f}\n",
            n_agents, n_buildings, frames, cell_grid_mismatches, compared, mismatches, first_bad_frame, replans, moving, (int)late.size(), uploaded,
+           map_changed_tris, map_changed_lines, map_update_bytes, map_full_bytes,
            1e3 * t_cpu / frames, 1e3 * t_gpu / frames);
     return (mismatches || cell_grid_mismatches) ? 3 : 0;
 }
