@@ -288,6 +288,19 @@ int32_t rts_find_triangles(RtsHandle h, const float* xy, uint32_t n, uint32_t* o
 int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uint32_t n, uint32_t cap,
                           uint32_t* counts, float* edges_out);
 
+/* ---- neighbour queries of the callers of the frame path (first slice), on the cell order the frame keeps ----
+   NeighbourSearcherContext::getNeighboursIndsFull (NeighbourSearcherContext.h:44-92; the game's click selection runs it on
+   the physics grid, Game.cpp:324) for n query points: per query the number of agents with dist^2 <= r_max^2 and up to `cap`
+   of their component indices in the reference's visit order (cells row-major, ascending index inside a cell); a query with
+   more hits than `cap` reports the true count and an unspecified selection of `cap` of them. */
+int32_t rts_query_radius(RtsHandle h, const float* xy, const float* r_max, uint32_t n, uint32_t cap, uint32_t* counts,
+                         uint32_t* indices_out);
+/* NeighbourSearcherStrategyAttack::execute (NeighbourSearcherStrategy.cpp:125-177) for every agent, AS WRITTEN: the reference
+   never lowers min_enemy_dist_sq from Geometry::BOX[0] (2560), so the "nearest enemy" of an agent is the LAST agent of another
+   player with dist^2 < range2 in visit order (calcNearestCells cells, own cell last). out[i] = its component index or -1
+   (rts_agent_count() entries). Follows the source text only: that translation unit cannot be built headless. */
+int32_t rts_attack_targets(RtsHandle h, float range2, int32_t* out);
+
 /* ---- multi-GPU: spatial slab decomposition, one handle (one process, one GPU) per y-slab -----------------------
    The reference has no distributed path; this is the north-star extension.  A handle created with
    params.slab_row_lo/hi owns the physics-grid rows [lo, hi).  Every frame the frame kernel packs (a) agents whose

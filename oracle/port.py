@@ -41,6 +41,10 @@ def load(fast=False):
     L.rts_oracle_contact_edges.argtypes = [C.POINTER(abi.RtsParams), C.POINTER(abi.RtsWallTable), vp, vp, C.c_uint32,
                                            C.c_uint32, vp, vp]
     L.rts_oracle_neighbours.argtypes = [C.POINTER(abi.RtsParams), C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
+    L.rts_oracle_query_radius.argtypes = [C.POINTER(abi.RtsParams), C.c_uint32, vp, C.c_float, C.c_float, C.c_float, vp, C.c_uint32]
+    L.rts_oracle_query_radius.restype = C.c_uint32
+    L.rts_oracle_attack_targets.argtypes = [C.POINTER(abi.RtsParams), C.c_uint32, vp, vp, C.c_float, vp]
+    L.rts_oracle_attack_targets.restype = None
     L.rts_oracle_neighbours.restype = C.c_uint32
     L.rts_oracle_acos_table.argtypes = [vp]
     L.rts_oracle_build_cell_grid.argtypes = [C.POINTER(abi.RtsParams), vp, C.c_uint32, C.c_uint32, vp]
@@ -117,6 +121,21 @@ class OracleWorld:
         self.L.rts_oracle_contact_edges(C.byref(self.params), C.byref(self.walls), xy.ctypes.data, radius.ctypes.data,
                                         n, cap, counts.ctypes.data, out.ctypes.data)
         return counts, out
+
+    def query_radius(self, r, q, r_max, cap=4096):
+        """NeighbourSearcherContext::getNeighboursIndsFull on the physics grid: indices within r_max of q, visit order"""
+        r = np.ascontiguousarray(r, np.float32)
+        out = np.zeros(cap, np.uint32)
+        n = self.L.rts_oracle_query_radius(C.byref(self.params), len(r), r.ctypes.data, float(q[0]), float(q[1]), float(r_max), out.ctypes.data, cap)
+        return out[:min(n, cap)].copy(), int(n)
+
+    def attack_targets(self, r, player, range2=2560.0):
+        """NeighbourSearcherStrategyAttack::execute: per agent the enemy the reference's loop ends on, or -1"""
+        r = np.ascontiguousarray(r, np.float32)
+        player = np.ascontiguousarray(player, np.uint8)
+        out = np.zeros(len(r), np.int32)
+        self.L.rts_oracle_attack_targets(C.byref(self.params), len(r), r.ctypes.data, player.ctypes.data, float(range2), out.ctypes.data)
+        return out
 
     def neighbours(self, r, i, cap=4096):
         r = np.ascontiguousarray(r, np.float32)

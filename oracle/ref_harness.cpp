@@ -477,6 +477,18 @@ int refh_seek_ns_full(float box, float cell, const float* xy, const float* radiu
     return (int)ns.getNeighboursIndsFull({qx, qy}, rmax).size();
 }
 
+// ... and the index list itself, in the reference's visit order (pins the oracle's restatement of getNeighboursIndsFull)
+int refh_ns_full_list(float box, float cell, const float* xy, int n, float qx, float qy, float rmax, int* out, int cap) {
+    NeighbourSearcherContext<PathFinderComponent, int> ns({box, box}, cell);
+    ns.setStrategy(NS_STRATEGY::BASIC);
+    std::vector<PathFinderComponent> comps(n);
+    for (int i = 0; i < n; ++i) comps[i].transform.r = {xy[2 * i], xy[2 * i + 1]};
+    ns.update(comps);
+    const auto inds = ns.getNeighboursIndsFull({qx, qy}, rmax);
+    for (int k = 0; k < (int)inds.size() && k < cap; ++k) out[k] = inds[k];
+    return (int)inds.size();
+}
+
 // full funnel path of one planner query (PathFinder2.cpp:388-438): waypoints (2 floats) and portals (5 floats)
 int refh_plan_path(void* h, float sx, float sy, float ex, float ey, float radius, float* path, float* portals, int cap) {
     auto* w = W(h);

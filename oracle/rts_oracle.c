@@ -555,6 +555,73 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
     return rc;
 }
 
+/* NeighbourSearcherContext::getNeighboursIndsFull (NeighbourSearcherContext.h:44-92): indices of the agents within r_max of
+   the point q, in the reference's visit order (cell rows j, columns i, ascending component index inside a cell); the cells
+   searched are rows cell.y +- (ceil(r_max/cs)+1) and columns cell.x +- (j_max - j_min), clipped to the grid. Used by the game
+   for click selection on the physics grid (Game.cpp:324). Returns the count; writes at most cap indices. */
+uint32_t rts_oracle_query_radius(const RtsParams* P, uint32_t n, const float* r, float qx, float qy, float r_max, uint32_t* out, uint32_t cap) {
+    ns_grid g;
+    uint32_t* cell_of = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+    build_grid(P, n, r, &g, cell_of);
+    const float r_max2 = r_max * r_max;
+    const uint32_t cell_ind = (uint32_t)coord_to_cell(qx, qy, P->ns_nx, P->ns_ny, P->ns_cell_size);
+    const int ccx = (int)(cell_ind % (uint32_t)P->ns_nx), ccy = (int)(cell_ind / (uint32_t)P->ns_nx);   /* Grid::cellCoords(int), Grid.cpp:60-64 */
+    int j_max = ccy + (int)ceilf(r_max / P->ns_cell_size) + 1;
+    int j_min = ccy - (int)ceilf(r_max / P->ns_cell_size) - 1;
+    if (j_max > P->ns_ny - 1) j_max = P->ns_ny - 1;
+    if (j_min < 0) j_min = 0;
+    const int delta_j_max = j_max - j_min;
+    uint32_t cnt = 0;
+    for (int j = j_min; j <= j_max; ++j) {
+        int i_max = ccx + delta_j_max, i_min = ccx - delta_j_max;
+        if (i_max > P->ns_nx - 1) i_max = P->ns_nx - 1;
+        if (i_min < 0) i_min = 0;
+        for (int i = i_min; i <= i_max; ++i) {
+            const uint32_t c = (uint32_t)i + (uint32_t)j * (uint32_t)P->ns_nx;
+            for (uint32_t k = g.cell_start[c]; k < g.cell_start[c + 1]; ++k) {
+                const uint32_t a = g.cell_items[k];
+                const float d2 = vdist2(V(r[2 * a], r[2 * a + 1]), V(qx, qy));
+                if (d2 <= r_max2) { if (cnt < cap) out[cnt] = a; cnt++; }
+            }
+        }
+    }
+    free(cell_of); free(g.cell_start); free(g.cell_items);
+    return cnt;
+}
+
+/* NeighbourSearcherStrategyAttack::execute (NeighbourSearcherStrategy.cpp:125-177) as written: over the cells of
+   calcNearestCells + the own cell, in that order and ascending component index inside a cell, EVERY agent of another player
+   with dist^2 < range2 (the reference never lowers min_enemy_dist_sq from its initial Geometry::BOX[0] = 2560) overwrites slot
+   0 — so the "nearest enemy" it reports is the LAST such agent in visit order. out[i] = that index, or -1.
+   PARITY UNPINNED: the verbatim translation unit needs AttackSystem.h (-> VisionSystem -> glm) and cannot be built headless;
+   this follows the source text only. */
+void rts_oracle_attack_targets(const RtsParams* P, uint32_t n, const float* r, const uint8_t* player, float range2, int32_t* out) {
+    ns_grid g;
+    uint32_t* cell_of = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
+    build_grid(P, n, r, &g, cell_of);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ci = cell_of[i];
+        const int cx = (int)(ci % (uint32_t)P->ns_nx), cy = (int)((ci / (uint32_t)P->ns_nx) % (uint32_t)P->ns_ny);
+        uint32_t cells[9];
+        int ncells = 0;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy) {
+                const uint32_t cj = ci + dx + dy * P->ns_nx;
+                if (cx + dx >= 0 && cx + dx < P->ns_nx && cy + dy >= 0 && cy + dy < P->ns_ny && cj != ci) cells[ncells++] = cj;
+            }
+        cells[ncells++] = ci;
+        int32_t target = -1;
+        for (int c = 0; c < ncells; ++c)
+            for (uint32_t k = g.cell_start[cells[c]]; k < g.cell_start[cells[c] + 1]; ++k) {
+                const uint32_t j = g.cell_items[k];
+                const float dist_sq = vdist2(V(r[2 * j], r[2 * j + 1]), V(r[2 * i], r[2 * i + 1]));
+                if (dist_sq < range2 && player[i] != player[j]) target = (int32_t)j;
+            }
+        out[i] = target;
+    }
+    free(cell_of); free(g.cell_start); free(g.cell_items);
+}
+
 /* physics neighbour list of agent i in visit order (for the neighbour-set test T3) */
 uint32_t rts_oracle_neighbours(const RtsParams* P, uint32_t n, const float* r, uint32_t i, uint32_t* out, uint32_t cap) {
     ns_grid g;

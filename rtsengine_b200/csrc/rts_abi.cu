@@ -1755,6 +1755,57 @@ int32_t rts_contact_edges(RtsHandle h, const float* xy, const float* radius, uin
     return RTS_OK;
 }
 
+// ---- f4, first slice -----------------------------------------------------------------------------------------------
+int32_t rts_query_radius(RtsHandle h, const float* xy, const float* r_max, uint32_t n, uint32_t cap, uint32_t* counts, uint32_t* indices_out) {
+    if (!h) return RTS_E_ARG;
+    if (n == 0) return RTS_OK;
+    if (!xy || !r_max || !counts || (cap && !indices_out)) return h->fail(RTS_E_ARG, "rts_query_radius", "null");
+    if (h->multi) return h->fail(RTS_E_STATE, "rts_query_radius", "single-domain handles only");
+    CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    const size_t bytes = (size_t)n * 16 + (size_t)n * cap * 8;
+    int32_t rc = ensure_scratch(h, bytes);
+    if (rc != RTS_OK) return rc;
+    float2* d_xy = static_cast<float2*>(h->scratch);
+    float* d_r = reinterpret_cast<float*>(d_xy + n);
+    uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d_r + n);
+    uint2* d_out = reinterpret_cast<uint2*>(d_cnt + n);
+    CU(cudaMemcpyAsync(d_xy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(d_r, r_max, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_query_radius<<<blocks_for(n, 64), 64, 0, h->stream>>>(n, d_xy, d_r, cap, h->P, h->F, h->A, d_cnt, d_out);
+    h->launches += 1;
+    std::vector<uint2> pairs((size_t)n * cap);
+    CU(cudaMemcpyAsync(counts, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (cap) CU(cudaMemcpyAsync(pairs.data(), d_out, pairs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    for (uint32_t q = 0; q < n; ++q) {   // the reference's visit order: cells row-major, ascending component index inside a cell
+        uint2* first = pairs.data() + (size_t)q * cap;
+        const uint32_t m = std::min(counts[q], cap);
+        std::sort(first, first + m, [](const uint2& a, const uint2& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+        for (uint32_t k = 0; k < m; ++k) indices_out[(size_t)q * cap + k] = first[k].y;
+    }
+    return RTS_OK;
+}
+
+int32_t rts_attack_targets(RtsHandle h, float range2, int32_t* out) {
+    if (!h || !out) return RTS_E_ARG;
+    if (h->multi) return h->fail(RTS_E_STATE, "rts_attack_targets", "single-domain handles only");
+    if (!(range2 > 0)) return h->fail(RTS_E_ARG, "rts_attack_targets", "range2 must be positive");
+    if (h->n == 0) return RTS_OK;
+    CU(cudaSetDevice(h->device));
+    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    int32_t rc = ensure_scratch(h, (size_t)h->n * 4);
+    if (rc != RTS_OK) return rc;
+    int32_t* d_out = static_cast<int32_t*>(h->scratch);
+    k_attack_targets<<<blocks_for(h->n, 128), 128, 0, h->stream>>>(h->n, range2, h->P, h->F, h->A, d_out, h->gid_is_index ? 1 : 0);
+    h->launches += 1;
+    CU(cudaMemcpyAsync(out, d_out, (size_t)h->n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return RTS_OK;
+}
+
 // ---- slab decomposition ---------------------------------------------------------------------------
 int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t cap_migrants, uint32_t cap_halo) {
     if (!h) return RTS_E_ARG;

@@ -1867,6 +1867,81 @@ __global__ void k_scatter_tris(uint32_t n, const uint32_t* __restrict__ idx, con
     dst[3 * t] = val[3 * i]; dst[3 * t + 1] = val[3 * i + 1]; dst[3 * t + 2] = val[3 * i + 2];
 }
 
+// ---- f4, first slice: the two neighbour queries next to the frame path, on the cell order the frame maintains anyway ----
+// NeighbourSearcherContext::getNeighboursIndsFull (NeighbourSearcherContext.h:44-92) on the physics grid: one thread per
+// query scans the fine cells its disk touches and emits {physics cell index, gid} of every agent with dist2 <= r_max^2 whose
+// physics cell lies in the block of cells the reference searches; the host orders each result list by that pair, which is
+// the reference's visit order (cells row-major, ascending component index inside a cell).
+__global__ void k_query_radius(uint32_t nq, const float2* __restrict__ q_xy, const float* __restrict__ q_r, uint32_t cap, RtsParams P, FineGrid F,
+                               AgentArrays A, uint32_t* __restrict__ counts, uint2* __restrict__ out) {
+    const uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const v2 q = V(q_xy[qi].x, q_xy[qi].y);
+    const float r_max = q_r[qi], r_max2 = r_max * r_max;
+    const uint32_t cell_ind = coord_to_cell(q.x, q.y, P.ns_nx, P.ns_ny, P.ns_cell_size);
+    const int ccx = (int)(cell_ind % (uint32_t)P.ns_nx), ccy = (int)(cell_ind / (uint32_t)P.ns_nx);
+    int j_max = ccy + (int)ceilf(r_max / P.ns_cell_size) + 1, j_min = ccy - (int)ceilf(r_max / P.ns_cell_size) - 1;
+    j_max = min(j_max, P.ns_ny - 1);
+    j_min = max(j_min, 0);
+    const int delta = j_max - j_min;
+    const int i_max = min(ccx + delta, P.ns_nx - 1), i_min = max(ccx - delta, 0);
+    int fx0, fy0, fx1, fy1;
+    fine_coords(F, q.x - r_max, q.y - r_max, fx0, fy0);
+    fine_coords(F, q.x + r_max, q.y + r_max, fx1, fy1);
+    uint32_t cnt = 0;
+    for (int fy = fy0; fy <= fy1; ++fy) {
+        const uint32_t rowbase = (uint32_t)fy * (uint32_t)F.nx;
+        for (uint32_t s = __ldg(F.start + rowbase + fx0), e = __ldg(F.start + rowbase + fx1 + 1); s < e; ++s) {
+            const float4 o = A.pos4[s];
+            if (!(dist2(V(o.x, o.y), q) <= r_max2)) continue;
+            const uint2 key = A.key2[s];
+            if ((key.y >> 2) & 1u) continue;   // ghost
+            const int cx = cs_cx(key.y), cy = cs_cy(key.y);
+            if (cx < i_min || cx > i_max || cy < j_min || cy > j_max) continue;
+            if (cnt < cap) out[(size_t)qi * cap + cnt] = make_uint2((uint32_t)cx + (uint32_t)cy * (uint32_t)P.ns_nx, key.x);
+            ++cnt;
+        }
+    }
+    counts[qi] = cnt;
+}
+// NeighbourSearcherStrategyAttack::execute (NeighbourSearcherStrategy.cpp:125-177) as written: the enemy its loop ends on =
+// the agent of another player with dist2 < range2 that comes LAST in visit order (calcNearestCells cells, own cell last,
+// ascending component index). One thread per agent; the player of a candidate is fetched only when its key beats the best.
+__global__ void k_attack_targets(uint32_t n, float range2, RtsParams P, FineGrid F, AgentArrays A, int32_t* __restrict__ out, int by_gid) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float4 me = A.pos4[p];
+    const uint2 mykey = A.key2[p];
+    if ((mykey.y >> 2) & 1u) return;
+    const uint32_t my_player = (__float_as_uint(A.nav4[A.src[p]].w) >> 24) & 0xFu;
+    const v2 r = V(me.x, me.y);
+    const int cxi = cs_cx(mykey.y), cyi = cs_cy(mykey.y);
+    const float reach = sqrtf(range2);
+    int fx0, fy0, fx1, fy1;
+    fine_coords(F, r.x - reach, r.y - reach, fx0, fy0);
+    fine_coords(F, r.x + reach, r.y + reach, fx1, fy1);
+    uint32_t best_key = 0u;
+    int32_t best = -1;
+    for (int fy = fy0; fy <= fy1; ++fy) {
+        const uint32_t rowbase = (uint32_t)fy * (uint32_t)F.nx;
+        for (uint32_t s = __ldg(F.start + rowbase + fx0), e = __ldg(F.start + rowbase + fx1 + 1); s < e; ++s) {
+            const float4 o = A.pos4[s];
+            if (!(dist2(V(o.x, o.y), r) < range2)) continue;
+            const uint2 key = A.key2[s];
+            if (((key.y >> 2) & 1u) || !cell_is_adjacent(key.y, cxi, cyi)) continue;
+            const int idx = (cs_cx(key.y) - cxi + 1) * 3 + (cs_cy(key.y) - cyi + 1);
+            const uint32_t rank = (idx < 4) ? (uint32_t)idx : (idx == 4 ? 8u : (uint32_t)(idx - 1));
+            const uint32_t k = ((rank << 28) | key.x) + 1u;   // (+1: a key of 0 means "none yet")
+            if (k <= best_key) continue;
+            const uint32_t pl = (__float_as_uint(A.nav4[A.src[s]].w) >> 24) & 0xFu;
+            if (pl == my_player) continue;
+            best_key = k;
+            best = (int32_t)key.x;
+        }
+    }
+    out[by_gid ? mykey.x : p] = best;
+}
+
 // stand-alone queries
 __global__ void k_coord_to_cell(const float2* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -74,6 +74,8 @@ def load_library():
         "rts_build_cell_grid": (i32, [H, u32, vp]),
         "rts_contact_edges": (i32, [H, vp, vp, u32, u32, vp, vp]),
         "rts_stream": (vp, [H]),
+        "rts_query_radius": (i32, [H, vp, vp, u32, u32, vp, vp]),
+        "rts_attack_targets": (i32, [H, f32, vp]),
         "rts_slab_configure": (i32, [H, i32, i32, u32, u32]),
         "rts_comm_unique_id": (i32, [vp]),
         "rts_comm_init": (i32, [H, vp]),
@@ -337,6 +339,21 @@ class GpuAgentSystem:
         xy = np.ascontiguousarray(xy, np.float32)
         out = np.zeros(len(xy), np.uint32)
         self._chk(self.L.rts_find_triangles(self.h, xy.ctypes.data, len(xy), out.ctypes.data))
+        return out
+
+    def query_radius(self, xy, r_max, cap=256):
+        """NeighbourSearcherContext::getNeighboursIndsFull for every query point: (counts, indices[n, cap])"""
+        xy = np.ascontiguousarray(xy, np.float32)
+        r_max = np.ascontiguousarray(r_max, np.float32)
+        counts = np.zeros(len(xy), np.uint32)
+        out = np.zeros((len(xy), cap), np.uint32)
+        self._chk(self.L.rts_query_radius(self.h, xy.ctypes.data, r_max.ctypes.data, len(xy), cap, counts.ctypes.data, out.ctypes.data))
+        return counts, out
+
+    def attack_targets(self, range2=2560.0):
+        """NeighbourSearcherStrategyAttack::execute for every agent: the enemy index its loop ends on, or -1"""
+        out = np.zeros(self.n, np.int32)
+        self._chk(self.L.rts_attack_targets(self.h, float(range2), out.ctypes.data))
         return out
 
     def contact_edges(self, xy, radius, cap=8):

@@ -647,3 +647,43 @@ def test_incremental_map_update_after_a_building_insert():
             out = g.communicate(names)
             for k in names:
                 H.assert_same_bits(out[k], ref[k], f"frame {s} after the insert: {k}")
+
+
+def test_neighbour_queries_of_the_callers():
+    """f4, first slice: getNeighboursIndsFull (click selection, Game.cpp:324) and the Attack strategy's enemy search
+    (NeighbourSearcherStrategy.cpp:125-177) on the device's cell order — the reference's known answer
+    (src/Tests/test_neighbour_search.cc:42-66 and :68-94: 1 neighbour at radius 10, none at radius 1) and the oracle
+    (pinned to the verbatim template by tests/test_oracle_vs_ref.py) on a crowd with two players, during a run."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    # the known answer: box 100, cell 10 -> 11 x 11 cells; agents (25,25) (40,40) (24,24)
+    p = engine.default_params(20, 20)
+    p.ns_cell_size, p.ns_nx, p.ns_ny = 10.0, 11, 11
+    kat = H.load("kat.npz")
+    with engine.GpuAgentSystem(p) as g:
+        g.set_agents({"r": np.array([[25, 25], [40, 40], [24, 24]], np.float32)})
+        cnt, idx = g.query_radius(np.array([[39, 39], [39, 39]], np.float32), np.array([10, 1], np.float32))
+        assert (int(cnt[0]), int(cnt[1])) == (int(kat["ns_full_r10"]), int(kat["ns_full_r1"])) == (1, 0) and int(idx[0, 0]) == 1
+    a, paths = random_world(51, 30000, tables, 100.0, 1500.0)
+    rng = np.random.default_rng(8)
+    a["r"][:3000] = rng.uniform(600, 700, (3000, 2))
+    a["player"][:] = rng.integers(0, 3, len(a["r"]))
+    P = port.default_params(512, 512)
+    ow = port.OracleWorld(P, tables, paths)
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        g.update(5)
+        cur = g.communicate(("r", "player"))
+        q = np.concatenate([rng.uniform(50, 1550, (300, 2)), rng.uniform(590, 710, (100, 2)), [[3.0, 3.0], [2555.0, 40.0]]]).astype(np.float32)
+        rm = rng.choice([5.0, 15.0, 40.0, 150.0], len(q)).astype(np.float32)
+        cnt, idx = g.query_radius(q, rm, cap=4096)
+        for k in range(len(q)):
+            want, want_n = ow.query_radius(cur["r"], q[k], rm[k], cap=4096)
+            assert int(cnt[k]) == want_n, (k, q[k], rm[k])
+            assert want_n <= 4096                      # (beyond cap the count is still right, the selection unspecified)
+            assert np.array_equal(idx[k, :want_n], want), (k, q[k], rm[k])
+        assert cnt.max() > 2048
+        got = g.attack_targets()
+        want = ow.attack_targets(cur["r"], cur["player"])
+        assert np.array_equal(got, want), np.nonzero(got != want)[0][:5]
+        assert (want >= 0).mean() > 0.3

@@ -128,3 +128,29 @@ def test_cell_grid_restatement_matches_update_cell_grid(seed, buildings):
         ref = np.asarray(w.tables()["cell2tri"], np.uint32)
         got = ow.build_cell_grid(int(lf))
         assert np.array_equal(got, ref), (int(lf), np.nonzero(got != ref)[0][:8])
+
+
+def test_radius_query_matches_the_verbatim_reference():
+    """f4, first slice: NeighbourSearcherContext::getNeighboursIndsFull (NeighbourSearcherContext.h:44-92, the click-selection
+    query of Game.cpp:324) — the oracle's restatement returns the same indices in the same order as the verbatim template,
+    including queries next to the grid border and radii from 5 to 150 units."""
+    import ctypes as C
+    from oracle import port
+    L = refh.load()
+    L.refh_ns_full_list.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int]
+    L.refh_ns_full_list.restype = C.c_int
+    rng = np.random.default_rng(3)
+    n = 4000
+    xy = rng.uniform(5, 2555, (n, 2)).astype(np.float32)
+    xy[:600] = rng.uniform(900, 1100, (600, 2))                      # a crowd
+    P = port.default_params(512, 512)                                 # physics grid: box 2560, cell 60 -> 43 x 43
+    ow = port.OracleWorld.__new__(port.OracleWorld)
+    ow.L, ow.params = port.load(False), P
+    out = np.zeros(4096, np.int32)
+    for _ in range(100):
+        q = rng.uniform(0, 2559, 2).astype(np.float32) if rng.random() < 0.7 else rng.uniform(880, 1120, 2).astype(np.float32)
+        r_max = float(rng.choice([5.0, 15.0, 40.0, 150.0]))
+        cnt = L.refh_ns_full_list(2560.0, 60.0, xy.ctypes.data, n, float(q[0]), float(q[1]), r_max, out.ctypes.data, len(out))
+        got, got_n = ow.query_radius(xy, q, r_max)
+        assert got_n == cnt
+        assert np.array_equal(got.astype(np.int32), out[:cnt]), (q, r_max)
