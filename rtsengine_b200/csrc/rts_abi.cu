@@ -94,6 +94,7 @@ struct RtsContext {
     bool multi = false;
     bool overlap_walk = true;         // walk queue searched by the next frame kernel's leading CTAs (reserved[4] = 1: k_walk after k_scatter)
     bool fast = false;                // RtsParams.precision == RTS_PRECISION_FAST: tolerance-mode kernels
+    bool pdl = true;                  // frame kernels launched with programmatic stream serialization (reserved[5] bit 6, value 64, turns it off)
     int walk_ctas_per_sm = 4;         // (RTS_WALK_CTAS_PER_SM overrides: tuning runs)
     int n_sm = 148;                   // cudaDevAttrMultiProcessorCount of the handle's device (grids of the persistent-style kernels)
     SlabDev SL{};
@@ -191,6 +192,23 @@ void timer_collect(RtsContext* h) {  // after a stream sync
 }
 
 inline uint32_t blocks_for(uint32_t n, uint32_t b) { return (n + b - 1) / b; }
+
+// Launch of a kernel of the frame chain (k_step -> k_step_dense* -> [k_ingest_remote] -> k_scan_onepass -> k_scatter -> k_step ...).
+// With `pdl` the launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel's CTAs may become resident
+// while the previous kernel of the stream drains its last CTAs (launch latency, block scheduling and the prologue overlap
+// that tail); every such kernel executes griddepcontrol.wait (pdl_wait) before it touches global memory, which blocks until
+// the previous kernel — and, transitively, everything before it — has completed and flushed. Works inside stream capture.
+template <typename... KArgs, typename... Args>
+inline void launch_chain(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+inline bool use_pdl(const RtsContext* h) { return h->pdl && !h->profiling; }
 inline uint32_t walk_ctas_of(const RtsContext* h) { return (uint32_t)h->n_sm * (uint32_t)h->walk_ctas_per_sm; }   // CTAs at the head of k_step's grid that search the previous frame's walk queue
 
 int32_t alloc_agents(RtsContext* h, uint32_t cap) {
@@ -216,9 +234,10 @@ int32_t alloc_agents(RtsContext* h, uint32_t cap) {
     {   // two queues of crowded agents (whole population / interior, and the edge rows of a slab) + their counters
         if ((rc = dev_alloc<uint32_t>(h, &A.dense_q, 2 * (size_t)cap, h->agent_allocs)) != RTS_OK) return rc;
         uint32_t* dn = nullptr;
-        if ((rc = dev_alloc<uint32_t>(h, &dn, 8, h->agent_allocs)) != RTS_OK) return rc;
-        CU(cudaMemsetAsync(dn, 0, 32, h->stream));
+        if ((rc = dev_alloc<uint32_t>(h, &dn, 64, h->agent_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(dn, 0, 256, h->stream));
         A.dense_n = dn;
+        A.work = dn + 32;   // tile counter of the persistent k_step, 128 bytes away from the queue counters
     }
     CU(cudaMemsetAsync(A.stop_req, 0, sizeof(uint32_t) * (size_t)cap, h->stream));
     A.n_dev = h->n_dev;
@@ -306,7 +325,7 @@ int32_t join_walk(RtsContext* h) {
 int32_t launch_scan_reorder(RtsContext* h) {
     const uint32_t nb = blocks_for(((h->F.n_cells + 1u + 7u) & ~7u), SCAN_TILE);
     timer_begin(h, KT_SCAN);
-    k_scan_onepass<<<nb, SCAN_THREADS, 0, h->stream>>>(h->F, h->n_dev);
+    launch_chain(use_pdl(h), k_scan_onepass, dim3(nb), dim3(SCAN_THREADS), h->stream, h->F, h->n_dev);
     timer_end(h, KT_SCAN);
     int32_t rc = join_walk(h);   // a pending walk queue refers to what the scatter is about to overwrite (normally none is pending)
     if (rc != RTS_OK) return rc;
@@ -316,7 +335,7 @@ int32_t launch_scan_reorder(RtsContext* h) {
     const int do_walk = h->map_ready ? 1 : 0;
     const int tick = (h->multi && h->SL.peer_mode && h->exchange_pending) ? 1 : 0;
     h->exchange_pending = false;
-    if (n_slots) k_scatter<<<blocks_for(n_slots, 256), 256, 0, h->stream>>>(n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0, h->P, h->M, wpar, do_walk, tick);
+    if (n_slots) launch_chain(use_pdl(h), k_scatter, dim3(blocks_for(n_slots, 256)), dim3(256), h->stream, n_slots, h->F, h->A, h->SL, h->multi ? 1 : 0, h->P, h->M, wpar, do_walk, tick);
     timer_end(h, KT_REORDER);
     h->launches += 2;
     swap_prev_order(h);
@@ -364,8 +383,8 @@ bool split_frame(const RtsContext* h) {
 
 #define LAUNCH_DENSE(KV, MU)                                                                         \
     do {                                                                                             \
-        if (h->fast) k_step_dense_fast<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq);   \
-        else k_step_dense<KV, MU><<<dgrid, 128, 0, st>>>(h->P, h->M, h->F, Aq, SLq);                \
+        if (h->fast) launch_chain(pdl_ok, k_step_dense_fast<KV, MU>, dgrid, dim3(128), st, h->P, h->M, h->F, Aq, SLq);   \
+        else launch_chain(pdl_ok, k_step_dense<KV, MU>, dgrid, dim3(128), st, h->P, h->M, h->F, Aq, SLq);                \
     } while (0)
 
 // arrival kernels, then — slab handles with a neighbour — the edge rows on the comm stream (their own queue of crowded
@@ -393,12 +412,13 @@ void launch_step_edges(RtsContext* h) {
     Aq.dense_n = h->A.dense_n + 4;
     const SlabDev SLq = h->SL;
     const dim3 grid(2 * SLq.edge_blocks);
-    if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0);
-    else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0);
+    if (h->keep_vel) k_step<true, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0, 0u);
+    else k_step<false, true, false, 1><<<grid, STEP_BLOCK, 0, h->stream4>>>(nb, h->P, h->M, h->F, Aq, SLq, 0u, 0, 0u);
     h->launches += 1;
     if (USE_DENSE_KERNEL) {
         const dim3 dgrid(h->n_sm * 2);
         cudaStream_t st = h->stream4;
+        const bool pdl_ok = false;
         if (h->keep_vel) LAUNCH_DENSE(true, true);
         else LAUNCH_DENSE(false, true);
         h->launches += 1;
@@ -421,15 +441,22 @@ void launch_step_interior(RtsContext* h) {
     const int wp = h->walkq_parity;
     if (wc) h->walkq_pending = false;
     const dim3 grid_w(grid.x + wc);
+    // persistent launches (every launch but the two halves of a split frame): one residency of the device, warps take
+    // 32-slot tiles — the walk queue's first — from A.work (see k_step)
+    const uint32_t wt = wc * (block / 32u);                   // walk tiles
+    const uint32_t n_tiles = wt + blocks_for(nb, 32u);
+    const uint32_t resident = (uint32_t)h->n_sm * (uint32_t)(h->fast ? FAST_MIN_BLOCKS : STEP_MIN_BLOCKS);
+    const dim3 grid_p(USE_PERSISTENT_STEP ? std::max(1u, std::min(resident, blocks_for(n_tiles, block / 32u))) : grid_w.x);
+    const uint32_t wq = USE_PERSISTENT_STEP ? wt : wc;        // leading walk tiles, in the launch's own tile unit
     timer_begin(h, KT_STEP);
     if (split) {   // (exact mode only, see split_frame)
-        if (h->keep_vel) k_step<true, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
-        else k_step<false, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
+        if (h->keep_vel) k_step<true, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp, 0u);
+        else k_step<false, true, false, 2><<<grid_w, STEP_BLOCK, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp, 0u);
     } else if (nb && h->P.enable_alignment) {   // extension: single-domain handles that keep the velocity (checked by check_params)
-        if (h->fast) k_step<true, false, true, 0, true><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
-        else k_step<true, false, false, 0, true><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp);
+        if (h->fast) launch_chain(use_pdl(h), k_step<true, false, true, 0, true>, grid_p, dim3(block), h->stream, nb, h->P, h->M, h->F, Aq, SLq, wq, wp, n_tiles);
+        else launch_chain(use_pdl(h), k_step<true, false, false, 0, true>, grid_p, dim3(block), h->stream, nb, h->P, h->M, h->F, Aq, SLq, wq, wp, n_tiles);
     } else if (nb) {
-#define LAUNCH_STEP(KV, MU, FA) k_step<KV, MU, FA><<<grid_w, block, 0, h->stream>>>(nb, h->P, h->M, h->F, Aq, SLq, wc, wp)
+#define LAUNCH_STEP(KV, MU, FA) launch_chain(use_pdl(h), k_step<KV, MU, FA>, grid_p, dim3(block), h->stream, nb, h->P, h->M, h->F, Aq, SLq, wq, wp, n_tiles)
         const int variant = (h->keep_vel ? 4 : 0) | (h->multi ? 2 : 0) | (h->fast ? 1 : 0);
         switch (variant) {
             case 0: LAUNCH_STEP(false, false, false); break;
@@ -448,6 +475,7 @@ void launch_step_interior(RtsContext* h) {
         timer_begin(h, KT_DENSE);
         const dim3 dgrid(h->n_sm * RTS_DENSE_GRID_PER_SM);
         cudaStream_t st = h->stream;
+        const bool pdl_ok = use_pdl(h) && !split;
         if (dv == 0) LAUNCH_DENSE(false, false);
         else if (dv == 1) LAUNCH_DENSE(false, true);
         else if (dv == 2) LAUNCH_DENSE(true, false);
@@ -473,7 +501,7 @@ cudaStream_t comm_stream(const RtsContext* h) { return h->frame_is_split ? h->st
 void launch_ingest(RtsContext* h) {
     const uint32_t per_dir = h->SL.cap_mig + h->SL.cap_halo;
     timer_begin(h, KT_INGEST);
-    k_ingest_remote<<<dim3(blocks_for(per_dir, 256), 2), 256, 0, comm_stream(h)>>>(h->cap_main, h->SL, h->F, h->A);
+    launch_chain(use_pdl(h) && !h->frame_is_split, k_ingest_remote, dim3(blocks_for(per_dir, 256), 2), dim3(256), comm_stream(h), h->cap_main, h->SL, h->F, h->A);
     timer_end(h, KT_INGEST);
     h->launches += 1;
     h->ingest_done = true;
@@ -648,6 +676,7 @@ int32_t rts_create(const RtsParams* params, int32_t device_id, RtsHandle* out) {
     h->overlap_exchange = (params->reserved[5] & 8u) != 0;
     h->graph_slabs = (params->reserved[5] & 16u) != 0;
     h->want_peer = (params->reserved[5] & 32u) == 0;
+    h->pdl = (params->reserved[5] & 64u) == 0;
     *out = h;
     int prio_lo = 0, prio_hi = 0;   // the comm stream (edge rows, exchange, ingest of a slab) outranks the bulk kernels
     cudaSetDevice(device_id);

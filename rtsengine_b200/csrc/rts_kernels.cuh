@@ -43,6 +43,14 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 #ifndef RTS_FAST_MIN_BLOCKS
 #define RTS_FAST_MIN_BLOCKS 10
 #endif
+#ifndef RTS_PERSISTENT_STEP
+#define RTS_PERSISTENT_STEP 0
+#endif
+// k_step as one residency of the device whose warps take 32-slot tiles from a device-wide counter (see k_step). Built to
+// remove the idle tail of the 5.7-wave grid (ncu: the average SM is idle for 16 % of the launch); measured SLOWER on config 3
+// (k_step 97 us against 74.6 us; static striding without the counter 91 us; whole CTAs taking 128 slots at a time 80.5 us —
+// profiles/README.md), so the plain grid stays the default and this is a build switch for further experiments.
+constexpr bool USE_PERSISTENT_STEP = RTS_PERSISTENT_STEP != 0;
 constexpr int FAST_BLOCK = RTS_FAST_BLOCK;             // threads per CTA of the tolerance-mode k_step (no shared memory: registers set the occupancy)
 constexpr int FAST_MIN_BLOCKS = RTS_FAST_MIN_BLOCKS;
 #ifndef RTS_FAST_DENSE_CAND
@@ -77,6 +85,13 @@ constexpr bool USE_SPILL = true;
 constexpr bool USE_SPILL = !(USE_DENSE_KERNEL && RTS_NBR_CAP >= RTS_DENSE_MIN);
 #endif
 constexpr uint32_t INVALID_CELL = 0xFFFFFFFFu;
+
+// Programmatic dependent launch (see launch_chain in rts_abi.cu). pdl_wait: nothing of the previous kernels' output may be
+// read, and nothing they read may be overwritten, before this returns. pdl_trigger: the next kernel of the stream may start
+// making its CTAs resident (it blocks in its own pdl_wait until this grid has completed). Both are no-ops in a kernel that
+// was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // key2.y = cy << 16 | cx << 3 | ghost << 2 | state, (cx, cy) = 2-D coordinates of the physics-grid cell (13 bits each)
 __device__ __forceinline__ uint32_t pack_cs(uint32_t cx, uint32_t cy, uint32_t ghost, uint32_t state) {
@@ -257,6 +272,7 @@ struct AgentArrays {
     uint32_t* walk_n;    // [parity] their number; k_scatter of the next frame resets it
     uint32_t* dense_q;   // slots of the agents deferred to k_step_dense this frame
     uint32_t* dense_n;   // [0] their number (reset by k_scatter); [4] the same for the queue of a slab's edge-row launch
+    uint32_t* work;      // tiles handed out by the persistent k_step beyond each warp's first (reset by k_scatter); a cache line of its own
     uint32_t n_tris_dev_hint;  // != 0 once a map is uploaded (a missing triangle index then means the walk failed)
 };
 
@@ -308,6 +324,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(FineGrid F, uint3
     __shared__ uint32_t smem[32];
     __shared__ uint32_t warp_tot[SCAN_THREADS / 32];
     __shared__ uint32_t s_tile, s_prefix, s_epoch;
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0) {
         s_epoch = *((volatile uint32_t*)(F.ticket + 1));
         s_tile = atomicAdd(F.ticket, 1u);
@@ -459,10 +477,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(FineGrid F, uint32_
 // for k_walk, which runs the reference's own search for them.
 __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentArrays A, SlabDev SL, int multi, RtsParams P, MapDev M,
                                                  int parity, int do_walk, int tick_epoch) {
+    pdl_wait();
+    pdl_trigger();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0 && tick_epoch) SL.epoch[0] += 1u;   // one peer exchange has been delivered and ingested (see k_push)
     if (p == 0) {
         A.dense_n[0] = 0u; A.dense_n[4] = 0u;   // the dense queues of this frame (whole / interior, edge rows) have been consumed
+        A.work[0] = 0u;                         // ... and the tile counter of its frame kernel
         A.walk_n[parity ^ 1] = 0u;              // ... and the walk queue of the previous frame (its k_walk was joined before this launch)
     }
     if (multi && p < 8u) {              // ... and so have the exchange headers (the frame kernel packs into them again)
@@ -514,10 +535,10 @@ __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentAr
 // second stream: a few agents outside the map need 100+ dependent hops, ~40 us for one thread) and by k_walk.
 template <bool WIDE>
 __device__ __forceinline__ void drain_walk_queue(const RtsParams& P, const MapDev& M, const AgentArrays& A, int parity, uint32_t cta,
-                                                 uint32_t n_ctas, uint32_t threads_per_cta) {
+                                                 uint32_t n_ctas, uint32_t threads_per_cta, uint32_t t_in) {
     const uint32_t qn = A.walk_n[parity];
     for (uint32_t base = cta * threads_per_cta; base < qn; base += n_ctas * threads_per_cta) {
-        const uint32_t i = base + threadIdx.x;
+        const uint32_t i = base + t_in;
         const unsigned mask = __ballot_sync(0xffffffffu, i < qn);
         if (i < qn) {
             const uint32_t d = A.walk_q[i];
@@ -535,7 +556,7 @@ __device__ __forceinline__ void drain_walk_queue(const RtsParams& P, const MapDe
 }
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_walk(RtsParams P, MapDev M, AgentArrays A, int parity) {
-    drain_walk_queue<WIDE>(P, M, A, parity, blockIdx.x, gridDim.x, blockDim.x);
+    drain_walk_queue<WIDE>(P, M, A, parity, blockIdx.x, gridDim.x, blockDim.x, threadIdx.x);
 }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
@@ -591,6 +612,8 @@ __global__ void __launch_bounds__(256) k_push(SlabDev SL) {
 // Peer mode: waits for the neighbour's flag of this epoch first (bounded: a neighbour that never delivers is reported
 // through SL.overflow = 3 after ~20 s instead of hanging the device).
 __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArrays A) {
+    pdl_wait();
+    pdl_trigger();
     const uint32_t cap_mig = SL.cap_mig, cap_halo = SL.cap_halo;
     const int dir = (int)blockIdx.y;                       // both directions in one launch
     ExBuf B = SL.recv[dir];
@@ -1058,27 +1081,30 @@ __device__ __forceinline__ void fast_candidate(ForceSums& S, const FastScan& c, 
     }
     const float mass_j = fabsf(o.w);
     const float rc = fabsf(o.z) + c.radius;
-    const float rc2 = rc * rc;
     const float inv_d = rsqrt_fast(d2);
-    const float x = rc2 * (inv_d * inv_d);
+    const float u = rc * inv_d;
+    const float x = u * u;                               // r_collision^2 / |dr|^2
     const float w = mass_j * rcp_fast(c.mass_i + mass_j);
-    const float m3 = (3.f * x) * (x * x);
-    const float mag = fminf(m3, 50000.0f);
-    const float s_rep = (acc && x > 0.8f) ? (mag * w) * inv_d : 0.f;
+    // min(50000, 3 x^3) = 3 min(50000/3, x^3): the factor 3 is applied once, to the sum (fast_accumulate)
+    const float mag = fminf((x * x) * x, 16666.666f);
+    const bool rep_on = acc & (x > 0.8f);
+    const float s_rep = rep_on ? (mag * w) * inv_d : 0.f;
     S.repulsion.x = __fmaf_rn(-dx, s_rep, S.repulsion.x);
     S.repulsion.y = __fmaf_rn(-dy, s_rep, S.repulsion.y);
     // state_j == MOVING (= 0): both sign bits of {radius, mass} clear
-    const bool moving_j = acc && (__float_as_int(o.z) | __float_as_int(o.w)) >= 0;
+    const bool moving_j = acc & ((__float_as_int(o.z) | __float_as_int(o.w)) >= 0);
     if (PUSH) {
-        const float s_push = (c.standing && moving_j && x > 0.75f) ? x * w : 0.f;
+        const bool push_on = c.standing & moving_j & (x > 0.75f);
+        const float s_push = push_on ? x * w : 0.f;
         S.push.x = __fmaf_rn(-dx, s_push, S.push.x);
         S.push.y = __fmaf_rn(-dy, s_push, S.push.y);
     }
     // x > rc2 / RSCATTER^2  <=>  d2 < RSCATTER^2, implied by d2 < r_max2 unless RSCATTER^2 < r_max2
-    const bool sc = CHECKS ? (moving_j && d2 < c.rscatter2) : moving_j;
-    S.dr_nn.x += sc ? dx : 0.f;
-    S.dr_nn.y += sc ? dy : 0.f;
-    S.n_neighbours += sc ? 1.f : 0.f;
+    const bool sc = CHECKS ? (moving_j & (d2 < c.rscatter2)) : moving_j;
+    const float m = sc ? 1.f : 0.f;
+    S.dr_nn.x = __fmaf_rn(dx, m, S.dr_nn.x);             // (exact: m is 0 or 1)
+    S.dr_nn.y = __fmaf_rn(dy, m, S.dr_nn.y);
+    S.n_neighbours += m;
     if (ALIGN) {
         if (c.moving && moving_j && d2 < c.ralign2) {
             const float2 vj = c.vel_out[c.src[q]];
@@ -1109,13 +1135,16 @@ __device__ __forceinline__ void fast_loop(ForceSums& S, const FastScan& c, const
 template <bool ALIGN>
 __device__ __forceinline__ void fast_accumulate(ForceSums& S, const FastScan& c, const float4* __restrict__ pos4, const uint2* __restrict__ key2,
                                                 uint32_t v0, uint32_t vstep, unsigned lanes) {
-    if (ALIGN) { fast_loop<true, true, true>(S, c, pos4, key2, v0, vstep); return; }   // (the opt-in extension takes the general loop)
-    const bool push = __any_sync(lanes, c.standing);
-    const bool checks = __any_sync(lanes, c.near_edge) || !(c.rscatter2 >= c.r_max2);
-    if (!push && !checks) fast_loop<false, false, false>(S, c, pos4, key2, v0, vstep);
-    else if (push && !checks) fast_loop<true, false, false>(S, c, pos4, key2, v0, vstep);
-    else if (!push) fast_loop<false, true, false>(S, c, pos4, key2, v0, vstep);
-    else fast_loop<true, true, false>(S, c, pos4, key2, v0, vstep);
+    if (ALIGN) fast_loop<true, true, true>(S, c, pos4, key2, v0, vstep);   // (the opt-in extension takes the general loop)
+    else {
+        const bool push = __any_sync(lanes, c.standing);
+        const bool checks = __any_sync(lanes, c.near_edge) || !(c.rscatter2 >= c.r_max2);
+        if (!push && !checks) fast_loop<false, false, false>(S, c, pos4, key2, v0, vstep);
+        else if (push && !checks) fast_loop<true, false, false>(S, c, pos4, key2, v0, vstep);
+        else if (!push) fast_loop<false, true, false>(S, c, pos4, key2, v0, vstep);
+        else fast_loop<true, true, false>(S, c, pos4, key2, v0, vstep);
+    }
+    S.repulsion = S.repulsion * 3.f;   // see fast_candidate: the sum was built with min(50000/3, x^3)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1126,18 +1155,20 @@ __device__ __forceinline__ void fast_accumulate(ForceSums& S, const FastScan& c,
 // PHASE 0: every slot; PHASE 1: the edge rows of a slab only (see SlabDev), PHASE 2: everything else.
 template <bool KEEP_VEL, bool MULTI, bool FAST, int PHASE = 0, bool ALIGN = false>
 __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MIN_BLOCKS : STEP_MIN_BLOCKS) k_step(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL,
-                                                                                 uint32_t walk_ctas, int walk_parity) {
-    // the first walk_ctas CTAs finish the triangle walk of the previous frame (the agents its k_scatter queued)
-    if (blockIdx.x < walk_ctas) {
-        if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, blockIdx.x, walk_ctas, FAST ? FAST_BLOCK : STEP_BLOCK);
-        else drain_walk_queue<true>(P, M, A, walk_parity, blockIdx.x, walk_ctas, FAST ? FAST_BLOCK : STEP_BLOCK);
-        return;
-    }
-    const uint32_t bid = blockIdx.x - walk_ctas;
+                                                                                 uint32_t walk_ctas, int walk_parity, uint32_t n_tiles) {
+    // Work is handed out in TILES. Default: a tile is a CTA's worth of slots, tile = blockIdx.x. PERSIST (build switch
+    // RTS_PERSISTENT_STEP, launches that cover all slots): a tile is 32 slots, the grid is one residency of the device, and
+    // every WARP takes tiles from a device-wide counter (A.work, reset by k_scatter) until none is left.
+    // The first walk_ctas tiles finish the triangle walk of the previous frame (the agents its k_scatter queued).
+    constexpr bool PERSIST = USE_PERSISTENT_STEP && PHASE == 0;
     constexpr uint32_t BLOCK = FAST ? FAST_BLOCK : STEP_BLOCK;
+    constexpr uint32_t TILE = PERSIST ? 32u : BLOCK;   // slots per tile
     __shared__ uint2 s_kq[FAST ? 1 : NBR_CAP][FAST ? 1 : STEP_BLOCK];   // {key, candidate index} of the NBR_CAP smallest keys seen, ascending
 
+    pdl_wait();
+    pdl_trigger();
     const int tid = threadIdx.x;
+    const uint32_t t_in = PERSIST ? ((uint32_t)tid & 31u) : (uint32_t)tid;   // index inside the tile
     const uint32_t n = MULTI ? *A.n_dev : n_bound;   // slabs: the population changes every frame, the count lives on the device
     // edge slots of a slab: [0, edge_a) and [edge_b, n)
     // (the first and the last fine row are always edge rows: positions outside the slab's grid are clamped into them,
@@ -1149,9 +1180,22 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
         edge_b = max(edge_b, edge_a);
     }
     const uint32_t cover = SL.edge_blocks * BLOCK;   // slots the PHASE 1 grid reaches on either side
-    uint32_t block0 = bid * BLOCK;
+    const uint32_t warps_in_grid = gridDim.x * (BLOCK / 32u);
+    uint32_t tile = PERSIST ? blockIdx.x * (BLOCK / 32u) + ((uint32_t)tid >> 5) : blockIdx.x;   // first tile: the warp's own number
+    for (;;) {
+    uint32_t next_raw = 0u;
+    if (PERSIST) {
+        if (tile >= n_tiles) break;
+        if (t_in == 0u) next_raw = atomicAdd(A.work, 1u);   // (consumed at the end of the loop body)
+    }
+    if (tile < walk_ctas) {
+        if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, tile, walk_ctas, TILE, t_in);
+        else drain_walk_queue<true>(P, M, A, walk_parity, tile, walk_ctas, TILE, t_in);
+    } else {
+    const uint32_t bid = tile - walk_ctas;
+    uint32_t block0 = bid * TILE;
     if (PHASE == 1 && bid >= SL.edge_blocks) block0 = edge_b + (bid - SL.edge_blocks) * BLOCK;
-    const uint32_t p = block0 + tid;
+    const uint32_t p = block0 + t_in;
     const bool in_range = p < n;
 
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1372,6 +1416,10 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     const uint32_t rank = warp_aggregated_rank(F.count, cell, active);
     if (!to_dense) A.cellrank[p] = make_uint2(cell, rank);
     }
+    }   // (tile of slots)
+    if (!PERSIST) break;
+    tile = warps_in_grid + __shfl_sync(0xffffffffu, next_raw, 0);
+    }   // (tiles)
 }
 
 // One lane GROUP per crowded agent (see k_step), DENSE_LANES = 16 lanes: two agents per warp. The kernel's duration is the
@@ -1394,6 +1442,8 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     __shared__ uint2 s_list[4 * DENSE_GROUPS][DENSE_MAX];
     __shared__ uint2 s_sorted[4 * DENSE_GROUPS][DENSE_MAX];
     __shared__ float s_terms[4 * DENSE_GROUPS][7][DENSE_LANES];
+    pdl_wait();
+    pdl_trigger();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned grp = lane / DENSE_LANES;        // which agent of the warp
     const unsigned gl = lane % DENSE_LANES;         // lane inside the group
@@ -1553,6 +1603,8 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
 template <bool KEEP_VEL, bool MULTI>
 __global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, FineGrid F, AgentArrays A, SlabDev SL) {
     constexpr uint32_t GL = FAST_DENSE_LANES, GROUPS = 32u / GL;
+    pdl_wait();
+    pdl_trigger();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned grp = lane / GL, gl = lane % GL;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

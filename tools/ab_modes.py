@@ -12,7 +12,11 @@ WINDOWS = [(5, 20), (25, 95), (120, 100)]          # (frames to skip from the pr
 for prec in modes:
     p = engine.default_params(1024, 1024)
     p.precision = prec
-    res = {"lib": os.path.basename(engine.LIB_PATH), "precision": prec}
+    if os.environ.get("RTS_FINE_CS"):   # explicit gather-cell size (RtsParams.reserved[1] = the float's bits)
+        import struct
+        p.reserved[1] = struct.unpack("I", struct.pack("f", float(os.environ["RTS_FINE_CS"])))[0]
+    p.reserved[5] = int(os.environ.get("RTS_RESERVED5", "0"))   # e.g. 64 = no programmatic dependent launch
+    res = {"lib": os.path.basename(engine.LIB_PATH), "precision": prec, "reserved5": int(p.reserved[5]), "fine_cs": os.environ.get("RTS_FINE_CS", "auto")}
     with engine.GpuAgentSystem(p) as g:
         g.upload_map(tables); g.upload_paths(paths)
         for profiling in (False, True):

@@ -1,4 +1,6 @@
-"""Per-rank timing of the slab path (diagnostic). torchrun --nproc-per-node N tools/slab_trace.py [agents_per_gpu] [frames] [cap_halo] [cap_mig]"""
+"""Per-rank timing of the slab path (diagnostic). torchrun --nproc-per-node N tools/slab_trace.py [agents_per_gpu] [frames] [cap_halo] [cap_mig]
+RTS_TRACE_CONFIG4=1: BASELINE config 4 instead (8x8 config-3 tiles, agents_per_gpu * N agents in total, strong-scaling layout);
+RTS_TRACE_PRECISION / RTS_RESERVED5 select the arithmetic mode and the exchange switches."""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -12,11 +14,18 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 tile = scenario.load_map("map_c3.npz")
-fx = scenario.tile_map(tile, 1, world)
+c4 = os.environ.get("RTS_TRACE_CONFIG4") == "1"
+fx = scenario.tile_map(tile, 8, 8) if c4 else scenario.tile_map(tile, 1, world)
 nx, ny = (int(v) for v in fx["n_cells"])
 base = engine.default_params(nx, ny)
-agents = scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
-agents["gid"] = np.arange(per_gpu * world, dtype=np.uint32)
+base.precision = int(os.environ.get("RTS_TRACE_PRECISION", "1"))
+base.reserved[5] = int(os.environ.get("RTS_RESERVED5", "0"))
+agents = scenario.tiled_agents(tile, 8, 8, per_gpu * world // 64, seed=1237) if c4 else scenario.tiled_agents(tile, 1, world, per_gpu, seed=1236)
+agents["gid"] = np.arange(len(agents["r"]), dtype=np.uint32)
+if c4 and len(sys.argv) <= 3:   # capacities as the bench leg sizes them (slabs._slab_case)
+    per_unit_height = len(agents["r"]) / (ny * 5.0)
+    cap_halo = int(max(4096, 6 * per_unit_height * slabs.halo_width(base.r_max2)))
+    cap_mig = int(max(1024, 6 * per_unit_height * 2.0))
 bounds = slabs.partition_rows(agents["r"][:, 1], base.ns_ny, base.ns_cell_size, world)
 parts = slabs.split_agents(agents, bounds, base.ns_cell_size, base.ns_ny)
 sr = slabs.SlabRank(base, bounds, rank, local, cap_migrants=cap_mig, cap_halo=cap_halo)
@@ -36,9 +45,9 @@ for mode in ("profiled", "plain", "profiled2"):
     res[mode] = {"enqueue_ms_per_frame": 1e3 * (t1 - t0) / frames, "wall_ms_per_frame": 1e3 * (t2 - t0) / frames,
                  "dev_ms_per_frame": sr.g.timings().last_step_ms / frames}
     if mode.startswith("profiled"):
-        res[mode]["kernels"] = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in ("step", "scan", "reorder", "exchange", "ingest")}
+        res[mode]["kernels"] = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in ("step", "dense", "scan", "reorder", "exchange", "ingest")}
 own = sr.owned(("r",))
-res["owned"] = len(own["gid"]); res["rank"] = rank
+res["owned"] = len(own["gid"]); res["rank"] = rank; res["config4"] = c4; res["caps"] = [cap_halo, cap_mig]; res["fine_cells"] = [int(v) for v in sr.g.fine_grid()] if hasattr(sr.g, "fine_grid") else None
 for r in range(world):
     dist.barrier()
     if r == rank: print(json.dumps(res), flush=True)
