@@ -86,7 +86,9 @@ typedef struct RtsParams {
        [5] 8 = slab handles step their edge rows first on a comm stream, followed there by the exchange and the ingest,
            while the interior is stepped on the main stream (measured equal to the plain layout);
            16 = slab frames are replayed from a CUDA graph as well, ncclSend/ncclRecv captured with them
-           32 = keep the ncclSend/ncclRecv exchange instead of the peer-memory exchange (rts_slab_exchange_mode) */
+           32 = keep the ncclSend/ncclRecv exchange instead of the peer-memory exchange (rts_slab_exchange_mode)
+           64 = launch the frame kernels without programmatic dependent launch (by default every kernel of the frame chain
+                is launched with cudaLaunchAttributeProgrammaticStreamSerialization and waits in griddepcontrol.wait) */
     uint32_t reserved[6];
     /* arithmetic of the frame kernel:
        RTS_PRECISION_EXACT (0, the default): IEEE division / square root, no FMA contraction, neighbour sums added in the

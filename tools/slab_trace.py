@@ -35,15 +35,19 @@ sr.init_comm(uid[0])
 sr.g.upload_map(scenario.tables_of(fx)); sr.g.upload_paths(scenario.paths_of(fx)); sr.g.set_agents(parts[rank]); sr.halo_refresh()
 sr.g.update(10, sync=True)
 res = {}
-for mode in ("profiled", "plain", "profiled2"):
+for mode, nf in (("profiled", frames), ("plain20_a", 20), ("plain20_b", 20), ("plain20_c", 20), ("plain", frames), ("plain_b", frames), ("profiled2", frames)):
     sr.g.set_profiling(mode.startswith("profiled"))
     dist.barrier(); torch.cuda.synchronize()
+    t_enter = time.perf_counter()
     sr.g.reset_timings()
     t0 = time.perf_counter()
-    sr.g.update(frames); t1 = time.perf_counter()
+    sr.g.update(nf); t1 = time.perf_counter()
     sr.g.sync(); t2 = time.perf_counter()
-    res[mode] = {"enqueue_ms_per_frame": 1e3 * (t1 - t0) / frames, "wall_ms_per_frame": 1e3 * (t2 - t0) / frames,
-                 "dev_ms_per_frame": sr.g.timings().last_step_ms / frames}
+    tt = torch.tensor([t_enter], dtype=torch.float64, device="cuda")   # (CLOCK_MONOTONIC is shared by the ranks of one box)
+    lo, hi = tt.clone(), tt.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    res[mode] = {"frames": nf, "enqueue_ms_per_frame": round(1e3 * (t1 - t0) / nf, 5), "wall_ms_per_frame": round(1e3 * (t2 - t0) / nf, 5),
+                 "dev_ms_per_frame": round(sr.g.timings().last_step_ms / nf, 5), "start_skew_ms_over_ranks": round(1e3 * float((hi - lo).item()), 4)}
     if mode.startswith("profiled"):
         res[mode]["kernels"] = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in ("step", "dense", "scan", "reorder", "exchange", "ingest")}
 own = sr.owned(("r",))
