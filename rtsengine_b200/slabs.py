@@ -272,6 +272,9 @@ def bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
         os._exit(1)
 
 
+ALIGN_FRAMES = 8   # untimed frames between the host barrier and the timed window of a multi-GPU leg (one CUDA-graph replay)
+
+
 def _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, precision, K, Wm, repeats, reserved5=0, clock_sampler=None):
     """One multi-GPU workload: the population cut into `world` y-slabs at agent-count quantiles of physics-grid rows, `repeats`
     repetitions of the same K frames (re-uploaded + Wm warm-up frames each time), device time = max over ranks, median over
@@ -306,8 +309,13 @@ def _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, pre
         sr.halo_refresh()
         sr.g.update(Wm, sync=True)
         barrier()                   # every rank enters the timed region together
-        sr.g.reset_timings()
+        # ... on the HOST. The ranks leave the barrier a few hundred microseconds apart (Python), which is 10 % of a 20-frame
+        # window; ALIGN_FRAMES further untimed frames are enqueued first, during which the exchange itself brings the
+        # devices into step. The K timed frames follow in the same stream without a host synchronisation; their CUDA events
+        # bracket exactly K frames on every rank.
         t0 = time.perf_counter()
+        sr.g.update(ALIGN_FRAMES)
+        sr.g.reset_timings()
         sr.g.update(K)
         sr.g.sync()
         wall = time.perf_counter() - t0
@@ -324,7 +332,7 @@ def _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, pre
            "conservation": {"agents_after": int(cnt.item()), "agents_before": n_total},
            "exchange": {0: "none", 1: "ncclSend/ncclRecv per frame", 2: "peer memory over NVLink (CUDA IPC, k_push + epoch flags), frames replayed from a CUDA graph"}[
                int(sr.g.L.rts_slab_exchange_mode(sr.g.h))],
-           "wall_s_last_repeat": wall}
+           "wall_s_last_repeat": wall, "wall_frames": ALIGN_FRAMES + K}
     return res, sr
 
 
@@ -488,7 +496,7 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
         a4 = scenario.tiled_agents(tile, 8, 8, args.agents4 // 64, seed=1237)
         n4 = len(a4["r"])
         a4["gid"] = np.arange(n4, dtype=np.uint32)
-        c4, sr4 = _slab_case(dist, torch, engine, rank, world, local, fx4, a4, n4, precision, K, Wm, 3, reserved5)
+        c4, sr4 = _slab_case(dist, torch, engine, rank, world, local, fx4, a4, n4, precision, K, Wm, args.repeats, reserved5)
         sr4.close()
         del a4
         c4["workload"] = (f"config4: {n4} agents on the 8192x8192-cell map (8x8 config-3 tiles, 12 800 buildings, 4096 groups) cut into "
@@ -516,12 +524,13 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
                                    f"{200 * world} buildings, {64 * world} groups), y-slabs aligned to physics-grid rows, halo + migration "
                                    f"exchange every frame ({main['exchange']})",
                        "agents": n_total, "agents_per_gpu": per_gpu, "slab_rows": main["slab_rows"], "precision": PRECISION_LABEL[precision],
-                       "timing": f"median of {args.repeats} repetitions of the same {K} frames, max over ranks of the device time",
+                       "timing": f"median of {args.repeats} repetitions of the same {K} frames (each: re-upload, {Wm} warm-up frames, host barrier, "
+                                 f"{ALIGN_FRAMES} untimed frames that bring the devices into step, then the {K} timed frames), max over ranks of the device time",
                        "l2_policy": "inputs larger than L2 (per-GPU state > 126 MB); no explicit flush"},
             "repeat_ms_per_step": main["repeat_ms_per_step"],
             "clocks": clocks.summary(), "gpu_launches": main["gpu_launches"],
             "conservation": main["conservation"],
-            "e2e": {"value": n_total * K / main["wall_s_last_repeat"], "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+            "e2e": {"value": n_total * main["wall_frames"] / main["wall_s_last_repeat"], "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "multi-GPU leg keeps state device-resident; host wall-clock around rts_step on rank 0 (no end-to-end claim at N>1)"},
             "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9 / peak,
