@@ -357,7 +357,7 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
             one.upload_map(scenario.tables_of(fx))
             one.upload_paths(scenario.paths_of(fx))
             one.set_agents({k: v for k, v in agents.items() if k != "gid"})
-            one.update(3 + frames, sync=True)
+            one.update(3 + ALIGN_FRAMES + frames, sync=True)   # (what _slab_case stepped: warm-up + alignment + timed frames)
             ref = one.communicate(names)
     bad = np.zeros(len(own["gid"]), bool)
     for k in names:
@@ -373,7 +373,7 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
             bad |= (got != want).reshape(len(got), -1).any(1)
     n_bad = torch.tensor([int(bad.sum()), len(own["gid"])], device="cuda", dtype=torch.int64)
     dist.all_reduce(n_bad)
-    return {"mismatching_agents": int(n_bad[0].item()), "agents_compared": int(n_bad[1].item()), "frames": 3 + frames,
+    return {"mismatching_agents": int(n_bad[0].item()), "agents_compared": int(n_bad[1].item()), "frames": 3 + ALIGN_FRAMES + frames,
             "fields": list(names), "precision": "exact", "exchange": res["exchange"],
             "what": f"{world} slabs over the real inter-GPU exchange vs ONE single-domain handle on rank 0, same {n_total} agents "
                     f"({world} config-3 tiles), every agent, bitwise"}
