@@ -72,7 +72,12 @@ typedef struct RtsParams {
                                 a MOVING agent on its last leg within 2*radius + sqrt(finished_area(group)/pi) of path_end stops
                                 and stops its same-group neighbours of the seek neighbour list within finish_radius
                                 (SeekSystem.cpp:235-275, CommandGroupManager.h:141-177); the reference runs this inside its serial
-                                per-agent loop, here every agent sees the group areas and neighbour states of the frame start */
+                                per-agent loop, here every agent sees the group areas and neighbour states of the frame start.
+                                On slab handles the halo band widens to finish_radius (< ns_cell_size required), halo records
+                                carry the navigation record so that every rank evaluates the rule for its ghosts too and stops
+                                only agents it owns, and the per-group stop COUNTS are all-reduced every frame (ncclAllReduce,
+                                the only collective on the frame path; such frames are not replayed from a CUDA graph): the
+                                result stays bit-identical to the single-domain run for any number of slabs */
     uint32_t walk_all;       /* 1: keep tri_idx for every agent; 0: MOVING agents only (as SeekSystem.cpp:206) */
     /* multi-GPU slab owned by this handle: physics-grid rows [slab_row_lo, slab_row_hi); 0,ns_ny = whole map */
     int32_t slab_row_lo, slab_row_hi;

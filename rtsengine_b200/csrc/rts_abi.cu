@@ -104,7 +104,7 @@ struct RtsContext {
     void* ex_send[2] = {nullptr, nullptr};
     void* ex_recv[2] = {nullptr, nullptr};
     uint32_t* n_dev = nullptr;
-    // peer exchange over NVLink (CUDA IPC): see SlabDev / k_push
+    // peer exchange over NVLink (CUDA IPC): see SlabDev
     void* arena = nullptr;            // this rank's receive buffers (2 directions x 2 parities) + flags + epoch words, exported to the neighbours
     void* peer_arena[2] = {nullptr, nullptr};   // the neighbours' arenas as mapped into this process
     bool want_peer = true;            // reserved[5] bit 5 (value 32): keep the per-frame ncclSend/ncclRecv exchange instead
@@ -358,6 +358,13 @@ int32_t launch_scan_reorder(RtsContext* h) {
     return RTS_OK;
 }
 
+// Width of the band along a slab boundary whose agents are mirrored on the neighbour: the interaction range; with the arrival
+// rule on, finish_radius — an agent can stop (and be stopped by) same-group agents that far away (k_arrive).
+float halo_band(const RtsParams& P) {
+    const float physics = std::sqrt(P.r_max2) * 1.05f + 0.25f;
+    return P.enable_arrival ? std::max(physics, P.finish_radius + 0.25f) : physics;
+}
+
 // Edge rows of a slab (SlabDev): the fine rows that reach into the halo band plus the farthest an agent can travel in one
 // frame (velocity clamp of the fastest unit type + its seek speed), with one more fine row of margin.
 void set_edge_rows(RtsContext* h) {
@@ -392,7 +399,8 @@ bool split_frame(const RtsContext* h) {
 void launch_step_edges(RtsContext* h) {
     const uint32_t nb = h->multi ? h->cap_main : h->n;
     if (h->P.enable_arrival && nb && h->M.n_groups) {
-        k_area_sync<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M);
+        if (h->multi) k_area_sync_counts<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M, 3.14159265358979323846f * h->P.rhard * h->P.rhard);
+        else k_area_sync<<<blocks_for(h->M.n_groups, 256), 256, 0, h->stream>>>(h->M);
         k_arrive<<<blocks_for(nb, 256), 256, 0, h->stream>>>(nb, h->P, h->M, h->F, h->A, h->multi ? 1 : 0);
         h->launches += 2;
     }
@@ -550,7 +558,24 @@ int32_t exchange_peer(RtsContext* h, bool published_by_frame) {
     h->exchange_pending = true;
     return RTS_OK;
 }
-int32_t exchange(RtsContext* h, bool published_by_frame) { return h->SL.peer_mode ? exchange_peer(h, published_by_frame) : exchange_nccl(h); }
+// slab handles with the arrival rule: the stops each rank has claimed so far, summed over the ranks (k_area_sync_counts of the
+// next frame turns the sum into the groups' finished areas). The one collective on the frame path — and only with the rule on.
+int32_t reduce_stop_counts(RtsContext* h) {
+    if (!h->multi || !h->P.enable_arrival || !h->M.n_groups) return RTS_OK;
+    cudaStream_t st = comm_stream(h);
+    if (h->nranks > 1) {
+        if (!h->comm) return h->fail(RTS_E_STATE, "exchange", "rts_comm_init has not been called");
+        const ncclResult_t r = h->p_ncclAllReduce(h->M.stop_local, h->M.stop_global, h->M.n_groups, ncclUint32, ncclSum, h->comm, st);
+        if (r != ncclSuccess) return h->fail(RTS_E_NCCL, "ncclAllReduce", h->p_ncclGetErrorString(r));
+    } else {
+        CU(cudaMemcpyAsync(h->M.stop_global, h->M.stop_local, sizeof(uint32_t) * h->M.n_groups, cudaMemcpyDeviceToDevice, st));
+    }
+    return RTS_OK;
+}
+int32_t exchange(RtsContext* h, bool published_by_frame) {
+    const int32_t rc = h->SL.peer_mode ? exchange_peer(h, published_by_frame) : exchange_nccl(h);
+    return rc != RTS_OK ? rc : reduce_stop_counts(h);
+}
 
 int32_t launch_frame(RtsContext* h) {
     // a split slab frame enqueues edge rows -> exchange -> ingest on the (high-priority) comm stream BEFORE the interior
@@ -563,6 +588,7 @@ int32_t launch_frame(RtsContext* h) {
     }
     launch_step_interior(h);
     if (h->multi && h->nranks > 1 && !h->ingest_done && (rc = exchange(h, USE_DENSE_KERNEL)) != RTS_OK) return rc;
+    if (h->multi && h->nranks <= 1 && (rc = reduce_stop_counts(h)) != RTS_OK) return rc;
     return frame_end(h);
 }
 
@@ -644,9 +670,9 @@ static int32_t check_params(RtsContext* h, const RtsParams* p) {
     if (p->enable_alignment && (h->multi || p->reserved[0] != 0))
         return h->fail(RTS_E_STATE, "params", "enable_alignment needs a single-domain handle that keeps the per-step velocity (halo records carry no velocity)");
     if (p->enable_alignment && !(p->ralign > 0)) return h->fail(RTS_E_ARG, "params", "ralign must be positive");
-    if (p->enable_arrival && h->multi)
-        return h->fail(RTS_E_STATE, "params", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's finished "
-                                              "area and the stop requests of ghost agents across slabs (run arrival on a single-domain handle)");
+    if (p->enable_arrival && h->multi && !(p->finish_radius + 0.25f < p->ns_cell_size))
+        return h->fail(RTS_E_ARG, "params", "enable_arrival on a slab handle needs finish_radius < ns_cell_size (the halo band is finish_radius wide "
+                                            "and a slab keeps one physics row of its neighbour)");
     if (p->ns_cell_size * p->ns_cell_size < p->r_max2)
         return h->fail(RTS_E_ARG, "params", "ns_cell_size is smaller than the interaction range");
     return RTS_OK;
@@ -766,6 +792,7 @@ int32_t rts_set_params(RtsHandle h, const RtsParams* params) {
     h->fast = params->precision == RTS_PRECISION_FAST;
     h->M.inv_ns_cs = 1.0f / params->ns_cell_size;
     h->M.inv_map_cs = 1.0f / params->map_cell_size;
+    if (h->multi) h->SL.halo = halo_band(h->P);   // (takes effect with the next frame's packing; call rts_halo_refresh after switching the arrival rule on)
     h->drop_graphs();
     if (regrid || rens) {
         CU(cudaStreamSynchronize(h->stream));
@@ -1269,10 +1296,17 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
         if (grp[p] < 0 || (uint32_t)grp[p] >= ng) return h->fail(RTS_E_ARG, "rts_upload_paths", "group id out of range");
     }
     // finished areas survive a re-upload with the same number of groups (the planner rewrites windows every few frames)
-    std::vector<float> keep_area;
+    std::vector<float> keep_area, keep_read;
+    std::vector<uint32_t> keep_cnt[3];
     if (h->M.n_groups == ng && ng && h->M.area_acc) {
-        keep_area.resize(ng);
+        keep_area.resize(ng); keep_read.resize(ng);
         CU(cudaMemcpy(keep_area.data(), h->M.area_acc, sizeof(float) * ng, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(keep_read.data(), h->M.area_read, sizeof(float) * ng, cudaMemcpyDeviceToHost));
+        const uint32_t* src[3] = {h->M.stop_local, h->M.stop_global, h->M.stop_applied};
+        for (int k = 0; k < 3; ++k) {
+            keep_cnt[k].resize(ng);
+            CU(cudaMemcpy(keep_cnt[k].data(), src[k], sizeof(uint32_t) * ng, cudaMemcpyDeviceToHost));
+        }
     }
     free_all(h->path_allocs);
     std::vector<float4> wp(2 * (size_t)nw);
@@ -1301,9 +1335,16 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
     CU(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int32_t) * std::max<uint32_t>(np, 1), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(d_ar, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
     CU(cudaMemsetAsync(d_aa, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
+    uint32_t* d_cnt[3];
+    for (int k = 0; k < 3; ++k) {
+        if ((rc = dev_alloc(h, &d_cnt[k], ng, h->path_allocs)) != RTS_OK) return rc;
+        CU(cudaMemsetAsync(d_cnt[k], 0, sizeof(uint32_t) * std::max<uint32_t>(ng, 1), h->stream));
+    }
     if (!keep_area.empty()) {
-        CU(cudaMemcpyAsync(d_ar, keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
+        // (single-domain handles read area_acc into area_read at the start of every frame; slab handles keep adding to area_read)
+        CU(cudaMemcpyAsync(d_ar, h->multi ? keep_read.data() : keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(d_aa, keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
+        for (int k = 0; k < 3; ++k) CU(cudaMemcpyAsync(d_cnt[k], keep_cnt[k].data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice, h->stream));
     }
     if ((rc = dev_alloc(h, &d_off, np + 1, h->path_allocs)) != RTS_OK) return rc;
     if ((rc = dev_alloc(h, &d_wp, wp.size(), h->path_allocs)) != RTS_OK) return rc;
@@ -1314,6 +1355,7 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
     CU(cudaStreamSynchronize(h->stream));
     h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np; h->M.path_hdr = d_hdr;
     h->M.path_group = d_grp; h->M.n_groups = ng; h->M.area_read = d_ar; h->M.area_acc = d_aa;
+    h->M.stop_local = d_cnt[0]; h->M.stop_global = d_cnt[1]; h->M.stop_applied = d_cnt[2];
     h->drop_graphs();
     return RTS_OK;
 }
@@ -1488,7 +1530,16 @@ int32_t rts_get_finished_area(RtsHandle h, float* out, uint32_t n) {
     if (n > h->M.n_groups) return h->fail(RTS_E_ARG, "rts_get_finished_area", "more groups requested than uploaded");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    if (n) CU(cudaMemcpy(out, h->M.area_acc, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (n && !h->multi) CU(cudaMemcpy(out, h->M.area_acc, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (n && h->multi) {   // the area the next frame will see: area_read + the stops (of all ranks) not yet added to it
+        std::vector<uint32_t> tot(n), done(n);
+        CU(cudaMemcpy(out, h->M.area_read, sizeof(float) * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(tot.data(), h->M.stop_global, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(done.data(), h->M.stop_applied, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        const float unit = 3.14159265358979323846f * h->P.rhard * h->P.rhard;
+        for (uint32_t g = 0; g < n; ++g)
+            for (uint32_t k = done[g]; k < tot[g]; ++k) out[g] += unit;
+    }
     return RTS_OK;
 }
 
@@ -1500,6 +1551,7 @@ int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n) {
     if (n) {
         CU(cudaMemcpy(h->M.area_acc, area, sizeof(float) * n, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->M.area_read, area, sizeof(float) * n, cudaMemcpyHostToDevice));
+        if (h->multi) CU(cudaMemcpy(h->M.stop_applied, h->M.stop_global, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice));   // (nothing pending)
     }
     return RTS_OK;
 }
@@ -1540,7 +1592,8 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     bool ev0_recorded = false;
     // (slab handles: only with the peer exchange — every node is a kernel; capturing ncclSend/ncclRecv measured slower than
     //  launching frame by frame)
-    if (h->use_graph && !h->profiling && (!h->multi || h->graph_slabs || h->SL.peer_mode) && n_steps >= GRAPH_FRAMES) {
+    // (... and not with the arrival rule on a slab handle: its frames carry an ncclAllReduce)
+    if (h->use_graph && !h->profiling && (!h->multi || ((h->graph_slabs || h->SL.peer_mode) && !h->P.enable_arrival)) && n_steps >= GRAPH_FRAMES) {
         const int par = h->parity;
         // (a slab handle's kernels take the live count from the device and cover fixed slot capacities: its graph does not
         //  depend on h->n, which rts_sync refreshes with a different value after every frame)
@@ -1841,9 +1894,8 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     if (nranks < 1 || rank < 0 || rank >= nranks) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad rank");
     if (h->n) return h->fail(RTS_E_STATE, "rts_slab_configure", "configure the slab before uploading agents");
     if (h->P.enable_alignment) return h->fail(RTS_E_STATE, "rts_slab_configure", "enable_alignment is not supported on a slab handle (halo records carry no velocity)");
-    if (h->P.enable_arrival)
-        return h->fail(RTS_E_STATE, "rts_slab_configure", "enable_arrival is not supported on a slab handle: the arrival rule needs the group's "
-                                                          "finished area and the stop requests of ghost agents across slabs");
+    if (h->P.enable_arrival && !(h->P.finish_radius + 0.25f < h->P.ns_cell_size))
+        return h->fail(RTS_E_ARG, "rts_slab_configure", "enable_arrival on a slab handle needs finish_radius < ns_cell_size");
     const RtsParams& P = h->P;
     if (P.slab_row_lo < 0 || P.slab_row_hi > P.ns_ny || P.slab_row_lo >= P.slab_row_hi) return h->fail(RTS_E_ARG, "rts_slab_configure", "bad slab rows in the params");
     CU(cudaSetDevice(h->device));
@@ -1855,7 +1907,7 @@ int32_t rts_slab_configure(RtsHandle h, int32_t rank, int32_t nranks, uint32_t c
     SlabDev SL{};
     SL.row_lo = P.slab_row_lo; SL.row_hi = P.slab_row_hi;
     SL.y_lo = P.slab_row_lo * P.ns_cell_size; SL.y_hi = P.slab_row_hi * P.ns_cell_size;
-    SL.halo = std::sqrt(P.r_max2) * 1.05f + 0.25f;
+    SL.halo = halo_band(P);
     SL.has[0] = P.slab_row_lo > 0; SL.has[1] = P.slab_row_hi < P.ns_ny;
     SL.cap_mig = cap_migrants; SL.cap_halo = cap_halo;
     const size_t bytes = exbuf_bytes(cap_migrants, cap_halo);   // layout: carve_exbuf
@@ -2073,6 +2125,16 @@ int32_t rts_slab_exchange_local(RtsHandle lower, RtsHandle upper) {
     CU(cudaStreamSynchronize(upper->stream4));
     CU(cudaMemcpy(upper->ex_recv[0], lower->ex_send[1], lower->ex_bytes, cudaMemcpyDeviceToDevice));
     CU(cudaMemcpy(lower->ex_recv[1], upper->ex_send[0], lower->ex_bytes, cudaMemcpyDeviceToDevice));
+    // ... and reduce_stop_counts over the two "ranks"
+    if (lower->P.enable_arrival && upper->P.enable_arrival && lower->M.n_groups && lower->M.n_groups == upper->M.n_groups) {
+        const uint32_t ng = lower->M.n_groups;
+        std::vector<uint32_t> a(ng), b(ng);
+        CU(cudaMemcpy(a.data(), lower->M.stop_local, sizeof(uint32_t) * ng, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(b.data(), upper->M.stop_local, sizeof(uint32_t) * ng, cudaMemcpyDeviceToHost));
+        for (uint32_t g = 0; g < ng; ++g) a[g] += b[g];
+        CU(cudaMemcpy(lower->M.stop_global, a.data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(upper->M.stop_global, a.data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice));
+    }
     return RTS_OK;
 }
 

@@ -34,6 +34,12 @@ struct MapDev {
     uint32_t n_groups;
     float* area_read;    // CommandGroupManager2::group2finished_surface_area_, value at the start of the frame
     float* area_acc;     // ... accumulating this frame's stops
+    // slab handles: the finished area is the same float sum, rebuilt on every rank from COUNTS — stop_local = stops this rank has
+    // claimed (cumulative), stop_global = their sum over the ranks after the last exchange, stop_applied = how many of those
+    // k_area_sync has already added (one by one, pi*RHARD^2 each: the float sequence of the single-domain atomicAdds)
+    uint32_t* stop_local;
+    uint32_t* stop_global;
+    uint32_t* stop_applied;
     const RtsUnitType* __restrict__ unit_types;
     uint32_t n_types;
     const float* __restrict__ acos_table;   // AcosTable<1000>, built on the host (src/core.h:115-124)

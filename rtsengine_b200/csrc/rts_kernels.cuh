@@ -161,10 +161,11 @@ struct ExBuf {
     float4* m_nav4;
     uint32_t* m_tri;
     float2* m_velout;
-    float4* h_pos4;     // halo: the neighbour record only
+    float4* h_pos4;     // halo: the neighbour record ...
     uint2* h_key2;
+    float4* h_nav4;     // ... and the navigation record {r_next, path_id, misc}: the arrival rule evaluates ghosts too (k_arrive)
 };
-// one exchange buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][m_key2][h_key2][m_velout][m_tri]
+// one exchange buffer = [hdr 16 B][m_pos4][m_vel4][m_nav4][h_pos4][h_nav4][m_key2][h_key2][m_velout][m_tri]
 __host__ __device__ inline ExBuf carve_exbuf(void* base, uint32_t cap_mig, uint32_t cap_halo) {
     ExBuf B;
     char* p = static_cast<char*>(base);
@@ -173,6 +174,7 @@ __host__ __device__ inline ExBuf carve_exbuf(void* base, uint32_t cap_mig, uint3
     B.m_vel4 = reinterpret_cast<float4*>(p); p += (size_t)cap_mig * 16;
     B.m_nav4 = reinterpret_cast<float4*>(p); p += (size_t)cap_mig * 16;
     B.h_pos4 = reinterpret_cast<float4*>(p); p += (size_t)cap_halo * 16;
+    B.h_nav4 = reinterpret_cast<float4*>(p); p += (size_t)cap_halo * 16;
     B.m_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_mig * 8;
     B.h_key2 = reinterpret_cast<uint2*>(p); p += (size_t)cap_halo * 8;
     B.m_velout = reinterpret_cast<float2*>(p); p += (size_t)cap_mig * 8;
@@ -180,7 +182,7 @@ __host__ __device__ inline ExBuf carve_exbuf(void* base, uint32_t cap_mig, uint3
     return B;
 }
 __host__ __device__ inline size_t exbuf_bytes(uint32_t cap_mig, uint32_t cap_halo) {
-    return (16 + (size_t)cap_mig * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 8) + 15) & ~(size_t)15;
+    return (16 + (size_t)cap_mig * (16 + 16 + 16 + 8 + 8 + 4) + (size_t)cap_halo * (16 + 16 + 8) + 15) & ~(size_t)15;
 }
 struct SlabDev {
     int32_t row_lo, row_hi;   // physics-grid rows owned: [row_lo, row_hi)
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentAr
     pdl_wait();
     pdl_trigger();
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p == 0 && tick_epoch) SL.epoch[0] += 1u;   // one peer exchange has been delivered and ingested (see k_push)
+    if (p == 0 && tick_epoch) SL.epoch[0] += 1u;   // one peer exchange has been delivered and ingested (see SlabDev)
     if (p == 0) {
         A.dense_n[0] = 0u; A.dense_n[4] = 0u;   // the dense queues of this frame (whole / interior, edge rows) have been consumed
         A.work[0] = 0u;                         // ... and the tile counter of its frame kernel
@@ -576,39 +578,6 @@ __global__ void k_publish(SlabDev SL) { publish_to_peers(SL); }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
-// Peer exchange, sending side: the records k_step (or k_halo_seed) packed into the local send buffers are copied — exactly
-// as many as the headers count — into the neighbour's receive buffer of this epoch's parity over NVLink; the last CTA of a
-// direction then publishes epoch + 1 in the neighbour's flag. grid = (CTAs, 2 directions).
-__global__ void __launch_bounds__(256) k_push(SlabDev SL) {
-    const int dir = (int)blockIdx.y;
-    if (!SL.has[dir]) return;
-    const uint32_t e = *((volatile uint32_t*)SL.epoch);
-    const ExBuf src = SL.send[dir];
-    const ExBuf dst = carve_exbuf(SL.peer_base[dir][e & 1u], SL.cap_mig, SL.cap_halo);
-    const uint32_t nm = min(src.hdr[0], SL.cap_mig), nh = min(src.hdr[1], SL.cap_halo);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < max(nm, nh); i += stride) {
-        if (i < nm) {
-            dst.m_pos4[i] = src.m_pos4[i]; dst.m_vel4[i] = src.m_vel4[i]; dst.m_nav4[i] = src.m_nav4[i];
-            dst.m_key2[i] = src.m_key2[i]; dst.m_velout[i] = src.m_velout[i]; dst.m_tri[i] = src.m_tri[i];
-        }
-        if (i < nh) { dst.h_pos4[i] = src.h_pos4[i]; dst.h_key2[i] = src.h_key2[i]; }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { dst.hdr[0] = nm; dst.hdr[1] = nh; dst.hdr[2] = src.hdr[2]; dst.hdr[3] = e; }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t done = atomicAdd(SL.epoch + 1 + dir, 1u);
-        if (done == gridDim.x - 1) {          // every CTA of this direction has written and fenced its share
-            SL.epoch[1 + dir] = 0u;
-            __threadfence_system();
-            *((volatile uint32_t*)SL.flag_peer[dir]) = e + 1u;
-        }
-    }
-}
-
-// Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
-// frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
 // Peer mode: waits for the neighbour's flag of this epoch first (bounded: a neighbour that never delivers is reported
 // through SL.overflow = 3 after ~20 s instead of hanging the device).
 __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArrays A) {
@@ -666,7 +635,7 @@ __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArr
         A.pos4n[slot] = pos;
         A.key2n[slot] = B.h_key2[k];   // ghost bit set by the sender
         A.vel4n[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-        A.nav4n[slot] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+        A.nav4n[slot] = B.h_nav4[k];   // (read by k_arrive only: a ghost is never stepped)
         A.trin[slot] = 0xFFFFFFFFu;
         if (A.vel_outn) A.vel_outn[slot] = make_float2(0.f, 0.f);
     }
@@ -703,13 +672,13 @@ __global__ void k_halo_seed(uint32_t n_bound, RtsParams P, FineGrid F, AgentArra
     if (SL.has[0] && pos.y < SL.y_lo + SL.halo) {
         const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
         const ExBuf B = pack_target(SL, 0);
-        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); B.h_nav4[k] = A.nav4[sp]; }
         else *SL.overflow = 1u;
     }
     if (SL.has[1] && pos.y >= SL.y_hi - SL.halo) {
         const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
         const ExBuf B = pack_target(SL, 1);
-        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); }
+        if (k < SL.cap_halo) { B.h_pos4[k] = pos; B.h_key2[k] = make_uint2(key.x, key.y | 4u); B.h_nav4[k] = A.nav4[sp]; }
         else *SL.overflow = 1u;
     }
     if (SL.peer_mode && ((SL.has[0] && pos.y < SL.y_lo + SL.halo) || (SL.has[1] && pos.y >= SL.y_hi - SL.halo))) __threadfence_system();
@@ -728,13 +697,30 @@ __global__ void k_area_sync(MapDev M) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < M.n_groups) M.area_read[g] = M.area_acc[g];
 }
+// ... on a slab handle: the stops every rank has claimed up to the last exchange, added one by one
+__global__ void k_area_sync_counts(MapDev M, float area_unit) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= M.n_groups) return;
+    const uint32_t total = M.stop_global[g];
+    uint32_t done = M.stop_applied[g];
+    float area = M.area_read[g];
+    for (; done < total; ++done) area += area_unit;
+    M.area_read[g] = area;
+    M.stop_applied[g] = total;
+}
 
+// Slab handles (multi): an agent near a slab boundary has neighbours on both sides. Every rank evaluates the rule for the
+// agents it owns AND for its ghosts (halo records carry the navigation record, and the halo band is finish_radius wide
+// while the rule is on: every agent that can stop one of this rank's agents is present here, with the same position,
+// waypoint state and — the counts being all-reduced every frame — the same finished area as on its owner), and stops only
+// agents it owns: each agent is stopped, and counted, exactly once, by its owner.
 __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, AgentArrays A, int multi) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = multi ? *A.n_dev : n_bound;
     if (p >= n) return;
     const uint2 key = A.key2[p];
-    if ((key.y & 3u) != RTS_MOVING || ((key.y >> 2) & 1u)) return;
+    const bool ghost_i = (key.y >> 2) & 1u;
+    if ((key.y & 3u) != RTS_MOVING || (ghost_i && !multi)) return;
     const float4 nav4 = A.nav4[A.src[p]];
     const int32_t pid = __float_as_int(nav4.z);
     if (pid < 0 || (uint32_t)pid >= M.n_paths) return;   // (a stale id beyond the uploaded table counts as "no path")
@@ -753,7 +739,13 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
     const float dist_to_end = sqrtf(dist2(path_end, r));
     if (!(dist_to_end < 2 * me.z + finish_radius)) return;
     const float area_unit = 3.14159265358979323846f * P.rhard * P.rhard;
-    if (atomicExch(A.stop_req + p, 1u) == 0u) atomicAdd(M.area_acc + g_i, area_unit);
+    auto claim = [&](uint32_t q) {   // stop agent q (owned by this handle); the first claim of the frame counts it
+        if (atomicExch(A.stop_req + q, 1u) == 0u) {
+            if (multi) atomicAdd(M.stop_local + g_i, 1u);
+            else atomicAdd(M.area_acc + g_i, area_unit);
+        }
+    };
+    if (!ghost_i) claim(p);
     // neighbours: every fine cell that can hold an agent within finish_radius
     int fx, fy;
     fine_coords(F, r.x, r.y, fx, fy);
@@ -770,10 +762,10 @@ __global__ void k_arrive(uint32_t n_bound, RtsParams P, MapDev M, FineGrid F, Ag
             if (!(norm2(dr) < 10.f * rr * rr)) continue;
             if (!(sqrtf(norm2(r - V(o.x, o.y))) < P.finish_radius)) continue;
             const uint2 ok = A.key2[q];
-            if ((ok.y & 3u) != RTS_MOVING || ((ok.y >> 2) & 1u)) continue;
+            if ((ok.y & 3u) != RTS_MOVING || ((ok.y >> 2) & 1u)) continue;   // (a ghost is stopped by its owner)
             const int32_t pj = __float_as_int(A.nav4[A.src[q]].z);
             if (pj < 0 || (uint32_t)pj >= M.n_paths || __ldg(M.path_group + pj) != g_i) continue;
-            if (atomicExch(A.stop_req + q, 1u) == 0u) atomicAdd(M.area_acc + g_i, area_unit);
+            claim(q);
         }
     }
 }
@@ -1021,13 +1013,13 @@ __device__ __forceinline__ uint32_t finish_agent(uint32_t p, uint32_t sp, float4
             if (SL.has[0] && r_new.y < SL.y_lo + SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[0].hdr + 1, 1u);
                 const ExBuf B = pack_target(SL, 0);
-                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); B.h_nav4[k] = nav_new; }
                 else *SL.overflow = 1u;
             }
             if (SL.has[1] && r_new.y >= SL.y_hi - SL.halo) {
                 const uint32_t k = atomicAdd(SL.send[1].hdr + 1, 1u);
                 const ExBuf B = pack_target(SL, 1);
-                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); }
+                if (k < SL.cap_halo) { B.h_pos4[k] = pos_new; B.h_key2[k] = make_uint2(gid, cs_new | 4u); B.h_nav4[k] = nav_new; }
                 else *SL.overflow = 1u;
             }
         }

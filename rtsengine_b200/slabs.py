@@ -330,7 +330,7 @@ def _slab_case(dist, torch, engine, rank, world, local, fx, agents, n_total, pre
     res = {"value": n_total * K / (med * 1e-3), "unit": "agent-updates/s", "ms_per_step": med / K, "repeat_ms_per_step": [m / K for m in ms],
            "agents": n_total, "slab_rows": bounds, "gpu_launches": launches,
            "conservation": {"agents_after": int(cnt.item()), "agents_before": n_total},
-           "exchange": {0: "none", 1: "ncclSend/ncclRecv per frame", 2: "peer memory over NVLink (CUDA IPC, k_push + epoch flags), frames replayed from a CUDA graph"}[
+           "exchange": {0: "none", 1: "ncclSend/ncclRecv per frame", 2: "peer memory over NVLink (CUDA IPC: the frame kernels write their records into the neighbour's buffers, one flag word per frame), frames replayed from a CUDA graph"}[
                int(sr.g.L.rts_slab_exchange_mode(sr.g.h))],
            "wall_s_last_repeat": wall, "wall_frames": ALIGN_FRAMES + K}
     return res, sr

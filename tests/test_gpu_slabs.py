@@ -221,3 +221,75 @@ def test_moving_the_slab_boundary_keeps_the_result_bit_identical():
         finally:
             for sr in ranks:
                 sr.close()
+
+
+def test_arrival_rule_on_two_slabs_equals_one_domain():
+    """SeekSystem::finalizeSeek across a slab boundary (SURVEY §8e: the group's finished area is global, CommandGroupManager.h:
+    163-172): two groups arrive at destinations ON the cut, so arriving agents stop same-group neighbours owned by the other
+    slab, and both slabs must see the same finished area every frame. Two slabs (local exchange emulation, which also sums
+    the per-group stop counts as ncclAllReduce does between ranks) == one domain, every agent, bitwise, over the whole arrival."""
+    fx = H.load("map_empty.npz")
+    tables = H.tables_of(fx)
+    n = 3000
+    rng = np.random.default_rng(15)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = np.stack([rng.uniform(780, 1080, n), rng.uniform(720, 1080, n)], 1)
+    a["radius"][:] = np.where(rng.random(n) < 0.2, 5.0, 3.0)
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = rng.integers(0, 2, n)
+    a["r_next"][:] = np.nan
+    base = engine.default_params(512, 512)
+    cut_row = 15                                            # y = 900
+    ends = np.array([[1150.0, 900.0], [1230.0, 893.0]], np.float32)   # both blobs straddle the cut
+    paths = {"offsets": np.array([0, 1, 2], np.uint32), "waypoints": ends.copy(), "portals": np.zeros((2, 5), np.float32),
+             "path_end": ends.copy(), "group": np.array([0, 1], np.int32)}
+    base.enable_arrival = 1
+    names = ("r", "inertia", "angle", "angle_vel", "state", "path_id", "waypoint", "r_next", "flags")
+    bounds = [0, cut_row, int(base.ns_ny)]
+    with engine.GpuAgentSystem(base) as one:
+        one.upload_map(tables)
+        one.upload_paths(paths)
+        one.set_agents(a)
+        a2 = dict(a)
+        a2["gid"] = np.arange(n, dtype=np.uint32)
+        parts = slabs.split_agents(a2, bounds, base.ns_cell_size, base.ns_ny)
+        assert min(len(p["gid"]) for p in parts) > 500
+        ranks = [slabs.SlabRank(base, bounds, r, 0, cap_migrants=4096, cap_halo=16384) for r in range(2)]
+        L = ranks[0].g.L
+        try:
+            for r, sr in enumerate(ranks):
+                sr.g.upload_map(tables)
+                sr.g.upload_paths(paths)
+                sr.g.set_agents(parts[r])
+            for sr in ranks:
+                sr.g._chk(L.rts_halo_begin(sr.g.h))
+            ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+            for sr in ranks:
+                sr.g._chk(L.rts_step_end(sr.g.h))
+            standing, cross = [], 0
+            for f in range(600):
+                one.update(1)
+                for sr in ranks:
+                    sr.g._chk(L.rts_step_begin(sr.g.h))
+                ranks[0].g._chk(L.rts_slab_exchange_local(ranks[0].g.h, ranks[1].g.h))
+                for sr in ranks:
+                    sr.g._chk(L.rts_step_end(sr.g.h))
+                if f % 20 == 19:
+                    ref = one.communicate(names)
+                    got = [sr.owned(names) for sr in ranks]
+                    gid = np.concatenate([g["gid"] for g in got])
+                    assert len(gid) == n and len(np.unique(gid)) == n
+                    order = np.argsort(gid)
+                    for k in names:
+                        H.assert_same_bits(np.concatenate([g[k] for g in got])[order], ref[k], f"frame {f} {k}")
+                    area = one.finished_area(2)
+                    for sr in ranks:
+                        H.assert_same_bits(sr.g.finished_area(2), area, f"frame {f}: finished area per group on every slab")
+                    standing.append(int((ref["state"] == abi.STANDING).sum()))
+                    cross = max(cross, min(int((g["state"] == abi.STANDING).sum()) for g in got))
+            assert standing[0] == 0 and standing[-1] > 0.8 * n, standing
+            assert cross > 100, "agents stopped on both sides of the cut"
+        finally:
+            for sr in ranks:
+                sr.close()
