@@ -379,6 +379,89 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
                     f"({world} config-3 tiles), every agent, bitwise"}
 
 
+def _arrival_parity(dist, torch, engine, rank, world, local, frames=400):
+    """The arrival rule (RtsParams.enable_arrival, SeekSystem::finalizeSeek) over the REAL inter-GPU path — peer-memory
+    exchange plus the per-frame ncclAllReduce of the groups' stop counts: `world` slabs against ONE single-domain handle on
+    rank 0, bit-exact mode, every agent, bitwise. Groups arrive at destinations on the slab boundaries, so agents stop
+    same-group neighbours owned by another rank."""
+    from . import scenario
+    fx = scenario.load_map("map_empty.npz")
+    tables = scenario.tables_of(fx)
+    nx, ny = (int(v) for v in fx["n_cells"])
+    base = engine.default_params(nx, ny)
+    base.enable_arrival = 1
+    n = 1500 * world
+    rng = np.random.default_rng(15)
+    a = scenario._blank(n)
+    # the map's physics rows cut into `world` equal slabs; one group per boundary (and one in the middle of slab 0)
+    rows = int(base.ns_ny)
+    bounds = [round(r * rows / world) for r in range(world + 1)]
+    H = ny * 5.0
+    ends = [[1200.0, b * base.ns_cell_size + rng.uniform(-8, 8)] for b in bounds[1:-1]] + [[1200.0, 0.5 * bounds[1] * base.ns_cell_size]]
+    ends = np.array(ends, np.float32)
+    g = rng.integers(0, len(ends), n)
+    a["r"][:] = ends[g] + np.stack([rng.uniform(-420, -120, n), rng.uniform(-min(180.0, 0.4 * H / world), min(180.0, 0.4 * H / world), n)], 1)
+    a["radius"][:] = np.where(rng.random(n) < 0.2, 5.0, 3.0)
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = g
+    a["r_next"][:] = np.nan
+    a["gid"] = np.arange(n, dtype=np.uint32)
+    m = len(ends)
+    paths = {"offsets": np.arange(m + 1, dtype=np.uint32), "waypoints": ends.copy(), "portals": np.zeros((m, 5), np.float32),
+             "path_end": ends.copy(), "group": np.arange(m, dtype=np.int32)}
+    parts = split_agents(a, bounds, base.ns_cell_size, base.ns_ny)
+    sr = SlabRank(base, bounds, rank, local, cap_migrants=8192, cap_halo=32768)
+    uid = [make_unique_id(sr.g.L) if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    sr.init_comm(uid[0])
+    sr.g.upload_map(tables)
+    sr.g.upload_paths(paths)
+    sr.g.set_agents(parts[rank])
+    sr.halo_refresh()
+    sr.g.update(frames, sync=True)
+    names = ("r", "inertia", "angle", "angle_vel", "state", "path_id", "waypoint", "r_next")
+    own = sr.owned(names)
+    area = sr.g.finished_area(m)
+    mode = int(sr.g.L.rts_slab_exchange_mode(sr.g.h))
+    sr.close()
+    dtypes = {name: dt for name, dt, _ in abi.AGENT_FIELDS}
+    comps = {name: k for name, _, k in abi.AGENT_FIELDS}
+    ref, ref_area = {}, np.zeros(m, np.float32)
+    if rank == 0:
+        with engine.GpuAgentSystem(base, device=local) as one:
+            one.upload_map(tables)
+            one.upload_paths(paths)
+            one.set_agents({k: v for k, v in a.items() if k != "gid"})
+            one.update(frames, sync=True)
+            ref = one.communicate(names)
+            ref_area = one.finished_area(m)
+    bad = np.zeros(len(own["gid"]), bool)
+    standing = 0
+    for k in names:
+        shape = (n, comps[k]) if comps[k] > 1 else (n,)
+        width = np.dtype(dtypes[k]).itemsize
+        t = torch.empty(shape, dtype={4: torch.int32, 1: torch.uint8}[width], device="cuda")
+        if rank == 0:
+            t.copy_(torch.from_numpy(ref[k].view({4: np.int32, 1: np.uint8}[width]).reshape(shape)))
+        dist.broadcast(t, src=0)
+        want = t.cpu().numpy()[own["gid"].astype(np.int64)]
+        got = own[k].view({4: np.int32, 1: np.uint8}[width]).reshape(want.shape)
+        if len(got):
+            bad |= (got != want).reshape(len(got), -1).any(1)
+        if k == "state":
+            standing = int((want == abi.STANDING).sum())
+    ta = torch.from_numpy(ref_area.view(np.int32).copy()).cuda()
+    dist.broadcast(ta, src=0)
+    area_bad = int((ta.cpu().numpy() != area.view(np.int32)).sum())
+    tot = torch.tensor([int(bad.sum()), len(own["gid"]), standing, area_bad], device="cuda", dtype=torch.int64)
+    dist.all_reduce(tot)
+    return {"mismatching_agents": int(tot[0].item()), "agents_compared": int(tot[1].item()), "standing_at_end": int(tot[2].item()),
+            "finished_area_mismatches_over_ranks": int(tot[3].item()), "groups": m, "frames": frames, "precision": "exact",
+            "exchange_mode": mode,
+            "what": f"arrival rule on: {world} slabs (peer exchange + ncclAllReduce of the groups' stop counts every frame) vs ONE "
+                    f"single-domain handle on rank 0, {n} agents in {m} groups arriving on the slab boundaries, every agent, bitwise"}
+
+
 def _config5_case(dist, torch, engine, rank, world, local, n5, precision, frames, chunk, reserved5=0):
     """BASELINE config 5: 4M agents funnelled through the corridor map, `world` slabs, counter-flow; the crowd drains
     unevenly, so every `chunk` frames the per-row agent counts are all-reduced and the slab boundaries follow the quantiles
@@ -514,6 +597,10 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
         parity = _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, min(per_gpu, 250_000),
                                           frames=int(os.environ.get("RTS_PARITY_FRAMES", "24")))
 
+    parity_arrival = None
+    if not os.environ.get("RTS_BENCH_NO_PARITY"):
+        parity_arrival = _arrival_parity(dist, torch, engine, rank, world, local)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         line = {
@@ -535,7 +622,7 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
             "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": algo_bytes * per_gpu / (main["ms_per_step"] * 1e-3) / 1e9 / peak,
                          "traffic": None, "peak_source": peak_src},
-            "config4": c4, "config5": c5, "parity_vs_single_domain": parity,
+            "config4": c4, "config5": c5, "parity_vs_single_domain": parity, "parity_arrival_vs_single_domain": parity_arrival,
             "cpu_baseline": None,
         }
         print(json.dumps(line))
