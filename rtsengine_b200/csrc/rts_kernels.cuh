@@ -513,7 +513,14 @@ __global__ void __launch_bounds__(256) k_scatter(uint32_t n, FineGrid F, AgentAr
                     load_tri_verts(M, hint, a, b, c, w1);
                     // 64-bit products: identical to the reference's int32 wherever that does not overflow
                     const float d1 = tri_sign<true>(q, a, b), d2 = tri_sign<true>(q, b, c), d3 = tri_sign<true>(q, c, a);
-                    slow = !((d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0));
+                    // ... in a triangle of the map proper. The fan that ties the map's border to the super-triangle is not
+                    // trusted: "strictly inside => in no other triangle" needs a planar triangulation, and the fans of a map
+                    // stitched from tiles (scenario.tile_map) overlap each other and the map. Agents out there (pushed over
+                    // the map edge) are always searched the reference's way.
+                    const int W = (int)(P.map_nx * P.map_cell_size), Hh = (int)(P.map_ny * P.map_cell_size);
+                    const bool proper = min(min(a.x, b.x), c.x) >= 0 && max(max(a.x, b.x), c.x) <= W &&
+                                        min(min(a.y, b.y), c.y) >= 0 && max(max(a.y, b.y), c.y) <= Hh;
+                    slow = !(proper && ((d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0)));
                 }
             }
         }

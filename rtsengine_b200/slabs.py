@@ -360,6 +360,7 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
             one.update(3 + ALIGN_FRAMES + frames, sync=True)   # (what _slab_case stepped: warm-up + alignment + timed frames)
             ref = one.communicate(names)
     bad = np.zeros(len(own["gid"]), bool)
+    examples = []
     for k in names:
         shape = (n_total, comps[k]) if comps[k] > 1 else (n_total,)
         width = np.dtype(dtypes[k]).itemsize
@@ -370,7 +371,13 @@ def _parity_vs_single_domain(dist, torch, engine, rank, world, local, tile, per_
         want = t.cpu().numpy()[own["gid"].astype(np.int64)]
         got = own[k].view({4: np.int32, 1: np.uint8}[width]).reshape(want.shape)
         if len(got):
-            bad |= (got != want).reshape(len(got), -1).any(1)
+            diff = (got != want).reshape(len(got), -1).any(1)
+            bad |= diff
+            for i in np.nonzero(diff)[0][:3]:
+                examples.append({"rank": rank, "gid": int(own["gid"][i]), "field": k, "slabs": own[k][i].tolist(),
+                                 "single_domain": want[i].view(dtypes[k]).tolist(), "r": own["r"][i].tolist()})
+    if examples:
+        print(json.dumps({"parity_mismatch_examples": examples[:12]}), file=sys.stderr, flush=True)
     n_bad = torch.tensor([int(bad.sum()), len(own["gid"])], device="cuda", dtype=torch.int64)
     dist.all_reduce(n_bad)
     return {"mismatching_agents": int(n_bad[0].item()), "agents_compared": int(n_bad[1].item()), "frames": 3 + ALIGN_FRAMES + frames,
