@@ -538,6 +538,38 @@ def test_baseline_config4_map_tiles_wide_arithmetic():
             H.assert_same_bits(out[k][idx][core], sub[k][core], f"window {k}")
 
 
+def test_triangle_index_is_a_function_of_the_position_where_fans_overlap():
+    """A map stitched from tiles (scenario.tile_map, the config-4 geometry) keeps every tile's super-triangle fan: out there
+    triangles overlap, "strictly inside" is not unique, and a carried triangle hint could be confirmed although the reference's
+    findTriangle — a walk from the cache cell of the position — ends elsewhere. Agents pushed over the map edge and back:
+    after every frame the carried index must equal the stand-alone query of the same position (rts_find_triangles: the walk,
+    no hint), i.e. it depends on the position only, not on where the agent has been."""
+    from rtsengine_b200 import scenario
+    tile = H.load("map_c3.npz")
+    fx = scenario.tile_map(tile, 1, 2)
+    tables, paths = scenario.tables_of(fx), scenario.paths_of(fx)
+    rng = np.random.default_rng(77)
+    n = 30000
+    a = scenario._blank(n)
+    W = 1024 * 5.0
+    a["r"][:] = np.stack([rng.uniform(W - 12, W + 8, n), rng.uniform(200, 2 * W - 200, n)], 1)   # a dense strip on the right edge
+    a["r"][: n // 3, 0] = rng.uniform(-8, 12, n // 3)                                            # ... and on the left one
+    a["inertia"][:] = rng.normal(0, 30, (n, 2))
+    p = engine.default_params(1024, 2048)
+    with engine.GpuAgentSystem(p) as g:
+        g.upload_map(tables)
+        g.upload_paths(paths)
+        g.set_agents(a)
+        outside = 0
+        for f in range(12):
+            g.update(2)
+            out = g.communicate(("r", "tri_idx"))
+            ok = np.isfinite(out["r"]).all(1)
+            H.assert_same_bits(out["tri_idx"][ok], g.find_triangles(out["r"][ok]), f"frame {2 * f + 1}: triangle of every agent")
+            outside = max(outside, int(((out["r"][ok, 0] > W) | (out["r"][ok, 0] < 0)).sum()))
+        assert outside > 2000
+
+
 # ---- f3: Triangulation::updateCellGrid on the device ------------------------------------------------------------
 # (map_empty: the first cell centre (20,20) lies on the diagonal shared by triangles 2 and 4, the reference's
 #  last_found_tri_ind_ was 2 when it built the recorded table)
