@@ -48,8 +48,9 @@ constexpr int NBR_CAP = RTS_NBR_CAP;   // neighbours kept sorted in shared memor
 #endif
 // k_step as one residency of the device whose warps take 32-slot tiles from a device-wide counter (see k_step). Built to
 // remove the idle tail of the 5.7-wave grid (ncu: the average SM is idle for 16 % of the launch); measured SLOWER on config 3
-// (k_step 97 us against 74.6 us; static striding without the counter 91 us; whole CTAs taking 128 slots at a time 80.5 us —
-// profiles/README.md), so the plain grid stays the default and this is a build switch for further experiments.
+// (k_step 97 us against 74.6 us — also with the counter's round trip really hidden, see the loop head; static striding without
+// the counter 91 us; whole CTAs taking 128 slots at a time 80.5 us — profiles/README.md), so the plain grid stays the default
+// and this is a build switch for further experiments.
 constexpr bool USE_PERSISTENT_STEP = RTS_PERSISTENT_STEP != 0;
 constexpr int FAST_BLOCK = RTS_FAST_BLOCK;             // threads per CTA of the tolerance-mode k_step (no shared memory: registers set the occupancy)
 constexpr int FAST_MIN_BLOCKS = RTS_FAST_MIN_BLOCKS;
@@ -1185,7 +1186,12 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     uint32_t next_raw = 0u;
     if (PERSIST) {
         if (tile >= n_tiles) break;
-        if (t_in == 0u) next_raw = atomicAdd(A.work, 1u);   // (consumed at the end of the loop body)
+        // (ptxas turns an atomic add on a warp-uniform address into elect + atomic + SHUFFLE of the result — even for one
+        //  active lane, even from inline PTX, even spelled atom.inc — and the shuffle waits for the round trip right here,
+        //  while the result is only needed at the end of the loop body. The address below is A.work for every lane, but not
+        //  provably so: tiles stay far below 2^25.)
+        const uint32_t opaque_zero = (tile * 32u + t_in) >> 30;
+        if (t_in == 0u) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(next_raw) : "l"(A.work + opaque_zero) : "memory");
     }
     if (tile < walk_ctas) {
         if (M.coords_fit_i32) drain_walk_queue<false>(P, M, A, walk_parity, tile, walk_ctas, TILE, t_in);
@@ -1417,7 +1423,12 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     }
     }   // (tile of slots)
     if (!PERSIST) break;
-    tile = warps_in_grid + __shfl_sync(0xffffffffu, next_raw, 0);
+    {   // (volatile + memory clobber: the compiler must not move the shuffle — and with it the wait for the counter's round
+        //  trip — up to the atomicAdd at the head of the loop body)
+        uint32_t nxt;
+        asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(nxt) : "r"(next_raw) : "memory");
+        tile = warps_in_grid + nxt;
+    }
     }   // (tiles)
 }
 
