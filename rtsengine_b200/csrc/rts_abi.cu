@@ -51,6 +51,9 @@ struct RtsContext {
     std::string err;
     // owned device allocations of the tables
     std::vector<void*> table_allocs, path_allocs, type_allocs;
+    void* path_arena = nullptr; size_t path_arena_cap = 0;      // rts_upload_paths: the path tables, one allocation
+    void* group_arena = nullptr; uint32_t group_arena_ng = 0;   // ... and the groups' arrival state (kept across re-uploads)
+    std::vector<char> path_image;                                // host image of the path arena
     // host mirrors + writable device aliases of the map tables: rts_update_map_region patches them in place
     std::vector<RtsTriangle> tris_host;
     std::vector<uint2> line_se_host, scan_se_host;
@@ -754,6 +757,8 @@ int32_t rts_destroy(RtsHandle h) {
     cudaStreamSynchronize(h->stream);
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
+    if (h->path_arena) cudaFree(h->path_arena);
+    if (h->group_arena) cudaFree(h->group_arena);
     free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
     for (auto& pa : h->peer_arena)
         if (pa) { cudaIpcCloseMemHandle(pa); pa = nullptr; }
@@ -1295,67 +1300,76 @@ int32_t rts_upload_paths(RtsHandle h, const RtsPathTable* paths) {
         grp[p] = paths->group ? paths->group[p] : (int32_t)p;
         if (grp[p] < 0 || (uint32_t)grp[p] >= ng) return h->fail(RTS_E_ARG, "rts_upload_paths", "group id out of range");
     }
-    // finished areas survive a re-upload with the same number of groups (the planner rewrites windows every few frames)
-    std::vector<float> keep_area, keep_read;
-    std::vector<uint32_t> keep_cnt[3];
-    if (h->M.n_groups == ng && ng && h->M.area_acc) {
-        keep_area.resize(ng); keep_read.resize(ng);
-        CU(cudaMemcpy(keep_area.data(), h->M.area_acc, sizeof(float) * ng, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(keep_read.data(), h->M.area_read, sizeof(float) * ng, cudaMemcpyDeviceToHost));
-        const uint32_t* src[3] = {h->M.stop_local, h->M.stop_global, h->M.stop_applied};
-        for (int k = 0; k < 3; ++k) {
-            keep_cnt[k].resize(ng);
-            CU(cudaMemcpy(keep_cnt[k].data(), src[k], sizeof(uint32_t) * ng, cudaMemcpyDeviceToHost));
+    // One device arena for the tables (grown by half when it gets too small, otherwise reused: the adapter re-sends its
+    // per-agent windows whenever the planner has rewritten some, and eleven cudaMalloc / cudaFree per call cost more than the
+    // frame), filled from one host image with one copy. The groups' arrival state (finished areas, stop counts) lives in an
+    // arena of its own that survives every re-upload with the same number of groups.
+    auto align256 = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_hdr = 0;
+    const size_t o_grp = align256(o_hdr + sizeof(float4) * std::max<uint32_t>(np, 1));
+    const size_t o_off = align256(o_grp + sizeof(int32_t) * std::max<uint32_t>(np, 1));
+    const size_t o_wp = align256(o_off + sizeof(uint32_t) * ((size_t)np + 1));
+    const size_t o_end = align256(o_wp + sizeof(float4) * 2 * std::max<size_t>(nw, 1));
+    const size_t need = align256(o_end + sizeof(float2) * std::max<uint32_t>(np, 1));
+    if (need > h->path_arena_cap) {
+        if (h->path_arena) cudaFree(h->path_arena);
+        h->path_arena = nullptr; h->path_arena_cap = 0;
+        const size_t cap = need + need / 2;
+        CU(cudaMalloc(&h->path_arena, cap));
+        h->path_arena_cap = cap;
+    }
+    std::vector<char>& img = h->path_image;
+    img.assign(need, 0);
+    {
+        float4* hdr = reinterpret_cast<float4*>(img.data() + o_hdr);   // {offset, end offset (as bits), path_end}: one load per agent in the frame kernel
+        for (uint32_t p = 0; p < np; ++p) {
+            float4 w;
+            std::memcpy(&w.x, &paths->offsets[p], 4);
+            std::memcpy(&w.y, &paths->offsets[p + 1], 4);
+            w.z = paths->path_end[2 * p];
+            w.w = paths->path_end[2 * p + 1];
+            hdr[p] = w;
         }
+        std::memcpy(img.data() + o_grp, grp.data(), sizeof(int32_t) * np);
+        std::memcpy(img.data() + o_off, paths->offsets, sizeof(uint32_t) * ((size_t)np + 1));
+        float4* wp = reinterpret_cast<float4*>(img.data() + o_wp);
+        for (uint32_t k = 0; k < nw; ++k) {
+            const RtsEdge& e = paths->portals[k];
+            wp[2 * k] = make_float4(paths->waypoints[2 * k], paths->waypoints[2 * k + 1], e.from_x, e.from_y);
+            wp[2 * k + 1] = make_float4(e.t_x, e.t_y, e.l, 0.f);
+        }
+        if (np) std::memcpy(img.data() + o_end, paths->path_end, sizeof(float2) * np);
     }
-    free_all(h->path_allocs);
-    std::vector<float4> wp(2 * (size_t)nw);
-    for (uint32_t k = 0; k < nw; ++k) {
-        const RtsEdge& e = paths->portals[k];
-        wp[2 * k] = make_float4(paths->waypoints[2 * k], paths->waypoints[2 * k + 1], e.from_x, e.from_y);
-        wp[2 * k + 1] = make_float4(e.t_x, e.t_y, e.l, 0.f);
+    CU(cudaMemcpyAsync(h->path_arena, img.data(), need, cudaMemcpyHostToDevice, h->stream));
+    if (!h->group_arena || h->group_arena_ng != ng) {   // finished areas and stop counts start from zero for a new set of groups
+        if (h->group_arena) cudaFree(h->group_arena);
+        h->group_arena = nullptr;
+        const size_t per = align256(sizeof(float) * std::max<uint32_t>(ng, 1));
+        CU(cudaMalloc(&h->group_arena, 5 * per));
+        CU(cudaMemsetAsync(h->group_arena, 0, 5 * per, h->stream));
+        h->group_arena_ng = ng;
     }
-    uint32_t* d_off; float4* d_wp; float2* d_end; int32_t* d_grp; float *d_ar, *d_aa;
-    float4* d_hdr;
-    int32_t rc;
-    std::vector<float4> hdr(std::max<uint32_t>(np, 1));   // {offset, end offset (as bits), path_end}: one load per agent in the frame kernel
-    for (uint32_t p = 0; p < np; ++p) {
-        float4 w;
-        std::memcpy(&w.x, &paths->offsets[p], 4);
-        std::memcpy(&w.y, &paths->offsets[p + 1], 4);
-        w.z = paths->path_end[2 * p];
-        w.w = paths->path_end[2 * p + 1];
-        hdr[p] = w;
+    CU(cudaStreamSynchronize(h->stream));   // (the host image may be rewritten by the next call)
+    const MapDev before = h->M;
+    {
+        char* base = static_cast<char*>(h->path_arena);
+        h->M.path_hdr = reinterpret_cast<float4*>(base + o_hdr);
+        h->M.path_group = reinterpret_cast<int32_t*>(base + o_grp);
+        h->M.path_off = reinterpret_cast<uint32_t*>(base + o_off);
+        h->M.waypoints = reinterpret_cast<float4*>(base + o_wp);
+        h->M.path_end = reinterpret_cast<float2*>(base + o_end);
+        h->M.n_paths = np;
+        h->M.n_groups = ng;
+        char* gb = static_cast<char*>(h->group_arena);
+        const size_t per = align256(sizeof(float) * std::max<uint32_t>(ng, 1));
+        h->M.area_read = reinterpret_cast<float*>(gb);
+        h->M.area_acc = reinterpret_cast<float*>(gb + per);
+        h->M.stop_local = reinterpret_cast<uint32_t*>(gb + 2 * per);
+        h->M.stop_global = reinterpret_cast<uint32_t*>(gb + 3 * per);
+        h->M.stop_applied = reinterpret_cast<uint32_t*>(gb + 4 * per);
     }
-    if ((rc = dev_alloc(h, &d_hdr, hdr.size(), h->path_allocs)) != RTS_OK) return rc;
-    CU(cudaMemcpyAsync(d_hdr, hdr.data(), hdr.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    if ((rc = dev_alloc(h, &d_grp, np, h->path_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_ar, ng, h->path_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_aa, ng, h->path_allocs)) != RTS_OK) return rc;
-    CU(cudaMemcpyAsync(d_grp, grp.data(), sizeof(int32_t) * std::max<uint32_t>(np, 1), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemsetAsync(d_ar, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
-    CU(cudaMemsetAsync(d_aa, 0, sizeof(float) * std::max<uint32_t>(ng, 1), h->stream));
-    uint32_t* d_cnt[3];
-    for (int k = 0; k < 3; ++k) {
-        if ((rc = dev_alloc(h, &d_cnt[k], ng, h->path_allocs)) != RTS_OK) return rc;
-        CU(cudaMemsetAsync(d_cnt[k], 0, sizeof(uint32_t) * std::max<uint32_t>(ng, 1), h->stream));
-    }
-    if (!keep_area.empty()) {
-        // (single-domain handles read area_acc into area_read at the start of every frame; slab handles keep adding to area_read)
-        CU(cudaMemcpyAsync(d_ar, h->multi ? keep_read.data() : keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(d_aa, keep_area.data(), sizeof(float) * ng, cudaMemcpyHostToDevice, h->stream));
-        for (int k = 0; k < 3; ++k) CU(cudaMemcpyAsync(d_cnt[k], keep_cnt[k].data(), sizeof(uint32_t) * ng, cudaMemcpyHostToDevice, h->stream));
-    }
-    if ((rc = dev_alloc(h, &d_off, np + 1, h->path_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_wp, wp.size(), h->path_allocs)) != RTS_OK) return rc;
-    if ((rc = dev_alloc(h, &d_end, np, h->path_allocs)) != RTS_OK) return rc;
-    CU(cudaMemcpyAsync(d_off, paths->offsets, 4 * (size_t)(np + 1), cudaMemcpyHostToDevice, h->stream));
-    if (nw) CU(cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    if (np) CU(cudaMemcpyAsync(d_end, paths->path_end, 8 * (size_t)np, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    h->M.path_off = d_off; h->M.waypoints = d_wp; h->M.path_end = d_end; h->M.n_paths = np; h->M.path_hdr = d_hdr;
-    h->M.path_group = d_grp; h->M.n_groups = ng; h->M.area_read = d_ar; h->M.area_acc = d_aa;
-    h->M.stop_local = d_cnt[0]; h->M.stop_global = d_cnt[1]; h->M.stop_applied = d_cnt[2];
+    // (a CUDA graph holds the table pointers and sizes by value: it stays valid when only the contents changed)
+    if (std::memcmp(&before, &h->M, sizeof(MapDev)) == 0) return RTS_OK;
     h->drop_graphs();
     return RTS_OK;
 }
