@@ -1514,7 +1514,8 @@ int32_t rts_update_agents_indexed(RtsHandle h, const uint32_t* indices, uint32_t
         for (uint32_t k = 0; k < m; ++k)
             if (fields->path_id[k] >= (int32_t)h->M.n_paths) return h->fail(RTS_E_ARG, "rts_update_agents_indexed", "path_id out of range");
     CU(cudaSetDevice(h->device));
-    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    // (only a position edit re-bins, i.e. overwrites what a pending walk queue refers to; the in-place edits below do not)
+    if (fields->r) { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     Staging S;
     int32_t rc = stage_in(h, fields, m, &S);   // m entries per field, compact
     if (rc != RTS_OK) return rc;
@@ -1639,10 +1640,11 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
     return RTS_OK;
 }
 
-int32_t rts_sync(RtsHandle h) {
+// join = false: a pending walk queue is left to the leading CTAs of the next frame kernel (the caller reads no triangle index)
+static int32_t sync_impl(RtsHandle h, bool join) {
     if (!h) return RTS_E_ARG;
     CU(cudaSetDevice(h->device));
-    {
+    if (join) {
         const int32_t rcj = join_walk(h);
         if (rcj != RTS_OK) return rcj;
     }
@@ -1661,11 +1663,16 @@ int32_t rts_sync(RtsHandle h) {
     }
     return RTS_OK;
 }
+int32_t rts_sync(RtsHandle h) { return sync_impl(h, true); }
 
 int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     if (!h || !out) return RTS_E_ARG;
     CU(cudaSetDevice(h->device));
-    { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
+    // the triangle indices of the last frame are complete only after its walk queue has been searched; a download that does
+    // not ask for them (the per-frame communicate of the System2 adapter: vel, angle_vel, state, target) leaves the queue to
+    // the next frame kernel, as between two frames of one rts_step call
+    const bool need_walk = out->tri_idx != nullptr || out->flags != nullptr;
+    if (need_walk) { const int32_t rcj = join_walk(h); if (rcj != RTS_OK) return rcj; }
     int32_t rc = alloc_staging(h, h->cap);
     if (rc != RTS_OK) return rc;
     Staging S = h->S;
@@ -1674,7 +1681,7 @@ int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     WANT(unit_type) WANT(path_id) WANT(waypoint) WANT(r_next) WANT(gid) WANT(tri_idx) WANT(ns_cell) WANT(map_cell) WANT(flags)
 #undef WANT
     if (h->multi) {
-        rc = rts_sync(h);
+        rc = sync_impl(h, need_walk);
         if (rc != RTS_OK) return rc;
     }
     const uint32_t n = h->n;
@@ -1687,7 +1694,7 @@ int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     DOWN(path_id, int32_t, 1) DOWN(waypoint, int32_t, 1) DOWN(r_next, float, 2) DOWN(gid, uint32_t, 1) DOWN(tri_idx, uint32_t, 1)
     DOWN(ns_cell, uint32_t, 1) DOWN(map_cell, uint32_t, 1) DOWN(flags, uint32_t, 1)
 #undef DOWN
-    return rts_sync(h);
+    return sync_impl(h, need_walk);
 }
 
 // swap-with-last removal (System2::remove, ECS.h:197-214): rare, done through the host
