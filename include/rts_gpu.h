@@ -269,7 +269,9 @@ int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n);
    (ECS.cpp:65-113), n_steps frames, asynchronous on the handle's stream */
 int32_t rts_step(RtsHandle h, uint32_t n_steps);
 /* (The point-in-triangle search of the last frame's few unconfirmed agents is finished by the next rts_step — inside its
-   frame kernel — or by whichever call reads or replaces the indices first: rts_sync, rts_download, the uploads.) */
+   frame kernel — or by whichever call reads or replaces the indices first: rts_sync, an rts_download that asks for tri_idx
+   or flags, the uploads that edit positions. A download of other fields only — the per-frame communicate of the adapter —
+   leaves it to the next frame.) */
 /* replaces: System2::communicate → SharedData (ECS.h:136-145); synchronises.  Arrays hold rts_agent_count() entries
    (for a slab handle: call rts_sync first, the count then includes ghost slots, which come back with gid 0xFFFFFFFF) */
 int32_t rts_download(RtsHandle h, const RtsAgentView* out);
