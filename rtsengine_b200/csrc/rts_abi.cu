@@ -51,6 +51,7 @@ struct RtsContext {
     std::string err;
     // owned device allocations of the tables
     std::vector<void*> table_allocs, path_allocs, type_allocs;
+    uint32_t* border_dev = nullptr; size_t border_cap = 0;     // MapDev::border_top / border_right (one allocation)
     void* path_arena = nullptr; size_t path_arena_cap = 0;      // rts_upload_paths: the path tables, one allocation
     void* group_arena = nullptr; uint32_t group_arena_ng = 0;   // ... and the groups' arrival state (kept across re-uploads)
     std::vector<char> path_image;                                // host image of the path arena
@@ -758,6 +759,7 @@ int32_t rts_destroy(RtsHandle h) {
     h->drop_graphs();
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
     if (h->path_arena) cudaFree(h->path_arena);
+    if (h->border_dev) cudaFree(h->border_dev);
     if (h->group_arena) cudaFree(h->group_arena);
     free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
     for (auto& pa : h->peer_arena)
@@ -880,6 +882,31 @@ inline void wall_blocks(const RtsParams& P, int32_t bx, int32_t by, float filter
 }
 }  // namespace
 }  // extern "C++"
+
+// MapDev::border_top / border_right, after every change of the triangle table or the cell -> triangle cache
+int32_t build_border_cache(RtsContext* h) {
+    const RtsParams& P = h->P;
+    const float gwf = P.tri_nx * P.tri_cell_size, ghf = P.tri_ny * P.tri_cell_size;
+    h->M.border_top = nullptr; h->M.border_right = nullptr; h->M.border_gw = 0; h->M.border_gh = 0;
+    if (!(gwf == std::floor(gwf) && ghf == std::floor(ghf) && gwf >= 1.f && ghf >= 1.f && gwf < 1.0e6f && ghf < 1.0e6f) || !h->M.n_tris) return RTS_OK;
+    const int32_t gw = (int32_t)gwf, gh = (int32_t)ghf;
+    const size_t need = (size_t)gw + 1 + (size_t)gh + 1;
+    if (need > h->border_cap) {
+        if (h->border_dev) cudaFree(h->border_dev);
+        h->border_dev = nullptr; h->border_cap = 0;
+        CU(cudaMalloc(&h->border_dev, need * sizeof(uint32_t)));
+        h->border_cap = need;
+    }
+    uint32_t* top = h->border_dev;
+    uint32_t* right = h->border_dev + gw + 1;
+    const dim3 grid(blocks_for((uint32_t)need, 128));
+    if (h->M.coords_fit_i32) k_border_cache<false><<<grid, 128, 0, h->stream>>>(P, h->M, top, right, gw, gh);
+    else k_border_cache<true><<<grid, 128, 0, h->stream>>>(P, h->M, top, right, gw, gh);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    h->M.border_top = top; h->M.border_right = right; h->M.border_gw = gw; h->M.border_gh = gh;
+    return RTS_OK;
+}
 
 int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri, const RtsWallTable* walls) {
     if (!h) return RTS_E_ARG;
@@ -1022,6 +1049,7 @@ int32_t rts_upload_map(RtsHandle h, const RtsTriangle* tris, uint32_t n_tris, co
     h->scan_large_w = d_slarge; h->scan_outer_w = d_souter; h->wall_bits_w = d_bits;
     h->upload_bytes_last = h->upload_bytes_full = bytes;
     if (!cell2tri && (rc = build_cell_grid(h, 0u)) != RTS_OK) return rc;   // no host cache given: built here
+    if ((rc = build_border_cache(h)) != RTS_OK) return rc;
     h->map_ready = true;
     h->drop_graphs();
     if (h->n) {   // agents uploaded before the map: give them their triangle index now
@@ -1238,6 +1266,7 @@ int32_t rts_update_map_region(RtsHandle h, uint32_t n_tris_total, const uint32_t
         if ((rc = build_cell_grid(h, last_found_tri, j0 * (uint32_t)P.tri_nx, (j1 + 1) * (uint32_t)P.tri_nx)) != RTS_OK) return rc;
     }
     if (any_large && (rc = build_cell_grid(h, last_found_tri)) != RTS_OK) return rc;   // a triangle spanning > 1024 cells changed: whole grid
+    if ((rc = build_border_cache(h)) != RTS_OK) return rc;   // (the walk across the map may pass through the changed triangles)
     h->upload_bytes_last = bytes;
     h->drop_graphs();
     return RTS_OK;
@@ -1829,6 +1858,8 @@ int32_t rts_build_cell_grid(RtsHandle h, uint32_t last_found_tri, uint32_t* cell
     if (rc != RTS_OK) return rc;
     CU(cudaStreamSynchronize(h->stream));
     if ((rc = build_cell_grid(h, last_found_tri)) != RTS_OK) return rc;
+    if ((rc = build_border_cache(h)) != RTS_OK) return rc;
+    h->drop_graphs();
     if (cell2tri_out)
         CU(cudaMemcpy(cell2tri_out, h->c2t_dev, sizeof(uint32_t) * (size_t)h->P.tri_nx * h->P.tri_ny, cudaMemcpyDeviceToHost));
     return RTS_OK;

@@ -59,6 +59,13 @@ struct MapDev {
     uint32_t n_scan_large;
     const uint32_t* __restrict__ scan_outer;   // triangles reaching beyond the cache grid (the super-triangle fan)
     uint32_t n_scan_outer;
+    // findTriangle's answers for the integer points ON the far border lines of the cache grid (x == W or y == H): the cache cell
+    // of such a point wraps to the opposite side of the map (Grid.cpp:18-24) and the reference's walk crosses the whole map —
+    // hundreds of dependent hops for every agent that is just crossing the line (config 5: ~0.28 ms per frame for a handful of
+    // agents). Filled after every map change by that very walk (k_border_cache), so the answers are the reference's own.
+    const uint32_t* __restrict__ border_top;     // [border_gw + 1]: q = (x, border_gh)
+    const uint32_t* __restrict__ border_right;   // [border_gh + 1]: q = (border_gw, y)
+    int32_t border_gw, border_gh;                // extent of the cache grid in map units (integers); pointers null = no cache
     // per path {offset, end offset, path_end.x, path_end.y} in one 16-byte word (same numbers as path_off / path_end)
     const float4* __restrict__ path_hdr;
     // RN(1 / ns_cell_size), RN(1 / map_cell_size): used by floor_div() to skip the IEEE division on its common path
@@ -251,7 +258,7 @@ __device__ __forceinline__ uint32_t find_triangle_from(const MapDev& M, iv2 q, u
 
 // findTriangle for the lanes of one warp. `want` says whether this lane has a query; every lane of `mask` must call.
 // The rare linear scans are served by the whole warp: 32 triangles per iteration, lowest index wins.
-template <bool WIDE>
+template <bool WIDE, bool BORDER = true>
 __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const RtsParams& P, bool want, float fx, float fy,
                                                        uint32_t& flags, unsigned mask) {
     const iv2 q{(int32_t)fx, (int32_t)fy};  // static_cast<Vertex>(Vector2f): truncation, Triangulation.cpp:1588-1590
@@ -271,6 +278,10 @@ __device__ __forceinline__ uint32_t find_triangle_warp(const MapDev& M, const Rt
                 load_tri_verts(M, i, a, b, c, w1);
                 const float d1 = tri_sign<WIDE>(q, a, b), d2 = tri_sign<WIDE>(q, b, c), d3 = tri_sign<WIDE>(q, c, a);
                 if ((d1 > 0 && d2 > 0 && d3 > 0) || (d1 < 0 && d2 < 0 && d3 < 0)) { t = i; done = true; }
+            }
+            if (BORDER && !done && M.border_top) {   // ON the far border line: the walk's own answer, recorded at the last map change
+                if (q.y == M.border_gh && q.x >= 0 && q.x <= M.border_gw) { t = __ldg(M.border_top + q.x); done = true; }
+                else if (q.x == M.border_gw && q.y >= 0 && q.y <= M.border_gh) { t = __ldg(M.border_right + q.y); done = true; }
             }
         }
     }

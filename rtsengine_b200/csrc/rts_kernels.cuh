@@ -2005,6 +2005,23 @@ __global__ void k_attack_targets(uint32_t n, float range2, RtsParams P, FineGrid
 }
 
 // stand-alone queries
+// MapDev::border_top / border_right: the reference's walk (no shortcut through the table being filled) for every integer point
+// on the two far border lines of the cache grid
+template <bool WIDE>
+__global__ void __launch_bounds__(128) k_border_cache(RtsParams P, MapDev M, uint32_t* top, uint32_t* right, int32_t gw, int32_t gh) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_top = (uint32_t)gw + 1u, total = n_top + (uint32_t)gh + 1u;
+    const bool want = i < total;
+    const float fx = (i < n_top) ? (float)i : (float)gw;
+    const float fy = (i < n_top) ? (float)gh : (float)(i - n_top);
+    uint32_t flags = 0u;
+    const uint32_t t = find_triangle_warp<WIDE, false>(M, P, want, fx, fy, flags, 0xffffffffu);
+    if (want) {
+        if (i < n_top) top[i] = t;
+        else right[i - n_top] = t;
+    }
+}
+
 __global__ void k_coord_to_cell(const float2* xy, uint32_t n, int32_t nx, int32_t ny, float cs, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = coord_to_cell(xy[i].x, xy[i].y, nx, ny, cs);

@@ -528,6 +528,14 @@ def _config5_case(dist, torch, engine, rank, world, local, n5, precision, frames
     own = sr.owned(("r",))
     cnt = torch.tensor([len(own["gid"])], device="cuda", dtype=torch.int64)
     dist.all_reduce(cnt)
+    if os.environ.get("RTS_BENCH_RANK_TRACE"):   # diagnostic: per-rank kernel times of a further (serialised) 20 frames
+        sr.g.set_profiling(True)
+        sr.g.reset_timings()
+        sr.g.update(20, sync=True)
+        ms = {k: round(sr.g.kernel_time_ms(k)[0], 4) for k in ("step", "dense", "scan", "reorder", "ingest")}
+        print(json.dumps({"config5_rank": rank, "owned": len(own["gid"]), "slots": int(sr.g.n), "kernel_ms": ms}), file=sys.stderr, flush=True)
+        sr.g.set_profiling(False)
+        dist.barrier()
     res = {"workload": f"config5: {n5} agents on the 2048x2048-cell corridor map (64 corridors 6 cells wide, 1 890 wall blocks), counter-flow, "
                        f"{world} y-slabs re-balanced every {chunk} frames", "agents": n5, "frames": frames,
            "value": n5 * frames / (dev_ms * 1e-3), "unit": "agent-updates/s", "ms_per_step": dev_ms / frames,
@@ -596,7 +604,7 @@ def _bench_multi_gpu(args, measured_peak, ClockSampler, algo_bytes):
     # ---- BASELINE config 5: dense corridors, slabs re-balanced while the crowd drains
     c5 = None
     if not args.no_config5:
-        c5 = _config5_case(dist, torch, engine, rank, world, local, args.agents5, precision, max(K, 100), 25, reserved5)
+        c5 = _config5_case(dist, torch, engine, rank, world, local, args.agents5, precision, max(K, 100), int(os.environ.get("RTS_C5_CHUNK", "25")), reserved5)
 
     # ---- the slabs against a single domain, bitwise, over the real exchange
     parity = None

@@ -538,6 +538,33 @@ def test_baseline_config4_map_tiles_wide_arithmetic():
             H.assert_same_bits(out[k][idx][core], sub[k][core], f"window {k}")
 
 
+@pytest.mark.parametrize("name,cells", [("frame_small.npz", (512, 512)), ("map_c3.npz", (1024, 1024)), ("map_c5.npz", (2048, 2048))])
+def test_points_on_the_far_border_lines_of_the_map(name, cells):
+    """An agent that is just crossing the top or the right edge of the map truncates to an integer point ON the border line; its
+    cache cell wraps to the opposite side (Grid.cpp:18-24) and the reference's findTriangle walks across the whole map. The
+    library answers those points from a table it fills with that very walk after every map change (MapDev::border_top /
+    border_right): every integer point of both lines, plus fractional positions that truncate onto them, against the oracle."""
+    fx = H.load(name)
+    tables = H.tables_of(fx)
+    W, Hh = cells[0] * 5, cells[1] * 5
+    rng = np.random.default_rng(3)
+    top = np.stack([np.arange(W + 1), np.full(W + 1, Hh)], 1).astype(np.float32)
+    right = np.stack([np.full(Hh + 1, W), np.arange(Hh + 1)], 1).astype(np.float32)
+    pts = np.concatenate([top, right])
+    frac = pts[rng.integers(0, len(pts), 4000)] + rng.uniform(0, 0.999, (4000, 2)).astype(np.float32)
+    near = np.concatenate([top[::7] + np.float32([0, 1]), top[::7] - np.float32([0, 1]), right[::7] + np.float32([1, 0]), right[::7] - np.float32([1, 0])])
+    pts = np.concatenate([pts, frac, near]).astype(np.float32)
+    P = port.default_params(*cells)
+    ow = port.OracleWorld(P, tables, None)
+    with engine.GpuAgentSystem(engine.default_params(*cells)) as g:
+        g.upload_map(tables)
+        H.assert_same_bits(g.find_triangles(pts), ow.find_triangles(pts), f"{name}: findTriangle on and around the far border lines")
+        # ... and the same after the cell -> triangle cache has been rebuilt on the device (the table is refilled)
+        c2t = g.build_cell_grid(0)
+        ow2 = port.OracleWorld(P, {**tables, "cell2tri": c2t}, None)
+        H.assert_same_bits(g.find_triangles(pts), ow2.find_triangles(pts), f"{name}: after rts_build_cell_grid")
+
+
 def test_triangle_index_is_a_function_of_the_position_where_fans_overlap():
     """A map stitched from tiles (scenario.tile_map, the config-4 geometry) keeps every tile's super-triangle fan: out there
     triangles overlap, "strictly inside" is not unique, and a carried triangle hint could be confirmed although the reference's

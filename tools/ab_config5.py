@@ -14,5 +14,5 @@ with engine.GpuAgentSystem(p) as g:
     ms = g.timings().last_step_ms / 96
     g.set_agents(agents); g.update(8, sync=True)
     g.set_profiling(True); g.reset_timings(); g.update(96, sync=True)
-    kt = {k: round(g.kernel_time_ms(k)[0], 4) for k in ("step", "dense", "scan", "reorder")}
+    kt = {k: round(g.kernel_time_ms(k)[0], 4) for k in ("step", "dense", "scan", "reorder", "walk")}
 print(json.dumps({"lib": os.path.basename(engine.LIB_PATH), "agents": n, "ms_per_frame": round(ms, 4), "kernel_ms": kt}), flush=True)
