@@ -18,16 +18,20 @@ else:
     agents = scenario.tiled_agents(tile, 8, 8, n // 64, seed=1237)
     paths = scenario.paths_of(fx)
     cells = (8192, 8192)
-    keep = agents["r"][:, 1] < 0.25 * 8192 * 5.0 - 200.0       # rank 0 of 4, away from the boundary
+    parts = int(os.environ.get("RTS_SLAB_PARTS", "4"))         # rank 0 of `parts`
+    keep = agents["r"][:, 1] < (683 // parts) * 60.0 - 100.0   # ... away from the boundary
     agents = {k: v[keep] for k, v in agents.items()}
 agents["gid"] = np.arange(len(agents["r"]), dtype=np.uint32)
 tables = scenario.tables_of(fx)
 base = engine.default_params(*cells)
 base.precision = abi.PRECISION_FAST
+if os.environ.get("RTS_FINE_CS"):   # explicit gather-cell size
+    import struct
+    base.reserved[1] = struct.unpack("I", struct.pack("f", float(os.environ["RTS_FINE_CS"])))[0]
 F0, F1 = 10, 60
 def run(g, label):
     g.upload_map(tables); g.upload_paths(paths)
-    res = {"handle": label, "agents": len(agents["r"])}
+    res = {"handle": label, "agents": len(agents["r"]), "fine_cs": os.environ.get("RTS_FINE_CS", "auto")}
     for profiling in (False, True):
         g.set_agents(agents if label == "slab" else {k: v for k, v in agents.items() if k != "gid"})
         g.set_profiling(profiling)
@@ -39,6 +43,7 @@ def run(g, label):
     print(json.dumps(res), flush=True)
 with engine.GpuAgentSystem(base) as g:
     run(g, "single")
-sr = slabs.SlabRank(base, [0, int(base.ns_ny)], 0, 0, cap_migrants=4096, cap_halo=16384)
+rows_hi = int(base.ns_ny) if which == "c3" else 683 // int(os.environ.get("RTS_SLAB_PARTS", "4"))   # c4: the slab's own gather grid
+sr = slabs.SlabRank(base, [0, rows_hi], 0, 0, cap_migrants=4096, cap_halo=16384)
 run(sr.g, "slab")
 sr.close()
