@@ -284,6 +284,36 @@ def test_alignment_extension_matches_oracle(precision):
         assert ok.mean() > 0.995, ok.mean()
 
 
+def test_path_tables_can_be_replaced_by_larger_and_smaller_ones():
+    """rts_upload_paths keeps one device arena and refills it (the adapter re-sends its per-agent windows whenever the planner
+    has rewritten some): a handle that went through smaller and larger tables must step exactly like a fresh one, and the
+    groups' finished areas must survive a re-upload with the same number of groups."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(31, 6000, tables, 150.0, 900.0)
+    a2, small = random_world(32, 50, tables, 150.0, 900.0)
+    small = {k: (v[:3] if k == "offsets" else v) for k, v in small.items()}          # two paths only
+    small["waypoints"] = small["waypoints"][: int(small["offsets"][-1])]
+    small["portals"] = small["portals"][: int(small["offsets"][-1])]
+    small["path_end"] = small["path_end"][:2]
+    names = ("r", "inertia", "angle", "angle_vel", "state", "waypoint", "r_next", "flags", "tri_idx")
+    with make_system(tables, paths) as fresh, make_system(tables, small) as used:
+        for table in (paths, small, paths):
+            used.upload_paths(table)
+        area = np.array([3.5, 0.0, 7.25, 1.0, 0.0, 2.0, 0.0, 9.0], np.float32)
+        used._chk(used.L.rts_set_finished_area(used.h, area.ctypes.data, 8))
+        used.upload_paths(paths)                                                      # same number of groups: areas kept
+        H.assert_same_bits(used.finished_area(8), area, "finished areas across a re-upload")
+        used._chk(used.L.rts_set_finished_area(used.h, np.zeros(8, np.float32).ctypes.data, 8))
+        fresh.set_agents(a)
+        used.set_agents(a)
+        fresh.update(9)
+        used.update(9)
+        x, y = fresh.communicate(names), used.communicate(names)
+        for k in names:
+            H.assert_same_bits(y[k], x[k], f"{k} after the table went small -> large -> small -> large")
+
+
 def test_single_agent():
     fx = H.load("frame_small.npz")
     tables = H.tables_of(fx)
