@@ -227,9 +227,15 @@ def e2e_leg(g, n, agents, K, Wm):
                             frame)                                           -> rts_update_agents_indexed   (H2D)
          update           : rts_step(1)
          communicate      : what the two systems write into SharedData — vel, angle_vel, state, target (21 B per agent,
-                            PhysicsSystem.cpp:118-127, SeekSystem.cpp:322-342)  -> rts_download              (D2H, synchronises)
+                            PhysicsSystem.cpp:118-127, SeekSystem.cpp:322-342) — as a DIFFERENCE, the mirror image of the
+                            upload: vel of every agent (it changes for everyone, 8 B) and {index, angle_vel, target, state} of
+                            the entities for which one of the three changed (a few per cent per frame)
+                                                                             -> rts_download_delta          (D2H, synchronises)
+                            Before and after the timed frames the blackboard kept this way is compared bit for bit with a full
+                            rts_download of the four fields.
        The loop's own integration r += vel*dt (ECS.cpp:98-113) reproduces the device's position bit for bit, so positions
        never travel (tests/test_gpu_adapter.py runs exactly this protocol inside the reference's frame loop)."""
+    from rtsengine_b200 import abi
     g.set_agents(agents)
     g.update(Wm, sync=True)
     board = {"vel": pinned((n, 2), np.float32), "angle_vel": pinned((n,), np.float32), "state": pinned((n,), np.uint8),
@@ -242,11 +248,20 @@ def e2e_leg(g, n, agents, K, Wm):
     cmd["state"][1][:] = agents["state"][:m]
     cmd["waypoint"][1][:] = 1
     cmd["r_next"][1][:] = np.nan
-    down_ptrs = {k: v[1].ctypes.data for k, v in board.items()}
     cmd_ptrs = {k: v[1].ctypes.data for k, v in cmd.items()}
     h2d = idx.nbytes + sum(v[1].nbytes for v in cmd.values())
-    d2h = sum(v[1].nbytes for v in board.values())
+    host_board = {k: v[1] for k, v in board.items()}
+    chg_t, chg_raw = pinned((n * abi.DELTA_DTYPE.itemsize,), np.uint8)
+    changes = chg_raw.view(abi.DELTA_DTYPE)
+    moved = []
     rng = np.random.default_rng(7)
+
+    def board_equals_full_download(what):
+        full = g.communicate(("vel", "angle_vel", "state", "r_next"))
+        for k in full:
+            a, b = host_board[k], full[k]
+            if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+                raise RuntimeError(f"e2e leg: blackboard field {k} kept through rts_download_delta differs from a full rts_download ({what})")
 
     def frame(f):
         # the command of this frame: m distinct agents are sent (again) onto the path of their start region
@@ -256,19 +271,28 @@ def e2e_leg(g, n, agents, K, Wm):
         cmd["state"][1][:] = agents["state"][first:first + m]
         g.update_shared_data_indexed_ptrs(idx.ctypes.data, m, cmd_ptrs)   # System2::updateSharedData   (H2D)
         g.update(1)                                                      # System2::update
-        g.communicate_ptrs(down_ptrs)                                    # System2::communicate        (D2H, synchronises)
+        moved.append(g.communicate_delta(host_board, changes))           # System2::communicate        (D2H, synchronises)
 
     for f in range(3):
         frame(f)
+    board_equals_full_download("before the timed frames")
     Ke = min(K, 100)
+    moved.clear()
     t0 = time.perf_counter()
     for f in range(Ke):
         frame(f)
     e2e_s = time.perf_counter() - t0
+    board_equals_full_download("after the timed frames")
+    per_frame = float(np.mean(moved))
+    d2h = int(round(8 * n + 4 + abi.DELTA_DTYPE.itemsize * per_frame))
     return {"value": n * Ke / e2e_s, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
-            "api": "GpuAgentSystem.update_shared_data_indexed -> update -> communicate (rts_update_agents_indexed / rts_step / "
-                   "rts_download), pinned host buffers; 1000 commanded agents up, {vel, angle_vel, state, target} of every agent down"}
+            "entities_with_changed_fields_per_step": per_frame, "d2h_bytes_per_step_full_download": 21 * n,
+            "blackboard_equals_full_download": True,
+            "api": "GpuAgentSystem.update_shared_data_indexed -> update -> communicate_delta (rts_update_agents_indexed / rts_step / "
+                   "rts_download_delta), pinned host buffers; 1000 commanded agents up; down: vel of every agent + {index, angle_vel, "
+                   "target, state} of the entities where one of them changed; the host blackboard {vel, angle_vel, state, target} is "
+                   "bit-identical to a full rts_download (checked before and after the timed frames)"}
 
 
 def config4_single_gpu(args, local, K, Wm):

@@ -275,6 +275,31 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps);
 /* replaces: System2::communicate → SharedData (ECS.h:136-145); synchronises.  Arrays hold rts_agent_count() entries
    (for a slab handle: call rts_sync first, the count then includes ghost slots, which come back with gid 0xFFFFFFFF) */
 int32_t rts_download(RtsHandle h, const RtsAgentView* out);
+/* One entry of rts_download_delta: component `index` now has these values of the slow-changing SharedData fields. */
+typedef struct RtsAgentDelta {
+    uint32_t index;
+    float angle_vel;          /* SharedData::angle_vel (SeekSystem.cpp:322-342) */
+    float target_x, target_y; /* SharedData::target = r_next                    */
+    uint32_t state;           /* MoveState                                      */
+} RtsAgentDelta;
+/* replaces: the same System2::communicate (ECS.h:233), as a DIFFERENCE against what this handle's previous
+   rts_download_delta reported — the mirror image of rts_update_agents_indexed. The frame's merged, wall-projected velocity
+   changes for every agent and travels in full (vel[n][2]); angle_vel, state and target change for a few per cent of the agents
+   per frame (a turn finished, a waypoint reached, a stop), and only those entities travel: one RtsAgentDelta for every agent
+   whose value of any of the three differs BITWISE from the value last reported for it. Applying the entries to the blackboard
+   of the previous frame gives exactly the blackboard a full rts_download would give (tests/test_gpu_parity.py). The first call
+   after the population changed (rts_set_agents / append / remove) reports every agent.
+     changes [cap], n_changes   RTS_E_CAPACITY if more than cap agents changed (the next call then reports everyone again):
+                                cap = rts_agent_count() always suffices
+     angle_vel, state, target   optional blackboard arrays in component order ([n], [n] bytes, [n][2]): when given, the library
+                                writes the entries into them itself (rts_apply_delta) while the velocities are still arriving
+   Single-domain handles with component-index gids. Leaves a pending walk queue to the next frame (no index is read).
+   Synchronises. */
+int32_t rts_download_delta(RtsHandle h, float* vel, RtsAgentDelta* changes, uint32_t cap, uint32_t* n_changes,
+                           float* angle_vel, uint8_t* state, float* target);
+/* Host-side helper (no device work): writes the entries of a change list into blackboard arrays in component order —
+   angle_vel[n], state[n] (MoveState as a byte), target[n][2]; any of the three may be NULL. */
+int32_t rts_apply_delta(const RtsAgentDelta* changes, uint32_t n_changes, uint32_t n, float* angle_vel, uint8_t* state, float* target);
 int32_t rts_sync(RtsHandle h);
 int32_t rts_get_timings(RtsHandle h, RtsTimings* out);
 /* device time (ms, CUDA events on the handle's stream) of the last `count` kernels of kind `which`

@@ -188,3 +188,7 @@ def default_unit_types() -> np.ndarray:
     u["turn_rate"] = 5.0
     u["desired_angle"] = 0.0
     return u
+
+
+# RtsAgentDelta (rts_download_delta), 20 bytes
+DELTA_DTYPE = np.dtype([("index", np.uint32), ("angle_vel", np.float32), ("target_x", np.float32), ("target_y", np.float32), ("state", np.uint32)])

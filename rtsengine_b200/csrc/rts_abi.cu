@@ -51,6 +51,9 @@ struct RtsContext {
     std::string err;
     // owned device allocations of the tables
     std::vector<void*> table_allocs, path_allocs, type_allocs;
+    // rts_download_delta: what the host was last told (caller order), the change list, its counter (device + pinned host copy)
+    float4* delta_shadow = nullptr; DeltaRec* delta_changes = nullptr; uint32_t* delta_count = nullptr; uint32_t* delta_count_host = nullptr;
+    uint32_t delta_cap = 0; bool delta_valid = false; cudaEvent_t ev_delta = nullptr;
     uint32_t* border_dev = nullptr; size_t border_cap = 0;     // MapDev::border_top / border_right (one allocation)
     void* path_arena = nullptr; size_t path_arena_cap = 0;      // rts_upload_paths: the path tables, one allocation
     void* group_arena = nullptr; uint32_t group_arena_ng = 0;   // ... and the groups' arrival state (kept across re-uploads)
@@ -656,6 +659,7 @@ size_t rts_abi_sizeof(int32_t which) {
         case 5: return sizeof(RtsUnitType);
         case 6: return sizeof(RtsAgentView);
         case 7: return sizeof(RtsTimings);
+        case 8: return sizeof(RtsAgentDelta);
         default: return 0;
     }
 }
@@ -760,6 +764,11 @@ int32_t rts_destroy(RtsHandle h) {
     free_all(h->table_allocs); free_all(h->path_allocs); free_all(h->type_allocs);
     if (h->path_arena) cudaFree(h->path_arena);
     if (h->border_dev) cudaFree(h->border_dev);
+    if (h->delta_shadow) cudaFree(h->delta_shadow);
+    if (h->delta_changes) cudaFree(h->delta_changes);
+    if (h->delta_count) cudaFree(h->delta_count);
+    if (h->delta_count_host) cudaFreeHost(h->delta_count_host);
+    if (h->ev_delta) cudaEventDestroy(h->ev_delta);
     if (h->group_arena) cudaFree(h->group_arena);
     free_all(h->agent_allocs); free_all(h->staging_allocs); free_all(h->slab_allocs);
     for (auto& pa : h->peer_arena)
@@ -1459,6 +1468,7 @@ int32_t rts_set_agents(RtsHandle h, uint32_t n, const RtsAgentView* agents) {
         }
     }
     h->n = n;
+    h->delta_valid = false;   // (rts_download_delta reports everyone after a population change)
     h->gid_is_index = !(agents && agents->gid);
     if ((rc = ingest(h, 0, n, agents)) != RTS_OK) return rc;
     if ((rc = rebin(h)) != RTS_OK) return rc;
@@ -1512,6 +1522,7 @@ int32_t rts_append_agents(RtsHandle h, uint32_t m, const RtsAgentView* agents) {
     // gid of the old agents is kept; new ones get n..n+m-1 (component indices) or their explicit gid
     if ((rc = ingest(h, h->n, m, agents)) != RTS_OK) return rc;
     h->n += m;
+    h->delta_valid = false;
     if ((rc = rebin(h)) != RTS_OK) return rc;
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -1724,6 +1735,78 @@ int32_t rts_download(RtsHandle h, const RtsAgentView* out) {
     DOWN(ns_cell, uint32_t, 1) DOWN(map_cell, uint32_t, 1) DOWN(flags, uint32_t, 1)
 #undef DOWN
     return sync_impl(h, need_walk);
+}
+
+int32_t rts_download_delta(RtsHandle h, float* vel, RtsAgentDelta* changes, uint32_t cap, uint32_t* n_changes,
+                           float* angle_vel, uint8_t* state, float* target) {
+    if (!h || !vel || !n_changes || (cap && !changes)) return RTS_E_ARG;
+    static_assert(sizeof(DeltaRec) == sizeof(RtsAgentDelta), "device record = ABI record");
+    *n_changes = 0;
+    if (h->multi || !h->gid_is_index) return h->fail(RTS_E_STATE, "rts_download_delta", "needs a single-domain handle with component-index gids");
+    CU(cudaSetDevice(h->device));
+    const uint32_t n = h->n;
+    if (n == 0) return sync_impl(h, false);
+    int32_t rc = alloc_staging(h, h->cap);
+    if (rc != RTS_OK) return rc;
+    if (h->delta_cap < h->cap) {
+        if (h->delta_shadow) cudaFree(h->delta_shadow);
+        if (h->delta_changes) cudaFree(h->delta_changes);
+        h->delta_shadow = nullptr; h->delta_changes = nullptr; h->delta_cap = 0;
+        CU(cudaMalloc(&h->delta_shadow, sizeof(float4) * (size_t)h->cap));
+        CU(cudaMalloc(&h->delta_changes, sizeof(DeltaRec) * (size_t)h->cap));
+        if (!h->delta_count) CU(cudaMalloc(&h->delta_count, 16));
+        if (!h->delta_count_host) CU(cudaHostAlloc(&h->delta_count_host, 16, cudaHostAllocDefault));
+        if (!h->ev_delta) CU(cudaEventCreateWithFlags(&h->ev_delta, cudaEventDisableTiming));
+        h->delta_cap = h->cap;
+        h->delta_valid = false;
+    }
+    CU(cudaMemsetAsync(h->delta_count, 0, 4, h->stream));
+    k_gather_delta<<<blocks_for(n, 256), 256, 0, h->stream>>>(n, h->A, h->S.vel, h->delta_shadow, h->delta_changes, h->delta_count, h->delta_cap, h->delta_valid ? 0 : 1);
+    h->launches += 1;
+    // the count first (the host needs it to size the next copy), then the change list, then the velocities — the big copy last,
+    // so that the host can write the changes into the blackboard while the velocities are still arriving
+    CU(cudaMemcpyAsync(h->delta_count_host, h->delta_count, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_delta, h->stream));
+    CU(cudaEventSynchronize(h->ev_delta));
+    const uint32_t count = *h->delta_count_host;
+    h->delta_valid = true;
+    if (count > cap) {   // (the shadow has moved on: start over with the next call)
+        h->delta_valid = false;
+        sync_impl(h, false);
+        return h->fail(RTS_E_CAPACITY, "rts_download_delta", "more agents changed than the change list holds (cap = rts_agent_count() always suffices)");
+    }
+    if (count) CU(cudaMemcpyAsync(changes, h->delta_changes, sizeof(DeltaRec) * (size_t)count, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_delta, h->stream));
+    CU(cudaMemcpyAsync(vel, h->S.vel, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    *n_changes = count;
+    if (count && (angle_vel || state || target)) {
+        CU(cudaEventSynchronize(h->ev_delta));
+        const int32_t rca = rts_apply_delta(changes, count, n, angle_vel, state, target);
+        if (rca != RTS_OK) { sync_impl(h, false); return h->fail(rca, "rts_download_delta", "change list entry out of range"); }
+    }
+    return sync_impl(h, false);
+}
+
+int32_t rts_apply_delta(const RtsAgentDelta* changes, uint32_t n_changes, uint32_t n, float* angle_vel, uint8_t* state, float* target) {
+    if (n_changes && !changes) return RTS_E_ARG;
+    constexpr uint32_t AHEAD = 24;   // the entries come in the device's cell order, i.e. at random places of the arrays: the
+                                     // lines of the entries a little further down the list are requested early
+    for (uint32_t k = 0; k < n_changes; ++k) {
+        if (k + AHEAD < n_changes) {
+            const uint32_t j = changes[k + AHEAD].index;
+            if (j < n) {
+                if (angle_vel) __builtin_prefetch(angle_vel + j, 1);
+                if (state) __builtin_prefetch(state + j, 1);
+                if (target) __builtin_prefetch(target + 2 * (size_t)j, 1);
+            }
+        }
+        const RtsAgentDelta& c = changes[k];
+        if (c.index >= n) return RTS_E_ARG;
+        if (angle_vel) angle_vel[c.index] = c.angle_vel;
+        if (state) state[c.index] = (uint8_t)c.state;
+        if (target) { target[2 * (size_t)c.index] = c.target_x; target[2 * (size_t)c.index + 1] = c.target_y; }
+    }
+    return RTS_OK;
 }
 
 // swap-with-last removal (System2::remove, ECS.h:197-214): rare, done through the host

@@ -1744,6 +1744,41 @@ __global__ void k_gather(uint32_t n, RtsParams P, AgentArrays A, Staging S, int 
 }
 
 // rts_set_agents: caller-order staging -> the "n" buffers (index = caller index), then k_bin/scan/reorder
+// rts_download_delta: the velocity of every agent in caller order, and {index, angle_vel, target, state} of the agents for which
+// one of the three differs bitwise from `shadow` (what the host was last told; caller order), appended with a warp-aggregated
+// atomic; `all` = report everyone (no valid shadow yet). The shadow is brought up to date on the way.
+struct DeltaRec { uint32_t index; float angle_vel, tx, ty; uint32_t state; };
+__global__ void __launch_bounds__(256) k_gather_delta(uint32_t n, AgentArrays A, float2* __restrict__ vel_out, float4* __restrict__ shadow,
+                                                      DeltaRec* __restrict__ changes, uint32_t* __restrict__ counter, uint32_t cap, int all) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    DeltaRec rec{0u, 0.f, 0.f, 0.f, 0u};
+    if (d < n) {
+        const uint2 key = A.key2[d];
+        const uint32_t sp = A.src[d];
+        const uint32_t o = key.x;   // component-index gids
+        vel_out[o] = A.vel_out ? A.vel_out[sp] : make_float2(0.f, 0.f);
+        const float av = A.vel4[sp].w;
+        const float4 nav4 = A.nav4[sp];
+        const uint32_t st = key.y & 3u;
+        const float4 now = make_float4(av, nav4.x, nav4.y, __uint_as_float(st));
+        const float4 old = shadow[o];
+        changed = all || __float_as_uint(old.x) != __float_as_uint(now.x) || __float_as_uint(old.y) != __float_as_uint(now.y) ||
+                  __float_as_uint(old.z) != __float_as_uint(now.z) || __float_as_uint(old.w) != __float_as_uint(now.w);
+        if (changed) shadow[o] = now;
+        rec = DeltaRec{o, av, nav4.x, nav4.y, st};
+    }
+    const unsigned need = __ballot_sync(0xffffffffu, changed);
+    if (need) {
+        const unsigned lane = threadIdx.x & 31u;
+        uint32_t base = 0u;
+        if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(counter, (uint32_t)__popc(need));
+        base = __shfl_sync(0xffffffffu, base, __ffs(need) - 1);
+        const uint32_t k = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+        if (changed && k < cap) changes[k] = rec;
+    }
+}
+
 __global__ void k_ingest(uint32_t n, uint32_t first, Staging S, AgentArrays A) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -63,6 +63,8 @@ def load_library():
         "rts_set_finished_area": (i32, [H, vp, u32]),
         "rts_step": (i32, [H, u32]),
         "rts_download": (i32, [H, AV]),
+        "rts_download_delta": (i32, [H, vp, vp, u32, C.POINTER(C.c_uint32), vp, vp, vp]),
+        "rts_apply_delta": (i32, [vp, u32, u32, vp, vp, vp]),
         "rts_sync": (i32, [H]),
         "rts_get_timings": (i32, [H, C.POINTER(abi.RtsTimings)]),
         "rts_kernel_time_ms": (i32, [H, i32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -293,6 +295,18 @@ class GpuAgentSystem:
         return arrays
 
     download = communicate
+
+    def communicate_delta(self, board: dict, changes: np.ndarray | None = None) -> int:
+        """System2::communicate as a difference (rts_download_delta): `board` holds the blackboard of the previous frame —
+        vel (n,2) f32, angle_vel (n,) f32, state (n,) u8, r_next (n,2) f32 — and is brought up to date in place; returns the
+        number of entities whose angle_vel / state / target travelled."""
+        n = self.n
+        if changes is None:
+            changes = np.zeros(n, abi.DELTA_DTYPE)
+        cnt = C.c_uint32(0)
+        self._chk(self.L.rts_download_delta(self.h, board["vel"].ctypes.data, changes.ctypes.data, len(changes), C.byref(cnt),
+                                            board["angle_vel"].ctypes.data, board["state"].ctypes.data, board["r_next"].ctypes.data))
+        return int(cnt.value)
 
     def sync(self):
         self._chk(self.L.rts_sync(self.h))

@@ -284,6 +284,49 @@ def test_alignment_extension_matches_oracle(precision):
         assert ok.mean() > 0.995, ok.mean()
 
 
+def test_download_delta_keeps_the_blackboard_identical_to_full_downloads():
+    """rts_download_delta (System2::communicate as a difference): a host blackboard brought up to date from the change lists
+    must equal a full rts_download of {vel, angle_vel, state, target} after every frame — through commands issued by the host
+    (indexed uploads), stops (arrival rule on), a too-small change list (RTS_E_CAPACITY, then everything again) and a
+    population edit."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(41, 20000, tables, 150.0, 1100.0)
+    rng = np.random.default_rng(4)
+    names = ("vel", "angle_vel", "state", "r_next")
+    with make_system(tables, paths, enable_arrival=1) as g:
+        g.set_agents(a)
+        n = g.n
+        board = {"vel": np.zeros((n, 2), np.float32), "angle_vel": np.zeros(n, np.float32), "state": np.zeros(n, np.uint8),
+                 "r_next": np.zeros((n, 2), np.float32)}
+        counts = []
+        for f in range(40):
+            if f % 7 == 3:      # the host commands 300 agents
+                idx = rng.choice(n, 300, replace=False).astype(np.uint32)
+                g.update_shared_data_indexed(idx, {"state": np.full(300, abi.MOVING, np.uint8), "path_id": rng.integers(0, 8, 300).astype(np.int32),
+                                                   "waypoint": np.zeros(300, np.int32), "r_next": np.full((300, 2), np.nan, np.float32)})
+            g.update(1)
+            if f == 20:         # a change list that is too small: reported, and the next call starts over
+                with pytest.raises(engine.RtsError) as e:
+                    g.communicate_delta(board, np.zeros(3, abi.DELTA_DTYPE))
+                assert e.value.code == abi.RTS_E_CAPACITY
+            counts.append(g.communicate_delta(board))
+            full = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(board[k], full[k], f"frame {f}: {k} kept through the change lists")
+        assert counts[0] == n and counts[20] == n and max(counts[1:20]) < 0.5 * n and min(counts[1:20]) > 0
+        # population edit: everyone is reported again
+        extra, _ = random_world(42, 500, tables, 150.0, 1100.0)
+        g.append_agents(extra)
+        n2 = g.n
+        board = {k: np.concatenate([v, np.zeros((500,) + v.shape[1:], v.dtype)]) for k, v in board.items()}
+        g.update(1)
+        assert g.communicate_delta(board) == n2
+        full = g.communicate(names)
+        for k in names:
+            H.assert_same_bits(board[k], full[k], f"after append: {k}")
+
+
 def test_path_tables_can_be_replaced_by_larger_and_smaller_ones():
     """rts_upload_paths keeps one device arena and refills it (the adapter re-sends its per-agent windows whenever the planner
     has rewritten some): a handle that went through smaller and larger tables must step exactly like a fresh one, and the
