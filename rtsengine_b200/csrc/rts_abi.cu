@@ -92,9 +92,12 @@ struct RtsContext {
     double last_step_ms = 0;
     uint64_t launches = 0, steps = 0;
     // step graph (two frames: the previous-order buffers ping-pong)
-    cudaGraphExec_t graph2[2] = {nullptr, nullptr};   // one per ping-pong parity
+    cudaGraphExec_t graph2[2] = {nullptr, nullptr};   // GRAPH_FRAMES frames, one per ping-pong parity
     uint32_t graph_n[2] = {0, 0};
     uint64_t graph_launches = 0;
+    cudaGraphExec_t graph1[2] = {nullptr, nullptr};   // ONE frame (rts_step(h, 1), the per-frame call of the System2 adapter), one per parity
+    uint32_t graph1_n[2] = {0, 0};
+    uint64_t graph1_launches = 0;
     int parity = 0;
     bool use_graph = true;
     // ---- slab decomposition (multi-GPU) ----
@@ -132,6 +135,8 @@ struct RtsContext {
 
     void drop_graphs() {
         for (auto& g : graph2)
+            if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        for (auto& g : graph1)
             if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     }
 
@@ -1613,9 +1618,11 @@ int32_t rts_set_finished_area(RtsHandle h, const float* area, uint32_t n) {
 
 constexpr uint32_t GRAPH_FRAMES = 8;   // even (the previous-order buffers ping-pong); more frames = more walks overlapped
 
-static int32_t build_graph(RtsContext* h) {
+// frames = GRAPH_FRAMES, or 1: the frame of an rts_step(h, 1) call (single-domain handles)
+static int32_t build_graph(RtsContext* h, uint32_t frames = GRAPH_FRAMES) {
     const int par = h->parity;
-    if (h->graph2[par]) { cudaGraphExecDestroy(h->graph2[par]); h->graph2[par] = nullptr; }
+    cudaGraphExec_t& slot = frames == 1 ? h->graph1[par] : h->graph2[par];
+    if (slot) { cudaGraphExecDestroy(slot); slot = nullptr; }
     int32_t rc = join_walk(h);
     if (rc != RTS_OK) return rc;
     cudaGraph_t g = nullptr;
@@ -1626,16 +1633,17 @@ static int32_t build_graph(RtsContext* h) {
     const bool deferred_walk = h->P.walk_all != 0 && h->overlap_walk && !h->profiling;
     if (deferred_walk) { h->walkq_pending = true; h->walkq_parity = par ^ 1; }
     CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    for (uint32_t f = 0; f < GRAPH_FRAMES && rc == RTS_OK; ++f) rc = launch_frame(h);
+    for (uint32_t f = 0; f < frames && rc == RTS_OK; ++f) rc = launch_frame(h);
     h->walkq_pending = false;   // (nothing has run; rts_step marks the queue pending after every replay)
     cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
-    h->graph_launches = h->launches - launches0;
+    if (frames & 1u) swap_prev_order(h);   // (the capture swapped the host's view of the ping-pong buffers an odd number of times)
+    (frames == 1 ? h->graph1_launches : h->graph_launches) = h->launches - launches0;
     h->launches = launches0;
     if (rc != RTS_OK) { if (g) cudaGraphDestroy(g); return rc; }
     if (ce != cudaSuccess) return h->fail(RTS_E_CUDA, "cudaStreamEndCapture", cudaGetErrorString(ce));
-    CU(cudaGraphInstantiate(&h->graph2[par], g, 0));
+    CU(cudaGraphInstantiate(&slot, g, 0));
     cudaGraphDestroy(g);
-    h->graph_n[par] = h->n;
+    (frames == 1 ? h->graph1_n[par] : h->graph_n[par]) = h->n;
     return RTS_OK;
 }
 
@@ -1670,7 +1678,27 @@ int32_t rts_step(RtsHandle h, uint32_t n_steps) {
         }
     }
     if (!ev0_recorded) CU(cudaEventRecord(h->ev0, h->stream));
+    // the remaining frames — every frame of the adapter's rts_step(h, 1) — one by one: single-domain handles replay a one-frame
+    // graph per ping-pong parity (the host's view of the buffers is swapped by hand, as launch_frame would have)
+    const bool one_frame_graphs = h->use_graph && !h->profiling && !h->multi && h->n > 0;
     for (; done < n_steps; ++done) {
+        if (one_frame_graphs) {
+            const int par = h->parity;
+            if (!h->graph1[par] || h->graph1_n[par] != h->n) {
+                const int32_t rc = build_graph(h, 1u);
+                if (rc != RTS_OK) return rc;
+            }
+            const bool deferred_walk = h->P.walk_all != 0 && h->overlap_walk;
+            if (!deferred_walk) {
+                const int32_t rc = join_walk(h);
+                if (rc != RTS_OK) return rc;
+            }
+            CU(cudaGraphLaunch(h->graph1[par], h->stream));
+            swap_prev_order(h);
+            h->launches += h->graph1_launches;
+            if (deferred_walk) { h->walkq_pending = true; h->walkq_parity = par; }   // this frame's queue
+            continue;
+        }
         const int32_t rc = launch_frame(h);
         if (rc != RTS_OK) return rc;
     }
