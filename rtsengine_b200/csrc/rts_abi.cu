@@ -560,13 +560,10 @@ int32_t exchange_nccl(RtsContext* h) {
     return RTS_OK;
 }
 
-// neighbour exchange over peer memory: the frame's kernels have written their records into the neighbours' buffers and the
-// last CTA of k_step_dense* has published them (publish_to_peers); only a halo refresh without a frame needs a launch
-int32_t exchange_peer(RtsContext* h, bool published_by_frame) {
-    if (!published_by_frame) {
-        k_publish<<<1, 32, 0, comm_stream(h)>>>(h->SL);
-        h->launches += 1;
-    }
+// neighbour exchange over peer memory: the packing kernels (k_step, k_step_dense*, k_halo_seed) have written their records
+// into the neighbours' buffers; the first thread of k_ingest_remote, the next kernel of the stream, publishes them
+// (publish_to_peers) — nothing to launch here
+int32_t exchange_peer(RtsContext* h, bool) {
     h->exchange_pending = true;
     return RTS_OK;
 }

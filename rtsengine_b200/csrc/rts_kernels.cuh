@@ -199,14 +199,15 @@ struct SlabDev {
     // delivery. Receive buffers are double-buffered by epoch parity: the neighbour may already deliver frame e+1 while
     // frame e is being ingested (it cannot be two frames ahead: its frame e+2 needs this rank's frame e+1 delivery).
     // k_step / k_step_dense* / k_halo_seed write their records directly into the neighbour's buffer (pack_target); the slot
-    // counters stay local, and the last CTA of the frame's last packing kernel copies them across and raises the flag.
+    // counters stay local, and the first thread of k_ingest_remote — the next kernel of the stream — copies them across and
+    // raises the flag (publish_to_peers).
     int32_t peer_mode;
     char* recv_base[2][2];    // [direction][parity] this rank's receive buffers (same layout as send / recv: carve_exbuf)
     char* peer_base[2][2];    // [direction][parity] where records sent in `direction` land: the neighbour's recv_base[1 - direction]
     unsigned long long* flag_local[2];  // [direction] peer_word of the last delivery that arrived from that direction
     unsigned long long* flag_peer[2];   // [direction] the neighbour's flag_local[1 - direction]
-    uint32_t* epoch;          // [0] exchanges completed (k_scatter ticks it), [1] CTA counter of publish_to_peers
-    int32_t publish_here;     // set in the copy handed to the last packing kernel of a frame: it publishes (publish_to_peers)
+    uint32_t* epoch;          // [0] exchanges completed (k_scatter ticks it)
+    int32_t publish_here;     // (unused since the first thread of k_ingest_remote publishes: publish_to_peers)
     // Edge rows (fine-grid rows relative to FineGrid::row0): slots of rows < edge_row_lo or >= edge_row_hi can send
     // something to a neighbour this frame (halo band + one frame of travel). k_step<PHASE 1> steps exactly those, so that
     // the exchange can start while k_step<PHASE 2> is still working on the interior.
@@ -225,29 +226,21 @@ __device__ __forceinline__ ExBuf pack_target(const SlabDev& SL, int dir) {
     const uint32_t e = *((volatile uint32_t*)SL.epoch);
     return carve_exbuf(SL.peer_base[dir][e & 1u], SL.cap_mig, SL.cap_halo);
 }
-// Peer exchange, end of the packing: called by every CTA of the LAST kernel of a frame that packs (k_step_dense*, or
-// k_publish after k_halo_seed). Every thread that wrote a record into a neighbour's buffer has already executed a
-// system-scope fence behind it (finish_agent, k_halo_seed), and the frame kernel ended before this one started, so when the
-// last CTA arrives here every record of the frame has landed. It then publishes ONE 64-bit word per neighbour:
-// {epoch + 1 : 24 | migrants : 20 | halo records : 20} — flag and header in a single store, no second round trip.
+// Peer exchange, end of the packing. Every thread that wrote a record into a neighbour's buffer has executed a system-scope
+// fence behind it (finish_agent, k_halo_seed), and the kernels that pack have ended before k_ingest_remote starts: when its
+// first thread runs, every record of the frame has landed. That thread publishes ONE 64-bit word per neighbour —
+// {epoch + 1 : 24 | migrants : 20 | halo records : 20}: flag and header in a single store, no second round trip — before
+// anything of that kernel waits for the neighbours' words (so no rank waits for a word whose sender is waiting itself).
 __device__ __forceinline__ unsigned long long peer_word(uint32_t epoch1, uint32_t nm, uint32_t nh) {
     return ((unsigned long long)(epoch1 & 0xFFFFFFu) << 40) | ((unsigned long long)(nm & 0xFFFFFu) << 20) | (unsigned long long)(nh & 0xFFFFFu);
 }
-__device__ __forceinline__ void publish_to_peers(const SlabDev& SL) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(SL.epoch + 1, 1u);
-        if (done == gridDim.x * gridDim.y - 1) {
-            SL.epoch[1] = 0u;
-            __threadfence();
-            const uint32_t e = *((volatile uint32_t*)SL.epoch);
-            for (int dir = 0; dir < 2; ++dir) {
-                if (!SL.has[dir]) continue;
-                volatile uint32_t* lh = SL.send[dir].hdr;
-                *((volatile unsigned long long*)SL.flag_peer[dir]) = peer_word(e + 1u, min(lh[0], SL.cap_mig), min(lh[1], SL.cap_halo));
-            }
-        }
+__device__ __forceinline__ void publish_to_peers(const SlabDev& SL) {   // one thread
+    __threadfence_system();
+    const uint32_t e = *((volatile uint32_t*)SL.epoch);
+    for (int dir = 0; dir < 2; ++dir) {
+        if (!SL.has[dir]) continue;
+        volatile uint32_t* lh = SL.send[dir].hdr;
+        *((volatile unsigned long long*)SL.flag_peer[dir]) = peer_word(e + 1u, min(lh[0], SL.cap_mig), min(lh[1], SL.cap_halo));
     }
 }
 
@@ -582,7 +575,6 @@ __global__ void k_row_hist(const uint32_t* __restrict__ n_dev, const uint2* __re
 }
 
 // Peer exchange after k_halo_seed (no frame, hence no k_step_dense to do it): publish what was packed
-__global__ void k_publish(SlabDev SL) { publish_to_peers(SL); }
 
 // Slab exchange, receiving side: records that arrived from direction `dir` are appended behind the slots of the
 // frame kernel (base = first slot of this direction's range), migrants as owned agents, halo records as ghosts.
@@ -591,6 +583,7 @@ __global__ void k_publish(SlabDev SL) { publish_to_peers(SL); }
 __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArrays A) {
     pdl_wait();
     pdl_trigger();
+    if (SL.peer_mode && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) publish_to_peers(SL);   // (before this CTA waits below)
     const uint32_t cap_mig = SL.cap_mig, cap_halo = SL.cap_halo;
     const int dir = (int)blockIdx.y;                       // both directions in one launch
     ExBuf B = SL.recv[dir];
@@ -1604,7 +1597,6 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
         if (parked + DENSE_GROUPS > 32u) finish_parked();
     }
     if (parked) finish_parked();
-    if (MULTI && SL.peer_mode && SL.publish_here) publish_to_peers(SL);
 }
 
 // Tolerance-mode counterpart of k_step_dense: FAST_DENSE_LANES lanes share the candidates of one crowded agent (every lane
@@ -1694,7 +1686,6 @@ __global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, 
         if (parked + GROUPS > 32u) finish_parked();
     }
     if (parked) finish_parked();
-    if (MULTI && SL.peer_mode && SL.publish_here) publish_to_peers(SL);
 }
 
 // ------------------------------------------------------------------------------------------------
