@@ -8,10 +8,12 @@
 //   k_step     : the fused frame — neighbour gather, boids forces, clamp/decay, wall pass, seek, merge,
 //                wall pass, integrate, slab packing, re-bin of the new position
 //   k_step_dense : the same for the crowded agents k_step queues (one warp per agent)
-//   k_arrive / k_area_sync : arrival rule (finalizeSeek) with frame-start snapshot semantics
-//   k_ingest_remote / k_halo_seed : slab exchange (arrivals appended, halo bands packed without a frame)
+//   k_arrive / k_area_sync / k_area_sync_counts : arrival rule (finalizeSeek) with frame-start snapshot semantics, also across slabs
+//   k_ingest_remote / k_halo_seed : slab exchange (the frame's counts published, arrivals appended; halo bands packed without a frame)
 //   k_cellgrid_classify / k_cellgrid_resolve : Triangulation::updateCellGrid (cell -> triangle cache)
+//   k_border_cache : findTriangle's answers on the far border lines of the cache grid, recorded after every map change
 //   k_gather   : slot order -> caller order for rts_download
+//   k_gather_delta : ... as a difference against what the host was last told (rts_download_delta)
 //   k_apply    : caller order -> slot order for rts_update_agents
 //   k_coord_to_cell / k_find_triangles / k_contact_edges : stand-alone point queries
 #pragma once
