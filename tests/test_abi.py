@@ -52,3 +52,29 @@ def test_no_cpu_fallback(cuda_lib):
     with pytest.raises(engine.RtsError) as e:
         engine.GpuAgentSystem(map_cells=(512, 512))
     assert e.value.code == abi.RTS_E_CUDA
+
+
+def test_apply_delta_writes_the_change_list_into_the_blackboard(cuda_lib):
+    """rts_apply_delta is host-only: entries {index, angle_vel, target, state} land in component order, absent arrays are
+    skipped, an index beyond the population is refused."""
+    import numpy as np
+    n = 50
+    assert cuda_lib.rts_abi_sizeof(8) == abi.DELTA_DTYPE.itemsize == 20
+    ch = np.zeros(7, abi.DELTA_DTYPE)
+    ch["index"] = [3, 49, 0, 17, 3, 20, 21]            # (3 twice: the later entry wins)
+    ch["angle_vel"] = [1.5, -2.0, 0.25, 5.0, 7.0, 0.0, -0.5]
+    ch["target_x"] = np.arange(7) * 10.0
+    ch["target_y"] = np.arange(7) * -3.0
+    ch["target_x"][5] = np.nan
+    ch["state"] = [1, 0, 2, 1, 0, 1, 2]
+    av, st, tg = np.full(n, 9.0, np.float32), np.full(n, 7, np.uint8), np.full((n, 2), 8.0, np.float32)
+    assert cuda_lib.rts_apply_delta(ch.ctypes.data, 7, n, av.ctypes.data, st.ctypes.data, tg.ctypes.data) == abi.RTS_OK
+    want_av, want_st, want_tg = np.full(n, 9.0, np.float32), np.full(n, 7, np.uint8), np.full((n, 2), 8.0, np.float32)
+    for c in ch:
+        want_av[c["index"]] = c["angle_vel"]; want_st[c["index"]] = c["state"]; want_tg[c["index"]] = (c["target_x"], c["target_y"])
+    assert np.array_equal(av, want_av) and np.array_equal(st, want_st)
+    assert np.array_equal(tg.view(np.uint32), want_tg.view(np.uint32))
+    av2 = np.zeros(n, np.float32)
+    assert cuda_lib.rts_apply_delta(ch.ctypes.data, 7, n, av2.ctypes.data, None, None) == abi.RTS_OK and av2[17] == 5.0
+    ch["index"][6] = n
+    assert cuda_lib.rts_apply_delta(ch.ctypes.data, 7, n, av.ctypes.data, st.ctypes.data, tg.ctypes.data) == abi.RTS_E_ARG
