@@ -1196,13 +1196,18 @@ __global__ void __launch_bounds__(FAST ? FAST_BLOCK : STEP_BLOCK, FAST ? FAST_MI
     uint32_t block0 = bid * TILE;
     if (PHASE == 1 && bid >= SL.edge_blocks) block0 = edge_b + (bid - SL.edge_blocks) * BLOCK;
     const uint32_t p = block0 + t_in;
-    const bool in_range = p < n;
-
+    // (slabs: the live count n is a word in device memory; the slot's record is requested for every slot of the handle's
+    //  capacity — allocated, possibly stale beyond n — so that the two round trips overlap instead of following each other)
     float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
     uint2 mykey = make_uint2(0u, 4u);
-    if (in_range) {
+    if (p < n_bound) {
         me = A.pos4[p];
         mykey = A.key2[p];
+    }
+    const bool in_range = p < n;
+    if (MULTI && !in_range) {
+        me = make_float4(0.f, 0.f, 0.f, 0.f);
+        mykey = make_uint2(0u, 4u);
     }
     const v2 r = V(me.x, me.y);
     const bool ghost = (mykey.y >> 2) & 1u;
