@@ -25,6 +25,7 @@ agents["gid"] = np.arange(len(agents["r"]), dtype=np.uint32)
 tables = scenario.tables_of(fx)
 base = engine.default_params(*cells)
 base.precision = abi.PRECISION_FAST
+base.reserved[5] = int(os.environ.get("RTS_RESERVED5", "0"))   # e.g. 16: the one-rank slab's frames from a CUDA graph too
 if os.environ.get("RTS_FINE_CS"):   # explicit gather-cell size
     import struct
     base.reserved[1] = struct.unpack("I", struct.pack("f", float(os.environ["RTS_FINE_CS"])))[0]
