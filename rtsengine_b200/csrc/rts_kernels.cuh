@@ -246,6 +246,14 @@ __device__ __forceinline__ void publish_to_peers(const SlabDev& SL) {   // one t
     }
 }
 
+// ... and already by the first thread of k_step_dense* when the frame kernel queued no crowded agent (qn == 0: nothing more will
+// be packed in this frame): the word is then on its way to the neighbour while this kernel and the launch of k_ingest_remote are
+// still ahead. k_ingest_remote publishes in any case — the same word.
+template <bool MULTI>
+__device__ __forceinline__ void publish_early(const SlabDev& SL, uint32_t queued) {
+    if (MULTI && SL.peer_mode && queued == 0u && blockIdx.x == 0 && threadIdx.x == 0) publish_to_peers(SL);
+}
+
 struct AgentArrays {
     uint32_t* n_dev;  // live slots of the CURRENT order (owned agents + ghosts); written by the scan
     // neighbour record, CURRENT cell order
@@ -1467,6 +1475,7 @@ __global__ void __launch_bounds__(128, RTS_DENSE_MIN_BLOCKS) k_step_dense(RtsPar
     const float rscatter2 = P.rscatter * P.rscatter;
     const uint32_t stride = gridDim.x * 4u * DENSE_GROUPS;
     const uint32_t qn = *A.dense_n;
+    publish_early<MULTI>(SL, qn);
     // The tail of the frame (finish_agent: walls, seek, integration, ~2/3 of an agent's instructions) is not done by one
     // lane per agent as the sums come out: the agents a warp works through are parked one per lane (slot index, state
     // and sums in registers) and finished together, every lane its own agent, when 32 are parked or the queue ends.
@@ -1619,6 +1628,7 @@ __global__ void __launch_bounds__(128) k_step_dense_fast(RtsParams P, MapDev M, 
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t stride = gridDim.x * (blockDim.x >> 5) * GROUPS;
     const uint32_t qn = *A.dense_n;
+    publish_early<MULTI>(SL, qn);
     const float rscatter2 = P.rscatter * P.rscatter;
     uint32_t parked = 0;                       // agents parked in this warp (lane k holds the k-th)
     uint32_t my_p = 0, my_sp = 0;
