@@ -1,3 +1,8 @@
+"""Per-rank frame time of coupled slabs, of the same slabs without any agent near the boundary (RTS_DIAG_GAP=units), and of the
+same half-maps as independent one-rank slabs (RTS_DIAG_SOLO=1, optionally RTS_DIAG_SOLO_COMM=1) — diagnostic. With a debug build
+that exports rts_debug_wait_ns (k_ingest_remote clocking its spin into SlabDev::overflow[2..3]; not part of the product library)
+it also prints the time actually spent waiting for the neighbour's word.
+    torchrun --nproc-per-node 2 tools/wait_diag.py"""
 import os, sys, json, ctypes as C
 sys.path.insert(0, "/root/repo")
 import numpy as np, torch, torch.distributed as dist
@@ -31,12 +36,15 @@ else:
 sr.g.upload_map(scenario.tables_of(fx)); sr.g.upload_paths(scenario.paths_of(fx)); sr.g.set_agents(parts[rank])
 if not solo: sr.halo_refresh()
 sr.g.update(16, sync=True)
-L = sr.g.L; L.rts_debug_wait_ns.restype = C.c_uint32; L.rts_debug_wait_ns.argtypes = [C.c_void_p, C.c_int, C.c_int]
-for d in (0, 1): L.rts_debug_wait_ns(sr.g.h, d, 1)
+L = sr.g.L
+has_dbg = hasattr(L, "rts_debug_wait_ns")
+if has_dbg:
+    L.rts_debug_wait_ns.restype = C.c_uint32; L.rts_debug_wait_ns.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for d in (0, 1): L.rts_debug_wait_ns(sr.g.h, d, 1)
 dist.barrier(); torch.cuda.synchronize()
 sr.g.update(8); sr.g.reset_timings(); F = 80; sr.g.update(F); sr.g.sync()
 ms = sr.g.timings().last_step_ms / F
-w = [L.rts_debug_wait_ns(sr.g.h, d, 0) / (F + 8) / 1000.0 for d in (0, 1)]
+w = [L.rts_debug_wait_ns(sr.g.h, d, 0) / (F + 8) / 1000.0 for d in (0, 1)] if has_dbg else [float('nan')] * 2
 for r in range(world):
     dist.barrier()
     if r == rank: print(json.dumps({"solo": solo, "gap": os.environ.get("RTS_DIAG_GAP"), "owned": len(parts[rank]["gid"]), "rank": rank, "ms_per_frame": round(ms, 5), "wait_us_per_frame_dir0_dir1": [round(x, 2) for x in w]}), flush=True)
