@@ -607,13 +607,16 @@ __global__ void k_ingest_remote(uint32_t base0, SlabDev SL, FineGrid F, AgentArr
                 unsigned long long t0 = 0, now = 0, w;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
                 // (24-bit epochs: "arrived" = not behind this frame's epoch + 1, modulo 2^24)
-                while ((((uint32_t)((w = *flag) >> 40) - (e + 1u)) & 0xFFFFFFu) >= 0x800000u) {
-                    __nanosleep(100);
+                // (acquire loads at system scope: everything the neighbour wrote before it released the word — fence + store in
+                //  publish_to_peers — is visible behind the load that sees it, and through the barrier below to the whole CTA;
+                //  no fence of its own: 2 us per frame less than volatile polling followed by a system-scope fence)
+                auto poll = [&]() { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory"); return v; };
+                while ((((uint32_t)((w = poll()) >> 40) - (e + 1u)) & 0xFFFFFFu) >= 0x800000u) {
+                    __nanosleep(20);
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                     if (now - t0 > 20000000000ull) { *SL.overflow = 3u; w = 0ull; break; }
                 }
                 s_word = w;
-                __threadfence_system();
             }
             __syncthreads();
             peer_nm = (uint32_t)(s_word >> 20) & 0xFFFFFu;
