@@ -98,6 +98,12 @@ class OracleWorld:
             if rc != 0:
                 raise RuntimeError(f"oracle step failed: {rc}")
 
+    def set_slab_arrival(self, on: bool, counts=None):
+        """slab model of the arrival rule (see rts_oracle_set_slab_arrival): ghosts evaluate the rule too; `counts` (uint32 per
+        group, kept alive by the caller) accumulates the agents stopped by the following steps"""
+        self._stop_counts = counts
+        self.L.rts_oracle_set_slab_arrival(1 if on else 0, None if counts is None else counts.ctypes.data)
+
     def find_triangles(self, xy):
         xy = np.ascontiguousarray(xy, np.float32)
         out = np.zeros(len(xy), np.uint32)

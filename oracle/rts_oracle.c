@@ -305,6 +305,9 @@ static void build_grid(const RtsParams* P, uint32_t n, const float* r, ns_grid* 
     free(fill);
 }
 
+static int g_slab_arrival = 0;          /* see rts_oracle_set_slab_arrival */
+static uint32_t* g_stop_counts = 0;
+
 /*
  * One frame for agents [0, n).  `ghost` (may be NULL) marks agents that only act as neighbours
  * (halo copies in the slab decomposition); they are not updated.  Arrays of `a` are updated in
@@ -341,7 +344,8 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
     if (P->enable_arrival && fin_area && a->path_id) {
         const float area_unit = (float)3.14159265358979323846 * P->rhard * P->rhard; /* M_PIf * RHARD * RHARD */
         for (uint32_t i = 0; i < n; ++i) {
-            if (ghost && ghost[i]) continue;
+            const int ghost_i = ghost && ghost[i];
+            if (ghost_i && !g_slab_arrival) continue;
             const int32_t pid = a->path_id[i];
             if (s0[i] != RTS_MOVING || pid < 0) continue;
             const uint32_t p0 = paths->offsets[pid], last = paths->offsets[pid + 1] - 1;
@@ -356,7 +360,7 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
             const float finish_radius = sqrtf(fin_area[g_i] / (float)3.14159265358979323846);
             const float dist_to_end = sqrtf(vdist2(path_end, r));
             if (!(dist_to_end < 2 * a->radius[i] + finish_radius)) continue; /* :258 */
-            stop[i] = 1;
+            if (!ghost_i) stop[i] = 1;
             const uint32_t ci = cell_of[i];
             const int cx = (int)(ci % (uint32_t)P->ns_nx), cy = (int)((ci / (uint32_t)P->ns_nx) % (uint32_t)P->ns_ny);
             for (int dx = -1; dx <= 1; ++dx)
@@ -379,6 +383,7 @@ int32_t rts_oracle_step(const RtsParams* P, const RtsTriangle* tris, uint32_t n_
             if (stop[i]) {
                 const int32_t pid = a->path_id[i];
                 fin_area[paths->group ? paths->group[pid] : pid] += area_unit; /* CommandGroupManager.h:150 */
+                if (g_stop_counts) g_stop_counts[paths->group ? paths->group[pid] : pid] += 1u;
             }
     }
 
@@ -667,6 +672,11 @@ void rts_oracle_default_params(RtsParams* p, int32_t map_nx, int32_t map_ny) {
 
 int rts_oracle_threads(void) { return omp_get_max_threads(); }
 void rts_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+/* Slab model of the arrival rule (tests/test_slabs_gloo.py): with `on`, agents marked as ghosts also EVALUATE the rule — they
+   stop the owned agents among their same-group neighbours, never themselves (their owner does) — which is what every rank of
+   the slab decomposition does for the halo copies it holds. `counts` (may be NULL): per-group number of agents stopped by the
+   following steps, accumulated. */
+void rts_oracle_set_slab_arrival(int on, uint32_t* counts) { g_slab_arrival = on; g_stop_counts = counts; }
 
 void rts_oracle_walk_hops(const RtsParams* P, const RtsTriangle* tris, uint32_t n_tris, const uint32_t* cell2tri,
                           const float* xy, uint32_t n, uint32_t* hops_out) {

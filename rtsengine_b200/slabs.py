@@ -129,9 +129,15 @@ class SlabModel:
         self.y_lo = np.float32(lo * params.ns_cell_size)
         self.y_hi = np.float32(hi * params.ns_cell_size)
         self.halo = np.float32(halo_width(params.r_max2))
+        # arrival rule on: the band is finish_radius wide and the halo records carry the navigation record, as in
+        # rts_abi.cu::halo_band / ExBuf::h_nav4 (every rank evaluates the rule for its ghosts and stops only agents it owns)
+        self.halo_fields = list(HALO_FIELDS)
+        if params.enable_arrival:
+            self.halo = np.float32(max(float(self.halo), float(params.finish_radius) + 0.25))
+            self.halo_fields += ["path_id", "waypoint", "r_next"]
         self.step_fn = step_fn
         self.owned: dict = {}
-        self.ghosts = {k: None for k in HALO_FIELDS}
+        self.ghosts = {k: None for k in self.halo_fields}
 
     def set_agents(self, agents: dict):
         self.owned = {k: np.ascontiguousarray(agents[k]).copy() for k in FULL_FIELDS}
@@ -139,7 +145,9 @@ class SlabModel:
 
     def _clear_ghosts(self):
         self.ghosts = {"r": np.zeros((0, 2), np.float32), "radius": np.zeros(0, np.float32), "mass": np.zeros(0, np.float32),
-                       "state": np.zeros(0, np.uint8), "gid": np.zeros(0, np.uint32)}
+                       "state": np.zeros(0, np.uint8), "gid": np.zeros(0, np.uint32), "path_id": np.zeros(0, np.int32),
+                       "waypoint": np.zeros(0, np.int32), "r_next": np.zeros((0, 2), np.float32)}
+        self.ghosts = {k: self.ghosts[k] for k in self.halo_fields}
 
     def halo_records(self):
         """(to_down, to_up) halo records of the owned agents' current positions"""
@@ -147,14 +155,14 @@ class SlabModel:
         out = []
         for d in (0, 1):
             if not self.has[d]:
-                out.append({k: self.owned[k][:0].copy() for k in HALO_FIELDS})
+                out.append({k: self.owned[k][:0].copy() for k in self.halo_fields})
                 continue
             sel = (y < self.y_lo + self.halo) if d == 0 else (y >= self.y_hi - self.halo)
-            out.append({k: self.owned[k][sel].copy() for k in HALO_FIELDS})
+            out.append({k: self.owned[k][sel].copy() for k in self.halo_fields})
         return out
 
     def add_ghosts(self, rec: dict):
-        for k in HALO_FIELDS:
+        for k in self.halo_fields:
             self.ghosts[k] = np.concatenate([self.ghosts[k], rec[k]])
 
     def frame(self):
@@ -167,7 +175,7 @@ class SlabModel:
         for k in FULL_FIELDS:
             if k == "gid":
                 continue
-            if k in HALO_FIELDS:
+            if k in self.halo_fields:
                 full = np.concatenate([self.owned[k], self.ghosts[k]])
             else:
                 pad = np.zeros((n_gh,) + self.owned[k].shape[1:], self.owned[k].dtype)
@@ -191,7 +199,7 @@ class SlabModel:
         # emigrants stay one more frame as ghosts on this rank
         self._clear_ghosts()
         for m in (go_down, go_up):
-            self.add_ghosts({k: new[k][m].copy() for k in HALO_FIELDS})
+            self.add_ghosts({k: new[k][m].copy() for k in self.halo_fields})
         self.owned = {k: new[k][stay] for k in FULL_FIELDS}
         self.last = {k: v[stay] for k, v in extra.items()}
         halo = self.halo_records()

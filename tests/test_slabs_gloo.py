@@ -119,6 +119,114 @@ def test_slab_protocol_world_size_2(tmp_path):
     assert ((start_rows < bounds[1]) != (end_rows < bounds[1])).sum() > 0
 
 
+# ---------------------------------------------------------------------------------------------------------
+# The arrival rule across a slab boundary (SeekSystem::finalizeSeek, SeekSystem.cpp:235-275; the group's finished
+# area is global, CommandGroupManager.h:163-172): the rules of k_arrive<multi> / k_area_sync_counts / the per-frame
+# all-reduce of the stop counts, modelled with the oracle (ghosts evaluate the rule, only owners stop and count) and
+# dist.all_reduce over gloo.
+# ---------------------------------------------------------------------------------------------------------
+ARRIVAL_N, ARRIVAL_FRAMES, ARRIVAL_CUT = 1500, 420, 15
+
+
+def _arrival_world():
+    from rtsengine_b200 import abi
+    from oracle import port
+    fx = H.load("map_empty.npz")
+    tables = H.tables_of(fx)
+    n = ARRIVAL_N
+    rng = np.random.default_rng(15)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = np.stack([rng.uniform(900, 1080, n), rng.uniform(780, 1020, n)], 1)
+    a["radius"][:] = np.where(rng.random(n) < 0.2, 5.0, 3.0)
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = rng.integers(0, 2, n)
+    a["r_next"][:] = np.nan
+    ends = np.array([[1150.0, 900.0], [1230.0, 893.0]], np.float32)     # both destinations lie on the cut (y = 900)
+    paths = {"offsets": np.array([0, 1, 2], np.uint32), "waypoints": ends.copy(), "portals": np.zeros((2, 5), np.float32),
+             "path_end": ends.copy(), "group": np.array([0, 1], np.int32)}
+    P = port.default_params(512, 512)
+    P.enable_arrival = 1
+    return P, tables, paths, a
+
+
+def _arrival_worker(rank, world, port_no, frames, result_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import port
+    from rtsengine_b200 import slabs
+
+    P, tables, paths, a = _arrival_world()
+    ow = port.OracleWorld(P, tables, paths)
+    counts = np.zeros(2, np.uint32)
+    ow.set_slab_arrival(True, counts)
+    a["gid"] = np.arange(len(a["r"]), dtype=np.uint32)
+    bounds = [0, ARRIVAL_CUT, int(P.ns_ny)]
+    parts = slabs.split_agents(a, bounds, P.ns_cell_size, P.ns_ny)
+    m = slabs.SlabModel(P, bounds[rank], bounds[rank + 1], lambda ag, gh: ow.step(ag, ghost=gh))
+    assert m.halo >= P.finish_radius and "path_id" in m.halo_fields
+    m.set_agents(parts[rank])
+    other = 1 - rank
+
+    def exchange(rec, fields):
+        if rank == 0:
+            _send(rec, other, fields)
+            return _recv(other, fields, parts[rank])
+        got = _recv(other, fields, parts[rank])
+        _send(rec, other, fields)
+        return got
+
+    d = 1 if rank == 0 else 0                 # direction of the one neighbour
+    m.add_ghosts(exchange(m.halo_records()[d], m.halo_fields))
+    area_unit = np.float32(np.float32(np.pi) * np.float32(P.rhard)) * np.float32(P.rhard)
+    area = np.zeros(2, np.float32)            # k_area_sync_counts: one addition of the unit per stop, in any order
+    applied = np.zeros(2, np.int64)
+    areas = []
+    for f in range(frames):
+        out = m.frame()
+        t = torch.from_numpy(counts.astype(np.int64))
+        dist.all_reduce(t)                    # ncclAllReduce of the stop counts (rts_abi.cu, "the one collective on the frame path")
+        total = t.numpy()
+        for g in range(2):
+            for _ in range(int(total[g] - applied[g])):
+                area[g] = area[g] + area_unit
+        applied[:] = total
+        ow.fin_area[:] = area                 # every rank enters the next frame with the global finished area
+        areas.append(area.copy())
+        m.add_migrants(exchange(out[d], slabs.FULL_FIELDS))
+        m.add_ghosts(exchange(out[2 + d], m.halo_fields))
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), areas=np.array(areas), own_stops=counts, **m.owned)
+    dist.destroy_process_group()
+
+
+def test_arrival_rule_across_the_cut_world_size_2(tmp_path):
+    from rtsengine_b200 import abi
+    from oracle import port
+    frames = ARRIVAL_FRAMES
+    port_no = 31500 + (os.getpid() % 2000)
+    mp.spawn(_arrival_worker, args=(2, port_no, frames, str(tmp_path)), nprocs=2, join=True)
+    P, tables, paths, a = _arrival_world()
+    ow = port.OracleWorld(P, tables, paths)
+    ref_areas = []
+    for _ in range(frames):
+        ow.step(a)
+        ref_areas.append(ow.fin_area.copy())
+    parts = [dict(np.load(os.path.join(tmp_path, f"rank{r}.npz"))) for r in range(2)]
+    gid = np.concatenate([p["gid"] for p in parts])
+    assert len(gid) == ARRIVAL_N and len(np.unique(gid)) == ARRIVAL_N
+    order = np.argsort(gid)
+    for k in ("r", "inertia", "angle", "angle_vel", "state", "path_id", "waypoint", "r_next"):
+        H.assert_same_bits(np.concatenate([p[k] for p in parts])[order], a[k], k)
+    for p in parts:                           # the same finished area on every rank, every frame
+        H.assert_same_bits(p["areas"], np.array(ref_areas), "finished area per frame")
+    standing = int((a["state"] == abi.STANDING).sum())
+    assert standing > 0.3 * ARRIVAL_N, standing
+    assert min(int(p["own_stops"].sum()) for p in parts) > 50, "agents were stopped on both sides of the cut"
+    assert sum(int(p["own_stops"].sum()) for p in parts) == standing   # each agent stopped, and counted, exactly once
+
+
 def test_partition_and_split():
     from rtsengine_b200 import slabs
     rng = np.random.default_rng(0)
