@@ -205,6 +205,19 @@ class SlabModel:
         halo = self.halo_records()
         return mig[0], mig[1], halo[0], halo[1]
 
+    def set_rows(self, lo: int, hi: int):
+        """rts_slab_set_rows: this slab now owns rows [lo, hi). Ownership is decided by frame() from the row of each agent's
+        new position, so the agents of the rows that changed hands migrate during the next frame; the halo records of that
+        frame are already cut along the new boundary."""
+        assert (lo > 0) == self.has[0] and (hi < self.P.ns_ny) == self.has[1], "the outermost slabs keep the map edge"
+        self.lo, self.hi = lo, hi
+        self.y_lo = np.float32(lo * self.P.ns_cell_size)
+        self.y_hi = np.float32(hi * self.P.ns_cell_size)
+
+    def row_counts(self) -> np.ndarray:
+        """rts_slab_row_counts: owned agents per physics-grid row"""
+        return np.bincount(row_of(self.owned["r"][:, 1], self.P.ns_cell_size, self.P.ns_ny), minlength=int(self.P.ns_ny))
+
     def add_migrants(self, rec: dict):
         for k in FULL_FIELDS:
             self.owned[k] = np.concatenate([self.owned[k], rec[k]])

@@ -39,7 +39,7 @@ def _recv(src, fields, template):
     return out
 
 
-def _worker(rank, world, port_no, frames, result_dir):
+def _worker(rank, world, port_no, frames, result_dir, start_bounds=None, rebalance_every=0, cap_migrants=0):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
@@ -56,9 +56,10 @@ def _worker(rank, world, port_no, frames, result_dir):
     P = port.default_params(512, 512)
     ow = port.OracleWorld(P, tables, paths)
     a["gid"] = np.arange(n, dtype=np.uint32)
-    bounds = slabs.partition_rows(a["r"][:, 1], P.ns_ny, P.ns_cell_size, world)
+    bounds = list(start_bounds) if start_bounds else slabs.partition_rows(a["r"][:, 1], P.ns_ny, P.ns_cell_size, world)
     parts = slabs.split_agents(a, bounds, P.ns_cell_size, P.ns_ny)
     m = slabs.SlabModel(P, bounds[rank], bounds[rank + 1], lambda ag, gh: ow.step(ag, ghost=gh))
+    history = [list(bounds)]
     m.set_agents(parts[rank])
     nb = {0: rank - 1, 1: rank + 1}
 
@@ -84,7 +85,16 @@ def _worker(rank, world, port_no, frames, result_dir):
             m.add_migrants(rec)
         for rec in exchange({0: hd, 1: hu}, slabs.HALO_FIELDS, parts[rank]).values():
             m.add_ghosts(rec)
-    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), **m.owned)
+        if rebalance_every and (f + 1) % rebalance_every == 0 and f + 1 < frames:
+            # the loop of slabs.run_config5: global row histogram (all-reduce) -> rebalanced_bounds -> rts_slab_set_rows
+            hist = torch.from_numpy(m.row_counts().astype(np.int64))
+            dist.all_reduce(hist)
+            new = slabs.rebalanced_bounds(hist.numpy(), bounds, cap_migrants)
+            if new != bounds:
+                m.set_rows(new[rank], new[rank + 1])
+                bounds = new
+                history.append(list(bounds))
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), bounds_history=np.array(history), **m.owned)
     dist.destroy_process_group()
 
 
@@ -225,6 +235,48 @@ def test_arrival_rule_across_the_cut_world_size_2(tmp_path):
     assert standing > 0.3 * ARRIVAL_N, standing
     assert min(int(p["own_stops"].sum()) for p in parts) > 50, "agents were stopped on both sides of the cut"
     assert sum(int(p["own_stops"].sum()) for p in parts) == standing   # each agent stopped, and counted, exactly once
+
+
+def test_slab_rebalancing_world_size_2(tmp_path):
+    """Rows change hands at run time (boundaries follow the agent-count quantiles every K frames): a lopsided
+    start (rank 0 owns 3 of 43 rows), the histogram all-reduced over gloo, rebalanced_bounds on every rank, the moved rows
+    migrating through the ordinary migrant records — and still every agent bit-identical to the single-domain oracle."""
+    from oracle import port
+    from rtsengine_b200 import slabs
+    from tests.test_gpu_parity import random_world
+    frames = 12
+    P = port.default_params(512, 512)
+    start = [0, 3, int(P.ns_ny)]
+    port_no = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port_no, frames, str(tmp_path), start, 3, 4000), nprocs=2, join=True)
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(33, 6000, tables, 150.0, 750.0)
+    a["inertia"][:] *= 4
+    ow = port.OracleWorld(P, tables, paths)
+    first_rows = slabs.row_of(a["r"][:, 1], P.ns_cell_size, P.ns_ny)
+    for _ in range(frames):
+        ow.step(a)
+    parts = [dict(np.load(os.path.join(tmp_path, f"rank{r}.npz"))) for r in range(2)]
+    gid = np.concatenate([p["gid"] for p in parts])
+    assert len(gid) == 6000 and len(np.unique(gid)) == 6000
+    order = np.argsort(gid)
+    for k in ("r", "inertia", "angle", "angle_vel", "state", "waypoint", "r_next"):
+        H.assert_same_bits(np.concatenate([p[k] for p in parts])[order], a[k], k)
+    hist = [h.tolist() for h in parts[0]["bounds_history"]]
+    assert hist == [h.tolist() for h in parts[1]["bounds_history"]], "both ranks took the same decisions"
+    assert len(hist) >= 3 and all(h2[1] > h1[1] for h1, h2 in zip(hist, hist[1:])), hist   # the cut climbed towards the median row
+    assert all(abs(h2[1] - h1[1]) <= 4 for h1, h2 in zip(hist, hist[1:]))
+    before = int((first_rows < start[1]).sum())
+    after = len(parts[0]["gid"])
+    assert before < 0.2 * 6000 and after > 0.4 * 6000, (before, after)
+    end_rows = slabs.row_of(a["r"][:, 1], P.ns_cell_size, P.ns_ny)
+    final = hist[-1]
+    # the last boundary move is at least two frames old: every agent sits on its owner again
+    for r, p in enumerate(parts):
+        rows = slabs.row_of(p["r"][:, 1], P.ns_cell_size, P.ns_ny)
+        assert ((rows >= final[r]) & (rows < final[r + 1])).all()
+    assert (end_rows < final[1]).sum() == after
 
 
 def test_partition_and_split():
