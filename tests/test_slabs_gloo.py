@@ -98,10 +98,11 @@ def _worker(rank, world, port_no, frames, result_dir, start_bounds=None, rebalan
     dist.destroy_process_group()
 
 
-def test_slab_protocol_world_size_2(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])          # 3: the middle rank has a neighbour on either side
+def test_slab_protocol_world_size_2(tmp_path, world):
     frames = 10
-    port_no = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port_no, frames, str(tmp_path)), nprocs=2, join=True)
+    port_no = 29500 + 2000 * (world - 2) + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port_no, frames, str(tmp_path)), nprocs=world, join=True)
     # single-domain oracle
     from oracle import port
     from tests.test_gpu_parity import random_world
@@ -113,20 +114,21 @@ def test_slab_protocol_world_size_2(tmp_path):
     r0 = a["r"].copy()
     for _ in range(frames):
         ow.step(a)
-    parts = [dict(np.load(os.path.join(tmp_path, f"rank{r}.npz"))) for r in range(2)]
+    parts = [dict(np.load(os.path.join(tmp_path, f"rank{r}.npz"))) for r in range(world)]
     gid = np.concatenate([p["gid"] for p in parts])
     assert len(gid) == 6000 and len(np.unique(gid)) == 6000
     order = np.argsort(gid)
     for k in ("r", "inertia", "angle", "angle_vel", "state", "waypoint", "r_next"):
         merged = np.concatenate([p[k] for p in parts])[order]
         H.assert_same_bits(merged, a[k], k)
-    # the cut was actually crossed
+    # every cut was actually crossed
     from rtsengine_b200 import slabs
     P = port.default_params(512, 512)
-    bounds = slabs.partition_rows(r0[:, 1], P.ns_ny, P.ns_cell_size, 2)
+    bounds = slabs.partition_rows(r0[:, 1], P.ns_ny, P.ns_cell_size, world)
     start_rows = slabs.row_of(r0[:, 1], P.ns_cell_size, P.ns_ny)
     end_rows = slabs.row_of(a["r"][:, 1], P.ns_cell_size, P.ns_ny)
-    assert ((start_rows < bounds[1]) != (end_rows < bounds[1])).sum() > 0
+    for b in bounds[1:-1]:
+        assert ((start_rows < b) != (end_rows < b)).sum() > 0
 
 
 # ---------------------------------------------------------------------------------------------------------
