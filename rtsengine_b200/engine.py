@@ -251,6 +251,12 @@ class GpuAgentSystem:
         self._chk(self.L.rts_get_finished_area(self.h, out.ctypes.data, n_groups))
         return out
 
+    def set_finished_area(self, area):
+        """the groups' finished areas (CommandGroupManager2::group2finished_surface_area_) — with the agent arrays, the whole
+        persistent state of the path: a run continues from a download on another handle (tests: snapshot and resume)"""
+        a = np.ascontiguousarray(area, np.float32)
+        self._chk(self.L.rts_set_finished_area(self.h, a.ctypes.data, len(a)))
+
     @property
     def n(self) -> int:
         return self.L.rts_agent_count(self.h)

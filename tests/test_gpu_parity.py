@@ -527,6 +527,78 @@ def test_arrival_rule_matches_oracle_and_tracks_the_reference_cascade():
         assert (out["path_id"][out["state"] == abi.STANDING] == -1).all()
 
 
+PERSISTENT = ("r", "inertia", "angle", "angle_vel", "radius", "mass", "state", "player", "unit_type", "path_id", "waypoint", "r_next")
+
+
+def _resume(tables, paths, snap, frames, names, area=None, **kw):
+    b = abi.alloc_agent_arrays(len(snap["r"]), set(H.ALL_FIELDS))
+    for k in PERSISTENT:
+        b[k][:] = snap[k]
+    with make_system(tables, paths, **kw) as g:
+        g.set_agents(b)
+        if area is not None:
+            g.set_finished_area(area)
+        g.update(frames)
+        return g.communicate(names), (g.finished_area(len(area)) if area is not None else None)
+
+
+def test_snapshot_and_resume_on_a_new_handle():
+    """SURVEY §5 (checkpoint / resume; the reference has none for simulation state): what rts_download returns IS the
+    persistent state of the path — per agent the PERSISTENT fields, per group the finished area; velocities, cell and
+    triangle indices, the triangle hints and the slot order are functions of it. A run continued from a download on a fresh
+    handle (other slot order, no hints, frames 12.. start a new CUDA graph) equals the uninterrupted run bit for bit (bit-exact
+    mode; the tolerance mode adds in memory order and is not reproducible from run to run by design)."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(21, 20000, tables, 100.0, 1000.0)
+    names = PERSISTENT + ("vel", "tri_idx", "ns_cell")
+    with make_system(tables, paths) as g:
+        g.set_agents(a)
+        g.update(12)
+        snap = g.communicate(PERSISTENT)
+        g.update(9)
+        ref = g.communicate(names)
+    out, _ = _resume(tables, paths, snap, 9, names)
+    for k in names:
+        H.assert_same_bits(out[k], ref[k], f"{k} after resume")
+    assert np.abs(ref["r"] - a["r"]).max() > 1.0
+
+
+def test_snapshot_and_resume_in_the_middle_of_an_arrival():
+    """the same with the arrival rule on, taken while a group is arriving: the groups' finished areas travel with the snapshot
+    (rts_get_finished_area / rts_set_finished_area); stopped agents have left their group (path_id -1) in the arrays."""
+    fx = H.load("map_empty.npz")
+    tables = H.tables_of(fx)
+    n = 1500
+    rng = np.random.default_rng(5)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = rng.uniform(700, 1000, (n, 2))
+    a["radius"][:] = 3
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = rng.integers(0, 2, n)
+    a["r_next"][:] = np.nan
+    ends = np.array([[1100.0, 1100.0], [1150.0, 800.0]], np.float32)
+    paths = {"offsets": np.array([0, 1, 2], np.uint32), "waypoints": ends.copy(), "portals": np.zeros((2, 5), np.float32),
+             "path_end": ends.copy(), "group": np.array([0, 1], np.int32)}
+    names = PERSISTENT + ("vel",)
+    with make_system(tables, paths, enable_arrival=1) as g:
+        g.set_agents(a)
+        g.update(330)
+        snap = g.communicate(PERSISTENT)
+        area = g.finished_area(2)
+        g.update(120)
+        ref = g.communicate(names)
+        ref_area = g.finished_area(2)
+    standing_then = int((snap["state"] == abi.STANDING).sum())
+    standing_now = int((ref["state"] == abi.STANDING).sum())
+    assert 0 < standing_then < standing_now and (area > 0).all(), (standing_then, standing_now, area)
+    out, out_area = _resume(tables, paths, snap, 120, names, area=area, enable_arrival=1)
+    for k in names:
+        H.assert_same_bits(out[k], ref[k], f"{k} after resume")
+    H.assert_same_bits(out_area, ref_area, "finished area after resume")
+
+
 def test_baseline_config1_1000_frames():
     """BASELINE configs[0]: 2 000 agents, boids + seek on an empty 512x512 map, 1 000 frames — bit-exact vs the oracle at
     the end (the verbatim reference runs the same case in bench.py --impl reference / tests/test_oracle_vs_ref.py)."""
