@@ -217,7 +217,7 @@ def test_arrival_rule_across_the_cut_world_size_2(tmp_path):
     from rtsengine_b200 import abi
     from oracle import port
     frames = ARRIVAL_FRAMES
-    port_no = 31500 + (os.getpid() % 2000)
+    port_no = 35500 + (os.getpid() % 2000)
     mp.spawn(_arrival_worker, args=(2, port_no, frames, str(tmp_path)), nprocs=2, join=True)
     P, tables, paths, a = _arrival_world()
     ow = port.OracleWorld(P, tables, paths)
