@@ -746,7 +746,8 @@ def test_triangle_index_is_a_function_of_the_position_where_fans_overlap():
 # (map_empty: the first cell centre (20,20) lies on the diagonal shared by triangles 2 and 4, the reference's
 #  last_found_tri_ind_ was 2 when it built the recorded table)
 @pytest.mark.parametrize("name,cells,last_found", [("frame_small.npz", (512, 512), 0), ("frame_dense.npz", (512, 512), 0),
-                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0)])
+                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0),
+                                                   ("map_c5.npz", (2048, 2048), 0)])
 def test_cell_grid_built_on_device_equals_the_reference_table(name, cells, last_found):
     fx = H.load(name)
     tables = H.tables_of(fx)

@@ -88,10 +88,11 @@ def test_ghosts_are_neighbours_only():
 
 
 @pytest.mark.parametrize("name,cells,last_found", [("frame_small.npz", (512, 512), 0), ("frame_dense.npz", (512, 512), 0),
-                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0)])
+                                                   ("map_empty.npz", (512, 512), 2), ("map_c3.npz", (1024, 1024), 0),
+                                                   ("map_c5.npz", (2048, 2048), 0)])
 def test_cell_grid_restatement_reproduces_recorded_tables(name, cells, last_found):
     """Triangulation::updateCellGrid (Triangulation.cpp:1829-1864): the tables in the fixtures were written by the
-    reference itself; 95 / 2 / 64 / 196 of their cell centres lie on triangle edges or vertices, where the entry depends
+    reference itself; 95 / 2 / 64 / 196 (and, on the corridor map, many more) of their cell centres lie on triangle edges or vertices, where the entry depends
     on the zig-zag walk (map_empty: the reference's last_found_tri_ind_ was 2 when it built the table)."""
     tables = H.tables_of(H.load(name))
     ow = port.OracleWorld(port.default_params(*cells), tables)
