@@ -10,12 +10,14 @@ from tests import helpers as H
 pytestmark = pytest.mark.skipif(not refh.available(), reason="oracle/_ref not built (needs /root/reference)")
 
 
-def test_frames_bit_exact_against_live_reference():
-    rng = np.random.default_rng(3)
+def _side_by_side(seed, n, n_buildings, lo, hi, commanded, big, frames, target=(1100.0, 1000.0)):
+    """the verbatim reference (its own map code, planner and systems) and the oracle, frame by frame from the same state;
+    returns the reference's final state"""
+    rng = np.random.default_rng(seed)
     w = refh.RefWorld(512, 512)
     occ = np.zeros((512, 512), bool)
     k = 0
-    while k < 30:
+    while k < n_buildings:
         cx, cy = (int(v) for v in rng.integers(30, 200, 2))
         if occ[cx - 7:cx + 7, cy - 7:cy + 7].any():
             continue
@@ -23,17 +25,16 @@ def test_frames_bit_exact_against_live_reference():
         occ[cx - 5:cx + 5, cy - 5:cy + 5] = True
         k += 1
     w.finalize_map()
-    n = 1200
     pos = []
     while len(pos) < n:
-        p = rng.uniform(150, 700, 2).astype(np.float32)
+        p = rng.uniform(lo, hi, 2).astype(np.float32)
         if not occ[int(p[0] // 5), int(p[1] // 5)]:
             pos.append(p)
-    radius = np.where(rng.random(n) < 0.3, 5.0, 3.0).astype(np.float32)
+    radius = np.where(rng.random(n) < big, 5.0, 3.0).astype(np.float32)
     mass = np.where(radius > 4, 50.0, 1.0).astype(np.float32)
     for i in range(n):
         w.add_agent(float(pos[i][0]), float(pos[i][1]), 0.0, float(radius[i]), float(mass[i]), 0, 1)
-    w.issue_paths(np.arange(0, n, 2, dtype=np.int32), 1100.0, 1000.0)
+    w.issue_paths(np.ascontiguousarray(commanded(rng, n), np.int32), *target)
     w.plan_now()
     tables = w.tables()
     P = port.default_params(512, 512)
@@ -42,7 +43,7 @@ def test_frames_bit_exact_against_live_reference():
     a["r"][:] = s["r"]
     a["radius"][:] = radius
     a["mass"][:] = mass
-    for f in range(150):
+    for f in range(frames):
         w.plan_now()
         win = w.seek_window()
         st = w.state()["state"]
@@ -54,8 +55,36 @@ def test_frames_bit_exact_against_live_reference():
         w.step(1)
         s = w.state()
         for k in ("r", "vel", "inertia", "angle", "angle_vel"):
-            H.assert_same_bits(a[k], s[k], f"frame {f} {k}")
-        H.assert_same_bits(a["tri_idx"], w.find_triangles(s["r"]), f"frame {f} tri")
+            H.assert_same_bits(a[k], s[k], f"seed {seed} frame {f} {k}")
+        H.assert_same_bits(a["tri_idx"], w.find_triangles(s["r"]), f"seed {seed} frame {f} tri")
+    return s
+
+
+def test_frames_bit_exact_against_live_reference():
+    _side_by_side(3, 1200, 30, 150, 700, lambda rng, n: np.arange(0, n, 2), 0.3, 150)
+
+
+def _some(frac):
+    return lambda rng, n: np.nonzero(rng.random(n) < frac)[0]
+
+
+@pytest.mark.parametrize("seed,n,n_buildings,lo,hi,frac,big,frames,target,what", [
+    (11, 1500, 20, 300, 520, 0.5, 0.3, 80, (1100.0, 1000.0), "crowd of 0.03 agents per unit^2, half of it standing and pushed"),
+    (12, 800, 40, 150, 900, 1.0, 0.0, 120, (1100.0, 1000.0), "everyone moving through 40 buildings"),
+    (13, 2500, 10, 400, 640, 0.2, 0.5, 60, (1100.0, 1000.0), "0.043 per unit^2, half of the units heavy: capped repulsion terms"),
+    (15, 900, 0, 3, 100, 0.3, 0.3, 150, (1100.0, 1000.0), "crowd in the map corner (0,0): pushed over x = 0 and y = 0"),
+    (16, 700, 0, 2440, 2555, 0.6, 0.2, 100, (300.0, 300.0), "crowd in the far corner: pushed over x = W and y = H"),
+])
+def test_more_live_scenarios(seed, n, n_buildings, lo, hi, frac, big, frames, target, what):
+    """the oracle's pin widened beyond the fixtures' scenario: crowds dense enough for the capped repulsion and the push term
+    on STANDING agents, heavy units, and agents leaving the map over each of its four edges (the reference has no outer wall:
+    their cells wrap, Grid.cpp:18-24) — every agent, every frame, bit for bit against the reference's own compiled systems."""
+    s = _side_by_side(seed, n, n_buildings, lo, hi, _some(frac), big, frames, target)
+    outside = ((s["r"] < 0) | (s["r"] >= 2560)).any(axis=1).sum()
+    if seed in (15, 16):
+        assert outside > 20, outside
+    if seed in (11, 13):
+        assert np.abs(s["inertia"]).max() > 1e4      # the repulsion cap (5e4 * 3x^3 ...) was reached on the way
 
 
 def test_snapshot_arrival_rule_tracks_the_serial_cascade():
