@@ -163,6 +163,17 @@ class RefWorld:
     def n(self):
         return self.L.refh_n_agents(self.h)
 
+    # PhysicsSystem::Multiplier (PhysicsSystem.h:21-29): the sliders of UI.cpp:121-131
+    PUSH, REPULSE, SCATTER, ALIGN, SEEK, DECAY, VELOCITY = range(7)
+
+    def set_multiplier(self, which: int, value: float):
+        self.L.refh_set_multiplier(self.h, int(which), float(value))
+
+    def set_unit_dynamics(self, i: int, lambda_: float, max_speed: float, seek_max_speed: float, turn_rate: float, desired_angle=0.0):
+        """per-component constants (Components.h:84-119) of agent i"""
+        self.L.refh_set_phys_params(self.h, int(i), float(lambda_), float(max_speed))
+        self.L.refh_set_seek_params(self.h, int(i), float(seek_max_speed), float(turn_rate), float(desired_angle))
+
     def issue_paths(self, ids, tx, ty):
         ids = np.ascontiguousarray(ids, np.int32)
         self._chk(self.L.refh_issue_paths(self.h, ids, len(ids), tx, ty))

@@ -527,6 +527,55 @@ def test_arrival_rule_matches_oracle_and_tracks_the_reference_cascade():
         assert (out["path_id"][out["state"] == abi.STANDING] == -1).all()
 
 
+def test_force_multipliers_and_unit_dynamics_changed_mid_run():
+    """PhysicsSystem::force_multipliers (the sliders of UI.cpp:121-131 -> RtsParams.mul_*, rts_set_params) and the per-type
+    dynamics constants (Components.h:84-119 -> rts_upload_unit_types) away from their defaults, the multipliers changed in the
+    middle of the run: GPU == oracle bit for bit, every agent; tolerance mode within its gate. The oracle's reading of these
+    fields is pinned on the live reference (tests/test_oracle_vs_ref.py::test_multipliers_and_unit_dynamics_against_live_reference)."""
+    fx = H.load("frame_small.npz")
+    tables = H.tables_of(fx)
+    a, paths = random_world(41, 20000, tables, 150.0, 950.0)
+    U = abi.default_unit_types()
+    for t, (lam, ms, sms, tr) in enumerate([(0.25, 20.0, 40.0, 8.0), (0.3, 18.0, 35.0, 9.0)]):
+        U[t]["lambda_"], U[t]["max_speed"], U[t]["seek_max_speed"], U[t]["turn_rate"] = lam, ms, sms, tr
+    phases = [dict(mul_push=1.7, mul_repulse=0.6, mul_scatter=2.5, mul_decay=0.5, mul_velocity=1.3),
+              dict(mul_push=0.0, mul_repulse=1.4, mul_scatter=0.0, mul_decay=4.5, mul_velocity=0.7)]   # (decay: min(1, lambda * DECAY) clamps)
+    names = ("r", "vel", "inertia", "angle", "angle_vel", "state", "waypoint", "r_next", "tri_idx")
+    P = port.default_params(512, 512)
+    for k, v in phases[0].items():
+        setattr(P, k, v)
+    ow = port.OracleWorld(P, tables, paths, unit_types=U)
+    ref = {k: v.copy() for k, v in a.items()}
+    first = {k: v.copy() for k, v in a.items()}
+    ow.step(first)                                          # (frame 1, for the tolerance mode below)
+    with make_system(tables, paths, **phases[0]) as g:
+        g.upload_unit_types(U)
+        g.set_agents(a)
+        for i, mult in enumerate(phases):
+            if i:
+                for k, v in mult.items():
+                    setattr(P, k, v)
+                    setattr(g.params, k, v)
+                g.set_params(g.params)
+            ow.step(ref, 6)
+            g.update(6)
+            out = g.communicate(names)
+            for k in names:
+                H.assert_same_bits(out[k], ref[k], f"phase {i} {k}")
+    plain = {k: v.copy() for k, v in a.items()}             # the same 12 frames with default multipliers and unit types: another result
+    port.OracleWorld(port.default_params(512, 512), tables, paths).step(plain, 12)
+    assert (np.abs(plain["r"] - ref["r"]).max(axis=1) > 0.5).mean() > 0.3
+    from tests.test_gpu_fast import NAMES, check_one_frame
+    for k, v in phases[0].items():
+        setattr(P, k, v)
+    with make_system(tables, paths, precision=abi.PRECISION_FAST, **phases[0]) as g:
+        g.upload_unit_types(U)
+        g.set_agents(a)
+        g.update(1)
+        out = g.communicate(NAMES)
+    print(check_one_frame(out, first, a, P, ow, (512, 512), "tolerance mode, multipliers and unit types", min_plain=0.98))
+
+
 PERSISTENT = ("r", "inertia", "angle", "angle_vel", "radius", "mass", "state", "player", "unit_type", "path_id", "waypoint", "r_next")
 
 

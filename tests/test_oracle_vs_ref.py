@@ -60,6 +60,73 @@ def _side_by_side(seed, n, n_buildings, lo, hi, commanded, big, frames, target=(
     return s
 
 
+@pytest.mark.parametrize("seed,mult,types", [
+    (22, {"mul_push": 1.7, "mul_repulse": 0.6, "mul_scatter": 2.5, "mul_decay": 0.5, "mul_velocity": 1.3}, [(0.169, 25.0, 50.0, 5.0)] * 2),
+    (23, {}, [(0.169, 25.0, 50.0, 5.0), (0.3, 18.0, 35.0, 9.0)]),
+    (24, {"mul_push": 0.0, "mul_scatter": 0.0, "mul_decay": 3.0, "mul_velocity": 0.7, "mul_seek": 2.0, "mul_align": 3.0},
+     [(0.05, 40.0, 80.0, 2.0), (0.3, 18.0, 35.0, 9.0)]),
+])
+def test_multipliers_and_unit_dynamics_against_live_reference(seed, mult, types):
+    """PhysicsSystem::force_multipliers (PhysicsSystem.h:21-31, the sliders of UI.cpp:121-131) and the per-component constants
+    (lambda, max_speed, seek max_speed, turn_rate: Components.h:84-119) away from their defaults: RtsParams.mul_* and
+    RtsUnitType mean what the reference's fields mean — 100 frames of a 1 200-agent crowd among 20 buildings, every agent, bit
+    for bit. (SEEK and ALIGN are carried by the reference and read nowhere: setting them changes nothing on either side.)"""
+    n, frames = 1200, 100
+    rng = np.random.default_rng(seed)
+    w = refh.RefWorld(512, 512)
+    occ = np.zeros((512, 512), bool)
+    k = 0
+    while k < 20:
+        cx, cy = (int(v) for v in rng.integers(30, 200, 2))
+        if occ[cx - 7:cx + 7, cy - 7:cy + 7].any():
+            continue
+        assert w.add_building(cx, cy, 8, 8, 1) == 0
+        occ[cx - 5:cx + 5, cy - 5:cy + 5] = True
+        k += 1
+    w.finalize_map()
+    pos = []
+    while len(pos) < n:
+        p = rng.uniform(250, 520, 2).astype(np.float32)
+        if not occ[int(p[0] // 5), int(p[1] // 5)]:
+            pos.append(p)
+    ut = (rng.random(n) < 0.4).astype(np.uint8)
+    radius = np.where(ut == 1, 5.0, 3.0).astype(np.float32)
+    mass = np.where(ut == 1, 50.0, 1.0).astype(np.float32)
+    U = abi.default_unit_types()
+    for t, (lam, ms, sms, tr) in enumerate(types):
+        U[t]["lambda_"], U[t]["max_speed"], U[t]["seek_max_speed"], U[t]["turn_rate"] = lam, ms, sms, tr
+    for i in range(n):
+        w.add_agent(float(pos[i][0]), float(pos[i][1]), 0.0, float(radius[i]), float(mass[i]), 0, 1)
+        w.set_unit_dynamics(i, *types[ut[i]])
+    P = port.default_params(512, 512)
+    for which, name in ((w.PUSH, "mul_push"), (w.REPULSE, "mul_repulse"), (w.SCATTER, "mul_scatter"), (w.ALIGN, "mul_align"),
+                        (w.SEEK, "mul_seek"), (w.DECAY, "mul_decay"), (w.VELOCITY, "mul_velocity")):
+        if name in mult:
+            w.set_multiplier(which, mult[name])
+            setattr(P, name, mult[name])
+    w.issue_paths(np.nonzero(rng.random(n) < 0.5)[0].astype(np.int32), 1100.0, 1000.0)
+    w.plan_now()
+    tables = w.tables()
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = w.state()["r"]
+    a["radius"][:] = radius
+    a["mass"][:] = mass
+    a["unit_type"][:] = ut
+    for f in range(frames):
+        w.plan_now()
+        win = w.seek_window()
+        st = w.state()["state"]
+        a["state"][:] = st
+        a["path_id"][:] = np.where(st == abi.MOVING, np.arange(n), -1)
+        a["waypoint"][:] = 0
+        a["r_next"][:] = win[:, 0:2]
+        port.OracleWorld(P, tables, H.windows_to_paths(win), unit_types=U).step(a)
+        w.step(1)
+        s = w.state()
+        for k in ("r", "vel", "inertia", "angle", "angle_vel"):
+            H.assert_same_bits(a[k], s[k], f"seed {seed} frame {f} {k}")
+
+
 def test_frames_bit_exact_against_live_reference():
     _side_by_side(3, 1200, 30, 150, 700, lambda rng, n: np.arange(0, n, 2), 0.3, 150)
 
