@@ -250,3 +250,40 @@ def test_radius_query_matches_the_verbatim_reference():
         got, got_n = ow.query_radius(xy, q, r_max)
         assert got_n == cnt
         assert np.array_equal(got.astype(np.int32), out[:cnt]), (q, r_max)
+
+
+@pytest.mark.parametrize("seed,n_buildings", [(40, 10), (45, 70), (51, 142)])
+def test_point_queries_fuzzed_against_live_reference(seed, n_buildings):
+    """findTriangle (Triangulation.cpp:1497-1567) and calcContactEdgesO (Edges.cpp:245-296) on fresh maps with both building
+    types of BuildingManager.h:19-20: random points, every kind of degenerate one (integer points — the CDT's vertices and edges
+    are integer —, points ON building outlines and corners, points outside the map), wall queries for both unit radii around
+    every building; index and edge list identical to the reference's own answers."""
+    rng = np.random.default_rng(seed)
+    w = refh.RefWorld(512, 512)
+    occ = np.zeros((512, 512), bool)
+    placed = []
+    while len(placed) < n_buildings:
+        cx, cy = (int(v) for v in rng.integers(20, 480, 2))
+        nn, mm = ((8, 8), (4, 6))[int(rng.integers(0, 2))]
+        if occ[cx - 7:cx + 7, cy - 7:cy + 7].any() or w.add_building(cx, cy, nn, mm, 1) != 0:
+            continue
+        occ[cx - 5:cx + 5, cy - 5:cy + 5] = True
+        placed.append((cx, cy))
+    w.finalize_map()
+    ow = port.OracleWorld(port.default_params(512, 512), w.tables())
+    centres = np.array(placed, np.float64) * 5.0
+    pts = [rng.uniform(-30, 2590, (4000, 2)), rng.integers(0, 2561, (3000, 2)).astype(np.float64)]
+    for c in centres:
+        pts += [c + rng.integers(-30, 31, (40, 2)), c + rng.uniform(-30, 30, (40, 2))]
+    pts = np.concatenate(pts).astype(np.float32)
+    H.assert_same_bits(ow.find_triangles(pts), w.find_triangles(pts), "findTriangle")
+    q = np.concatenate([c + off for c in centres[:40] for off in (rng.uniform(-32, 32, (30, 2)), rng.integers(-32, 33, (30, 2)))]).astype(np.float32)
+    rad = np.where(rng.random(len(q)) < 0.5, 3.0, 5.0).astype(np.float32)
+    cnt, ed = ow.contact_edges(q, rad, cap=16)
+    hits = 0
+    for i in range(len(q)):
+        ref = w.contact_edges(float(q[i, 0]), float(q[i, 1]), float(rad[i]), cap=16)
+        assert len(ref) == cnt[i], (i, q[i], rad[i])
+        H.assert_same_bits(ed[i, :cnt[i]], ref, f"contact edges of query {i}")
+        hits += len(ref)
+    assert hits > 100
