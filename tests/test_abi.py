@@ -78,3 +78,33 @@ def test_apply_delta_writes_the_change_list_into_the_blackboard(cuda_lib):
     assert cuda_lib.rts_apply_delta(ch.ctypes.data, 7, n, av2.ctypes.data, None, None) == abi.RTS_OK and av2[17] == 5.0
     ch["index"][6] = n
     assert cuda_lib.rts_apply_delta(ch.ctypes.data, 7, n, av.ctypes.data, st.ctypes.data, tg.ctypes.data) == abi.RTS_E_ARG
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """the drop-in boundary is a C ABI: include/rts_gpu.h compiles as C99 (-pedantic, no C++, no torch types) and a plain C
+    program links against librts_b200.so and gets the no-device error through the header's own prototypes"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "c_abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "rts_gpu.h"\n'
+        "int main(void) {\n"
+        "    RtsParams p; RtsHandle h = 0;\n"
+        "    rts_default_params(&p, 512, 512);\n"
+        "    int32_t rc = rts_create(&p, 0, &h);\n"
+        '    printf("%d %d %d\\n", (int)rc, (int)p.ns_nx, (int)sizeof(RtsAgentView));\n'
+        "    if (rc == RTS_OK) rts_destroy(h);\n"
+        "    return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "rtsengine_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)])
+    exe = tmp_path / "c_abi"
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-L", libdir, "-lrts_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rc, ns_nx, size = (int(v) for v in out.stdout.split())
+    assert ns_nx == 43 and size == C.sizeof(abi.RtsAgentView)
+    if not torch.cuda.is_available():
+        assert rc == abi.RTS_E_CUDA      # no device: an error code, never a CPU path
