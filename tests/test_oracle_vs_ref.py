@@ -287,3 +287,27 @@ def test_point_queries_fuzzed_against_live_reference(seed, n_buildings):
         H.assert_same_bits(ed[i, :cnt[i]], ref, f"contact edges of query {i}")
         hits += len(ref)
     assert hits > 100
+
+
+def test_golden_fixtures_are_reproduced_by_the_committed_script(tmp_path):
+    """provenance of tests/golden/*.npz: tests/golden/make_golden.py, run here against the verbatim reference build, writes
+    the committed fixtures again, array for array, bit for bit (map_c3.npz, ~8 minutes of planner queries, is left out)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    golden = os.path.join(root, "tests", "golden")
+    code = ("import importlib.util, sys\n"
+            f"sys.path.insert(0, {root!r})\n"
+            f"spec = importlib.util.spec_from_file_location('make_golden', {os.path.join(golden, 'make_golden.py')!r})\n"
+            "mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)\n"
+            f"mg.OUT = {str(tmp_path)!r}\n"
+            "sys.argv = ['make_golden.py']\n"
+            "mg.main(); mg.make_map_insert(); mg.make_map_c5()\n")
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=600, capture_output=True)   # (own process: main() sets an rlimit)
+    names = ("kat.npz", "frame_small.npz", "queries_small.npz", "frame_dense.npz", "map_empty.npz", "map_insert.npz", "map_c5.npz")
+    for name in names:
+        new, old = np.load(os.path.join(tmp_path, name)), np.load(os.path.join(golden, name))
+        assert set(new.files) == set(old.files), name
+        for k in old.files:
+            assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape and new[k].tobytes() == old[k].tobytes(), (name, k)
