@@ -44,6 +44,39 @@ def test_config3_population_and_paths():
     assert np.isfinite(paths["portals"]).all()
 
 
+def test_config5_population_and_paths():
+    """BASELINE configs[4]: the corridor population — free space only, everyone MOVING, the two halves of the map heading
+    through the corridor nearest to them in opposite directions (counter-flow), each agent already on the leg of its path
+    that lies ahead of it"""
+    fx = scenario.load_map("map_c5.npz")
+    n_corr, pitch, width, x0, n_seg, seg, gap = (int(v) for v in fx["corridors"])
+    a, paths = scenario.config5_agents(fx, n=60_000, seed=5)
+    W = int(fx["n_cells"][0]) * 5.0
+    assert len(paths["path_end"]) == 2 * n_corr and paths["offsets"][-1] == len(paths["waypoints"]) == 4 * 2 * n_corr
+    assert (a["state"] == abi.MOVING).all() and (a["radius"] == 3).all() and (a["mass"] == 1).all()
+    occ = scenario.occupancy(fx, 0)
+    x, y = a["r"][:, 0], a["r"][:, 1]
+    assert not occ[(x // 5).astype(int), (y // 5).astype(int)].any()
+    assert (a["r"] > 0).all() and (a["r"] < W).all()
+    pid, wp = a["path_id"], a["waypoint"]
+    assert pid.min() == 0 and pid.max() == 2 * n_corr - 1
+    heads_left = (pid % 2).astype(bool)
+    assert (heads_left == (x >= W / 2)).all() and 0.4 < heads_left.mean() < 0.6
+    # the corridor of an agent's path is the one nearest to it, and both directions share every corridor
+    lane_y = paths["waypoints"][paths["offsets"][pid] + 1][:, 1]
+    lanes = np.unique(paths["waypoints"][paths["offsets"][:-1] + 1][:, 1])
+    assert len(lanes) == n_corr
+    nearest = np.abs(y[:, None] - lanes[None, :]).min(axis=1)
+    assert np.abs(np.abs(lane_y - y) - nearest).max() < 1e-3
+    assert len(np.unique(pid[~heads_left] // 2)) == n_corr and len(np.unique(pid[heads_left] // 2)) == n_corr
+    # the waypoint an agent aims at lies ahead of it in its direction of travel
+    target = paths["waypoints"][paths["offsets"][pid] + wp]
+    ahead = np.where(heads_left, target[:, 0] <= x + 1e-3, target[:, 0] >= x - 1e-3)
+    assert wp.min() >= 1 and wp.max() <= 3 and ahead.mean() > 0.999
+    last = paths["offsets"][1:] - 1
+    assert np.array_equal(paths["waypoints"][last], paths["path_end"]) and np.isfinite(paths["portals"]).all()
+
+
 def test_tiled_map_is_the_tile_map_shifted():
     """a 2x3 tiling of the config-3 map must answer point queries like the single tile (oracle as the checker)"""
     tile = scenario.load_map("map_c3.npz")
