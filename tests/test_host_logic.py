@@ -44,6 +44,30 @@ def test_config3_population_and_paths():
     assert np.isfinite(paths["portals"]).all()
 
 
+def test_config1_and_config2_populations():
+    """BASELINE configs[0] (2 000 agents in [200,1200]^2 of the empty 512^2 map, one group bound for (2000,2000)) and
+    configs[1] (100k agents, the unit mix of UnitTypes.txt, half of them MOVING in 16 command groups, right up to the walls)"""
+    a, paths = scenario.config1_agents()
+    assert len(a["r"]) == 2000 and (a["r"] >= 200).all() and (a["r"] <= 1200).all()
+    assert (a["state"] == abi.MOVING).all() and (a["path_id"] == 0).all() and (a["radius"] == 3).all() and (a["mass"] == 1).all()
+    assert paths["path_end"].tolist() == [[2000.0, 2000.0]] and paths["offsets"].tolist() == [0, 1]
+    assert len(np.unique(a["r"], axis=0)) == 2000                                    # no two agents coincide
+    fx = scenario.load_map("map_c3.npz")
+    a, paths = scenario.config2_agents(fx, n=100_000)
+    big = a["unit_type"] == 1
+    assert 0.19 < big.mean() < 0.21
+    assert (a["radius"][big] == 5).all() and (a["mass"][big] == 50).all() and (a["radius"][~big] == 3).all() and (a["mass"][~big] == 1).all()
+    moving = a["state"] == abi.MOVING
+    assert 0.49 < moving.mean() < 0.51 and (a["path_id"][~moving] == -1).all() and (a["path_id"][moving] >= 0).all()
+    assert len(np.unique(fx["path_group"][a["path_id"][moving]])) == 16
+    occ = scenario.occupancy(fx, 0)
+    assert not occ[(a["r"][:, 0] // 5).astype(int), (a["r"][:, 1] // 5).astype(int)].any()
+    # ... and some of them start in contact with a wall (the oracle's wall query as the checker)
+    ow = port.OracleWorld(port.default_params(1024, 1024), scenario.tables_of(fx))
+    cnt, _ = ow.contact_edges(a["r"][:20000], a["radius"][:20000])
+    assert 20 < (cnt > 0).sum() < 2000
+
+
 def test_config5_population_and_paths():
     """BASELINE configs[4]: the corridor population — free space only, everyone MOVING, the two halves of the map heading
     through the corridor nearest to them in opposite directions (counter-flow), each agent already on the leg of its path
