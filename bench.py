@@ -439,35 +439,51 @@ def run_reference(args):
         L = refh.load(True)
         L.refh_set_omp_threads.argtypes = [__import__("ctypes").c_int]
         L.refh_set_omp_threads(os.cpu_count() or 1)   # (in case an OpenMP runtime was initialised before the variable was set)
-        rng = np.random.default_rng(1236)
-        w = refh.RefWorld(512, 512, fast=True)
-        placed = 0
-        occ = np.zeros((512, 512), bool)
-        while placed < 50:   # same building density as config 3 (200 per 1024² cells)
-            cx, cy = (int(v) for v in rng.integers(12, 500, 2))
-            nn, mm = (8, 8) if rng.random() < 0.5 else (4, 6)
-            x0, y0 = cx - nn // 2, cy - mm // 2
-            if occ[x0 - 2:x0 + nn + 2, y0 - 2:y0 + mm + 2].any():
-                continue
-            if w.add_building(cx, cy, nn, mm, 1) != 0:
-                continue
-            occ[x0 - 1:x0 + nn + 1, y0 - 1:y0 + mm + 1] = True
-            placed += 1
-        w.finalize_map()
         n = 5000
         side = float(np.sqrt(n / (1_000_000 / 5120.0 ** 2)))   # window with config-3 density
-        pos = []
-        while len(pos) < n:
-            p = rng.uniform(1000.0, 1000.0 + side, 2)
-            if not occ[int(p[0] // 5), int(p[1] // 5)]:
-                pos.append(p)
-        for p in pos:
-            w.add_agent(float(p[0]), float(p[1]))
-        w.issue_paths(np.arange(n, dtype=np.int32), 2300.0, 2200.0)
-        w.step(Wm)
-        t0 = time.perf_counter()
-        w.step(K)
-        dt = time.perf_counter() - t0
+
+        def timed_run(n_threads):
+            """a fresh world (same seed, same frames) stepped with n_threads OpenMP threads"""
+            L.refh_set_omp_threads(n_threads)
+            rng = np.random.default_rng(1236)
+            w = refh.RefWorld(512, 512, fast=True)
+            placed = 0
+            occ = np.zeros((512, 512), bool)
+            while placed < 50:   # same building density as config 3 (200 per 1024² cells)
+                cx, cy = (int(v) for v in rng.integers(12, 500, 2))
+                nn, mm = (8, 8) if rng.random() < 0.5 else (4, 6)
+                x0, y0 = cx - nn // 2, cy - mm // 2
+                if occ[x0 - 2:x0 + nn + 2, y0 - 2:y0 + mm + 2].any():
+                    continue
+                if w.add_building(cx, cy, nn, mm, 1) != 0:
+                    continue
+                occ[x0 - 1:x0 + nn + 1, y0 - 1:y0 + mm + 1] = True
+                placed += 1
+            w.finalize_map()
+            pos = []
+            while len(pos) < n:
+                p = rng.uniform(1000.0, 1000.0 + side, 2)
+                if not occ[int(p[0] // 5), int(p[1] // 5)]:
+                    pos.append(p)
+            for p in pos:
+                w.add_agent(float(p[0]), float(p[1]))
+            w.issue_paths(np.arange(n, dtype=np.int32), 2300.0, 2200.0)
+            w.step(Wm)
+            t0 = time.perf_counter()
+            w.step(K)
+            elapsed = time.perf_counter() - t0
+            w.close()
+            return elapsed
+
+        # the reference hard-codes 6 OpenMP threads for its parallel loops (NUM_OMP_NS_THREADS / NUM_OMP_WALLS_THREADS,
+        # src/core.h:27-38); the build here takes the team size from the OpenMP runtime instead, so both are one library:
+        # SURVEY §8d asks for the stock setting next to the all-cores one. The line's value is the all-cores run.
+        stock = None
+        if (os.cpu_count() or 1) >= 6:
+            dt6 = timed_run(6)
+            stock = {"cores": 6, "value": n * K / dt6, "ms_per_step": 1e3 * dt6 / K,
+                     "what": "the same frames with the reference's own hard-coded team size (NUM_OMP_*_THREADS 6, src/core.h:27-38)"}
+        dt = timed_run(os.cpu_count() or 1)
         threads = int(refh.load(True).refh_omp_threads())
         kind, sample = "reference", (f"{n} agents (reference cap N_MAX_NAVIGABLE_BOIDS) at config-3 density in a {side:.0f}² window, 50 buildings, "
                                      f"verbatim reference TUs -Ofast, {K} frames")
@@ -492,6 +508,8 @@ def run_reference(args):
                               "(1M agents) cannot run on it; the same-config CPU comparator is the GPU arm's cpu_baseline (oracle port, 1M agents)"},
             "cpu_baseline": {"value": value, "unit": "agent-updates/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if kind == "reference" and stock is not None:
+        line["cpu_baseline"]["stock_threads"] = stock
     print(json.dumps(line))
 
 

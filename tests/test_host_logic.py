@@ -144,6 +144,9 @@ def test_reference_arm_of_the_bench_emits_the_contract_line():
     assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 2
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["value"] == j["value"]
     assert j["cpu_baseline"]["cores"] == (os.cpu_count() or 1)       # every host thread, whatever OMP_NUM_THREADS said
+    if j["cpu_baseline"]["kind"] == "reference" and (os.cpu_count() or 1) >= 6:
+        stock = j["cpu_baseline"]["stock_threads"]                   # the reference's hard-coded 6 threads beside it
+        assert stock["cores"] == 6 and stock["value"] > 0
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # the record says what really ran: the reference cannot hold config 3 (5 000-agent cap), so the arm runs its density
     assert j["config"]["same_config_as_gpu_arm"] is False and j["config"]["agents"] in (5000, 200000)
