@@ -489,6 +489,21 @@ int refh_ns_full_list(float box, float cell, const float* xy, int n, float qx, f
     return (int)inds.size();
 }
 
+// The Attack strategy's nearest-enemy search as the reference runs it (AttackSystem.cpp:24: a context of 20*RHARD = 60-unit cells,
+// NeighbourSearcherStrategy.cpp:125-177): out[i] = the enemy index the reference reports for agent i, or -1 when it reports none.
+int refh_attack_ns(float box, float cell, const float* xy, const unsigned char* player, int n, int* out) {
+    NeighbourSearcherContext<AttackComponent, int> ns({box, box}, cell);
+    ns.setStrategy(NS_STRATEGY::ATTACK);
+    std::vector<AttackComponent> comps(n);
+    for (int i = 0; i < n; ++i) {
+        comps[i].transform.r = {xy[2 * i], xy[2 * i + 1]};
+        comps[i].player_ind = player[i];
+    }
+    ns.update(comps);
+    for (int i = 0; i < n; ++i) out[i] = ns.last_i.at(i) > 0 ? ns.getInteractionData(i).at(0) : -1;
+    return 0;
+}
+
 // full funnel path of one planner query (PathFinder2.cpp:388-438): waypoints (2 floats) and portals (5 floats)
 int refh_plan_path(void* h, float sx, float sy, float ex, float ey, float radius, float* path, float* portals, int cap) {
     auto* w = W(h);

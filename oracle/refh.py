@@ -234,6 +234,18 @@ class RefWorld:
         return path[:k], portals[:k]
 
 
+def attack_targets(box, cell, xy, player):
+    """NeighbourSearcherStrategyAttack::execute through the reference's own context (AttackSystem.cpp:24): per agent the enemy
+    index it reports, or -1"""
+    L = load()
+    L.refh_attack_ns.argtypes = [C.c_float, C.c_float, f32p, u8p, C.c_int, i32p]
+    xy = np.ascontiguousarray(xy, np.float32)
+    player = np.ascontiguousarray(player, np.uint8)
+    out = np.zeros(len(xy), np.int32)
+    L.refh_attack_ns(float(box), float(cell), xy, player, len(xy), out)
+    return out
+
+
 def coord_to_cell(nx, ny, cs, xy, fast=False):
     xy = np.ascontiguousarray(xy, np.float32)
     out = np.zeros(len(xy), np.uint64)

@@ -598,8 +598,9 @@ uint32_t rts_oracle_query_radius(const RtsParams* P, uint32_t n, const float* r,
    calcNearestCells + the own cell, in that order and ascending component index inside a cell, EVERY agent of another player
    with dist^2 < range2 (the reference never lowers min_enemy_dist_sq from its initial Geometry::BOX[0] = 2560) overwrites slot
    0 — so the "nearest enemy" it reports is the LAST such agent in visit order. out[i] = that index, or -1.
-   PARITY UNPINNED: the verbatim translation unit needs AttackSystem.h (-> VisionSystem -> glm) and cannot be built headless;
-   this follows the source text only. */
+   Pinned: the verbatim strategy runs headless through NeighbourSearcherContext<AttackComponent, int> (ref_harness.cpp::
+   refh_attack_ns; only AttackSystem.h itself needs glm, and the strategy's translation unit is built without it) and
+   tests/test_oracle_vs_ref.py compares every agent's answer on random two- and three-player crowds. */
 void rts_oracle_attack_targets(const RtsParams* P, uint32_t n, const float* r, const uint8_t* player, float range2, int32_t* out) {
     ns_grid g;
     uint32_t* cell_of = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));

@@ -312,3 +312,30 @@ def test_golden_fixtures_are_reproduced_by_the_committed_script(tmp_path):
         assert set(new.files) == set(old.files), name
         for k in old.files:
             assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape and new[k].tobytes() == old[k].tobytes(), (name, k)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_attack_strategy_targets_against_live_reference(seed):
+    """NeighbourSearcherStrategyAttack::execute (NeighbourSearcherStrategy.cpp:125-177) through the reference's own context on
+    the AttackSystem's 60-unit grid (AttackSystem.cpp:24): the enemy every agent ends up with — the LAST agent of another player
+    in the visit order, since the loop never lowers its distance bound — is what the oracle answers; crowds in the open, in
+    the map corners and with agents exactly on cell boundaries, two to four players."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(200, 3000))
+    lo, hi = ((100, 900), (5, 200), (2300, 2555), (0, 2559))[seed % 4]
+    xy = rng.uniform(lo, hi, (n, 2)).astype(np.float32)
+    if seed % 2:
+        xy[: n // 4] = np.round(xy[: n // 4] / 60) * 60
+    player = rng.integers(0, 2 + seed % 3, n).astype(np.uint8)
+    ref = refh.attack_targets(2560.0, 60.0, xy, player)
+    ow = port.OracleWorld(port.default_params(512, 512), H.tables_of(H.load("map_empty.npz")))
+    got = ow.attack_targets(xy, player, 2560.0)
+    H.assert_same_bits(got, ref, "attack targets")
+    assert (ref >= 0).sum() > n // 2
+    # the geometry of the reference's own test (test_neighbour_search.cc:68-94: agents at (25,25), (40,40), (24,24)), two players:
+    # on its 10-unit grid (40,40) is two cells away from the others; on the AttackSystem's 60-unit grid all three share a cell
+    kat_xy = np.array([[25, 25], [40, 40], [24, 24]], np.float32)
+    kat_pl = np.array([0, 1, 1], np.uint8)
+    assert refh.attack_targets(100.0, 10.0, kat_xy, kat_pl).tolist() == [2, -1, 0]
+    assert refh.attack_targets(2560.0, 60.0, kat_xy, kat_pl).tolist() == [2, 0, 0]
+    assert ow.attack_targets(kat_xy, kat_pl, 2560.0).tolist() == [2, 0, 0]
