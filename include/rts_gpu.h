@@ -332,7 +332,7 @@ int32_t rts_query_radius(RtsHandle h, const float* xy, const float* r_max, uint3
 /* NeighbourSearcherStrategyAttack::execute (NeighbourSearcherStrategy.cpp:125-177) for every agent, AS WRITTEN: the reference
    never lowers min_enemy_dist_sq from Geometry::BOX[0] (2560), so the "nearest enemy" of an agent is the LAST agent of another
    player with dist^2 < range2 in visit order (calcNearestCells cells, own cell last). out[i] = its component index or -1
-   (rts_agent_count() entries). Follows the source text only: that translation unit cannot be built headless. */
+   (rts_agent_count() entries). The oracle's version is pinned on the reference's own context (tests/test_oracle_vs_ref.py). */
 int32_t rts_attack_targets(RtsHandle h, float range2, int32_t* out);
 
 /* ---- multi-GPU: spatial slab decomposition, one handle (one process, one GPU) per y-slab -----------------------
