@@ -339,3 +339,39 @@ def test_attack_strategy_targets_against_live_reference(seed):
     assert refh.attack_targets(100.0, 10.0, kat_xy, kat_pl).tolist() == [2, -1, 0]
     assert refh.attack_targets(2560.0, 60.0, kat_xy, kat_pl).tolist() == [2, 0, 0]
     assert ow.attack_targets(kat_xy, kat_pl, 2560.0).tolist() == [2, 0, 0]
+
+
+def test_coord_to_cell_outside_the_map_against_live_reference():
+    """Grid::coordToCell (Grid.cpp:18-24) where the fixtures do not go: negative, beyond-map and huge coordinates (the
+    reference converts a negative float to size_t and wraps modulo the grid — what an agent pushed over the map edge gets),
+    -0.0, denormals, the far border itself; the four grids of the path."""
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.uniform(-500, 3200, (20000, 2)), rng.uniform(-1e6, 1e6, (2000, 2)), rng.uniform(-60, 60, (4000, 2)),
+                          np.array([[-0.0, 0.0], [-1e-30, 5.0], [2560.0, 2560.0], [2559.9998, -59.99999], [-60.0, -120.0],
+                                    [1e9, -1e9]])]).astype(np.float32)
+    for nx, cs in ((43, 60.0), (86, 30.0), (512, 5.0), (64, 40.0)):
+        ref = refh.coord_to_cell(nx, nx, cs, pts)
+        assert ref.max() < nx * nx
+        H.assert_same_bits(port.coord_to_cell(pts, nx, nx, cs), ref.astype(np.uint32), f"coordToCell on the {nx}x{nx} grid of {cs}")
+
+
+def test_physics_neighbour_lists_against_live_reference():
+    """SURVEY T3: NeighbourSearcherStrategyPhysics::execute (NeighbourSearcherStrategy.cpp:10-68) — the neighbour SET and its
+    ORDER (the summation order of the force pass) of every agent, two crowds in opposite map corners with agents off the map
+    (wrapped cells: an agent beyond the edge is no neighbour of the agent beside it)."""
+    rng = np.random.default_rng(1)
+    w = refh.RefWorld(512, 512)
+    w.finalize_map()
+    xy = np.concatenate([rng.uniform(-20, 200, (1500, 2)), rng.uniform(2450, 2580, (1000, 2))]).astype(np.float32)
+    for p in xy:
+        w.add_agent(float(p[0]), float(p[1]))
+    w.L.refh_physics_ns_update(w.h)
+    ow = port.OracleWorld(port.default_params(512, 512), w.tables())
+    total = 0
+    for i in range(len(xy)):
+        ref = w.physics_neighbours(i)
+        H.assert_same_bits(ow.neighbours(xy, i).astype(np.int32), ref, f"neighbour list of agent {i}")
+        total += len(ref)
+    assert total > 5000
+    outside = np.nonzero((xy < 0).any(axis=1) | (xy >= 2560).any(axis=1))[0]
+    assert len(outside) > 100
