@@ -43,6 +43,7 @@ def _side_by_side(seed, n, n_buildings, lo, hi, commanded, big, frames, target=(
     a["r"][:] = s["r"]
     a["radius"][:] = radius
     a["mass"][:] = mass
+    window_events = {"advanced": 0, "slid": 0, "replan_flags": 0}
     for f in range(frames):
         w.plan_now()
         win = w.seek_window()
@@ -51,12 +52,22 @@ def _side_by_side(seed, n, n_buildings, lo, hi, commanded, big, frames, target=(
         a["path_id"][:] = np.where(st == abi.MOVING, np.arange(n), -1)
         a["waypoint"][:] = 0
         a["r_next"][:] = win[:, 0:2]
+        a["flags"][:] = 0
         port.OracleWorld(P, tables, H.windows_to_paths(win)).step(a)
         w.step(1)
         s = w.state()
         for k in ("r", "vel", "inertia", "angle", "angle_vel"):
             H.assert_same_bits(a[k], s[k], f"seed {seed} frame {f} {k}")
         H.assert_same_bits(a["tri_idx"], w.find_triangles(s["r"]), f"seed {seed} frame {f} tri")
+        # what the frame did to the seek window (needsUpdating's portal slide, updateTarget's shift, SeekSystem.cpp:181-233,
+        # 277-304): the reference's windows right after its frame, before its planner runs again
+        mv = st == abi.MOVING
+        H.assert_same_bits(a["r_next"][mv], w.seek_window()[mv, 0:2], f"seed {seed} frame {f}: r_next after the frame")
+        advanced = mv & (a["waypoint"] == 1)
+        window_events["advanced"] += int(advanced.sum())
+        window_events["slid"] += int((mv & ~advanced & (a["r_next"] != win[:, 0:2]).any(axis=1)).sum())
+        window_events["replan_flags"] += int(((a["flags"] & abi.FLAG_REPLAN) != 0).sum())
+    s["window_events"] = window_events
     return s
 
 
@@ -128,7 +139,9 @@ def test_multipliers_and_unit_dynamics_against_live_reference(seed, mult, types)
 
 
 def test_frames_bit_exact_against_live_reference():
-    _side_by_side(3, 1200, 30, 150, 700, lambda rng, n: np.arange(0, n, 2), 0.3, 150)
+    s = _side_by_side(3, 1200, 30, 150, 700, lambda rng, n: np.arange(0, n, 2), 0.3, 150)
+    ev = s["window_events"]          # waypoints were reached, targets slid along portals, re-plans were requested — and agreed
+    assert ev["advanced"] > 50 and ev["slid"] > 50 and ev["replan_flags"] > 0, ev
 
 
 def _some(frac):
