@@ -210,6 +210,51 @@ def test_snapshot_arrival_rule_tracks_the_serial_cascade():
     assert abs(ow.fin_area[0] - n_or * np.float32(np.pi) * 9) < 1.0
 
 
+def test_arrival_rule_is_bit_exact_where_the_cascade_order_cannot_matter():
+    """finalizeSeek (SeekSystem.cpp:235-275) with ONE agent per command group (100 groups, agents 60 units apart, every agent its
+    own target 0 - 57 units away, some of them inside 2*radius from the start): no agent can stop another and no agent shares a
+    finished area, so the reference's serial loop and the oracle's frame-start snapshot must agree exactly — the arrival
+    predicate, the frame an agent stops in, what stopping does to vel / angle_vel / state: every agent, every frame, bit for
+    bit. (In a crowd the two differ only in whether an agent sees the stops of the agents processed before it in the SAME
+    frame: test_snapshot_arrival_rule_tracks_the_serial_cascade.)"""
+    n, frames = 100, 120
+    rng = np.random.default_rng(1)
+    w = refh.RefWorld(512, 512)
+    w.finalize_map()
+    pos = np.array([[300 + 60 * (i % 10), 300 + 60 * (i // 10)] for i in range(n)], np.float32) + rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+    tgt = pos + rng.uniform(-40, 40, (n, 2)).astype(np.float32)
+    radius = np.where(rng.random(n) < 0.3, 5.0, 3.0).astype(np.float32)
+    for p, rad in zip(pos, radius):
+        w.add_agent(float(p[0]), float(p[1]), 0.0, float(rad), 1.0, 0, 1)
+    for i in range(n):
+        w.issue_paths(np.array([i], np.int32), float(tgt[i, 0]), float(tgt[i, 1]))
+    w.plan_now()
+    assert len(set(w.groups().tolist())) == n
+    P = port.default_params(512, 512)
+    P.enable_arrival = 1
+    paths = {"offsets": np.arange(n + 1, dtype=np.uint32), "waypoints": tgt.copy(), "portals": np.zeros((n, 5), np.float32),
+             "path_end": tgt.copy(), "group": np.arange(n, dtype=np.int32)}
+    ow = port.OracleWorld(P, w.tables(), paths)
+    a = abi.alloc_agent_arrays(n, set(H.ALL_FIELDS))
+    a["r"][:] = pos
+    a["radius"][:] = radius
+    a["mass"][:] = 1
+    a["state"][:] = abi.MOVING
+    a["path_id"][:] = np.arange(n)
+    a["r_next"][:] = np.nan
+    stopped_in = np.full(n, -1)
+    for f in range(frames):
+        w.step(1)
+        ow.step(a, 1)
+        s = w.state()
+        for k in ("r", "vel", "inertia", "angle", "angle_vel"):
+            H.assert_same_bits(a[k], s[k], f"frame {f} {k}")
+        assert (a["state"] == s["state"]).all(), (f, np.nonzero(a["state"] != s["state"])[0][:5])
+        stopped_in[(stopped_in < 0) & (s["state"] == abi.STANDING)] = f
+    assert (stopped_in >= 0).all() and (stopped_in == 0).sum() >= 1 and len(np.unique(stopped_in)) > 20
+    H.assert_same_bits(ow.fin_area, np.full(n, np.float32(np.pi) * np.float32(3) * np.float32(3), np.float32), "one unit of area per group")
+
+
 @pytest.mark.parametrize("seed,buildings", [(0, 0), (1, 12), (2, 45)])
 def test_cell_grid_restatement_matches_update_cell_grid(seed, buildings):
     """f3: oracle build_cell_grid == Triangulation::updateCellGrid (Triangulation.cpp:1829-1864) on live CDTs, for every
